@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- bank-CE forward+backward throughput of the B200-native path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C3]
+
+One "step" = one pass of the hot path over one batch of synthetic queries: forward statistics + loss and
+the backward dL/dq against the device-resident bank (config C3: 512 queries x 100k x 640-d bank, bf16).
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, L2 flushed between timed
+iterations, max over ranks, clocks sampled with nvidia-smi during the timed region.
+`--impl reference` times the reference's CPU torch path (the oracle restatement of
+clip4cir/models_negplus.py:150-154 + backward) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+from spn4cir_b200 import synth  # noqa: E402
+
+METRIC = "bank_ce_fwd_bwd_queries_per_sec"
+
+
+def measured_peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(tflops=float(d["bf16_tflops"]), tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    hbm=float(d["hbm_gbs"]), src="measured")
+    return dict(tflops=1590.0, tflops_sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_step(q, bank, labels, tau):
+    """The reference's CPU path: oracle restatement of infonce_loss + autograd backward, fp32, all host threads."""
+    from oracle import bank_ce as obank
+    qq = q.clone().requires_grad_(True)
+    loss = obank.infonce_loss(qq, bank, labels, tau)
+    loss.backward()
+    return loss.item(), qq.grad
+
+
+def time_cpu_reference(cfg, budget_s: float, steps: int, warmup: int):
+    """Bounded sample: full query batch against the first N' bank rows, N' chosen to fit `budget_s`."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, N, D, tau = cfg["B"], cfg["N"], cfg["D"], cfg["tau"]
+    n_probe = min(N, 8192)
+    q, bank, labels = synth.make_bank_case(B, n_probe, D, 1, "S", 0)
+    cpu_reference_step(q, bank, labels, tau)
+    t0 = time.perf_counter()
+    cpu_reference_step(q, bank, labels, tau)
+    t_probe = time.perf_counter() - t0
+    est_full = t_probe * N / n_probe
+    frac = min(1.0, budget_s / max(1e-9, est_full * (steps + warmup)))
+    n_s = max(1024, int(N * frac))
+    n_s = min(N, n_s)
+    q, bank, labels = synth.make_bank_case(B, n_s, D, 1, "S", 0)
+    for _ in range(warmup):
+        cpu_reference_step(q, bank, labels, tau)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_reference_step(q, bank, labels, tau)
+        times.append(time.perf_counter() - t0)
+    t_step_full = (sum(times) / len(times)) * (N / n_s)  # linear in bank rows
+    return dict(value=B / t_step_full, unit="queries/s", cores=cores, kind="port",
+                sample=f"{steps} timed steps (+{warmup} warm-up) of B={B} x N'={n_s} of {N} bank rows x D={D} fp32 fwd+bwd, "
+                       f"scaled linearly to N={N}; torch {torch.__version__} CPU, {torch.get_num_threads()} threads"), t_step_full
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, t_step = time_cpu_reference(cfg, budget_s=150.0, steps=max(1, args.steps), warmup=max(0, args.warmup))
+    line = {"metric": METRIC, "value": cb["value"], "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"{args.config}: bank-CE fwd+bwd, B={cfg['B']} queries x N={cfg['N']} x D={cfg['D']} "
+                                   "bank, reference CPU torch path (oracle port of clip4cir/models_negplus.py:150-154)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_ours(args, cfg):
+    import torch.distributed as dist
+
+    import spn4cir_b200 as spn
+    from spn4cir_b200.dist import bank_infonce_sharded, shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, N, D, tau = cfg["B"], cfg["N"], cfg["D"], cfg["tau"]
+    peaks = measured_peaks()
+
+    # ---- synthetic inputs (same generator as the tests); bank row-sharded when world > 1
+    bank_cpu = synth.make_bank(N, D, 1, seed=1234)
+    labels_cpu = synth.make_labels(B, N, seed=1235 + rank)
+    q_cpu = synth.make_queries(bank_cpu, labels_cpu, "S", seed=1236 + rank)
+    bank = spn.DeviceBank.from_tensor(bank_cpu, dev, shard_rank=rank, shard_world=world)
+    q_dev = q_cpu.to(dev)
+    labels_dev = labels_cpu.to(dev)
+    q_pin = q_cpu.pin_memory()
+    lab_pin = labels_cpu.pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(qin, lab):
+        qx = qin.detach().requires_grad_(True)
+        if world > 1:
+            loss = bank_infonce_sharded(qx, bank, lab, tau)
+        else:
+            loss = spn.bank_infonce(qx, bank, lab, tau)
+        loss.backward()
+        return loss, qx.grad
+
+    def step_e2e():
+        qd = q_pin.to(dev, non_blocking=True)
+        ld = lab_pin.to(dev, non_blocking=True)
+        loss, dq = step(qd, ld)
+        out = dq.to("cpu", non_blocking=True)
+        lv = loss.to("cpu", non_blocking=True)
+        return lv, out
+
+    def timed(fn, iters):
+        """sum of per-iteration CUDA-event times (L2 flushed, untimed, before each); max over ranks."""
+        evs = []
+        for _ in range(iters):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize(dev)
+        return sum(s.elapsed_time(e) for s, e in evs) / 1e3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step(q_dev, labels_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_dev = timed(lambda: step(q_dev, labels_dev), args.steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t_e2e = timed(step_e2e, args.steps)
+    barrier()
+
+    # ---- dominant-kernel roofline: backward kernel (and forward kernel) timed alone, same events/stream
+    from spn4cir_b200.ops import _bwd, _fwd_stats, _loss_from_stats, cast_to_bf16
+    Bt = B * world
+    q16 = cast_to_bf16(torch.cat([q_dev] * world) if world > 1 else q_dev)
+    lab_all = torch.cat([labels_dev] * world) if world > 1 else labels_dev
+    stats = _fwd_stats(q16, bank, lab_all, 1.0 / tau, False)
+    if world > 1:
+        from spn4cir_b200.dist import merge_stats_across_ranks
+        stats = merge_stats_across_ranks(stats)
+    lse, _, _ = _loss_from_stats(stats, bank.n_total, 0.0)
+    dq_acc = torch.zeros((Bt, D), dtype=torch.float32, device=dev)
+    t_fwd = timed(lambda: _fwd_stats(q16, bank, lab_all, 1.0 / tau, False), args.steps) / args.steps
+    t_bwd = timed(lambda: _bwd(q16, bank, lab_all, 1.0 / tau, lse, (1.0 / tau) / B, None, 0.0, dq_acc, None),
+                  args.steps) / args.steps
+    barrier()
+
+    red = torch.tensor([t_dev, t_e2e, t_fwd, t_bwd], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e, t_fwd, t_bwd = red.tolist()
+
+    if rank == 0:
+        n_local = bank.N
+        flops_alg_kernel = 2.0 * Bt * n_local * D  # per launch, per rank (dq = P . bank; the S recompute is not credited)
+        step_flops_rank = 4.0 * Bt * n_local * D
+        ms_step = t_dev / args.steps * 1e3
+        value = (B * world) * args.steps / t_dev
+        peak = peaks["tflops"]
+        roof = {"bound": "tensor", "kernel": "bank_ce_kernel<MODE=1> (backward: recompute S, dq += P.bank)",
+                "achieved": flops_alg_kernel / t_bwd / 1e12, "peak": peak, "unit": "TFLOP/s",
+                "frac": flops_alg_kernel / t_bwd / 1e12 / peak, "traffic": None, "peak_source": peaks["src"] + " burst bf16",
+                "kernel_ms": t_bwd * 1e3,
+                "forward_kernel": {"achieved": flops_alg_kernel / t_fwd / 1e12, "frac": flops_alg_kernel / t_fwd / 1e12 / peak,
+                                   "kernel_ms": t_fwd * 1e3},
+                "step": {"algorithmic_tflops": step_flops_rank / (t_dev / args.steps) / 1e12,
+                         "frac": step_flops_rank / (t_dev / args.steps) / 1e12 / peak}}
+        prof = REPO / "profiles" / "r01_ncu_bank_ce_bwd.json"
+        if prof.exists():
+            try:
+                roof["traffic"] = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{args.config}: bank-CE fwd+bwd, B={B} queries/rank x N={N} x D={D} bank (bf16, fp32 accumulate), tau={tau}",
+                           "parallelism": f"bank row-sharded x{world}, queries data-parallel (all-gathered), stats all-gather + dq reduce-scatter" if world > 1 else "single GPU",
+                           "l2": "256 MiB flush buffer written before every timed iteration",
+                           "global_batch": B * world},
+                "clocks": clocks, "roofline": roof,
+                "e2e": {"value": (B * world) * args.steps / t_e2e, "unit": "queries/s",
+                        "h2d_bytes_per_step": q_pin.numel() * 4 + lab_pin.numel() * 8,
+                        "d2h_bytes_per_step": B * D * 4 + 4, "ms_per_step": t_e2e / args.steps * 1e3,
+                        "note": "pinned host q/labels -> device, fwd+bwd, loss + dq back to host; the bank stays resident in HBM"},
+                "gpu_launches": 5 * args.steps,
+                "gpu_launches_detail": "per step: spn_cast_to_bf16, bank_ce_kernel<0>, merge_stats_kernel, loss_kernel, bank_ce_kernel<1>"}
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = time_cpu_reference(cfg, budget_s=20.0, steps=3, warmup=1)
+            line["cpu_baseline"] = cb
+        if world == 1 and not args.no_retrieval:
+            line["retrieval"] = bench_retrieval(dev, args)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_retrieval(dev, args):
+    """C2: CIRR-shaped validation retrieval, 4181 queries x 2297 gallery x 640-d, top-50 (+ rank) on one GPU."""
+    import spn4cir_b200 as spn
+    c = synth.CONFIGS["C2"]
+    q, gal, _, ref, tgt, grp = synth.make_retrieval_case(c["Q"], c["G"], c["D"], 1, 0, noise=8.0)
+    qd, gd = q.to(dev), gal.to(dev)
+    refd = ref.to(dev, torch.int32)
+    for _ in range(3):
+        spn.sim_topk(qd, gd, c["K"], exclude=refd)
+    torch.cuda.synchronize(dev)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = max(3, min(args.steps, 20))
+    s.record()
+    for _ in range(iters):
+        spn.sim_topk(qd, gd, c["K"], exclude=refd)
+    e.record()
+    torch.cuda.synchronize(dev)
+    t = s.elapsed_time(e) / 1e3 / iters
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        qh = q.to(dev)
+        gh = gal.to(dev)
+        v, i = spn.sim_topk(qh, gh, c["K"], exclude=refd)
+        i.cpu()
+    torch.cuda.synchronize(dev)
+    t_e2e = (time.perf_counter() - t0) / iters
+    # reference CPU lines: `1 - q @ g.T` + argsort (clip4cir/validate.py:126-127)
+    from oracle import retrieval as oretr
+    torch.set_num_threads(os.cpu_count() or 1)
+    oretr.reference_style_sorted_indices(q, gal)
+    t0 = time.perf_counter()
+    oretr.reference_style_sorted_indices(q, gal)
+    t_cpu = time.perf_counter() - t0
+    return {"workload": f"C2: {c['Q']} queries x {c['G']} gallery x {c['D']}-d fp32, fused sim + top-{c['K']}",
+            "value": c["Q"] / t, "unit": "queries/s", "ms": t * 1e3, "e2e_value": c["Q"] / t_e2e,
+            "cpu_reference_value": c["Q"] / t_cpu, "cpu_cores": os.cpu_count(),
+            "fp32_tflops": 2.0 * c["Q"] * c["G"] * c["D"] / t / 1e12}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3", choices=["C1", "C3", "C5"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-retrieval", action="store_true")
+    args = ap.parse_args()
+    cfg = synth.CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

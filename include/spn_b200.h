@@ -1,0 +1,159 @@
+/* spn_b200.h -- C ABI of the B200-native SPN4CIR hot path.
+ *
+ * The reference (BUAADreamer/SPN4CIR) is pure Python/PyTorch and has no FFI; the "operator API" of
+ * its hot path is three Python call shapes.  This header is the C boundary a
+ * torch-free host (ctypes, cffi, a C++ trainer) binds instead.  Each entry point cites the reference
+ * lines it replaces.  The Python mirror of the reference call sites lives in spn4cir_b200/compat.py.
+ *
+ * Conventions
+ *  - every function returns SPN_OK (0) or a negative spn_status; spn_last_error() gives a
+ *    thread-local human readable message; nothing throws.
+ *  - all data pointers are DEVICE pointers, 16-byte aligned, row-major, rows contiguous.
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*); the library never
+ *    allocates device memory: the caller owns outputs and the workspace (spn_workspace_bytes).
+ *  - bank-CE operands are bf16 (the arithmetic type of the path: bf16 x bf16 -> fp32 on tcgen05);
+ *    use spn_cast_to_bf16 as the prologue for fp32/fp16 tensors.  Retrieval operands are fp32.
+ *  - "scaled logit" s[b][n] = inv_tau * <q[b], bank[n]>; with T > 1 (BLIP-2) a bank entry is T
+ *    consecutive token rows and s[b][n] = inv_tau * max_t <q[b], bank[n*T + t]>.
+ *  - there is no CPU fallback: on a machine without an sm_100 device every compute call fails with
+ *    SPN_ERR_CUDA.
+ */
+#ifndef SPN_B200_H_
+#define SPN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum spn_status {
+  SPN_OK = 0,
+  SPN_ERR_BAD_SHAPE = -1,
+  SPN_ERR_BAD_ALIGN = -2,
+  SPN_ERR_BAD_DTYPE = -3,
+  SPN_ERR_WORKSPACE = -4,
+  SPN_ERR_CUDA = -5,
+  SPN_ERR_NCCL = -6,
+  SPN_ERR_BAD_ARG = -7
+} spn_status;
+
+enum spn_op {
+  SPN_OP_BANK_CE_FWD = 1,
+  SPN_OP_BANK_CE_BWD = 2,
+  SPN_OP_SIM_TOPK = 3,
+  SPN_OP_SIM_RANK = 4
+};
+
+enum spn_dtype { SPN_F32 = 0, SPN_F16 = 1, SPN_BF16 = 2 };
+
+/* ABI version, bumped on any signature change. */
+int spn_version(void);
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* spn_last_error(void);
+/* 1 if device `dev` is an sm_100 part this library can run on, else 0 (never fails). */
+int spn_device_supported(int dev);
+
+/* Workspace size for one call of `op` with these shapes (bytes, multiple of 256). */
+int spn_workspace_bytes(int op, int B, int64_t N, int D, int T, int K, size_t* out_bytes);
+
+/* Prologue: cast n elements of `src` (spn_dtype) to bf16.  Replaces the implicit autocast down-cast
+ * of clip4cir/train_negplus.py:110 and the per-step `.to(device)` of models_negplus.py:138 (the bank
+ * is cast once and stays resident). */
+int spn_cast_to_bf16(const void* src, int src_dtype, void* dst_bf16, int64_t n, void* stream);
+
+/* Prologue: q[b] = normalize(refer_bank[refer_idx[b]] + text[b]) -> bf16 (and fp32 copy
+ * + inverse norm for the normalize-backward).  Replaces clip4cir/models_negplus.py:133-137.
+ * refer_bank fp32 [R, D]; text fp32 [B, D]; q_f32 / inv_norm nullable. */
+int spn_query_assemble(const float* refer_bank, const int64_t* refer_idx, const float* text, int B, int D,
+                       void* q_bf16, float* q_f32, float* inv_norm, void* stream);
+
+/* Forward statistics of CrossEntropy((q @ bank^T) * inv_tau, labels) over one bank shard.
+ * Replaces the logits + log-softmax of CIRPlus.infonce_loss (clip4cir/models_negplus.py:150-154,
+ * zscir/models_bank.py:130-134, blip4cir/models.py:117-121, tgcir/models.py:289-293) and, with
+ * T = 32, the per-sample loop of Blip2QformerCirAlignPrompt.forward_stage2
+ * (blip24cir/lavis/models/blip2_models/blip2_qformer_cir_align_prompt.py:254-268).
+ *   q      bf16 [B, D]            bank  bf16 [N*T, D]  (N entries of this shard)
+ *   labels int64 [B], GLOBAL entry index; entries [row_base, row_base + N) live in this shard
+ * Outputs (fp32 [B], natural-log units):
+ *   m = max_n s, l = sum_n exp(s - m), s_t = s[label] or -inf when the label is not in this shard,
+ *   s_sum (nullable) = sum_n s  (only needed for label smoothing, zscir/models_bank.py:35).
+ * The B x N logit matrix is never written to memory. */
+int spn_bank_ce_fwd(const void* q_bf16, const void* bank_bf16, const int64_t* labels, float inv_tau, int B,
+                    int64_t N, int D, int T, int64_t row_base, float* m, float* l, float* s_t, float* s_sum,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* Merge P partial statistics laid out [P][B] (chunks of one shard, or the all-gathered shards of R
+ * ranks) into one [B] set: M = max m_p, L = sum l_p exp(m_p - M), s_t = max, s_sum = sum. */
+int spn_merge_stats(const float* m_parts, const float* l_parts, const float* st_parts, const float* ssum_parts,
+                    int P, int B, float* m, float* l, float* s_t, float* s_sum, void* stream);
+
+/* lse[b] = m + log(l); loss_b = lse - (1-eps) s_t - eps * s_sum / N_total; loss_mean = mean_b.
+ * Replaces nn.CrossEntropyLoss(reduction='mean') (clip4cir/models_negplus.py:33,154).
+ * loss_per_query nullable; s_sum may be NULL when eps == 0. */
+int spn_bank_ce_loss(const float* m, const float* l, const float* s_t, const float* s_sum, int B,
+                     int64_t N_total, float label_smoothing, float* lse, float* loss_per_query, float* loss_mean,
+                     void* stream);
+
+/* Backward over one bank shard, recomputing the softmax tile by tile from the GLOBAL lse:
+ *   dlogit[b][n] = softmax(s)[b][n] - (1-eps) [n == label_b] - eps / N_total
+ *   dq_partial[b] += g * sum_n dlogit[b][n] * bank[n]           (g = gscale * (gscale_dev ? *gscale_dev : 1);
+ *                                                                 the caller passes gscale = inv_tau / B_total and
+ *                                                                 the upstream scalar grad as a device pointer,
+ *                                                                 so no host sync is needed)
+ *   dlogit_dot[b] += sum_n dlogit[b][n] * s[b][n]               (nullable; gives d loss / d tau)
+ * Replaces autograd through clip4cir/models_negplus.py:151-154 (and the T = 32 loop, where the
+ * gradient flows through the arg-max token only).  dq_partial fp32 [B, D] must be zeroed by the
+ * caller before the first shard/call; the bank receives no gradient (it is detached,
+ * models_negplus.py:138). */
+int spn_bank_ce_bwd(const void* q_bf16, const void* bank_bf16, const int64_t* labels, float inv_tau,
+                    const float* lse, float gscale, const float* gscale_dev, float label_smoothing,
+                    int64_t N_total, int B, int64_t N, int D, int T, int64_t row_base, float* dq_partial,
+                    float* dlogit_dot, void* ws, size_t ws_bytes, void* stream);
+
+/* Fused cosine-similarity + per-row top-K over one gallery shard (descending score, ties -> lower
+ * index first).  Replaces `distances = 1 - pred @ index.T; torch.argsort(distances)` followed by the
+ * [:K] slices (clip4cir/validate.py:31-32,126-127; clip4cir/cirr_test_submission.py:91-92,106) and,
+ * with T = 32, the max-over-tokens of Blip2QformerCirAlignPrompt.inference (...align_prompt.py:311-319).
+ *   q fp32 [Q, D]; gallery fp32 [G*T, D]; exclude (nullable) int32 [Q] GLOBAL gallery index removed
+ *   from row b before ranking (the reference image, validate.py:131-134); col_base = global index of
+ *   this shard's first entry.  out_val fp32 [Q, K], out_idx int32 [Q, K] (global; -1 / -inf padding
+ *   when fewer than K candidates exist). */
+int spn_sim_topk(const float* q, const float* gallery, int Q, int G, int D, int T, int K, const int32_t* exclude,
+                 int32_t col_base, float* out_val, int32_t* out_idx, void* ws, size_t ws_bytes, void* stream);
+
+/* R-way merge of per-shard top-K lists laid out [R][Q][K] into one [Q][K] (same ordering rule). */
+int spn_merge_topk(const float* vals, const int32_t* idx, int R, int Q, int K, float* out_val, int32_t* out_idx,
+                   void* stream);
+
+/* score[b] = max_t <q[b], gallery[(target[b]-col_base)*T + t]> when target[b] is in this shard, else
+ * -inf.  First phase of the sharded rank computation. */
+int spn_sim_target_score(const float* q, const float* gallery, int Q, int G, int D, int T,
+                         const int32_t* target, int32_t col_base, float* score, void* stream);
+
+/* Rank of the target = number of gallery entries (minus `exclude`) that sort before it, i.e. with a
+ * larger score or an equal score and a smaller global index.  Gives Recall@K for every K without a
+ * sort (clip4cir/validate.py:136-154).  target_score: fp32 [Q] from spn_sim_target_score (after a
+ * max all-reduce when sharded).  group (nullable) int32 [Q, M] global indices of the CIRR subset
+ * (validate.py:140-142): group_rank counts only those members.  rank / group_rank int32 [Q] are
+ * ACCUMULATED (+=): zero them first, sum across shards afterwards. */
+int spn_sim_rank(const float* q, const float* gallery, int Q, int G, int D, int T, const int32_t* target,
+                 const float* target_score, const int32_t* exclude, const int32_t* group, int M,
+                 int32_t col_base, int32_t* rank, int32_t* group_rank, void* ws, size_t ws_bytes, void* stream);
+
+/* Compatibility mode only: the dense fp32 score matrix out[Q, G] (max over T tokens), for callers that
+ * still want `pred_sim` itself (blip24cir/validate.py:30,116).  The fused top-K / rank entry points
+ * above never materialise it. */
+int spn_sim_matrix(const float* q, const float* gallery, int Q, int G, int D, int T, float* out, void* stream);
+
+/* Debug / bring-up: one-CTA tcgen05 GEMM  C[128, N] = A[128, K] * op(B)  used by tests to pin the
+ * UMMA descriptor encodings.  mode bit0: A from TMEM (else smem); bit1: B is MN-major [K, N]
+ * (else K-major [N, K]).  a, b bf16; c fp32 [128, N]; N in {64,128}, K multiple of 64 (<= 256),
+ * MN-major requires K == 128. */
+int spn_debug_umma_gemm(const void* a_bf16, const void* b_bf16, float* c, int N, int K, int mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPN_B200_H_ */

@@ -1,0 +1,150 @@
+"""Generate tests/golden/*.npz by EXECUTING THE REFERENCE ITSELF (build container only).
+
+Imports /root/reference/clip4cir/{models_negplus,validate}.py unmodified (ftfy stubbed: it is only used by
+the CLIP tokenizer), runs them on the seeded synthetic inputs of spn4cir_b200.synth, checks the oracle
+restatement against them and stores the reference's outputs as small fixtures.  /root/reference does
+not exist on the GPU box; the tests only read the committed fixtures.
+
+    python oracle/make_golden.py            # rewrites tests/golden/
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+import types
+import warnings
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+REF = Path("/root/reference/clip4cir")
+OUT = REPO / "tests" / "golden"
+
+from oracle import bank_ce as obank  # noqa: E402
+from oracle import retrieval as oretr  # noqa: E402
+from spn4cir_b200 import synth  # noqa: E402
+
+
+def import_reference():
+    sys.dont_write_bytecode = True  # the reference tree is read-only
+    sys.modules.setdefault("ftfy", types.ModuleType("ftfy"))
+    sys.path.insert(0, str(REF))
+    warnings.filterwarnings("ignore")
+    import models_negplus  # noqa
+    import validate  # noqa
+    return models_negplus, validate
+
+
+def digest(*tensors) -> str:
+    h = hashlib.sha256()
+    for t in tensors:
+        h.update(t.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()[:16]
+
+
+def ref_infonce(models_negplus, q, bank, labels, tau, grad_out=1.0):
+    stub = types.SimpleNamespace(crossentropy_criterion=nn.CrossEntropyLoss(), device="cpu")
+    qq = q.clone().requires_grad_(True)
+    loss = models_negplus.CIRPlus.infonce_loss(stub, qq, bank, labels, tau)
+    loss.backward(torch.tensor(float(grad_out)))
+    return loss.detach(), qq.grad.detach()
+
+
+def bank_cases(models_negplus):
+    cases = {
+        # name: (B, N, D, mode, tau, seed)
+        "small_ragged": (16, 333, 128, "S", 0.02, 1),
+        "small_uniform": (8, 1000, 64, "U", 0.05, 2),
+        "c1": (128, 32768, 640, "S", 0.02, 0),
+        "c1_uniform": (128, 32768, 640, "U", 0.02, 3),
+    }
+    for name, (B, N, D, mode, tau, seed) in cases.items():
+        q, bank, labels = synth.make_bank_case(B, N, D, 1, mode, seed)
+        loss, dq = ref_infonce(models_negplus, q, bank, labels, tau)
+        # oracle restatement must agree with the executed reference
+        o_loss, o_dq, o_dtau = obank.infonce_loss_and_grads(q, bank, labels, tau)
+        assert torch.allclose(o_loss, loss, rtol=1e-6, atol=1e-6), (name, o_loss, loss)
+        assert torch.allclose(o_dq, dq, rtol=1e-5, atol=1e-8), name
+        np.savez_compressed(OUT / f"bank_ce_{name}.npz", B=B, N=N, D=D, tau=tau, seed=seed, mode=mode,
+                            loss=loss.numpy(), dq=dq.numpy(), dtau=o_dtau.numpy(),
+                            input_digest=digest(q, bank, labels))
+        print(f"bank_ce_{name}: loss={loss.item():.6f} |dq|={dq.norm().item():.4e} dtau={o_dtau.item():.4e}")
+    # labels=None path (:152-153)
+    q, bank, _ = synth.make_bank_case(12, 40, 64, 1, "S", 5)
+    stub = types.SimpleNamespace(crossentropy_criterion=nn.CrossEntropyLoss(), device="cpu")
+    loss = models_negplus.CIRPlus.infonce_loss(stub, q, bank, None, 0.02)
+    assert torch.allclose(obank.infonce_loss(q, bank, None, 0.02), loss)
+    np.savez_compressed(OUT / "bank_ce_nolabels.npz", B=12, N=40, D=64, tau=0.02, seed=5, loss=loss.numpy(),
+                        input_digest=digest(q, bank))
+
+
+def retrieval_cases(validate):
+    cases = {"cirr_small": (200, 500, 64, 0, 3.0), "cirr_c2": (4181, 2297, 640, 0, 8.0)}
+    for name, (Q, G, D, seed, noise) in cases.items():
+        q, gallery, names, reference, target, groups = synth.make_retrieval_case(Q, G, D, 1, seed, noise=noise)
+        ds = synth.FakeCIRRDataset(names, reference, target, groups)
+        text = {f"q{i}": q[i] * 2.0 - gallery[reference[i]] for i in range(Q)}
+        model = synth.FakeModel(text, D)
+        ref = validate.compute_cirr_val_metrics(ds, model, gallery, names, device=torch.device("cpu"))
+        # predicted features as the reference builds them (normalize(ref_feat + text)), for the oracle
+        pred = torch.nn.functional.normalize(gallery[reference] + torch.stack([text[f"q{i}"] for i in range(Q)]), dim=-1)
+        if Q <= 500:
+            orc = oretr.cirr_metrics(pred, gallery, names, [names[int(i)] for i in reference],
+                                     [names[int(i)] for i in target], [[names[int(j)] for j in g] for g in groups])
+            assert np.allclose(orc, ref), (orc, ref)
+        rank, grank = oretr.rank_of_target(pred @ torch.nn.functional.normalize(gallery, dim=-1).T, target.tolist(),
+                                           reference.tolist(), groups.tolist())
+        rec = [100.0 * float(np.mean(rank < k)) for k in (1, 5, 10, 50)]
+        grec = [100.0 * float(np.mean(grank < k)) for k in (1, 2, 3)]
+        assert np.allclose((*grec, *rec), ref, atol=1e-4), ((*grec, *rec), ref)
+        np.savez_compressed(OUT / f"{name}.npz", Q=Q, G=G, D=D, seed=seed, noise=noise, metrics=np.array(ref, dtype=np.float64),
+                            rank=rank.astype(np.int32), group_rank=grank.astype(np.int32),
+                            input_digest=digest(q, gallery, reference, target, groups))
+        print(name, [round(x, 3) for x in ref])
+
+    for name, (Q, G, D, seed, noise) in {"fiq_small": (150, 400, 64, 7, 3.0), "fiq_dress": (2017, 3817, 640, 8, 8.5)}.items():
+        q, gallery, names, reference, target, _ = synth.make_retrieval_case(Q, G, D, 1, seed, noise=noise)
+        ds = synth.FakeFIQDataset(names, reference, target)
+        caps = [f"is q{i} and and more {i}" for i in range(Q)]
+        text = {c: q[i] * 2.0 - gallery[reference[i]] for i, c in enumerate(caps)}
+        model = synth.FakeModel(text, D)
+        ref = validate.compute_fiq_val_metrics(ds, model, gallery, names, device=torch.device("cpu"))
+        pred = torch.nn.functional.normalize(gallery[reference] + torch.stack([text[c] for c in caps]), dim=-1)
+        orc = oretr.fiq_metrics(pred, gallery, names, [names[int(i)] for i in target], [names[int(i)] for i in reference])
+        assert np.allclose(orc, ref), (orc, ref)
+        orc_noremove = oretr.fiq_metrics(pred, gallery, names, [names[int(i)] for i in target], None)
+        np.savez_compressed(OUT / f"{name}.npz", Q=Q, G=G, D=D, seed=seed, noise=noise, metrics=np.array(ref, dtype=np.float64),
+                            metrics_noremove=np.array(orc_noremove, dtype=np.float64),
+                            input_digest=digest(q, gallery, reference, target))
+        print(name, ref, orc_noremove)
+
+
+def blip2_cases():
+    # not importable offline -> line-faithful loop vs closed form only (parity unpinned, see oracle/__init__.py)
+    B, N, T, D, temp = 6, 50, 32, 256, 0.05
+    f, bank3, labels = synth.make_bank_case(B, N, D, T, "S", 11)
+    loop = obank.blip2_stage2_loss_loop(f, bank3, labels, torch.tensor(temp))
+    closed, df, dtemp = obank.blip2_loss_and_grads(f, bank3, labels, temp)
+    assert torch.allclose(loop, closed, atol=1e-6), (loop, closed)
+    np.savez_compressed(OUT / "blip2_small.npz", B=B, N=N, T=T, D=D, temp=temp, seed=11, loss=closed.numpy(),
+                        df=df.numpy(), dtemp=dtemp.numpy(), input_digest=digest(f, bank3, labels))
+    print(f"blip2_small: loop={loop.item():.6f} closed={closed.item():.6f} dtemp={dtemp.item():.4e}")
+
+
+def main():
+    assert REF.exists(), "run in the build container: /root/reference is required"
+    OUT.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    models_negplus, validate = import_reference()
+    bank_cases(models_negplus)
+    blip2_cases()
+    retrieval_cases(validate)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,111 @@
+"""Oracle for validation retrieval (TEST INFRASTRUCTURE -- see oracle/__init__.py)."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def similarity(q: torch.Tensor, gallery: torch.Tensor) -> torch.Tensor:
+    """fp32 similarity; 3-D gallery -> max over tokens as Blip2QformerCirAlignPrompt.inference,
+    /root/reference/blip24cir/lavis/models/blip2_models/blip2_qformer_cir_align_prompt.py:311-319."""
+    if gallery.dim() == 3:
+        sim_t2q = torch.matmul(q.unsqueeze(1).unsqueeze(1), gallery.permute(0, 2, 1)).squeeze(2)  # [b, G, 32]
+        return sim_t2q.max(-1).values
+    return q @ gallery.t()
+
+
+def ranking(sim: torch.Tensor) -> np.ndarray:
+    """Full ranking [Q, G] under the documented rule: descending similarity, ties -> lower index.
+    (The reference sorts `1 - sim` with an unstable argsort, clip4cir/validate.py:126-127.)"""
+    return torch.argsort(-sim, dim=-1, stable=True).numpy()
+
+
+def reference_style_sorted_indices(q: torch.Tensor, gallery: torch.Tensor) -> torch.Tensor:
+    """Exactly the reference lines clip4cir/validate.py:126-127."""
+    distances = 1 - q @ gallery.T
+    return torch.argsort(distances, dim=-1).cpu()
+
+
+def topk(sim: torch.Tensor, k: int, exclude: Optional[Sequence[int]] = None) -> Tuple[np.ndarray, np.ndarray]:
+    order = ranking(sim)
+    vals = sim.numpy()
+    out_i = np.full((sim.shape[0], k), -1, dtype=np.int64)
+    out_v = np.full((sim.shape[0], k), -np.inf, dtype=np.float32)
+    for r in range(sim.shape[0]):
+        row = order[r]
+        if exclude is not None:
+            row = row[row != int(exclude[r])]
+        row = row[:k]
+        out_i[r, : len(row)] = row
+        out_v[r, : len(row)] = vals[r, row]
+    return out_v, out_i
+
+
+def rank_of_target(sim: torch.Tensor, target: Sequence[int], exclude: Optional[Sequence[int]] = None,
+                   group: Optional[Sequence[Sequence[int]]] = None):
+    """Position of the target after dropping `exclude` (0 = first); with `group`, position among the group
+    members only (what labels[...]/group_labels[...] encode in clip4cir/validate.py:136-142)."""
+    order = ranking(sim)
+    Q = sim.shape[0]
+    rank = np.zeros(Q, dtype=np.int64)
+    grank = np.zeros(Q, dtype=np.int64) if group is not None else None
+    for r in range(Q):
+        row = order[r]
+        if exclude is not None:
+            row = row[row != int(exclude[r])]
+        rank[r] = int(np.nonzero(row == int(target[r]))[0][0])
+        if group is not None:
+            sub = row[np.isin(row, np.asarray(group[r]))]
+            grank[r] = int(np.nonzero(sub == int(target[r]))[0][0])
+    return rank, grank
+
+
+def cirr_metrics(q: torch.Tensor, index_features: torch.Tensor, index_names: List[str], reference_names: List[str],
+                 target_names: List[str], group_members: List[List[str]]):
+    """Restatement of compute_cirr_val_metrics' metric tail, /root/reference/clip4cir/validate.py:120-156,
+    on names with numpy exactly as the reference does (small sizes only)."""
+    if index_features.dim() > 2:                                                     # :121-122
+        index_features = torch.mean(index_features, dim=1)
+    index_features = F.normalize(index_features, dim=-1).float()                     # :123
+    sim = q @ index_features.T
+    sorted_indices = torch.from_numpy(ranking(sim))                                  # :126-127 (+ tie rule)
+    sorted_index_names = np.array(index_names)[sorted_indices]                       # :128
+    reference_mask = torch.tensor(sorted_index_names != np.repeat(np.array(reference_names), len(index_names))
+                                  .reshape(len(target_names), -1))                   # :131-132
+    sorted_index_names = sorted_index_names[reference_mask].reshape(sorted_index_names.shape[0],
+                                                                    sorted_index_names.shape[1] - 1)  # :133-134
+    labels = torch.tensor(sorted_index_names == np.repeat(np.array(target_names), len(index_names) - 1)
+                          .reshape(len(target_names), -1))                           # :136-137
+    gm = np.array(group_members)                                                     # :140
+    group_mask = (sorted_index_names[..., None] == gm[:, None, :]).sum(-1).astype(bool)  # :141
+    group_labels = labels[group_mask].reshape(labels.shape[0], -1)                   # :142
+    assert torch.equal(torch.sum(labels, dim=-1).int(), torch.ones(len(target_names)).int())        # :144
+    assert torch.equal(torch.sum(group_labels, dim=-1).int(), torch.ones(len(target_names)).int())  # :145
+    rec = [(torch.sum(labels[:, :k]) / len(labels)).item() * 100 for k in (1, 5, 10, 50)]           # :148-151
+    grec = [(torch.sum(group_labels[:, :k]) / len(group_labels)).item() * 100 for k in (1, 2, 3)]   # :152-154
+    return (*grec, *rec)                                                             # :156
+
+
+def fiq_metrics(q: torch.Tensor, index_features: torch.Tensor, index_names: List[str], target_names: List[str],
+                refer_names: Optional[List[str]]):
+    """Restatement of compute_fiq_val_metrics' tail: clip4cir flavour (reference removed,
+    /root/reference/clip4cir/validate.py:27-49) when refer_names is given, else the blip4cir/tgcir flavour
+    (/root/reference/blip4cir/validate.py:45-56)."""
+    index_features = F.normalize(index_features, dim=-1).float()                     # :28
+    sim = q @ index_features.T
+    sorted_index_names = np.array(index_names)[ranking(sim)]                         # :31-33
+    N = sim.shape[0]
+    r10 = r50 = 0
+    for i in range(N):                                                               # :38-45
+        row = sorted_index_names[i]
+        if refer_names is not None:
+            row = row[row != refer_names[i]]
+        if target_names[i] in row[:10]:
+            r10 += 1
+            r50 += 1
+        elif target_names[i] in row[:50]:
+            r50 += 1
+    return (r10 / N) * 100, (r50 / N) * 100                                          # :48-49

@@ -1,0 +1,213 @@
+"""Drop-in mirrors of the reference's Python call sites for the hot path.
+
+Same names, argument meaning and error behaviour as the reference, so a maintainer swaps an import:
+
+* ``infonce_loss(query_features, target_features, labels=None, tau=0.01)``
+  -- ``CIRPlus.infonce_loss`` (/root/reference/clip4cir/models_negplus.py:150-154 and its 7 copies)
+* ``BankLossMixin.bank_large_step(loss, text_feats, indexs, target_indexs, refer_indexs)``
+  -- /root/reference/clip4cir/models_negplus.py:130-142
+* ``forward_stage2_loss(fusion_feats, target_feats, target_indexs, temp)``
+  -- the loss tail of ``Blip2QformerCirAlignPrompt.forward_stage2`` (...align_prompt.py:254-268)
+* ``inference_sim(fusion_feats, target_feats)`` -- the sim tail of ``inference`` (...align_prompt.py:311-319)
+* ``compute_cirr_val_metrics`` / ``compute_fiq_val_metrics`` / ``generate_cirr_test_dicts``
+  -- /root/reference/clip4cir/validate.py:19-51,111-156, clip4cir/cirr_test_submission.py:63-111
+
+The retrieval tails work on integer gallery ids (names are mapped once on the host) and never build the
+[Q, G] argsort; ordering rule: descending similarity, ties -> lower gallery index.
+"""
+from __future__ import annotations
+
+from operator import itemgetter
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.nn.functional as F
+
+from ._lib import SpnError, call
+from .ops import DeviceBank, _ptr, _require_cuda, _stream, bank_infonce, cast_to_bf16
+from .retrieval import _prep_gallery, names_to_ids, recall_at, sim_rank, sim_topk
+
+
+# --------------------------------------------------------------------------------------- bank-CE
+def infonce_loss(query_features: torch.Tensor, target_features: Union[DeviceBank, torch.Tensor],
+                 labels: Optional[torch.Tensor] = None, tau=0.01, label_smoothing: float = 0.0) -> torch.Tensor:
+    """``CIRPlus.infonce_loss``: ``CE((q @ bank.T) / tau, labels)``; ``labels=None`` -> ``arange(B)``."""
+    return bank_infonce(query_features, target_features, labels, tau, label_smoothing=label_smoothing)
+
+
+class BankLossMixin:
+    """State + methods of ``CIRPlus`` that sit on the path: resident banks and ``bank_large_step``.
+
+    Expected attributes (as in the reference class): ``device``, ``tau``, ``plus``; call
+    :meth:`set_banks` once instead of keeping CPU banks that are re-uploaded every step.
+    """
+
+    label_smoothing = 0.0
+
+    def set_banks(self, refer_bank: torch.Tensor, target_bank: torch.Tensor) -> None:
+        self.refer_bank = refer_bank.detach().to(self.device, torch.float32).contiguous()
+        self.target_bank = DeviceBank.from_tensor(target_bank, self.device)
+
+    def combining_function(self, image_features, text_features):  # models_negplus.py:48-49
+        return image_features + text_features
+
+    def infonce_loss(self, query_features, target_features, labels=None, tau=0.01):
+        return infonce_loss(query_features, target_features, labels, tau, self.label_smoothing)
+
+    def bank_large_step(self, loss: dict, text_feats, indexs, target_indexs, refer_indexs=None):
+        idx = refer_indexs if getattr(self, "plus", False) else indexs
+        reference_image_feats = self.refer_bank[idx.to(self.refer_bank.device)].detach()
+        query_feats = F.normalize(self.combining_function(reference_image_feats, text_feats))
+        target_indexs = target_indexs.to(self.device)
+        loss["bank_loss"] = self.infonce_loss(query_feats, self.target_bank, target_indexs, tau=self.tau)
+
+
+def forward_stage2_loss(fusion_feats: torch.Tensor, target_feats: Union[DeviceBank, torch.Tensor],
+                        target_indexs: torch.Tensor, temp) -> Dict[str, torch.Tensor]:
+    """BLIP-2 stage-2 loss tail: per sample ``CE(max_k(f_i . bank[n,k,:]) / temp, label_i)``, mean over B.
+    ``target_feats``: ``[N, 32, 256]`` tensor or a DeviceBank with ``T == 32``; ``temp`` may be the
+    learnable ``nn.Parameter`` (its gradient is produced)."""
+    return {"loss_qtc": bank_infonce(fusion_feats, target_feats, target_indexs, temp)}
+
+
+def inference_sim(fusion_feats: torch.Tensor, target_feats: torch.Tensor) -> torch.Tensor:
+    """``sim_i2t`` of ``Blip2QformerCirAlignPrompt.inference``: ``max_k f . gallery[g, k, :]`` -> ``[b, G]``
+    (1-D when ``b == 1``, as the reference's ``.squeeze()`` does)."""
+    _require_cuda(fusion_feats, "fusion_feats")
+    g, G, T = _prep_gallery(target_feats)
+    q = fusion_feats.detach().float().contiguous()
+    out = torch.empty((q.shape[0], G), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        call("spn_sim_matrix", _ptr(q), _ptr(g), q.shape[0], G, q.shape[1], T, _ptr(out), _stream(q.device))
+    return out.squeeze(0) if out.shape[0] == 1 else out
+
+
+# --------------------------------------------------------------------------------------- retrieval
+def _normalize_gallery(index_features: torch.Tensor) -> torch.Tensor:
+    if index_features.dim() > 2:  # validate.py:121-122
+        index_features = torch.mean(index_features, dim=1)
+    return F.normalize(index_features, dim=-1).float()
+
+
+def cirr_metrics_from_features(predicted_features: torch.Tensor, index_features: torch.Tensor,
+                               index_names: Sequence, reference_names: Sequence, target_names: Sequence,
+                               group_members: Sequence[Sequence], *, pred_is_sim_gallery=None
+                               ) -> Tuple[float, float, float, float, float, float, float]:
+    """Metric tail of ``compute_cirr_val_metrics`` (validate.py:120-156) on integer ids."""
+    ref_ids, tgt_ids = names_to_ids(index_names, reference_names, target_names)
+    lut = {n: i for i, n in enumerate(index_names)}
+    grp_ids = [[lut[m] for m in row] for row in group_members]
+    gallery = _normalize_gallery(index_features) if pred_is_sim_gallery is None else pred_is_sim_gallery
+    rank, grank = sim_rank(predicted_features, gallery, tgt_ids, exclude=ref_ids, group=grp_ids)
+    # the reference asserts exactly one hit per row in the ranked list and in the subset (validate.py:144-145)
+    for r, t, row in zip(ref_ids, tgt_ids, grp_ids):
+        assert t != r, "target equals the removed reference image"
+        assert t in row, "target is not a member of its CIRR subset"
+    r1, r5, r10, r50 = recall_at(rank, (1, 5, 10, 50))
+    g1, g2, g3 = recall_at(grank, (1, 2, 3))
+    return g1, g2, g3, r1, r5, r10, r50
+
+
+def fiq_metrics_from_features(predicted_features: torch.Tensor, index_features: torch.Tensor, index_names: Sequence,
+                              target_names: Sequence, refer_names: Optional[Sequence] = None, *,
+                              pred_is_sim_gallery=None) -> Tuple[float, float]:
+    """Metric tail of ``compute_fiq_val_metrics``.  ``refer_names`` given -> clip4cir/zscir flavour that
+    removes the reference (validate.py:38-45); ``None`` -> blip4cir/tgcir/blip2 flavour (no removal)."""
+    (tgt_ids,) = names_to_ids(index_names, target_names)
+    ref_ids = names_to_ids(index_names, refer_names)[0] if refer_names is not None else None
+    gallery = _normalize_gallery(index_features) if pred_is_sim_gallery is None else pred_is_sim_gallery
+    rank, _ = sim_rank(predicted_features, gallery, tgt_ids, exclude=ref_ids)
+    n = rank.numel()
+    # python-int arithmetic like the reference loop: (count / N) * 100
+    r10 = (int(torch.sum(rank < 10).item()) / n) * 100
+    r50 = (int(torch.sum(rank < 50).item()) / n) * 100
+    return r10, r50
+
+
+def _predict_cirr(model, relative_val_dataset, index_names, index_features, device):
+    """Feature generation of ``generate_cirr_val_predictions`` (validate.py:159-213), batch 32, no workers."""
+    name_to_feat = dict(zip(index_names, index_features))
+    feats, target_names, group_members, reference_names = [], [], [], []
+    n = len(relative_val_dataset)
+    for s in range(0, n, 32):
+        items = [relative_val_dataset[i] for i in range(s, min(n, s + 32))]
+        items = [it for it in items if it is not None]
+        refs = [it[0] for it in items]
+        caps = [it[2] for it in items]
+        with torch.no_grad():
+            text_features = model.encode_text(caps)
+            if text_features.shape[0] == 1:
+                ref_feats = itemgetter(*refs)(name_to_feat).unsqueeze(0)
+            else:
+                ref_feats = torch.stack(itemgetter(*refs)(name_to_feat))
+            batch = model.combining_function(ref_feats.to(device), text_features.to(device))
+        feats.append(F.normalize(batch, dim=-1))
+        reference_names.extend(refs)
+        target_names.extend(it[1] for it in items)
+        group_members.extend(list(it[3]) for it in items)
+    return torch.vstack(feats), reference_names, target_names, group_members
+
+
+def compute_cirr_val_metrics(relative_val_dataset, model, index_features: torch.Tensor, index_names: List,
+                             device=torch.device("cuda")):
+    """Signature and return order of the reference (validate.py:111-156):
+    (group_recall@1, @2, @3, recall@1, @5, @10, @50)."""
+    pred, refs, tgts, groups = _predict_cirr(model, relative_val_dataset, index_names, index_features, device)
+    return cirr_metrics_from_features(pred.to(device), index_features.to(device), index_names, refs, tgts, groups)
+
+
+def _predict_fiq(model, relative_val_dataset, index_names, index_features, device):
+    name_to_feat = dict(zip(index_names, index_features))
+    feats, target_names, refer_names = [], [], []
+    n = len(relative_val_dataset)
+    for s in range(0, n, 32):
+        items = [relative_val_dataset[i] for i in range(s, min(n, s + 32))]
+        items = [it for it in items if it is not None]
+        refs = [it[0] for it in items]
+        caps = [f"{it[2][0].strip('.?, ')} and {it[2][1].strip('.?, ')}" for it in items]  # validate.py:78-80
+        with torch.no_grad():
+            text_features = model.encode_text(caps)
+            if text_features.shape[0] == 1:
+                ref_feats = itemgetter(*refs)(name_to_feat).unsqueeze(0)
+            else:
+                ref_feats = torch.stack(itemgetter(*refs)(name_to_feat))
+            batch = model.combining_function(ref_feats.to(device), text_features.to(device))
+        feats.append(F.normalize(batch, dim=-1))
+        target_names.extend(it[1] for it in items)
+        refer_names.extend(refs)
+    return torch.vstack(feats), target_names, refer_names
+
+
+def compute_fiq_val_metrics(relative_val_dataset, model, index_features: torch.Tensor, index_names: List,
+                            device=torch.device("cuda"), remove_reference: bool = True) -> Tuple[float, float]:
+    """(recall@10, recall@50) as validate.py:19-51; ``remove_reference=False`` gives the blip4cir/tgcir
+    flavour (/root/reference/blip4cir/validate.py:45-56)."""
+    pred, tgts, refs = _predict_fiq(model, relative_val_dataset, index_names, index_features, device)
+    return fiq_metrics_from_features(pred.to(device), index_features.to(device), index_names, tgts,
+                                     refs if remove_reference else None)
+
+
+def cirr_test_dicts_from_features(predicted_features: torch.Tensor, index_features: torch.Tensor,
+                                  index_names: Sequence, reference_names: Sequence,
+                                  group_members: Sequence[Sequence], pairs_id: Sequence
+                                  ) -> Tuple[Dict[str, list], Dict[str, list]]:
+    """Tail of ``generate_cirr_test_dicts`` (cirr_test_submission.py:84-111): top-50 names and top-3
+    in-subset names per pair id, from one fused top-K launch each (no argsort)."""
+    (ref_ids,) = names_to_ids(index_names, reference_names)
+    lut = {n: i for i, n in enumerate(index_names)}
+    gallery = _normalize_gallery(index_features)
+    k = min(50, len(index_names) - 1)
+    _, top = sim_topk(predicted_features, gallery, k, exclude=ref_ids)
+    top = top.cpu().tolist()
+    # subset ranking: the (<= 6)-member groups are scored as tiny per-query galleries on the device
+    grp_ids = torch.tensor([[lut[m] for m in row] for row in group_members], dtype=torch.int64,
+                           device=gallery.device)
+    q = predicted_features.float()
+    gs = torch.einsum("qd,qmd->qm", q, gallery[grp_ids])  # [Q, M] gather of at most 6 rows per query
+    keep = grp_ids != torch.tensor(ref_ids, device=gallery.device)[:, None]
+    gs = gs.masked_fill(~keep, float("-inf"))
+    order = torch.argsort(-gs, dim=-1, stable=True)[:, :3]
+    sub = torch.gather(grp_ids, 1, order).cpu().tolist()
+    pair_preds = {str(int(p)): [index_names[i] for i in row] for p, row in zip(pairs_id, top)}
+    pair_group = {str(int(p)): [index_names[i] for i in row] for p, row in zip(pairs_id, sub)}
+    return pair_preds, pair_group

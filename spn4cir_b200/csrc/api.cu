@@ -1,0 +1,142 @@
+// extern "C" surface of libspn_b200 (include/spn_b200.h): argument validation and dispatch only.
+#include "bank_ce.cuh"
+#include "sim_rank.cuh"
+
+using namespace spn;
+
+static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int spn_workspace_bytes(int op, int B, int64_t N, int D, int T, int K, size_t* out_bytes) {
+  SPN_REQUIRE(out_bytes != nullptr, SPN_ERR_BAD_ARG, "spn_workspace_bytes: out_bytes is NULL");
+  switch (op) {
+    case SPN_OP_BANK_CE_FWD:
+    case SPN_OP_BANK_CE_BWD: {
+      BankCEPlan plan;
+      int rc = bank_ce_plan(op == SPN_OP_BANK_CE_FWD ? 0 : 1, B, N, D, T, &plan);
+      if (rc != SPN_OK) return rc;
+      *out_bytes = plan.ws_bytes;
+      return SPN_OK;
+    }
+    case SPN_OP_SIM_TOPK:
+      SPN_REQUIRE(B > 0 && N > 0 && N < (1ll << 31) && K >= 1 && K <= 64 && (T == 1 || T == 32), SPN_ERR_BAD_SHAPE,
+                  "spn_workspace_bytes(SIM_TOPK): bad shape Q=%d G=%lld T=%d K=%d", B, (long long)N, T, K);
+      *out_bytes = sim_topk_ws_bytes(B, int(N), T, K);
+      return SPN_OK;
+    case SPN_OP_SIM_RANK:
+      *out_bytes = 256;
+      return SPN_OK;
+    default:
+      return fail(SPN_ERR_BAD_ARG, "spn_workspace_bytes: unknown op %d", op);
+  }
+}
+
+int spn_cast_to_bf16(const void* src, int src_dtype, void* dst_bf16, int64_t n, void* stream) {
+  SPN_REQUIRE(src && dst_bf16, SPN_ERR_BAD_ARG, "spn_cast_to_bf16: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return cast_to_bf16(src, src_dtype, dst_bf16, n, as_stream(stream));
+}
+
+int spn_query_assemble(const float* refer_bank, const int64_t* refer_idx, const float* text, int B, int D,
+                       void* q_bf16, float* q_f32, float* inv_norm, void* stream) {
+  SPN_REQUIRE(refer_bank && refer_idx && text && q_bf16, SPN_ERR_BAD_ARG, "spn_query_assemble: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return query_assemble(refer_bank, reinterpret_cast<const long long*>(refer_idx), text, B, D, q_bf16, q_f32, inv_norm,
+                        as_stream(stream));
+}
+
+int spn_bank_ce_fwd(const void* q_bf16, const void* bank_bf16, const int64_t* labels, float inv_tau, int B,
+                    int64_t N, int D, int T, int64_t row_base, float* m, float* l, float* s_t, float* s_sum,
+                    void* ws, size_t ws_bytes, void* stream) {
+  SPN_REQUIRE(q_bf16 && bank_bf16 && labels && m && l && s_t, SPN_ERR_BAD_ARG, "spn_bank_ce_fwd: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return bank_ce_forward(q_bf16, bank_bf16, reinterpret_cast<const long long*>(labels), inv_tau, B, N, D, T, row_base,
+                         m, l, s_t, s_sum, ws, ws_bytes, as_stream(stream));
+}
+
+int spn_merge_stats(const float* m_parts, const float* l_parts, const float* st_parts, const float* ssum_parts,
+                    int P, int B, float* m, float* l, float* s_t, float* s_sum, void* stream) {
+  SPN_REQUIRE(m_parts && l_parts && st_parts && m && l && s_t, SPN_ERR_BAD_ARG, "spn_merge_stats: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return merge_stats(m_parts, l_parts, st_parts, ssum_parts, P, B, m, l, s_t, s_sum, as_stream(stream));
+}
+
+int spn_bank_ce_loss(const float* m, const float* l, const float* s_t, const float* s_sum, int B,
+                     int64_t N_total, float label_smoothing, float* lse, float* loss_per_query, float* loss_mean,
+                     void* stream) {
+  SPN_REQUIRE(m && l && s_t && lse && loss_mean, SPN_ERR_BAD_ARG, "spn_bank_ce_loss: NULL pointer");
+  SPN_REQUIRE(label_smoothing >= 0.f && label_smoothing < 1.f, SPN_ERR_BAD_ARG, "label_smoothing must be in [0, 1)");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return bank_ce_loss(m, l, s_t, s_sum, B, N_total, label_smoothing, lse, loss_per_query, loss_mean, as_stream(stream));
+}
+
+int spn_bank_ce_bwd(const void* q_bf16, const void* bank_bf16, const int64_t* labels, float inv_tau,
+                    const float* lse, float gscale, const float* gscale_dev, float label_smoothing,
+                    int64_t N_total, int B, int64_t N, int D, int T, int64_t row_base, float* dq_partial,
+                    float* dlogit_dot, void* ws, size_t ws_bytes, void* stream) {
+  (void)ws;
+  (void)ws_bytes;
+  SPN_REQUIRE(q_bf16 && bank_bf16 && labels && lse && dq_partial, SPN_ERR_BAD_ARG, "spn_bank_ce_bwd: NULL pointer");
+  SPN_REQUIRE(aligned16(dq_partial), SPN_ERR_BAD_ALIGN, "spn_bank_ce_bwd: dq_partial must be 16-byte aligned");
+  SPN_REQUIRE(label_smoothing >= 0.f && label_smoothing < 1.f, SPN_ERR_BAD_ARG, "label_smoothing must be in [0, 1)");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return bank_ce_backward(q_bf16, bank_bf16, reinterpret_cast<const long long*>(labels), inv_tau, lse, gscale,
+                          gscale_dev, label_smoothing, N_total, B, N, D, T, row_base, dq_partial, dlogit_dot, as_stream(stream));
+}
+
+int spn_sim_topk(const float* q, const float* gallery, int Q, int G, int D, int T, int K, const int32_t* exclude,
+                 int32_t col_base, float* out_val, int32_t* out_idx, void* ws, size_t ws_bytes, void* stream) {
+  SPN_REQUIRE(q && gallery && out_val && out_idx, SPN_ERR_BAD_ARG, "spn_sim_topk: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return sim_topk(q, gallery, Q, G, D, T, K, exclude, col_base, out_val, out_idx, ws, ws_bytes, as_stream(stream));
+}
+
+int spn_merge_topk(const float* vals, const int32_t* idx, int R, int Q, int K, float* out_val, int32_t* out_idx,
+                   void* stream) {
+  SPN_REQUIRE(vals && idx && out_val && out_idx, SPN_ERR_BAD_ARG, "spn_merge_topk: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return merge_topk(vals, idx, R, Q, K, out_val, out_idx, as_stream(stream));
+}
+
+int spn_sim_target_score(const float* q, const float* gallery, int Q, int G, int D, int T, const int32_t* target,
+                         int32_t col_base, float* score, void* stream) {
+  SPN_REQUIRE(q && gallery && target && score, SPN_ERR_BAD_ARG, "spn_sim_target_score: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return sim_target_score(q, gallery, Q, G, D, T, target, col_base, score, as_stream(stream));
+}
+
+int spn_sim_rank(const float* q, const float* gallery, int Q, int G, int D, int T, const int32_t* target,
+                 const float* target_score, const int32_t* exclude, const int32_t* group, int M, int32_t col_base,
+                 int32_t* rank, int32_t* group_rank, void* ws, size_t ws_bytes, void* stream) {
+  (void)ws;
+  (void)ws_bytes;
+  SPN_REQUIRE(q && gallery, SPN_ERR_BAD_ARG, "spn_sim_rank: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return sim_rank(q, gallery, Q, G, D, T, target, target_score, exclude, group, M, col_base, rank, group_rank,
+                  as_stream(stream));
+}
+
+int spn_sim_matrix(const float* q, const float* gallery, int Q, int G, int D, int T, float* out, void* stream) {
+  SPN_REQUIRE(q && gallery && out, SPN_ERR_BAD_ARG, "spn_sim_matrix: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return sim_matrix(q, gallery, Q, G, D, T, out, as_stream(stream));
+}
+
+int spn_debug_umma_gemm(const void* a_bf16, const void* b_bf16, float* c, int N, int K, int mode, void* stream) {
+  SPN_REQUIRE(a_bf16 && b_bf16 && c, SPN_ERR_BAD_ARG, "spn_debug_umma_gemm: NULL pointer");
+  return debug_umma_gemm(a_bf16, b_bf16, c, N, K, mode, as_stream(stream));
+}
+
+}  // extern "C"

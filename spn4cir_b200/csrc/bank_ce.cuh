@@ -1,0 +1,69 @@
+// Shared declarations of the bank-CE translation units (kernel parameters, launch plan, host entry
+// points used by api.cu).
+#pragma once
+#include "common.cuh"
+
+namespace spn {
+
+constexpr int kBM = 128;      // queries per CTA  (UMMA M)
+constexpr int kBN = 128;      // bank rows per S tile (UMMA N of GEMM1, K extent of GEMM2)
+constexpr int kBK = 64;       // bf16 elements per 128-byte swizzle row
+constexpr int kUmmaK = 16;    // K per tcgen05.mma for 16-bit inputs
+constexpr uint32_t kBlockBytes = kBM * kBK * 2;  // one [128 x 64] bf16 block = 16 KiB
+constexpr int kBankCEThreads = 192;
+
+struct BankCEParams {
+  int B, D;
+  long long N;       // bank entries in this shard
+  long long n_rows;  // N * T token rows
+  int kblocks;       // D / 64
+  int stages;        // ring depth
+  int n_tiles;       // ceil(n_rows / 128)
+  int q_tiles;       // ceil(B / 128)
+  int num_chunks;    // bank-row chunks (grid = q_tiles * num_dsplit * num_chunks)
+  int num_dsplit;    // backward: splits of the output dim
+  int ow_blocks;     // backward: 64-column blocks of dq per split
+  float scale_log2;  // inv_tau * log2(e)
+  long long row_base;
+  const long long* labels;
+  // forward partials, [num_chunks][B], log2 units
+  float* part_m;
+  float* part_l;
+  float* part_st;
+  float* part_ssum;
+  // backward
+  const float* lse;  // [B] natural units, global over all shards
+  float gscale, eps_over_n, one_minus_eps;
+  const float* gscale_dev;  // nullable: upstream scalar gradient on the device
+  float* dq;          // [B, D] fp32, +=
+  float* dlogit_dot;  // [B] fp32, += (nullable)
+};
+
+struct BankCEPlan {
+  int kblocks, q_tiles, n_tiles, num_chunks, num_dsplit, ow_blocks, stages, grid;
+  size_t smem_bytes, ws_bytes;
+};
+
+// mode 0 = forward statistics, 1 = backward
+int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan);
+
+int bank_ce_forward(const void* q, const void* bank, const long long* labels, float inv_tau, int B, long long N,
+                    int D, int T, long long row_base, float* m, float* l, float* s_t, float* s_sum, void* ws,
+                    size_t ws_bytes, cudaStream_t stream);
+int bank_ce_backward(const void* q, const void* bank, const long long* labels, float inv_tau, const float* lse,
+                     float gscale, const float* gscale_dev, float label_smoothing, long long N_total, int B,
+                     long long N, int D, int T, long long row_base, float* dq, float* dlogit_dot, cudaStream_t stream);
+int merge_stats(const float* pm, const float* pl, const float* pst, const float* pss, int P, int B, float* m,
+                float* l, float* st, float* ss, cudaStream_t stream);
+int bank_ce_loss(const float* m, const float* l, const float* st, const float* ss, int B, long long N_total,
+                 float eps, float* lse, float* loss_q, float* loss_mean, cudaStream_t stream);
+
+// bring-up GEMM (umma_selftest.cu)
+int debug_umma_gemm(const void* a, const void* b, float* c, int N, int K, int mode, cudaStream_t stream);
+
+// prologue kernels (prologue.cu)
+int cast_to_bf16(const void* src, int src_dtype, void* dst, long long n, cudaStream_t stream);
+int query_assemble(const float* refer_bank, const long long* refer_idx, const float* text, int B, int D, void* q_bf16,
+                   float* q_f32, float* inv_norm, cudaStream_t stream);
+
+}  // namespace spn

@@ -1,0 +1,623 @@
+// bank-CE on tcgen05/TMEM: fused  S = q . bank^T  ->  online soft-max statistics (forward) and
+// recompute  ->  P = softmax - onehot  ->  dq += P . bank  (backward).  The B x N logit matrix only
+// ever exists as 128 x 128 fp32 tiles in tensor memory.
+//
+// Reference semantics: CIRPlus.infonce_loss (clip4cir/models_negplus.py:150-154) and, with T = 32, the
+// max-over-tokens loop of Blip2QformerCirAlignPrompt.forward_stage2 (...align_prompt.py:254-268).
+//
+// CTA = 6 warps:  warp 0 lane 0  TMA producer        (bank blocks [128 rows x 64 cols] bf16, SW128)
+//                 warp 1 lane 0  tcgen05.mma issuer  (+ warp 1 owns the TMEM allocation)
+//                 warps 2..5     soft-max / epilogue (one TMEM lane quarter each, thread == query row)
+// smem:  Q tile resident (D/64 blocks of 16 KiB) + a ring of 16 KiB bank blocks.
+// TMEM:  forward   2 x S[128 x 128 f32]                         (256 columns)
+//        backward  O[128 x <=320 f32] | S[128 x 128] | P bf16   (512 columns)
+// GEMM1 (S)  : SS, A = Q block (K-major), B = bank block (K-major), M128 N128 K16 x 4 per block.
+// GEMM2 (dq) : TS, A = P (TMEM, bf16), B = the same bank block bytes read MN-major, M128 N64 K16 x 8.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "bank_ce.cuh"
+#include "ptx.cuh"
+
+namespace spn {
+
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+constexpr uint32_t kTmemColsFwd = 256;
+constexpr uint32_t kTmemColsBwd = 512;
+constexpr uint32_t kBwdSCol = 320;  // S tile columns [320, 448)
+constexpr uint32_t kBwdPCol = 448;  // P tile columns [448, 512): 128 bf16 = 64 x 32-bit columns
+
+struct SmemView {
+  uint8_t* q;       // kblocks x 16 KiB
+  uint8_t* ring;    // stages  x 16 KiB
+  uint64_t* full;   // [stages]
+  uint64_t* empty;  // [stages]
+  uint64_t* q_full;
+  uint64_t* s_full;  // [2]
+  uint64_t* s_free;  // [2]
+  uint64_t* p_full;
+  uint64_t* p_free;
+  uint64_t* o_full;
+  uint32_t* tmem_slot;
+};
+
+__device__ __forceinline__ SmemView carve(uint8_t* raw, int kblocks, int stages) {
+  SmemView v;
+  uintptr_t base = (reinterpret_cast<uintptr_t>(raw) + 1023u) & ~uintptr_t(1023u);
+  v.q = reinterpret_cast<uint8_t*>(base);
+  v.ring = v.q + size_t(kblocks) * kBlockBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v.ring + size_t(stages) * kBlockBytes);
+  v.full = bars;
+  v.empty = bars + stages;
+  uint64_t* rest = bars + 2 * stages;
+  v.q_full = rest + 0;
+  v.s_full = rest + 1;
+  v.s_free = rest + 3;
+  v.p_full = rest + 5;
+  v.p_free = rest + 6;
+  v.o_full = rest + 7;
+  v.tmem_slot = reinterpret_cast<uint32_t*>(rest + 8);
+  return v;
+}
+
+struct Ring {
+  uint32_t stage = 0, phase = 0;
+  int stages;
+  __device__ __forceinline__ explicit Ring(int s) : stages(s) {}
+  __device__ __forceinline__ void advance() {
+    if (++stage == uint32_t(stages)) {
+      stage = 0;
+      phase ^= 1u;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Forward soft-max over one 32-column chunk held in registers (T == 1): online (m, l) update.
+// x[] are raw dot products; scaled logit in log2 units = x * scale.
+template <bool EXTRA>
+__device__ __forceinline__ void fwd_chunk_t1(const uint32_t (&xr)[32], int valid, float scale, long long col0,
+                                             long long lbl_row, float& m_run, float& l_run, float& st,
+                                             float& ssum) {
+  float x[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(xr[j]);
+  if (valid < 32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j >= valid) x[j] = -INFINITY;
+  }
+  float mx0 = x[0], mx1 = x[1], mx2 = x[2], mx3 = x[3];
+#pragma unroll
+  for (int j = 4; j < 32; j += 4) {
+    mx0 = fmaxf(mx0, x[j]);
+    mx1 = fmaxf(mx1, x[j + 1]);
+    mx2 = fmaxf(mx2, x[j + 2]);
+    mx3 = fmaxf(mx3, x[j + 3]);
+  }
+  const float cmax = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale;  // scale > 0
+  const float m_new = fmaxf(m_run, cmax);                              // finite: valid >= 1
+  const float alpha = ex2_approx(m_run - m_new);                       // m_run = -inf -> 0
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    s0 += ex2_approx(fmaf(x[j], scale, -m_new));
+    s1 += ex2_approx(fmaf(x[j + 1], scale, -m_new));
+    s2 += ex2_approx(fmaf(x[j + 2], scale, -m_new));
+    s3 += ex2_approx(fmaf(x[j + 3], scale, -m_new));
+  }
+  l_run = fmaf(l_run, alpha, (s0 + s1) + (s2 + s3));
+  m_run = m_new;
+  if (EXTRA) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a += (j < valid) ? x[j] : 0.f;
+    ssum = fmaf(a, scale, ssum);
+  }
+  if (lbl_row >= col0 && lbl_row < col0 + 32) {  // rare: once per query per pass
+    const int jj = int(lbl_row - col0);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j == jj) st = x[j] * scale;
+  }
+}
+
+// Forward, T == 32: the chunk is one bank entry (32 token columns) -> one logit = max over tokens.
+template <bool EXTRA>
+__device__ __forceinline__ void fwd_chunk_t32(const uint32_t (&xr)[32], bool entry_ok, float scale,
+                                              bool is_label, float& m_run, float& l_run, float& st, float& ssum) {
+  if (!entry_ok) return;
+  float mx0 = __uint_as_float(xr[0]), mx1 = __uint_as_float(xr[1]);
+#pragma unroll
+  for (int j = 2; j < 32; j += 2) {
+    mx0 = fmaxf(mx0, __uint_as_float(xr[j]));
+    mx1 = fmaxf(mx1, __uint_as_float(xr[j + 1]));
+  }
+  const float y = fmaxf(mx0, mx1) * scale;
+  const float m_new = fmaxf(m_run, y);
+  l_run = fmaf(l_run, ex2_approx(m_run - m_new), ex2_approx(y - m_new));
+  m_run = m_new;
+  if (EXTRA) ssum += y;
+  if (is_label) st = y;
+}
+
+// Backward, T == 1: dlogit for 32 columns, scaled by gscale, packed to bf16x2 into u[16].
+template <bool EXTRA>
+__device__ __forceinline__ void bwd_chunk_t1(const uint32_t (&xr)[32], int valid, float scale, float lse2,
+                                             float eps_over_n, float one_minus_eps, float gscale, long long col0,
+                                             long long lbl_row, float& es, uint32_t* u) {
+  float p[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float xs = __uint_as_float(xr[j]) * scale;
+    float pj = ex2_approx(xs - lse2) - eps_over_n;
+    if (j >= valid) pj = 0.f;
+    p[j] = pj;
+  }
+  if (lbl_row >= col0 && lbl_row < col0 + 32) {
+    const int jj = int(lbl_row - col0);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j == jj) p[j] -= one_minus_eps;
+  }
+  if (EXTRA) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      a0 = fmaf(p[j], __uint_as_float(xr[j]), a0);  // OOB rows are zero-filled: x = 0, p = 0
+      a1 = fmaf(p[j + 1], __uint_as_float(xr[j + 1]), a1);
+    }
+    es = fmaf(a0 + a1, scale, es);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) u[j >> 1] = pack_bf16x2(p[j] * gscale, p[j + 1] * gscale);
+}
+
+// Backward, T == 32: gradient flows through the (first) arg-max token of the entry only.
+template <bool EXTRA>
+__device__ __forceinline__ void bwd_chunk_t32(const uint32_t (&xr)[32], bool entry_ok, float scale, float lse2,
+                                              float eps_over_n, float one_minus_eps, float gscale, bool is_label,
+                                              float& es, uint32_t* u) {
+  float gm = __uint_as_float(xr[0]);
+  int ja = 0;
+#pragma unroll
+  for (int j = 1; j < 32; ++j) {
+    const float v = __uint_as_float(xr[j]);
+    if (v > gm) {
+      gm = v;
+      ja = j;
+    }
+  }
+  const float y = gm * scale;
+  float pg = ex2_approx(y - lse2) - eps_over_n;
+  if (is_label) pg -= one_minus_eps;
+  if (!entry_ok) pg = 0.f;
+  if (EXTRA) es = fmaf(pg, y, es);
+  pg *= gscale;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2)
+    u[j >> 1] = pack_bf16x2(j == ja ? pg : 0.f, (j + 1) == ja ? pg : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int T, bool EXTRA>
+__global__ void __launch_bounds__(kBankCEThreads, 1)
+bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_bank,
+               const BankCEParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  const SmemView sm = carve(smem_raw, p.kblocks, p.stages);
+
+  // block -> (query tile, d-split, bank chunk); query tile fastest so co-resident CTAs share bank rows in L2
+  int bid = blockIdx.x;
+  const int qt = bid % p.q_tiles;
+  bid /= p.q_tiles;
+  const int ds = bid % p.num_dsplit;
+  const int chunk = bid / p.num_dsplit;
+  const int q0 = qt * kBM;
+  const int t_begin = int((long long)chunk * p.n_tiles / p.num_chunks);
+  const int t_end = int((long long)(chunk + 1) * p.n_tiles / p.num_chunks);
+  const int ntl = t_end - t_begin;
+  const int my_blocks = (MODE == 1) ? min(p.ow_blocks, p.kblocks - ds * p.ow_blocks) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], 1);
+    }
+    mbar_init(sm.q_full, 1);
+    mbar_init(&sm.s_full[0], 1);
+    mbar_init(&sm.s_full[1], 1);
+    mbar_init(&sm.s_free[0], 4);
+    mbar_init(&sm.s_free[1], 4);
+    mbar_init(sm.p_full, 4);
+    mbar_init(sm.p_free, 1);
+    mbar_init(sm.o_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_bank);
+  }
+  if (warp == 1) {
+    tmem_alloc(sm.tmem_slot, MODE == 0 ? kTmemColsFwd : kTmemColsBwd);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *sm.tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(sm.q_full, uint32_t(p.kblocks) * kBlockBytes);
+      for (int kb = 0; kb < p.kblocks; ++kb)
+        tma_load_2d(sm.q + size_t(kb) * kBlockBytes, &tmap_q, sm.q_full, kb * kBK, q0);
+      Ring r(p.stages);
+      auto load_block = [&](int col_blk, int row) {
+        mbar_wait(&sm.empty[r.stage], r.phase ^ 1u);
+        mbar_arrive_expect_tx(&sm.full[r.stage], kBlockBytes);
+        tma_load_2d(sm.ring + size_t(r.stage) * kBlockBytes, &tmap_bank, &sm.full[r.stage], col_blk * kBK, row);
+        r.advance();
+      };
+      for (int t = t_begin; t < t_end; ++t) {
+        for (int kb = 0; kb < p.kblocks; ++kb) load_block(kb, t * kBN);
+        if (MODE == 1 && t > t_begin)
+          for (int j = 0; j < my_blocks; ++j) load_block(ds * p.ow_blocks + j, (t - 1) * kBN);
+      }
+      if (MODE == 1 && ntl > 0)
+        for (int j = 0; j < my_blocks; ++j) load_block(ds * p.ow_blocks + j, (t_end - 1) * kBN);
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16_f32(kBM, kBN, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16_f32(kBM, 64, 0, 1);
+      const uint32_t q_addr = smem_u32(sm.q);
+      const uint32_t ring_addr = smem_u32(sm.ring);
+      Ring r(p.stages);
+      mbar_wait(sm.q_full, 0);
+      tc_fence_after();
+
+      auto gemm_s = [&](uint32_t d_tmem) {
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&sm.full[r.stage], r.phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(q_addr + uint32_t(kb) * kBlockBytes, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(ring_addr + r.stage * kBlockBytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
+            umma_ss_f16(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc_s, (kb | k) != 0);
+          umma_commit(&sm.empty[r.stage]);
+          r.advance();
+        }
+      };
+
+      if (MODE == 0) {
+        for (int i = 0; i < ntl; ++i) {
+          const uint32_t buf = uint32_t(i) & 1u;
+          mbar_wait(&sm.s_free[buf], ((uint32_t(i) >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          gemm_s(tmem_base + buf * kBN);
+          umma_commit(&sm.s_full[buf]);
+        }
+      } else {
+        auto gemm_o = [&](int u) {
+          mbar_wait(sm.p_full, uint32_t(u) & 1u);
+          tc_fence_after();
+          for (int j = 0; j < my_blocks; ++j) {
+            mbar_wait(&sm.full[r.stage], r.phase);
+            tc_fence_after();
+            // the same 16 KiB block, read MN-major: rows are K (bank rows), 128 B span = 64 output columns
+            const uint64_t bdesc = make_smem_desc_sw128(ring_addr + r.stage * kBlockBytes, kBlockBytes, 1024);
+#pragma unroll
+            for (int k = 0; k < kBN / kUmmaK; ++k)  // 16 bank rows = 2048 B per K step; P: 8 columns per step
+              umma_ts_f16(tmem_base + uint32_t(j) * 64u, tmem_base + kBwdPCol + uint32_t(k) * 8u,
+                          bdesc + uint64_t(k * (2048 >> 4)), idesc_o, (u > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&sm.empty[r.stage]);
+            r.advance();
+          }
+          umma_commit(sm.p_free);
+        };
+        for (int i = 0; i < ntl; ++i) {
+          mbar_wait(&sm.s_free[0], (uint32_t(i) & 1u) ^ 1u);
+          tc_fence_after();
+          gemm_s(tmem_base + kBwdSCol);
+          umma_commit(&sm.s_full[0]);
+          if (i > 0) gemm_o(i - 1);
+        }
+        if (ntl > 0) gemm_o(ntl - 1);
+        umma_commit(sm.o_full);
+      }
+    }
+  } else {
+    // ===================================================================== soft-max / epilogue warps
+    const uint32_t quarter = warp & 3u;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    const int row = int(quarter * 32u + lane);
+    const int q = q0 + row;
+    const bool q_ok = q < p.B;
+    const uint32_t t_row = tmem_base + ((quarter * 32u) << 16);
+    const float scale = p.scale_log2;
+    // label as a LOCAL token-row (T == 1) / entry (T == 32) index; out of shard -> never matches
+    long long lbl = -1;
+    if (q_ok) {
+      const long long g = p.labels[q] - p.row_base;
+      if (g >= 0 && g < p.N) lbl = g;
+    }
+    uint32_t xr[32];
+
+    if (MODE == 0) {
+      float m_run = -INFINITY, l_run = 0.f, st = -INFINITY, ssum = 0.f;
+      for (int i = 0; i < ntl; ++i) {
+        const int t = t_begin + i;
+        const uint32_t buf = uint32_t(i) & 1u;
+        mbar_wait(&sm.s_full[buf], (uint32_t(i) >> 1) & 1u);
+        tc_fence_after();
+        const long long row0 = (long long)t * kBN;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_32x32b_x32(t_row + buf * kBN + uint32_t(c) * 32u, xr);
+          tmem_ld_wait();
+          if (c == 3) {  // S tile fully in registers: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.s_free[buf]);
+          }
+          const long long col0 = row0 + c * 32;
+          if (T == 1) {
+            const long long left = p.n_rows - col0;
+            const int valid = left >= 32 ? 32 : (left > 0 ? int(left) : 0);
+            if (valid > 0) fwd_chunk_t1<EXTRA>(xr, valid, scale, col0, lbl, m_run, l_run, st, ssum);
+          } else {
+            const long long entry = (long long)t * 4 + c;
+            fwd_chunk_t32<EXTRA>(xr, entry < p.N, scale, entry == lbl, m_run, l_run, st, ssum);
+          }
+        }
+      }
+      if (q_ok) {
+        const size_t o = size_t(chunk) * p.B + q;
+        p.part_m[o] = m_run;
+        p.part_l[o] = l_run;
+        p.part_st[o] = st;
+        if (EXTRA) p.part_ssum[o] = ssum;
+      }
+    } else {
+      const float lse2 = q_ok ? p.lse[q] * kLog2e : INFINITY;  // padded rows: p = exp2(-inf) = 0
+      const float gscale = p.gscale_dev ? p.gscale * __ldg(p.gscale_dev) : p.gscale;
+      float es = 0.f;
+      uint32_t u[64];
+      for (int i = 0; i < ntl; ++i) {
+        const int t = t_begin + i;
+        mbar_wait(&sm.s_full[0], uint32_t(i) & 1u);
+        tc_fence_after();
+        const long long row0 = (long long)t * kBN;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_32x32b_x32(t_row + kBwdSCol + uint32_t(c) * 32u, xr);
+          tmem_ld_wait();
+          if (c == 3) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.s_free[0]);
+          }
+          const long long col0 = row0 + c * 32;
+          if (T == 1) {
+            const long long left = p.n_rows - col0;
+            const int valid = left >= 32 ? 32 : (left > 0 ? int(left) : 0);
+            bwd_chunk_t1<EXTRA>(xr, valid, scale, lse2, p.eps_over_n, p.one_minus_eps, gscale, col0, lbl, es,
+                                &u[c * 16]);
+          } else {
+            const long long entry = (long long)t * 4 + c;
+            bwd_chunk_t32<EXTRA>(xr, entry < p.N, scale, lse2, p.eps_over_n, p.one_minus_eps, gscale,
+                                 entry == lbl, es, &u[c * 16]);
+          }
+        }
+        // P(i) -> TMEM once GEMM2 of the previous tile no longer reads the buffer
+        mbar_wait(sm.p_free, (uint32_t(i) & 1u) ^ 1u);
+        tc_fence_after();
+        tmem_st_32x32b_x32(t_row + kBwdPCol, *reinterpret_cast<const uint32_t(*)[32]>(&u[0]));
+        tmem_st_32x32b_x32(t_row + kBwdPCol + 32u, *reinterpret_cast<const uint32_t(*)[32]>(&u[32]));
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sm.p_full);
+      }
+      // epilogue: O[128 x my_blocks*64] fp32 -> dq (+=, other chunks / shards add into the same rows)
+      mbar_wait(sm.o_full, 0);
+      tc_fence_after();
+      if (ntl > 0) {
+        for (int c = 0; c < my_blocks * 2; ++c) {
+          tmem_ld_32x32b_x32(t_row + uint32_t(c) * 32u, xr);
+          tmem_ld_wait();
+          if (q_ok) {
+            float* dst = p.dq + size_t(q) * p.D + size_t(ds) * p.ow_blocks * 64 + size_t(c) * 32;
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+              red_add_v4_f32(dst + v * 4, __uint_as_float(xr[4 * v]), __uint_as_float(xr[4 * v + 1]),
+                             __uint_as_float(xr[4 * v + 2]), __uint_as_float(xr[4 * v + 3]));
+          }
+        }
+        if (EXTRA && q_ok && ds == 0) atomicAdd(&p.dlogit_dot[q], es * kLn2);
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, MODE == 0 ? kTmemColsFwd : kTmemColsBwd);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Chunk / shard merge of forward statistics.  Inputs in `in_scale` units (log2 for the kernel's own
+// chunk partials, natural for already-merged per-rank statistics); outputs natural-log units.
+__global__ void merge_stats_kernel(const float* __restrict__ pm, const float* __restrict__ pl,
+                                   const float* __restrict__ pst, const float* __restrict__ pss, int P, int B,
+                                   float unit, float* m, float* l, float* st, float* ss) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float M = -INFINITY;
+  for (int c = 0; c < P; ++c) M = fmaxf(M, pm[size_t(c) * B + b]);
+  float L = 0.f, S = -INFINITY, SS = 0.f;
+  for (int c = 0; c < P; ++c) {
+    const float mc = pm[size_t(c) * B + b];
+    if (mc > -INFINITY) L += pl[size_t(c) * B + b] * (unit == 1.f ? expf(mc - M) : exp2f(mc - M));
+    S = fmaxf(S, pst[size_t(c) * B + b]);
+    if (pss) SS += pss[size_t(c) * B + b];
+  }
+  m[b] = M * unit;
+  l[b] = L;
+  st[b] = S * unit;
+  if (ss) ss[b] = pss ? SS * unit : 0.f;
+}
+
+__global__ void loss_kernel(const float* __restrict__ m, const float* __restrict__ l, const float* __restrict__ st,
+                            const float* __restrict__ ss, int B, float inv_n_total, float eps, float* lse,
+                            float* loss_q, float* loss_mean) {
+  // single block: B is a batch size (<= a few thousand)
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float z = m[b] + logf(l[b]);
+    float lq = z - (1.f - eps) * st[b];
+    if (eps != 0.f) lq -= eps * ss[b] * inv_n_total;
+    lse[b] = z;
+    if (loss_q) loss_q[b] = lq;
+    acc += lq;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) *loss_mean = v / float(B);
+  }
+}
+
+template <int MODE, int T, bool EXTRA>
+int launch_one(const CUtensorMap& tq, const CUtensorMap& tb, const BankCEParams& p, int grid, size_t smem,
+               cudaStream_t stream) {
+  auto kfn = bank_ce_kernel<MODE, T, EXTRA>;
+  SPN_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  kfn<<<grid, kBankCEThreads, smem, stream>>>(tq, tb, p);
+  SPN_CUDA_CHECK(cudaGetLastError());
+  return SPN_OK;
+}
+
+}  // namespace
+
+int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan) {
+  SPN_REQUIRE(B > 0 && N > 0, SPN_ERR_BAD_SHAPE, "bank-CE needs B > 0 and N > 0 (B=%d N=%lld)", B, N);
+  SPN_REQUIRE(D >= 64 && D <= 768 && D % 64 == 0, SPN_ERR_BAD_SHAPE,
+              "feature dim D=%d unsupported: need a multiple of 64 in [64, 768]", D);
+  SPN_REQUIRE(T == 1 || T == 32, SPN_ERR_BAD_SHAPE, "tokens per entry T=%d unsupported (1 or 32)", T);
+  SPN_REQUIRE(N * T < (1ll << 31) - 256, SPN_ERR_BAD_SHAPE, "bank shard of %lld rows exceeds the TMA coordinate range", N * T);
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  int smem_max = device_max_smem_optin();
+  if (smem_max <= 0) smem_max = 232448;
+  plan->kblocks = D / 64;
+  plan->q_tiles = (B + kBM - 1) / kBM;
+  const long long n_rows = N * T;
+  plan->n_tiles = int((n_rows + kBN - 1) / kBN);
+  if (mode == 1) {
+    plan->num_dsplit = (plan->kblocks + 4) / 5;  // O tile <= 320 TMEM columns
+    plan->ow_blocks = (plan->kblocks + plan->num_dsplit - 1) / plan->num_dsplit;
+  } else {
+    plan->num_dsplit = 1;
+    plan->ow_blocks = 0;
+  }
+  int chunks = sms / (plan->q_tiles * plan->num_dsplit);
+  if (chunks < 1) chunks = 1;
+  if (chunks > plan->n_tiles) chunks = plan->n_tiles;
+  plan->num_chunks = chunks;
+  plan->grid = plan->q_tiles * plan->num_dsplit * chunks;
+  const size_t fixed = 1024 /*align slack*/ + size_t(plan->kblocks) * kBlockBytes + 256 /*barriers*/;
+  int stages = int((size_t(smem_max) - fixed) / kBlockBytes);
+  if (stages > 8) stages = 8;
+  SPN_REQUIRE(stages >= 2, SPN_ERR_BAD_SHAPE, "D=%d leaves no room for the bank ring in %d B of shared memory", D, smem_max);
+  plan->stages = stages;
+  plan->smem_bytes = fixed + size_t(stages) * kBlockBytes;
+  plan->ws_bytes = (mode == 0) ? ((size_t(4) * chunks * B * sizeof(float) + 255) / 256) * 256 : 256;
+  return SPN_OK;
+}
+
+int bank_ce_forward(const void* q, const void* bank, const long long* labels, float inv_tau, int B, long long N,
+                    int D, int T, long long row_base, float* m, float* l, float* s_t, float* s_sum, void* ws,
+                    size_t ws_bytes, cudaStream_t stream) {
+  BankCEPlan plan;
+  int rc = bank_ce_plan(0, B, N, D, T, &plan);
+  if (rc != SPN_OK) return rc;
+  SPN_REQUIRE(inv_tau > 0.f && isfinite(inv_tau), SPN_ERR_BAD_ARG, "inv_tau must be positive and finite (got %g)", inv_tau);
+  SPN_REQUIRE(ws && ws_bytes >= plan.ws_bytes, SPN_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, plan.ws_bytes);
+  CUtensorMap tq, tb;
+  if ((rc = make_tmap_bf16_2d(&tq, q, uint64_t(B), uint64_t(D), kBM)) != SPN_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tb, bank, uint64_t(N) * T, uint64_t(D), kBN)) != SPN_OK) return rc;
+  BankCEParams p{};
+  p.B = B; p.D = D; p.N = N; p.n_rows = N * T; p.kblocks = plan.kblocks; p.stages = plan.stages;
+  p.n_tiles = plan.n_tiles; p.q_tiles = plan.q_tiles; p.num_chunks = plan.num_chunks; p.num_dsplit = 1;
+  p.ow_blocks = 0; p.scale_log2 = inv_tau * kLog2e; p.row_base = row_base; p.labels = labels;
+  float* w = static_cast<float*>(ws);
+  const size_t stride = size_t(plan.num_chunks) * B;
+  p.part_m = w; p.part_l = w + stride; p.part_st = w + 2 * stride; p.part_ssum = w + 3 * stride;
+  const bool extra = s_sum != nullptr;
+  if (T == 1) rc = extra ? launch_one<0, 1, true>(tq, tb, p, plan.grid, plan.smem_bytes, stream)
+                         : launch_one<0, 1, false>(tq, tb, p, plan.grid, plan.smem_bytes, stream);
+  else        rc = extra ? launch_one<0, 32, true>(tq, tb, p, plan.grid, plan.smem_bytes, stream)
+                         : launch_one<0, 32, false>(tq, tb, p, plan.grid, plan.smem_bytes, stream);
+  if (rc != SPN_OK) return rc;
+  merge_stats_kernel<<<(B + 127) / 128, 128, 0, stream>>>(p.part_m, p.part_l, p.part_st, extra ? p.part_ssum : nullptr,
+                                                         plan.num_chunks, B, kLn2, m, l, s_t, s_sum);
+  SPN_CUDA_CHECK(cudaGetLastError());
+  return SPN_OK;
+}
+
+int bank_ce_backward(const void* q, const void* bank, const long long* labels, float inv_tau, const float* lse,
+                     float gscale, const float* gscale_dev, float label_smoothing, long long N_total, int B,
+                     long long N, int D, int T, long long row_base, float* dq, float* dlogit_dot, cudaStream_t stream) {
+  BankCEPlan plan;
+  int rc = bank_ce_plan(1, B, N, D, T, &plan);
+  if (rc != SPN_OK) return rc;
+  SPN_REQUIRE(inv_tau > 0.f && isfinite(inv_tau), SPN_ERR_BAD_ARG, "inv_tau must be positive and finite (got %g)", inv_tau);
+  SPN_REQUIRE(N_total >= N, SPN_ERR_BAD_ARG, "N_total=%lld smaller than the shard N=%lld", N_total, N);
+  CUtensorMap tq, tb;
+  if ((rc = make_tmap_bf16_2d(&tq, q, uint64_t(B), uint64_t(D), kBM)) != SPN_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tb, bank, uint64_t(N) * T, uint64_t(D), kBN)) != SPN_OK) return rc;
+  BankCEParams p{};
+  p.B = B; p.D = D; p.N = N; p.n_rows = N * T; p.kblocks = plan.kblocks; p.stages = plan.stages;
+  p.n_tiles = plan.n_tiles; p.q_tiles = plan.q_tiles; p.num_chunks = plan.num_chunks;
+  p.num_dsplit = plan.num_dsplit; p.ow_blocks = plan.ow_blocks; p.scale_log2 = inv_tau * kLog2e;
+  p.row_base = row_base; p.labels = labels; p.lse = lse; p.gscale = gscale; p.gscale_dev = gscale_dev;
+  p.eps_over_n = label_smoothing / float(N_total); p.one_minus_eps = 1.f - label_smoothing;
+  p.dq = dq; p.dlogit_dot = dlogit_dot;
+  const bool extra = dlogit_dot != nullptr;
+  if (T == 1) rc = extra ? launch_one<1, 1, true>(tq, tb, p, plan.grid, plan.smem_bytes, stream)
+                         : launch_one<1, 1, false>(tq, tb, p, plan.grid, plan.smem_bytes, stream);
+  else        rc = extra ? launch_one<1, 32, true>(tq, tb, p, plan.grid, plan.smem_bytes, stream)
+                         : launch_one<1, 32, false>(tq, tb, p, plan.grid, plan.smem_bytes, stream);
+  return rc;
+}
+
+int merge_stats(const float* pm, const float* pl, const float* pst, const float* pss, int P, int B, float* m,
+                float* l, float* st, float* ss, cudaStream_t stream) {
+  SPN_REQUIRE(P > 0 && B > 0, SPN_ERR_BAD_SHAPE, "merge_stats needs P > 0 and B > 0");
+  merge_stats_kernel<<<(B + 127) / 128, 128, 0, stream>>>(pm, pl, pst, pss, P, B, 1.f, m, l, st, ss);
+  SPN_CUDA_CHECK(cudaGetLastError());
+  return SPN_OK;
+}
+
+int bank_ce_loss(const float* m, const float* l, const float* st, const float* ss, int B, long long N_total,
+                 float eps, float* lse, float* loss_q, float* loss_mean, cudaStream_t stream) {
+  SPN_REQUIRE(B > 0 && N_total > 0, SPN_ERR_BAD_SHAPE, "bank_ce_loss needs B > 0 and N_total > 0");
+  SPN_REQUIRE(eps == 0.f || ss != nullptr, SPN_ERR_BAD_ARG, "label smoothing needs the s_sum statistic");
+  loss_kernel<<<1, 256, 0, stream>>>(m, l, st, ss, B, 1.f / float(N_total), eps, lse, loss_q, loss_mean);
+  SPN_CUDA_CHECK(cudaGetLastError());
+  return SPN_OK;
+}
+
+}  // namespace spn

@@ -1,0 +1,19 @@
+// Host entry points of the retrieval kernels (sim_rank.cu), used by api.cu.
+#pragma once
+#include "common.cuh"
+
+namespace spn {
+
+size_t sim_topk_ws_bytes(int Q, int G, int T, int K);
+int sim_topk(const float* q, const float* g, int Q, int G, int D, int T, int K, const int* exclude, int col_base,
+             float* out_val, int* out_idx, void* ws, size_t ws_bytes, cudaStream_t stream);
+int merge_topk(const float* vals, const int* idx, int R, int Q, int K, float* out_val, int* out_idx,
+               cudaStream_t stream);
+int sim_matrix(const float* q, const float* g, int Q, int G, int D, int T, float* out, cudaStream_t stream);
+int sim_target_score(const float* q, const float* g, int Q, int G, int D, int T, const int* target, int col_base,
+                     float* score, cudaStream_t stream);
+int sim_rank(const float* q, const float* g, int Q, int G, int D, int T, const int* target, const float* tscore,
+             const int* exclude, const int* group, int M, int col_base, int* rank, int* group_rank,
+             cudaStream_t stream);
+
+}  // namespace spn

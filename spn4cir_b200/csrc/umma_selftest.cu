@@ -1,0 +1,134 @@
+// One-CTA tcgen05 GEMM used by tests/test_umma_selftest.py to pin, on hardware, every encoding the
+// bank-CE kernels rely on: TMA 128B-swizzled boxes, K-major and MN-major shared-memory descriptors,
+// the bf16 instruction descriptor, A-operand-from-TMEM packing, and the 32x32b TMEM load/store map.
+//   C[128, N] = A[128, K] * B^T   (B K-major  [N, K])      mode bit1 = 0
+//   C[128, N] = A[128, K] * B     (B MN-major [K, N])      mode bit1 = 1 (K == 128)
+//   mode bit0 = 1: A is first written to TMEM as packed bf16 (tcgen05.st) and read by the MMA from there.
+#include <cuda_bf16.h>
+
+#include "bank_ce.cuh"
+#include "ptx.cuh"
+
+namespace spn {
+namespace {
+
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const uint32_t* __restrict__ a_gmem_u32, float* __restrict__ c, int N, int K, int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  uintptr_t base = (reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~uintptr_t(1023u);
+  uint8_t* a_smem = reinterpret_cast<uint8_t*>(base);       // up to 4 blocks of 16 KiB
+  uint8_t* b_smem = a_smem + 4 * kBlockBytes;               // up to 4 blocks of 16 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + 4 * kBlockBytes);
+  uint64_t* ld_full = bars;
+  uint64_t* mma_done = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const bool a_tmem = mode & 1, b_mn = mode & 2;
+  const int kblocks = K / 64;
+
+  if (threadIdx.x == 0) {
+    mbar_init(ld_full, 1);
+    mbar_init(mma_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_row = tmem_base + ((warp * 32u) << 16);
+  const int row = int(warp * 32u + lane);
+
+  if (a_tmem) {
+    // thread == row: pack its K bf16 (K/2 words) into TMEM columns [128, 128 + K/2)
+    uint32_t u[32];
+    for (int c = 0; c < K / 64; ++c) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) u[j] = a_gmem_u32[size_t(row) * (K / 2) + c * 32 + j];
+      tmem_st_32x32b_x32(t_row + 128u + uint32_t(c) * 32u, u);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+
+  if (threadIdx.x == 0) {
+    const int b_blocks = b_mn ? N / 64 : kblocks;
+    const uint32_t b_box_rows = b_mn ? 128u : uint32_t(N);
+    const uint32_t bytes = uint32_t(kblocks) * kBlockBytes + uint32_t(b_blocks) * b_box_rows * 128u;
+    mbar_arrive_expect_tx(ld_full, bytes);
+    for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(a_smem + size_t(kb) * kBlockBytes, &tmap_a, ld_full, kb * 64, 0);
+    for (int j = 0; j < b_blocks; ++j) tma_load_2d(b_smem + size_t(j) * kBlockBytes, &tmap_b, ld_full, j * 64, 0);
+    mbar_wait(ld_full, 0);
+    tc_fence_after();
+    const uint32_t a_addr = smem_u32(a_smem), b_addr = smem_u32(b_smem);
+    if (!b_mn) {
+      const uint32_t idesc = make_idesc_bf16_f32(128, N, 0, 0);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const uint64_t adesc = make_smem_desc_sw128(a_addr + uint32_t(kb) * kBlockBytes, 16, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(b_addr + uint32_t(kb) * kBlockBytes, 16, 1024);
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t acc = (kb | k) != 0;
+          if (a_tmem)
+            umma_ts_f16(tmem_base, tmem_base + 128u + uint32_t(kb * 4 + k) * 8u, bdesc + uint64_t(k * 2), idesc, acc);
+          else
+            umma_ss_f16(tmem_base, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, acc);
+        }
+      }
+    } else {
+      const uint32_t idesc = make_idesc_bf16_f32(128, 64, 0, 1);
+      for (int j = 0; j < N / 64; ++j) {
+        const uint64_t bdesc = make_smem_desc_sw128(b_addr + uint32_t(j) * kBlockBytes, kBlockBytes, 1024);
+        for (int k = 0; k < 8; ++k) {  // K = 128 = 8 steps of 16 rows (2048 B each)
+          const uint64_t adesc = make_smem_desc_sw128(a_addr + uint32_t(k / 4) * kBlockBytes, 16, 1024) + uint64_t((k % 4) * 2);
+          if (a_tmem)
+            umma_ts_f16(tmem_base + uint32_t(j) * 64u, tmem_base + 128u + uint32_t(k) * 8u, bdesc + uint64_t(k * 128), idesc, k != 0);
+          else
+            umma_ss_f16(tmem_base + uint32_t(j) * 64u, adesc, bdesc + uint64_t(k * 128), idesc, k != 0);
+        }
+      }
+    }
+    umma_commit(mma_done);
+  }
+  __syncwarp();
+  mbar_wait(mma_done, 0);
+  tc_fence_after();
+  uint32_t r[32];
+  for (int cb = 0; cb < N / 32; ++cb) {
+    tmem_ld_32x32b_x32(t_row + uint32_t(cb) * 32u, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) c[size_t(row) * N + cb * 32 + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace
+
+int debug_umma_gemm(const void* a, const void* b, float* c, int N, int K, int mode, cudaStream_t stream) {
+  SPN_REQUIRE(N == 64 || N == 128, SPN_ERR_BAD_SHAPE, "selftest N must be 64 or 128 (got %d)", N);
+  SPN_REQUIRE(K % 64 == 0 && K >= 64 && K <= 256, SPN_ERR_BAD_SHAPE, "selftest K must be 64..256, multiple of 64 (got %d)", K);
+  const bool b_mn = mode & 2;
+  SPN_REQUIRE(!b_mn || K == 128, SPN_ERR_BAD_SHAPE, "MN-major selftest needs K == 128 (got %d)", K);
+  int rc;
+  if ((rc = require_sm100()) != SPN_OK) return rc;
+  CUtensorMap ta, tb;
+  if ((rc = make_tmap_bf16_2d(&ta, a, 128, uint64_t(K), 128)) != SPN_OK) return rc;
+  if (b_mn) rc = make_tmap_bf16_2d(&tb, b, uint64_t(K), uint64_t(N), 128);
+  else      rc = make_tmap_bf16_2d(&tb, b, uint64_t(N), uint64_t(K), uint32_t(N));
+  if (rc != SPN_OK) return rc;
+  const size_t smem = 1024 + 8 * kBlockBytes + 64;
+  SPN_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  umma_selftest_kernel<<<1, 128, smem, stream>>>(ta, tb, static_cast<const uint32_t*>(a), c, N, K, mode);
+  SPN_CUDA_CHECK(cudaGetLastError());
+  return SPN_OK;
+}
+
+}  // namespace spn

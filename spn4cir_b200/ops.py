@@ -1,0 +1,242 @@
+"""Torch-facing operators over the C ABI: bank-CE (forward statistics / loss / backward) as an
+``autograd.Function`` and the device-resident bank.
+
+torch is plumbing here (device memory, streams, autograd graph); every arithmetic step of the path
+runs in libspn_b200's kernels.  Reference semantics: ``CIRPlus.infonce_loss``
+(/root/reference/clip4cir/models_negplus.py:150-154 and siblings) and the BLIP-2 ``forward_stage2``
+tail (/root/reference/blip24cir/lavis/models/blip2_models/blip2_qformer_cir_align_prompt.py:254-268).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Union
+
+import torch
+
+from . import _lib
+from ._lib import DT_BF16, DT_F16, DT_F32, OP_BANK_CE_FWD, SpnError, call
+
+_TORCH2SPN = {torch.float32: DT_F32, torch.float16: DT_F16, torch.bfloat16: DT_BF16}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device: torch.device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise SpnError("spn4cir_b200", -5, f"{name} must be a CUDA tensor: this path has no CPU fallback")
+
+
+def cast_to_bf16(x: torch.Tensor) -> torch.Tensor:
+    """Contiguous bf16 copy of a CUDA tensor through ``spn_cast_to_bf16`` (no-op if already bf16)."""
+    _require_cuda(x, "tensor")
+    x = x.detach()
+    if x.dtype == torch.bfloat16 and x.is_contiguous():
+        return x
+    if x.dtype not in _TORCH2SPN:
+        x = x.float()
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        call("spn_cast_to_bf16", _ptr(x), _TORCH2SPN[x.dtype], _ptr(out), x.numel(), _stream(x.device))
+    return out
+
+
+class DeviceBank:
+    """A static memory bank resident in HBM as bf16 rows.
+
+    Replaces the per-step ``self.target_bank.detach().to(self.device)``
+    (/root/reference/clip4cir/models_negplus.py:138, blip24cir/models.py:119): the bank is uploaded and cast
+    once; every step reads it in place.  ``data`` is ``[N * T, D]`` bf16; ``row_base`` / ``n_total``
+    describe the shard when the bank is row-sharded across ranks (whole entries per shard).
+    """
+
+    def __init__(self, data_bf16: torch.Tensor, tokens_per_entry: int = 1, row_base: int = 0,
+                 n_total: Optional[int] = None):
+        _require_cuda(data_bf16, "bank")
+        if data_bf16.dtype != torch.bfloat16 or data_bf16.dim() != 2 or not data_bf16.is_contiguous():
+            raise SpnError("DeviceBank", -3, "expects a contiguous 2-D bf16 CUDA tensor [N*T, D]")
+        if data_bf16.shape[0] % tokens_per_entry != 0:
+            raise SpnError("DeviceBank", -1, "row count is not a multiple of tokens_per_entry")
+        self.data = data_bf16
+        self.T = int(tokens_per_entry)
+        self.N = data_bf16.shape[0] // self.T
+        self.D = data_bf16.shape[1]
+        self.row_base = int(row_base)
+        self.n_total = int(n_total) if n_total is not None else self.N
+
+    @property
+    def device(self) -> torch.device:
+        return self.data.device
+
+    @classmethod
+    def from_tensor(cls, bank: torch.Tensor, device: Union[str, torch.device] = "cuda", *, shard_rank: int = 0,
+                    shard_world: int = 1) -> "DeviceBank":
+        """``bank``: ``[N, D]`` or ``[N, T, D]`` float tensor (CPU or CUDA).  With ``shard_world > 1`` only
+        rows ``[r * ceil(N/R), ...)`` are uploaded."""
+        if bank.dim() == 3:
+            n, t, d = bank.shape
+        elif bank.dim() == 2:
+            (n, d), t = bank.shape, 1
+        else:
+            raise SpnError("DeviceBank", -1, f"bank must be [N, D] or [N, T, D], got {tuple(bank.shape)}")
+        per = (n + shard_world - 1) // shard_world
+        lo, hi = min(n, shard_rank * per), min(n, (shard_rank + 1) * per)
+        if hi <= lo:
+            raise SpnError("DeviceBank", -1, f"rank {shard_rank} of {shard_world} owns no rows of a {n}-entry bank")
+        part = bank[lo:hi].detach().reshape((hi - lo) * t, d)
+        dev = torch.device(device)
+        if part.dtype not in _TORCH2SPN:
+            part = part.float()
+        part = part.to(dev, non_blocking=True).contiguous()
+        return cls(cast_to_bf16(part), t, row_base=lo, n_total=n)
+
+    @classmethod
+    def from_file(cls, path: str, device: Union[str, torch.device] = "cuda", index: int = 1, **kw) -> "DeviceBank":
+        """Load the reference's cached bank file: ``torch.save([refer_bank, target_bank])``
+        (/root/reference/clip4cir/models_negplus.py:78) -> element ``index`` (1 = target bank)."""
+        obj = torch.load(path, map_location="cpu")
+        bank = obj[index] if isinstance(obj, (list, tuple)) else obj
+        return cls.from_tensor(bank, device, **kw)
+
+
+def _fwd_stats(q_bf16: torch.Tensor, bank: DeviceBank, labels: torch.Tensor, inv_tau: float, want_ssum: bool):
+    B, D = q_bf16.shape
+    dev = q_bf16.device
+    stats = torch.empty((4, B), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws_bytes = _lib.workspace_bytes(OP_BANK_CE_FWD, B, bank.N, D, bank.T)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        call("spn_bank_ce_fwd", _ptr(q_bf16), _ptr(bank.data), _ptr(labels), inv_tau, B, bank.N, D, bank.T,
+             bank.row_base, _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), _ptr(stats[3]) if want_ssum else None,
+             _ptr(ws), ws_bytes, _stream(dev))
+    return stats
+
+
+def _loss_from_stats(stats: torch.Tensor, n_total: int, eps: float):
+    """stats [4, B] (m, l, s_t, s_sum) -> (lse [B], loss_per_query [B], loss_mean [])."""
+    B = stats.shape[1]
+    dev = stats.device
+    out = torch.empty((2, B), dtype=torch.float32, device=dev)
+    mean = torch.empty((), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        call("spn_bank_ce_loss", _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), _ptr(stats[3]) if eps != 0.0 else None,
+             B, n_total, eps, _ptr(out[0]), _ptr(out[1]), _ptr(mean), _stream(dev))
+    return out[0], out[1], mean
+
+
+def merge_stats(parts: torch.Tensor) -> torch.Tensor:
+    """parts [P, 4, B] (m, l, s_t, s_sum per partial) -> merged [4, B] (``spn_merge_stats``)."""
+    P, four, B = parts.shape
+    assert four == 4
+    dev = parts.device
+    flat = parts.permute(1, 0, 2).contiguous()  # [4, P, B]
+    out = torch.empty((4, B), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        call("spn_merge_stats", _ptr(flat[0]), _ptr(flat[1]), _ptr(flat[2]), _ptr(flat[3]), P, B, _ptr(out[0]),
+             _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _stream(dev))
+    return out
+
+
+def _bwd(q_bf16, bank: DeviceBank, labels, inv_tau, lse, gscale, gscale_dev, eps, dq, dlogit_dot):
+    B, D = q_bf16.shape
+    dev = q_bf16.device
+    with torch.cuda.device(dev):
+        call("spn_bank_ce_bwd", _ptr(q_bf16), _ptr(bank.data), _ptr(labels), inv_tau, _ptr(lse), gscale,
+             _ptr(gscale_dev), eps, bank.n_total, B, bank.N, D, bank.T, bank.row_base, _ptr(dq), _ptr(dlogit_dot),
+             None, 0, _stream(dev))
+
+
+class _BankCE(torch.autograd.Function):
+    """loss = mean_b CE(inv_tau * sim(q_b, bank), label_b); grads for q and (optionally) tau."""
+
+    @staticmethod
+    def forward(ctx, q, tau_t, bank: DeviceBank, labels, inv_tau: float, eps: float):
+        q_bf16 = cast_to_bf16(q)
+        stats = _fwd_stats(q_bf16, bank, labels, inv_tau, eps != 0.0)
+        lse, _, loss = _loss_from_stats(stats, bank.n_total, eps)
+        ctx.bank, ctx.inv_tau, ctx.eps = bank, inv_tau, eps
+        ctx.q_dtype = q.dtype
+        ctx.tau_needs_grad = tau_t is not None and tau_t.requires_grad
+        ctx.save_for_backward(q_bf16, labels, lse)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        q_bf16, labels, lse = ctx.saved_tensors
+        B, D = q_bf16.shape
+        dev = q_bf16.device
+        g32 = g.detach().to(torch.float32).contiguous()
+        dq = torch.zeros((B, D), dtype=torch.float32, device=dev)
+        ddot = torch.zeros(B, dtype=torch.float32, device=dev) if ctx.tau_needs_grad else None
+        _bwd(q_bf16, ctx.bank, labels, ctx.inv_tau, lse, ctx.inv_tau / B, g32, ctx.eps, dq, ddot)
+        dtau = None
+        if ctx.tau_needs_grad:
+            # dL/dtau = -(g / B) * inv_tau * sum_b sum_n dlogit[b,n] * s[b,n]
+            dtau = (-(ctx.inv_tau / B)) * ddot.sum() * g32
+        return dq.to(ctx.q_dtype), dtau, None, None, None, None
+
+
+def _prep_labels(labels: Optional[torch.Tensor], B: int, dev: torch.device) -> torch.Tensor:
+    if labels is None:  # models_negplus.py:152-153
+        return torch.arange(B, dtype=torch.int64, device=dev)
+    return labels.to(device=dev, dtype=torch.int64).contiguous()
+
+
+def _split_tau(tau):
+    if isinstance(tau, torch.Tensor):
+        val = float(tau.detach().float().item())  # learnable temperature (blip4cir/models.py:29): one host read
+        return tau, val
+    return None, float(tau)
+
+
+def bank_infonce(query_features: torch.Tensor, bank: Union[DeviceBank, torch.Tensor],
+                 labels: Optional[torch.Tensor] = None, tau=0.01, *, label_smoothing: float = 0.0) -> torch.Tensor:
+    """``CrossEntropy((q @ bank.T) / tau, labels)`` without materialising the logits.
+
+    ``bank``: a :class:`DeviceBank` (preferred: resident, cast once) or a CUDA float tensor
+    ``[N, D]`` / ``[N, T, D]`` (cast on every call).  With ``T > 1`` the logit of an entry is the max
+    over its T token rows (BLIP-2).  Differentiable w.r.t. ``query_features`` and ``tau`` (if it is a
+    tensor requiring grad); the bank is a constant.
+    """
+    _require_cuda(query_features, "query_features")
+    if query_features.dim() != 2:
+        raise SpnError("bank_infonce", -1, f"query_features must be [B, D], got {tuple(query_features.shape)}")
+    if not isinstance(bank, DeviceBank):
+        bank = DeviceBank.from_tensor(bank, query_features.device)
+    if bank.D != query_features.shape[1]:
+        raise SpnError("bank_infonce", -1, f"feature dims differ: q {query_features.shape[1]} vs bank {bank.D}")
+    tau_t, tau_v = _split_tau(tau)
+    if not (tau_v > 0.0 and math.isfinite(tau_v)):
+        raise SpnError("bank_infonce", -7, f"tau must be positive and finite, got {tau_v}")
+    lab = _prep_labels(labels, query_features.shape[0], query_features.device)
+    return _BankCE.apply(query_features, tau_t, bank, lab, 1.0 / tau_v, float(label_smoothing))
+
+
+def bank_ce_stats(query_features: torch.Tensor, bank: DeviceBank, labels: torch.Tensor, tau: float,
+                  want_ssum: bool = False) -> torch.Tensor:
+    """Forward statistics only: [4, B] = (m, l, s_t, s_sum) in natural-log units (no autograd)."""
+    q_bf16 = cast_to_bf16(query_features)
+    lab = _prep_labels(labels, q_bf16.shape[0], q_bf16.device)
+    return _fwd_stats(q_bf16, bank, lab, 1.0 / float(tau), want_ssum)
+
+
+def query_assemble(refer_bank: torch.Tensor, refer_idx: torch.Tensor, text_feats: torch.Tensor):
+    """normalize(refer_bank[idx] + text) -> (q_bf16, q_f32, inv_norm)  (models_negplus.py:133-137)."""
+    _require_cuda(refer_bank, "refer_bank")
+    B, D = text_feats.shape
+    dev = refer_bank.device
+    rb = refer_bank.detach().float().contiguous()
+    tx = text_feats.detach().float().contiguous()
+    idx = refer_idx.to(device=dev, dtype=torch.int64).contiguous()
+    q16 = torch.empty((B, D), dtype=torch.bfloat16, device=dev)
+    q32 = torch.empty((B, D), dtype=torch.float32, device=dev)
+    inv = torch.empty(B, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        call("spn_query_assemble", _ptr(rb), _ptr(idx), _ptr(tx), B, D, _ptr(q16), _ptr(q32), _ptr(inv), _stream(dev))
+    return q16, q32, inv

@@ -1,0 +1,125 @@
+"""Retrieval scoring over the C ABI: fused similarity + top-K / rank-of-target and the integer metric
+tails that replace the reference's numpy string matching.
+
+Reference: ``distances = 1 - q @ g.T; torch.argsort(distances)`` and the Recall arithmetic of
+``compute_cirr_val_metrics`` / ``compute_fiq_val_metrics``
+(/root/reference/clip4cir/validate.py:19-51,111-156; blip24cir/validate.py:19-43,107-146) and the
+max-over-32-tokens similarity of ``Blip2QformerCirAlignPrompt.inference``
+(/root/reference/blip24cir/lavis/models/blip2_models/blip2_qformer_cir_align_prompt.py:311-319).
+
+Ordering rule (the reference's argsort is unstable, so it has none): descending score, ties broken
+by the lower gallery index.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import OP_SIM_TOPK, SpnError, call
+from .ops import _ptr, _require_cuda, _stream
+
+
+def _prep_gallery(gallery: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
+    """[G, D] or [G, T, D] -> contiguous fp32 [G*T, D], G, T."""
+    _require_cuda(gallery, "gallery")
+    if gallery.dim() == 3:
+        G, T, D = gallery.shape
+    elif gallery.dim() == 2:
+        (G, D), T = gallery.shape, 1
+    else:
+        raise SpnError("retrieval", -1, f"gallery must be [G, D] or [G, T, D], got {tuple(gallery.shape)}")
+    return gallery.detach().float().reshape(G * T, D).contiguous(), G, T
+
+
+def _i32(x, dev) -> Optional[torch.Tensor]:
+    if x is None:
+        return None
+    return torch.as_tensor(x).to(device=dev, dtype=torch.int32).contiguous()
+
+
+def sim_topk(query: torch.Tensor, gallery: torch.Tensor, k: int, exclude=None, col_base: int = 0):
+    """Top-``k`` gallery entries per query: returns (values [Q, k] fp32, indices [Q, k] int32, global)."""
+    _require_cuda(query, "query")
+    g, G, T = _prep_gallery(gallery)
+    q = query.detach().float().contiguous()
+    Q, D = q.shape
+    dev = q.device
+    ex = _i32(exclude, dev)
+    vals = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((Q, k), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        ws_bytes = _lib.workspace_bytes(OP_SIM_TOPK, Q, G, D, T, k)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        call("spn_sim_topk", _ptr(q), _ptr(g), Q, G, D, T, k, _ptr(ex), col_base, _ptr(vals), _ptr(idx), _ptr(ws),
+             ws_bytes, _stream(dev))
+    return vals, idx
+
+
+def merge_topk(vals: torch.Tensor, idx: torch.Tensor):
+    """[R, Q, K] per-shard lists -> one [Q, K] list (``spn_merge_topk``)."""
+    R, Q, K = vals.shape
+    dev = vals.device
+    vals = vals.float().contiguous()
+    idx = idx.to(torch.int32).contiguous()
+    ov = torch.empty((Q, K), dtype=torch.float32, device=dev)
+    oi = torch.empty((Q, K), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        call("spn_merge_topk", _ptr(vals), _ptr(idx), R, Q, K, _ptr(ov), _ptr(oi), _stream(dev))
+    return ov, oi
+
+
+def sim_target_score(query: torch.Tensor, gallery: torch.Tensor, target, col_base: int = 0) -> torch.Tensor:
+    _require_cuda(query, "query")
+    g, G, T = _prep_gallery(gallery)
+    q = query.detach().float().contiguous()
+    Q, D = q.shape
+    dev = q.device
+    tg = _i32(target, dev)
+    out = torch.empty(Q, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        call("spn_sim_target_score", _ptr(q), _ptr(g), Q, G, D, T, _ptr(tg), col_base, _ptr(out), _stream(dev))
+    return out
+
+
+def sim_rank(query: torch.Tensor, gallery: torch.Tensor, target, exclude=None, group=None, *,
+             target_score: Optional[torch.Tensor] = None, col_base: int = 0, rank_out=None, group_rank_out=None):
+    """Rank of ``target`` per query (0 = best) after dropping ``exclude``; with ``group`` [Q, M] also the
+    rank restricted to the group members.  Returns (rank [Q] int32, group_rank [Q] int32 | None)."""
+    _require_cuda(query, "query")
+    g, G, T = _prep_gallery(gallery)
+    q = query.detach().float().contiguous()
+    Q, D = q.shape
+    dev = q.device
+    tg, ex, gr = _i32(target, dev), _i32(exclude, dev), _i32(group, dev)
+    M = 0 if gr is None else gr.shape[1]
+    with torch.cuda.device(dev):
+        if target_score is None:
+            target_score = torch.empty(Q, dtype=torch.float32, device=dev)
+            call("spn_sim_target_score", _ptr(q), _ptr(g), Q, G, D, T, _ptr(tg), col_base, _ptr(target_score),
+                 _stream(dev))
+        rank = rank_out if rank_out is not None else torch.zeros(Q, dtype=torch.int32, device=dev)
+        grank = None
+        if gr is not None:
+            grank = group_rank_out if group_rank_out is not None else torch.zeros(Q, dtype=torch.int32, device=dev)
+        call("spn_sim_rank", _ptr(q), _ptr(g), Q, G, D, T, _ptr(tg), _ptr(target_score), _ptr(ex), _ptr(gr), M,
+             col_base, _ptr(rank), _ptr(grank), None, 0, _stream(dev))
+    return rank, grank
+
+
+def recall_at(rank: torch.Tensor, ks: Sequence[int]) -> Tuple[float, ...]:
+    """100 * mean(rank < k), computed like the reference: float32 sum / len * 100 (validate.py:148-151)."""
+    n = rank.numel()
+    return tuple((torch.sum(rank < k).to(torch.float32) / n).item() * 100 for k in ks)
+
+
+def names_to_ids(index_names: Sequence, *name_lists: Sequence):
+    """Map gallery names to their row index so that matching is integer work on the device."""
+    lut = {n: i for i, n in enumerate(index_names)}
+    if len(lut) != len(index_names):
+        raise SpnError("names_to_ids", -7, "gallery names must be unique")
+    out = []
+    for names in name_lists:
+        out.append([lut[n] for n in names])
+    return out

@@ -1,0 +1,118 @@
+"""Deterministic synthetic inputs of the hot path: seeded CPU generators, fp32.
+
+Shared by tests, bench.py and the golden-vector script so that every arm sees identical tensors.
+No dataset or checkpoint is needed (none is reachable offline).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import torch
+import torch.nn.functional as F
+
+# the BASELINE.json configs (C1..C5)
+CONFIGS: Dict[str, dict] = {
+    "C1": dict(B=128, N=32768, D=640, T=1, tau=0.02),
+    "C2": dict(Q=4181, G=2297, D=640, T=1, K=50),
+    "C3": dict(B=512, N=100000, D=640, T=1, tau=0.02),
+    "C4": dict(B=256, N=200000, D=256, T=32, tau=0.05),
+    "C5": dict(B=1024, N=1000000, D=768, T=1, tau=0.02),
+}
+FIQ_SHAPES = [(2017, 3817), (2038, 6346), (1961, 5373)]  # (Q, G): dress / shirt / toptee, public statistics
+
+
+def _gen(seed: int) -> torch.Generator:
+    return torch.Generator().manual_seed(seed)
+
+
+def make_bank(N: int, D: int, T: int = 1, seed: int = 1234) -> torch.Tensor:
+    """Row-normalised bank [N, D] (or [N, T, D]) like extract_bank_features produces."""
+    shape = (N, D) if T == 1 else (N, T, D)
+    return F.normalize(torch.randn(shape, generator=_gen(seed)), dim=-1)
+
+
+def make_labels(B: int, M: int, seed: int = 1235) -> torch.Tensor:
+    """labels in [0, M) with at least one forced duplicate (duplicates are legal in a batch)."""
+    lab = torch.randint(0, M, (B,), generator=_gen(seed), dtype=torch.int64)
+    if B >= 2:
+        lab[1] = lab[0]
+    return lab
+
+
+def make_queries(bank: torch.Tensor, labels: torch.Tensor, mode: str = "S", seed: int = 1236) -> torch.Tensor:
+    """'U': uniform random unit vectors; 'S': signal = normalize(bank[label] + 3.2 * noise / sqrt(D))."""
+    B = labels.shape[0]
+    D = bank.shape[-1]
+    noise = torch.randn((B, D), generator=_gen(seed))
+    if mode == "U":
+        return F.normalize(noise, dim=-1)
+    tgt = bank[labels] if bank.dim() == 2 else bank[labels].mean(dim=1)
+    return F.normalize(tgt + 3.2 * noise / D ** 0.5, dim=-1)
+
+
+def make_bank_case(B: int, N: int, D: int, T: int = 1, mode: str = "S", seed: int = 0, label_frac: float = 1.0):
+    bank = make_bank(N, D, T, seed=1234 + seed)
+    labels = make_labels(B, max(1, int(N * label_frac)), seed=1235 + seed)
+    q = make_queries(bank, labels, mode, seed=1236 + seed)
+    return q, bank, labels
+
+
+def make_retrieval_case(Q: int, G: int, D: int, T: int = 1, seed: int = 0, group_size: int = 6,
+                        noise: float = 3.0):
+    """CIRR-shaped set: gallery [G, D] (or [G, T, D]); per query a group of `group_size` distinct gallery
+    members (reference = member 0, target = member 1); q = normalize(gallery[target] + noise * randn / sqrt(D))
+    (noise 3 -> easy, ~8 at D=640 -> target rank spread over the top few dozen)."""
+    g = _gen(4321 + seed)
+    shape = (G, D) if T == 1 else (G, T, D)
+    gallery = F.normalize(torch.randn(shape, generator=g), dim=-1)
+    groups = torch.stack([torch.randperm(G, generator=g)[:group_size] for _ in range(Q)])  # [Q, group_size]
+    reference, target = groups[:, 0].clone(), groups[:, 1].clone()
+    base = gallery[target] if T == 1 else gallery[target].mean(dim=1)
+    q = F.normalize(base + noise * torch.randn((Q, D), generator=g) / D ** 0.5, dim=-1)
+    names = [f"img{i:07d}" for i in range(G)]
+    return q, gallery, names, reference, target, groups
+
+
+class FakeCIRRDataset:
+    """Duck-typed `CIRDataset('cirr', 'val', 'relative')`: yields (reference_name, target_name, caption,
+    group_members) like /root/reference/clip4cir/data_utils.py's relative-val branch."""
+
+    def __init__(self, names: List[str], reference, target, groups):
+        self.names, self.reference, self.target, self.groups = names, reference, target, groups
+
+    def __len__(self):
+        return len(self.reference)
+
+    def __getitem__(self, i):
+        return (self.names[int(self.reference[i])], self.names[int(self.target[i])], f"q{i}",
+                [self.names[int(j)] for j in self.groups[i]])
+
+
+class FakeFIQDataset:
+    """Duck-typed FashionIQ relative-val dataset: (reference_name, target_name, [cap1, cap2])."""
+
+    dress_types = ["synthetic"]
+
+    def __init__(self, names: List[str], reference, target):
+        self.names, self.reference, self.target = names, reference, target
+
+    def __len__(self):
+        return len(self.reference)
+
+    def __getitem__(self, i):
+        return (self.names[int(self.reference[i])], self.names[int(self.target[i])], [f"is q{i}.", f"and more {i}?"])
+
+
+class FakeModel:
+    """Duck-typed CIRPlus for validation: `encode_text(captions)` returns a fixed text feature per caption
+    such that combining_function(reference_feature, text) reproduces the prepared query direction."""
+
+    def __init__(self, text_by_caption: Dict[str, torch.Tensor], output_dim: int):
+        self.text_by_caption, self.output_dim = text_by_caption, output_dim
+
+    def encode_text(self, captions):
+        return torch.stack([self.text_by_caption[c] for c in captions])
+
+    @staticmethod
+    def combining_function(a, b):
+        return a + b

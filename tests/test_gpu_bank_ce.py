@@ -1,0 +1,199 @@
+"""Parity of the CUDA bank-CE path (through the C ABI) against the oracle and the reference-generated fixtures.
+
+Tolerances (north_star): loss and dL/dq within 1e-2 relative of the fp32 reference (bf16 operands, fp32
+accumulation).  Against the oracle fed with the SAME bf16-rounded operands the kernel arithmetic itself is
+checked much tighter (2e-3 on dq: P is rounded to bf16 before the second contraction)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import spn4cir_b200 as spn
+from conftest import rel_l2
+from oracle import bank_ce as obank
+from spn4cir_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def bf16_round(x):
+    return x.to(torch.bfloat16).float()
+
+
+def run_ours(q, bank, labels, tau, eps=0.0, grad_out=1.0, tau_tensor=False):
+    qd = q.to(DEV).requires_grad_(True)
+    db = spn.DeviceBank.from_tensor(bank, DEV)
+    t = torch.tensor(tau, device=DEV, requires_grad=True) if tau_tensor else tau
+    loss = spn.bank_infonce(qd, db, labels.to(DEV), t, label_smoothing=eps)
+    (loss * grad_out).backward()
+    torch.cuda.synchronize()
+    return loss.detach().cpu(), qd.grad.detach().cpu(), (t.grad.detach().cpu() if tau_tensor else None)
+
+
+CASES = [
+    # B, N, D, mode, tau, seed
+    (16, 333, 128, "S", 0.02, 1),       # ragged N, ragged B, label in partial tile possible
+    (8, 1000, 64, "U", 0.05, 2),
+    (128, 4096, 256, "S", 0.03, 3),     # blip4cir dim
+    (130, 5000, 512, "S", 0.01, 4),     # tgcir dim, B not a tile multiple, tau = 0.01
+    (64, 3000, 640, "U", 0.02, 5),      # clip RN50x4 dim (2 d-splits in backward)
+    (64, 2500, 768, "S", 0.02, 6),      # ViT-L/14 dim (3 d-splits)
+    (1, 129, 64, "S", 0.02, 7),         # single query
+    (257, 128, 64, "U", 0.02, 8),       # exactly one bank tile, 3 query tiles
+]
+
+
+@pytest.mark.parametrize("B,N,D,mode,tau,seed", CASES)
+def test_loss_and_grad_match_oracle(B, N, D, mode, tau, seed):
+    q, bank, labels = synth.make_bank_case(B, N, D, 1, mode, seed)
+    loss, dq, dtau = run_ours(q, bank, labels, tau, tau_tensor=True)
+    # (i) end-to-end vs the fp32 oracle on the original operands
+    o_loss, o_dq, o_dtau = obank.infonce_loss_and_grads(q, bank, labels, tau, dtype=torch.float64)
+    assert abs(loss.item() - o_loss.item()) <= 1e-2 * max(abs(o_loss.item()), 1e-3), (loss, o_loss)
+    assert rel_l2(dq, o_dq) < 1e-2, rel_l2(dq, o_dq)
+    assert abs(dtau.item() - o_dtau.item()) <= 2e-2 * max(abs(o_dtau.item()), 1e-2), (dtau, o_dtau)
+    # (ii) kernel arithmetic vs the oracle on bf16-rounded operands
+    r_loss, r_dq, _ = obank.infonce_loss_and_grads(bf16_round(q), bf16_round(bank), labels, tau, dtype=torch.float64)
+    assert abs(loss.item() - r_loss.item()) <= 2e-4 * max(abs(r_loss.item()), 1.0), (loss, r_loss)
+    assert rel_l2(dq, r_dq) < 3e-3, rel_l2(dq, r_dq)
+
+
+@pytest.mark.parametrize("name", ["small_ragged", "small_uniform", "c1", "c1_uniform"])
+def test_against_reference_fixtures(golden, name):
+    g = golden(f"bank_ce_{name}")
+    q, bank, labels = synth.make_bank_case(int(g["B"]), int(g["N"]), int(g["D"]), 1, str(g["mode"]), int(g["seed"]))
+    loss, dq, _ = run_ours(q, bank, labels, float(g["tau"]))
+    ref_loss, ref_dq = float(g["loss"]), torch.from_numpy(g["dq"])
+    assert abs(loss.item() - ref_loss) <= 1e-2 * max(abs(ref_loss), 1e-3), (loss.item(), ref_loss)
+    assert rel_l2(dq, ref_dq) < 1e-2, rel_l2(dq, ref_dq)
+
+
+def test_default_labels_and_upstream_gradient(golden):
+    g = golden("bank_ce_nolabels")
+    q, bank, _ = synth.make_bank_case(int(g["B"]), int(g["N"]), int(g["D"]), 1, "S", int(g["seed"]))
+    qd = q.to(DEV).requires_grad_(True)
+    loss = spn.compat.infonce_loss(qd, bank.to(DEV), None, tau=float(g["tau"]))
+    (loss * 65536.0).backward()  # GradScaler-style scalar upstream gradient (train_negplus.py:121)
+    assert abs(loss.item() - float(g["loss"])) <= 1e-2 * abs(float(g["loss"]))
+    _, o_dq, _ = obank.infonce_loss_and_grads(q, bank, torch.arange(q.shape[0]), float(g["tau"]), grad_out=65536.0)
+    assert rel_l2(qd.grad.cpu(), o_dq) < 1e-2
+
+
+def test_input_dtypes_fp16_bf16():
+    q, bank, labels = synth.make_bank_case(32, 700, 128, 1, "S", 9)
+    ref, _, _ = obank.infonce_loss_and_grads(q, bank, labels, 0.02)
+    for dt in (torch.float16, torch.bfloat16):
+        qd = q.to(DEV, dt).requires_grad_(True)
+        loss = spn.bank_infonce(qd, bank.to(DEV, dt), labels.to(DEV), 0.02)
+        loss.backward()
+        assert qd.grad.dtype == dt and loss.dtype == torch.float32
+        assert abs(loss.item() - ref.item()) <= 2e-2 * abs(ref.item())
+
+
+def test_label_smoothing():
+    q, bank, labels = synth.make_bank_case(40, 900, 128, 1, "U", 10)
+    tau, eps = 0.05, 0.1
+    loss, dq, _ = run_ours(q, bank, labels, tau, eps=eps)
+    o_loss, o_dq, _ = obank.infonce_loss_and_grads(q, bank, labels, tau, label_smoothing=eps, dtype=torch.float64)
+    assert abs(loss.item() - o_loss.item()) <= 1e-2 * abs(o_loss.item())
+    assert rel_l2(dq, o_dq) < 1e-2
+
+
+@pytest.mark.parametrize("B,N,seed", [(6, 50, 11), (130, 1000, 12), (32, 37, 13)])
+def test_blip2_max_over_tokens(B, N, seed):
+    T, D, temp = 32, 256, 0.05
+    f, bank3, labels = synth.make_bank_case(B, N, D, T, "S", seed)
+    fd = f.to(DEV).requires_grad_(True)
+    tp = torch.nn.Parameter(torch.tensor(temp, device=DEV))
+    out = spn.compat.forward_stage2_loss(fd, bank3.to(DEV), labels.to(DEV), tp)
+    out["loss_qtc"].backward()
+    o_loss, o_df, o_dt = obank.blip2_loss_and_grads(f, bank3, labels, temp, dtype=torch.float64)
+    assert abs(out["loss_qtc"].item() - o_loss.item()) <= 1e-2 * max(abs(o_loss.item()), 1e-3)
+    assert rel_l2(fd.grad.cpu(), o_df) < 1.5e-2, rel_l2(fd.grad.cpu(), o_df)
+    assert abs(tp.grad.item() - o_dt.item()) <= 3e-2 * max(abs(o_dt.item()), 1e-2)
+    r_loss, r_df, _ = obank.blip2_loss_and_grads(bf16_round(f), bf16_round(bank3), labels, temp, dtype=torch.float64)
+    assert abs(out["loss_qtc"].item() - r_loss.item()) <= 2e-4 * max(abs(r_loss.item()), 1.0)
+    assert rel_l2(fd.grad.cpu(), r_df) < 3e-3
+
+
+def test_blip2_fixture(golden):
+    g = golden("blip2_small")
+    f, bank3, labels = synth.make_bank_case(int(g["B"]), int(g["N"]), int(g["D"]), int(g["T"]), "S", int(g["seed"]))
+    fd = f.to(DEV).requires_grad_(True)
+    loss = spn.bank_infonce(fd, bank3.to(DEV), labels.to(DEV), float(g["temp"]))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-2 * abs(float(g["loss"]))
+    assert rel_l2(fd.grad.cpu(), torch.from_numpy(g["df"])) < 1.5e-2
+
+
+def test_shards_merge_to_the_unsharded_result():
+    """8 'fake ranks' on one GPU: per-shard statistics merged by spn_merge_stats, dq accumulated shard by shard."""
+    q, bank, labels = synth.make_bank_case(96, 4000, 128, 1, "S", 14)
+    tau, R = 0.02, 8
+    full = spn.DeviceBank.from_tensor(bank, DEV)
+    st_full = spn.bank_ce_stats(q.to(DEV), full, labels.to(DEV), tau)
+    shards = [spn.DeviceBank.from_tensor(bank, DEV, shard_rank=r, shard_world=R) for r in range(R)]
+    assert sum(s.N for s in shards) == 4000 and shards[3].row_base == 1500
+    parts = torch.stack([spn.bank_ce_stats(q.to(DEV), s, labels.to(DEV), tau) for s in shards])
+    merged = spn.merge_stats(parts)
+    lse_m = merged[0] + torch.log(merged[1])
+    lse_f = st_full[0] + torch.log(st_full[1])
+    np.testing.assert_allclose(lse_m.cpu().numpy(), lse_f.cpu().numpy(), rtol=2e-6, atol=2e-5)
+    np.testing.assert_allclose(merged[2].cpu().numpy(), st_full[2].cpu().numpy(), rtol=1e-6, atol=1e-6)
+    m, l, st, _ = obank.shard_stats(bf16_round(q), bf16_round(bank), labels, tau)
+    np.testing.assert_allclose(lse_m.cpu().numpy(), (m + torch.log(l)).numpy(), rtol=1e-4, atol=1e-3)
+    # backward: shard-by-shard accumulation equals the single call
+    from spn4cir_b200.ops import _bwd, cast_to_bf16
+    q16 = cast_to_bf16(q.to(DEV))
+    lab = labels.to(DEV)
+    dq_full = torch.zeros((96, 128), device=DEV)
+    _bwd(q16, full, lab, 1 / tau, lse_f.contiguous(), (1 / tau) / 96, None, 0.0, dq_full, None)
+    dq_sh = torch.zeros((96, 128), device=DEV)
+    for s in shards:
+        _bwd(q16, s, lab, 1 / tau, lse_f.contiguous(), (1 / tau) / 96, None, 0.0, dq_sh, None)
+    assert rel_l2(dq_sh, dq_full) < 1e-5
+    _, o_dq, _ = obank.infonce_loss_and_grads(q, bank, labels, tau, dtype=torch.float64)
+    assert rel_l2(dq_sh, o_dq) < 1e-2
+
+
+def test_query_assemble_prologue():
+    g = torch.Generator().manual_seed(5)
+    refer = torch.randn((50, 640), generator=g)
+    text = torch.randn((20, 640), generator=g)
+    idx = torch.randint(0, 50, (20,), generator=g)
+    q16, q32, inv = spn.query_assemble(refer.to(DEV), idx.to(DEV), text.to(DEV))
+    want = obank.bank_large_step_query(refer, idx, text)
+    np.testing.assert_allclose(q32.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(q16.float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=1e-3)
+    np.testing.assert_allclose(inv.cpu().numpy(), (1 / (refer[idx] + text).norm(dim=1)).numpy(), rtol=1e-5)
+
+
+def test_c3_full_size_properties():
+    """BASELINE C3 (512 x 100k x 640): size-independent checks instead of a dense CPU oracle --
+    (a) agreement with a chunked fp32 torch evaluation on the GPU, (b) directional finite difference of our own
+    forward matches <dq, v>, (c) dlogit rows sum to zero => sum_b dq_b . q-independent check via shard additivity."""
+    cfg = synth.CONFIGS["C3"]
+    q, bank, labels = synth.make_bank_case(cfg["B"], cfg["N"], cfg["D"], 1, "S", 0)
+    tau = cfg["tau"]
+    qd = q.to(DEV).requires_grad_(True)
+    db = spn.DeviceBank.from_tensor(bank, DEV)
+    loss = spn.bank_infonce(qd, db, labels.to(DEV), tau)
+    loss.backward()
+    # (a) chunked dense fp32 reference on the device
+    qf = q.to(DEV).requires_grad_(True)
+    bf = bank.to(DEV)
+    ref = torch.nn.functional.cross_entropy((qf @ bf.T) / tau, labels.to(DEV))
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-2 * abs(ref.item()), (loss.item(), ref.item())
+    assert rel_l2(qd.grad, qf.grad) < 1e-2, rel_l2(qd.grad, qf.grad)
+    # (b) directional derivative of OUR forward
+    v = torch.randn_like(q).to(DEV)
+    v = v / v.norm()
+    h = 2e-2
+    lp = spn.bank_infonce(q.to(DEV) + h * v, db, labels.to(DEV), tau).item()
+    lm = spn.bank_infonce(q.to(DEV) - h * v, db, labels.to(DEV), tau).item()
+    fd = (lp - lm) / (2 * h)
+    an = float((qd.grad * v).sum())
+    assert abs(fd - an) <= 5e-2 * max(abs(an), 1e-3), (fd, an)

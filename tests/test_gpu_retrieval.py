@@ -1,0 +1,146 @@
+"""Parity of the fused similarity + top-K / rank kernels against the oracle and the reference-generated
+Recall fixtures.  Index parity rule (north_star): identical except where the two scores tie within 1e-3
+(the CPU oracle sums in a different order; observed gaps are ~1e-7)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import spn4cir_b200 as spn
+from oracle import retrieval as oretr
+from spn4cir_b200 import compat, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TIE = 1e-5  # far inside the 1e-3 the contract allows
+
+
+def assert_same_up_to_ties(got_idx, want_idx, sim):
+    bad = np.argwhere(got_idx != want_idx)
+    for r, c in bad:
+        a, b = got_idx[r, c], want_idx[r, c]
+        assert a >= 0 and b >= 0, (r, c, a, b)
+        assert abs(float(sim[r, a]) - float(sim[r, b])) < TIE, (r, c, a, b, sim[r, a], sim[r, b])
+    return len(bad)
+
+
+@pytest.mark.parametrize("Q,G,D,K,seed", [(40, 300, 64, 10, 1), (200, 2297, 640, 50, 2), (65, 129, 128, 64, 3),
+                                          (7, 20, 64, 20, 4), (300, 6346, 640, 51, 5)])
+def test_topk_matches_oracle(Q, G, D, K, seed):
+    q, gallery, _, reference, target, _ = synth.make_retrieval_case(Q, G, D, 1, seed, noise=6.0)
+    sim = q @ gallery.T
+    want_v, want_i = oretr.topk(sim, K, exclude=reference.tolist())
+    v, i = spn.sim_topk(q.to(DEV), gallery.to(DEV), K, exclude=reference)
+    v, i = v.cpu().numpy(), i.cpu().numpy().astype(np.int64)
+    assert_same_up_to_ties(i, want_i, sim.numpy())
+    np.testing.assert_allclose(v, want_v, rtol=1e-5, atol=2e-6)
+    for r in range(Q):
+        assert int(reference[r]) not in i[r]
+
+
+def test_topk_fewer_candidates_than_k_pads():
+    q, gallery, *_ = synth.make_retrieval_case(5, 6, 64, 1, 6)
+    v, i = spn.sim_topk(q.to(DEV), gallery.to(DEV), 10)
+    i = i.cpu().numpy()
+    assert (i[:, 6:] == -1).all() and (i[:, :6] >= 0).all()
+    assert torch.isinf(v[:, 6:]).all()
+
+
+@pytest.mark.parametrize("Q,G,D,seed", [(50, 400, 64, 7), (300, 2297, 640, 8), (1, 100, 64, 9)])
+def test_rank_matches_oracle(Q, G, D, seed):
+    q, gallery, _, reference, target, groups = synth.make_retrieval_case(Q, G, D, 1, seed, noise=7.0)
+    sim = q @ gallery.T
+    want_r, want_g = oretr.rank_of_target(sim, target.tolist(), reference.tolist(), groups.tolist())
+    r, g = spn.sim_rank(q.to(DEV), gallery.to(DEV), target, exclude=reference, group=groups)
+    r, g = r.cpu().numpy(), g.cpu().numpy()
+    # a rank can differ only through a near-tie with the target's score
+    for k in np.argwhere(r != want_r).ravel():
+        gaps = np.abs(sim[k].numpy() - float(sim[k, int(target[k])]))
+        gaps[int(target[k])] = np.inf
+        assert gaps.min() < TIE, (k, r[k], want_r[k])
+    assert (r != want_r).mean() < 0.01 and (g != want_g).mean() < 0.01
+
+
+@pytest.mark.parametrize("name", ["cirr_small", "cirr_c2"])
+def test_cirr_recall_identical_to_reference(golden, name):
+    g = golden(name)
+    Q, G, D = int(g["Q"]), int(g["G"]), int(g["D"])
+    q, gallery, names, reference, target, groups = synth.make_retrieval_case(Q, G, D, 1, int(g["seed"]), noise=float(g["noise"]))
+    ds = synth.FakeCIRRDataset(names, reference, target, groups)
+    text = {f"q{i}": (q[i] * 2.0 - gallery[reference[i]]).to(DEV) for i in range(Q)}
+    model = synth.FakeModel(text, D)
+    got = compat.compute_cirr_val_metrics(ds, model, gallery.to(DEV), names, device=torch.device(DEV))
+    np.testing.assert_allclose(got, g["metrics"], rtol=0, atol=1e-4)  # Recall@K / Rsub@K identical
+    pred = F.normalize(gallery[reference] + torch.stack([q[i] * 2.0 - gallery[reference[i]] for i in range(Q)]), dim=-1)
+    r, gr = spn.sim_rank(pred.to(DEV), F.normalize(gallery, dim=-1).to(DEV), target, exclude=reference, group=groups)
+    assert (r.cpu().numpy() != g["rank"]).mean() < 0.005
+    assert (gr.cpu().numpy() != g["group_rank"]).mean() < 0.005
+
+
+@pytest.mark.parametrize("name", ["fiq_small", "fiq_dress"])
+def test_fiq_recall_identical_to_reference(golden, name):
+    g = golden(name)
+    Q, G, D = int(g["Q"]), int(g["G"]), int(g["D"])
+    q, gallery, names, reference, target, _ = synth.make_retrieval_case(Q, G, D, 1, int(g["seed"]), noise=float(g["noise"]))
+    ds = synth.FakeFIQDataset(names, reference, target)
+    caps = [f"is q{i} and and more {i}" for i in range(Q)]
+    text = {c: (q[i] * 2.0 - gallery[reference[i]]).to(DEV) for i, c in enumerate(caps)}
+    model = synth.FakeModel(text, D)
+    got = compat.compute_fiq_val_metrics(ds, model, gallery.to(DEV), names, device=torch.device(DEV))
+    np.testing.assert_allclose(got, g["metrics"], rtol=0, atol=1e-9)
+    got2 = compat.compute_fiq_val_metrics(ds, model, gallery.to(DEV), names, device=torch.device(DEV), remove_reference=False)
+    np.testing.assert_allclose(got2, g["metrics_noremove"], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("Q,G,seed", [(5, 20, 4), (33, 150, 5), (1, 40, 6)])
+def test_blip2_max_over_tokens_similarity(Q, G, seed):
+    q, gallery, _, reference, target, groups = synth.make_retrieval_case(Q, G, 256, 32, seed)
+    sim = oretr.similarity(q, gallery)
+    got = compat.inference_sim(q.to(DEV), gallery.to(DEV)).cpu()
+    assert got.shape == (sim.squeeze(0).shape if Q == 1 else sim.shape)
+    np.testing.assert_allclose(got.reshape(Q, G).numpy(), sim.numpy(), rtol=1e-5, atol=2e-6)
+    K = min(10, G)
+    want_v, want_i = oretr.topk(sim, K, exclude=reference.tolist())
+    v, i = spn.sim_topk(q.to(DEV), gallery.to(DEV), K, exclude=reference)
+    assert_same_up_to_ties(i.cpu().numpy().astype(np.int64), want_i, sim.numpy())
+    want_r, want_g = oretr.rank_of_target(sim, target.tolist(), reference.tolist(), groups.tolist())
+    r, gr = spn.sim_rank(q.to(DEV), gallery.to(DEV), target, exclude=reference, group=groups)
+    assert (r.cpu().numpy() != want_r).sum() == 0 and (gr.cpu().numpy() != want_g).sum() == 0
+
+
+def test_sharded_gallery_topk_and_rank_merge():
+    q, gallery, _, reference, target, groups = synth.make_retrieval_case(70, 1000, 128, 1, 10, noise=6.0)
+    sim = q @ gallery.T
+    R, K = 4, 50
+    vs, is_, rank, grank = [], [], None, None
+    ts = torch.full((70,), float("-inf"), device=DEV)
+    for r in range(R):
+        lo, hi = r * 250, (r + 1) * 250
+        ts = torch.maximum(ts, spn.sim_target_score(q.to(DEV), gallery[lo:hi].to(DEV), target, col_base=lo))
+    for r in range(R):
+        lo, hi = r * 250, (r + 1) * 250
+        v, i = spn.sim_topk(q.to(DEV), gallery[lo:hi].to(DEV), K, exclude=reference, col_base=lo)
+        vs.append(v), is_.append(i)
+        rank, grank = spn.sim_rank(q.to(DEV), gallery[lo:hi].to(DEV), target, exclude=reference, group=groups,
+                                   target_score=ts, col_base=lo, rank_out=rank, group_rank_out=grank)
+    v, i = spn.merge_topk(torch.stack(vs), torch.stack(is_))
+    want_v, want_i = oretr.topk(sim, K, exclude=reference.tolist())
+    assert_same_up_to_ties(i.cpu().numpy().astype(np.int64), want_i, sim.numpy())
+    v1, i1 = spn.sim_topk(q.to(DEV), gallery.to(DEV), K, exclude=reference)
+    assert torch.equal(i1, i) and torch.equal(v1, v), "sharded + merged must be bit-identical to the single launch"
+    r1, g1 = spn.sim_rank(q.to(DEV), gallery.to(DEV), target, exclude=reference, group=groups)
+    assert torch.equal(r1, rank) and torch.equal(g1, grank)
+
+
+def test_cirr_test_submission_dicts():
+    Q, G, D = 30, 200, 64
+    q, gallery, names, reference, target, groups = synth.make_retrieval_case(Q, G, D, 1, 12)
+    preds, gpreds = compat.cirr_test_dicts_from_features(
+        q.to(DEV), gallery.to(DEV), names, [names[int(i)] for i in reference],
+        [[names[int(j)] for j in row] for row in groups], list(range(Q)))
+    sim = q @ F.normalize(gallery, dim=-1).T
+    _, want = oretr.topk(sim, 50, exclude=reference.tolist())
+    for r in range(Q):
+        assert preds[str(r)] == [names[j] for j in want[r]]
+        order = [j for j in oretr.ranking(sim)[r] if j in set(groups[r].tolist()) and j != int(reference[r])][:3]
+        assert gpreds[str(r)] == [names[j] for j in order]

@@ -1,0 +1,141 @@
+"""The oracle restatement against the fixtures produced by EXECUTING the reference (oracle/make_golden.py)."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import bank_ce as obank
+from oracle import retrieval as oretr
+from spn4cir_b200 import synth
+
+
+def digest(*tensors) -> str:
+    h = hashlib.sha256()
+    for t in tensors:
+        h.update(t.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()[:16]
+
+
+@pytest.mark.parametrize("name", ["small_ragged", "small_uniform", "c1", "c1_uniform"])
+def test_infonce_matches_reference_outputs(golden, name):
+    g = golden(f"bank_ce_{name}")
+    q, bank, labels = synth.make_bank_case(int(g["B"]), int(g["N"]), int(g["D"]), 1, str(g["mode"]), int(g["seed"]))
+    assert digest(q, bank, labels) == str(g["input_digest"]), "synthetic generator drifted from the fixture inputs"
+    loss, dq, dtau = obank.infonce_loss_and_grads(q, bank, labels, float(g["tau"]))
+    np.testing.assert_allclose(loss.numpy(), g["loss"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(dq.numpy(), g["dq"], rtol=1e-4, atol=1e-7)
+    # float64 oracle agrees with the fp32 reference to fp32 rounding
+    loss64, dq64, _ = obank.infonce_loss_and_grads(q, bank, labels, float(g["tau"]), dtype=torch.float64)
+    np.testing.assert_allclose(loss64.numpy(), g["loss"], rtol=2e-5, atol=2e-6)
+    assert float((dq64.float() - torch.from_numpy(g["dq"])).norm() / torch.from_numpy(g["dq"]).norm()) < 1e-4
+
+
+def test_infonce_default_labels(golden):
+    g = golden("bank_ce_nolabels")
+    q, bank, _ = synth.make_bank_case(int(g["B"]), int(g["N"]), int(g["D"]), 1, "S", int(g["seed"]))
+    np.testing.assert_allclose(obank.infonce_loss(q, bank, None, float(g["tau"])).numpy(), g["loss"], rtol=1e-6)
+
+
+def test_closed_form_gradient_identity():
+    """dq = (softmax - onehot) @ bank / (tau B); dtau = -(1/(tau B)) sum_b (E_p[s] - s_t)  (SURVEY 7.3)."""
+    q, bank, labels = synth.make_bank_case(9, 77, 64, 1, "S", 21)
+    tau = 0.03
+    loss, dq, dtau = obank.infonce_loss_and_grads(q, bank, labels, tau, dtype=torch.float64)
+    s = (q.double() @ bank.double().T) / tau
+    p = torch.softmax(s, dim=1)
+    p[torch.arange(9), labels] -= 1.0
+    np.testing.assert_allclose((p @ bank.double() / (tau * 9)).numpy(), dq.numpy(), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose((-(p * s).sum() / (tau * 9)).item(), dtau.item(), rtol=1e-9)
+
+
+def test_shard_merge_identity():
+    """8-way (m, l, s_t) merge reproduces the dense LSE and loss."""
+    q, bank, labels = synth.make_bank_case(10, 1000, 64, 1, "S", 22)
+    tau = 0.02
+    dense = obank.infonce_loss(q.double(), bank.double(), labels, tau)
+    parts = [obank.shard_stats(q, bank[r * 125:(r + 1) * 125], labels, tau, row_base=r * 125) for r in range(8)]
+    m = torch.stack([p[0] for p in parts])
+    l = torch.stack([p[1] for p in parts])
+    st = torch.stack([p[2] for p in parts])
+    M = m.max(dim=0).values
+    L = (l * torch.exp(m - M)).sum(dim=0)
+    loss = (M + torch.log(L) - st.max(dim=0).values).mean()
+    np.testing.assert_allclose(loss.item(), dense.item(), rtol=1e-10)
+
+
+def test_label_smoothing_identity():
+    q, bank, labels = synth.make_bank_case(7, 60, 64, 1, "U", 23)
+    tau, eps = 0.05, 0.1
+    ref = obank.infonce_loss(q.double(), bank.double(), labels, tau, label_smoothing=eps)
+    m, l, st, ss = obank.shard_stats(q, bank, labels, tau)
+    lse = m + torch.log(l)
+    mine = (lse - (1 - eps) * st - eps * ss / bank.shape[0]).mean()
+    np.testing.assert_allclose(mine.item(), ref.item(), rtol=1e-10)
+
+
+def test_blip2_loop_equals_closed_form(golden):
+    g = golden("blip2_small")
+    f, bank3, labels = synth.make_bank_case(int(g["B"]), int(g["N"]), int(g["D"]), int(g["T"]), "S", int(g["seed"]))
+    assert digest(f, bank3, labels) == str(g["input_digest"])
+    temp = torch.tensor(float(g["temp"]), requires_grad=True)
+    ff = f.clone().requires_grad_(True)
+    loop = obank.blip2_stage2_loss_loop(ff, bank3, labels, temp)
+    loop.backward()
+    np.testing.assert_allclose(loop.item(), g["loss"], rtol=1e-6)
+    np.testing.assert_allclose(ff.grad.numpy(), g["df"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(temp.grad.item(), g["dtemp"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["cirr_small", "cirr_c2"])
+def test_cirr_metrics_match_reference_outputs(golden, name):
+    g = golden(name)
+    Q, G, D = int(g["Q"]), int(g["G"]), int(g["D"])
+    q, gallery, names, reference, target, groups = synth.make_retrieval_case(Q, G, D, 1, int(g["seed"]), noise=float(g["noise"]))
+    assert digest(q, gallery, reference, target, groups) == str(g["input_digest"])
+    text = torch.stack([q[i] * 2.0 - gallery[reference[i]] for i in range(Q)])
+    pred = F.normalize(gallery[reference] + text, dim=-1)
+    sim = pred @ F.normalize(gallery, dim=-1).T
+    rank, grank = oretr.rank_of_target(sim, target.tolist(), reference.tolist(), groups.tolist())
+    np.testing.assert_array_equal(rank, g["rank"])
+    np.testing.assert_array_equal(grank, g["group_rank"])
+    rec = [100.0 * float(np.mean(rank < k)) for k in (1, 5, 10, 50)]
+    grec = [100.0 * float(np.mean(grank < k)) for k in (1, 2, 3)]
+    np.testing.assert_allclose((*grec, *rec), g["metrics"], atol=1e-4)
+    if Q <= 500:
+        full = oretr.cirr_metrics(pred, gallery, names, [names[int(i)] for i in reference],
+                                  [names[int(i)] for i in target], [[names[int(j)] for j in gg] for gg in groups])
+        np.testing.assert_allclose(full, g["metrics"], atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["fiq_small", "fiq_dress"])
+def test_fiq_metrics_match_reference_outputs(golden, name):
+    g = golden(name)
+    Q, G, D = int(g["Q"]), int(g["G"]), int(g["D"])
+    q, gallery, names, reference, target, _ = synth.make_retrieval_case(Q, G, D, 1, int(g["seed"]), noise=float(g["noise"]))
+    assert digest(q, gallery, reference, target) == str(g["input_digest"])
+    text = torch.stack([q[i] * 2.0 - gallery[reference[i]] for i in range(Q)])
+    pred = F.normalize(gallery[reference] + text, dim=-1)
+    got = oretr.fiq_metrics(pred, gallery, names, [names[int(i)] for i in target], [names[int(i)] for i in reference])
+    np.testing.assert_allclose(got, g["metrics"], atol=1e-9)
+
+
+def test_topk_and_rank_consistency():
+    q, gallery, names, reference, target, groups = synth.make_retrieval_case(40, 300, 64, 1, 3)
+    sim = q @ gallery.T
+    vals, idx = oretr.topk(sim, 51, exclude=reference.tolist())
+    rank, _ = oretr.rank_of_target(sim, target.tolist(), reference.tolist())
+    for r in range(40):
+        assert int(reference[r]) not in idx[r]
+        if rank[r] < 51:
+            assert idx[r, rank[r]] == int(target[r])
+        assert np.all(np.diff(vals[r]) <= 0)
+
+
+def test_blip2_inference_similarity_shape():
+    q, gallery, *_ = synth.make_retrieval_case(5, 20, 256, 32, 4)
+    sim = oretr.similarity(q, gallery)
+    assert sim.shape == (5, 20)
+    ref = torch.einsum("bd,gtd->bgt", q, gallery).amax(-1)
+    np.testing.assert_allclose(sim.numpy(), ref.numpy(), rtol=1e-6, atol=1e-7)
