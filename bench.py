@@ -200,12 +200,27 @@ def run_ours(args, cfg):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    if args.profile:
+        step(q_dev, labels_dev)
+        barrier()
+        t = timed(lambda: step(q_dev, labels_dev), args.steps)
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": t / args.steps * 1e3}))
+        return
     for _ in range(max(3, args.warmup)):
         step(q_dev, labels_dev)
     barrier()
+    # clocks: nvidia-smi samples every 100 ms, a K-step timed region lasts milliseconds -> keep the GPU under the
+    # same load for ~1.5 s (untimed) right before and sample through both regions
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    t_end_load = time.perf_counter() + 1.5
+    while time.perf_counter() < t_end_load:
+        for _ in range(20):
+            step(q_dev, labels_dev)
+        torch.cuda.synchronize(dev)
+    barrier()
     t_dev = timed(lambda: step(q_dev, labels_dev), args.steps)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -329,6 +344,7 @@ def main():
     ap.add_argument("--config", default="C3", choices=["C1", "C3", "C5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="under ncu: 1 warm-up + K timed steps, nothing else")
     args = ap.parse_args()
     cfg = synth.CONFIGS[args.config]
     if args.impl == "reference":
