@@ -15,6 +15,7 @@
 // GEMM2 (dq) : TS, A = P (TMEM, bf16), B = the same bank block bytes read MN-major, M128 N64 K16 x 8.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "bank_ce.cuh"
 #include "ptx.cuh"
@@ -252,87 +253,102 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const uint32_t tmem_base = *sm.tmem_slot;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================================== TMA producer (converged warp, one
+    // elected lane issues; see elect_one())
+    if (elect_one()) {
       mbar_arrive_expect_tx(sm.q_full, uint32_t(p.kblocks) * kBlockBytes);
       for (int kb = 0; kb < p.kblocks; ++kb)
         tma_load_2d(sm.q + size_t(kb) * kBlockBytes, &tmap_q, sm.q_full, kb * kBK, q0);
-      Ring r(p.stages);
-      auto load_block = [&](int col_blk, int row) {
-        mbar_wait(&sm.empty[r.stage], r.phase ^ 1u);
+    }
+    __syncwarp();
+    Ring r(p.stages);
+    auto load_block = [&](int col_blk, int row) {
+      mbar_wait(&sm.empty[r.stage], r.phase ^ 1u);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&sm.full[r.stage], kBlockBytes);
         tma_load_2d(sm.ring + size_t(r.stage) * kBlockBytes, &tmap_bank, &sm.full[r.stage], col_blk * kBK, row);
-        r.advance();
-      };
-      for (int t = t_begin; t < t_end; ++t) {
-        for (int kb = 0; kb < p.kblocks; ++kb) load_block(kb, t * kBN);
-        if (MODE == 1 && t > t_begin)
-          for (int j = 0; j < my_blocks; ++j) load_block(ds * p.ow_blocks + j, (t - 1) * kBN);
       }
-      if (MODE == 1 && ntl > 0)
-        for (int j = 0; j < my_blocks; ++j) load_block(ds * p.ow_blocks + j, (t_end - 1) * kBN);
+      __syncwarp();
+      r.advance();
+    };
+    for (int t = t_begin; t < t_end; ++t) {
+      for (int kb = 0; kb < p.kblocks; ++kb) load_block(kb, t * kBN);
+      if (MODE == 1 && t > t_begin)
+        for (int j = 0; j < my_blocks; ++j) load_block(ds * p.ow_blocks + j, (t - 1) * kBN);
     }
+    if (MODE == 1 && ntl > 0)
+      for (int j = 0; j < my_blocks; ++j) load_block(ds * p.ow_blocks + j, (t_end - 1) * kBN);
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16_f32(kBM, kBN, 0, 0);
-      constexpr uint32_t idesc_o = make_idesc_bf16_f32(kBM, 64, 0, 1);
-      const uint32_t q_addr = smem_u32(sm.q);
-      const uint32_t ring_addr = smem_u32(sm.ring);
-      Ring r(p.stages);
-      mbar_wait(sm.q_full, 0);
-      tc_fence_after();
+    // ===================================================================== MMA issuer (converged warp)
+    constexpr uint32_t idesc_s = make_idesc_bf16_f32(kBM, kBN, 0, 0);
+    constexpr uint32_t idesc_o = make_idesc_bf16_f32(kBM, 64, 0, 1);
+    // descriptors advance by whole 16 KiB blocks: +1024 in the 16-byte units of the address field
+    const uint64_t q_desc0 = make_smem_desc_sw128(smem_u32(sm.q), 16, 1024);
+    const uint64_t ring_desc_k0 = make_smem_desc_sw128(smem_u32(sm.ring), 16, 1024);            // K-major view
+    const uint64_t ring_desc_mn0 = make_smem_desc_sw128(smem_u32(sm.ring), kBlockBytes, 1024);  // MN-major view
+    Ring r(p.stages);
+    mbar_wait(sm.q_full, 0);
+    tc_fence_after();
 
-      auto gemm_s = [&](uint32_t d_tmem) {
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(&sm.full[r.stage], r.phase);
-          tc_fence_after();
-          const uint64_t adesc = make_smem_desc_sw128(q_addr + uint32_t(kb) * kBlockBytes, 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(ring_addr + r.stage * kBlockBytes, 16, 1024);
+    auto gemm_s = [&](uint32_t d_tmem) {
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(&sm.full[r.stage], r.phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc = q_desc0 + uint64_t(kb) * (kBlockBytes >> 4);
+          const uint64_t bdesc = ring_desc_k0 + uint64_t(r.stage) * (kBlockBytes >> 4);
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
             umma_ss_f16(d_tmem, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc_s, (kb | k) != 0);
           umma_commit(&sm.empty[r.stage]);
-          r.advance();
         }
-      };
+        __syncwarp();
+        r.advance();
+      }
+    };
 
-      if (MODE == 0) {
-        for (int i = 0; i < ntl; ++i) {
-          const uint32_t buf = uint32_t(i) & 1u;
-          mbar_wait(&sm.s_free[buf], ((uint32_t(i) >> 1) & 1u) ^ 1u);
+    if (MODE == 0) {
+      for (int i = 0; i < ntl; ++i) {
+        const uint32_t buf = uint32_t(i) & 1u;
+        mbar_wait(&sm.s_free[buf], ((uint32_t(i) >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        gemm_s(tmem_base + buf * kBN);
+        if (elect_one()) umma_commit(&sm.s_full[buf]);
+        __syncwarp();
+      }
+    } else {
+      auto gemm_o = [&](int u) {
+        mbar_wait(sm.p_full, uint32_t(u) & 1u);
+        tc_fence_after();
+        for (int j = 0; j < my_blocks; ++j) {
+          mbar_wait(&sm.full[r.stage], r.phase);
           tc_fence_after();
-          gemm_s(tmem_base + buf * kBN);
-          umma_commit(&sm.s_full[buf]);
-        }
-      } else {
-        auto gemm_o = [&](int u) {
-          mbar_wait(sm.p_full, uint32_t(u) & 1u);
-          tc_fence_after();
-          for (int j = 0; j < my_blocks; ++j) {
-            mbar_wait(&sm.full[r.stage], r.phase);
-            tc_fence_after();
+          if (elect_one()) {
             // the same 16 KiB block, read MN-major: rows are K (bank rows), 128 B span = 64 output columns
-            const uint64_t bdesc = make_smem_desc_sw128(ring_addr + r.stage * kBlockBytes, kBlockBytes, 1024);
+            const uint64_t bdesc = ring_desc_mn0 + uint64_t(r.stage) * (kBlockBytes >> 4);
 #pragma unroll
             for (int k = 0; k < kBN / kUmmaK; ++k)  // 16 bank rows = 2048 B per K step; P: 8 columns per step
               umma_ts_f16(tmem_base + uint32_t(j) * 64u, tmem_base + kBwdPCol + uint32_t(k) * 8u,
                           bdesc + uint64_t(k * (2048 >> 4)), idesc_o, (u > 0 || k > 0) ? 1u : 0u);
             umma_commit(&sm.empty[r.stage]);
-            r.advance();
           }
-          umma_commit(sm.p_free);
-        };
-        for (int i = 0; i < ntl; ++i) {
-          mbar_wait(&sm.s_free[0], (uint32_t(i) & 1u) ^ 1u);
-          tc_fence_after();
-          gemm_s(tmem_base + kBwdSCol);
-          umma_commit(&sm.s_full[0]);
-          if (i > 0) gemm_o(i - 1);
+          __syncwarp();
+          r.advance();
         }
-        if (ntl > 0) gemm_o(ntl - 1);
-        umma_commit(sm.o_full);
+        if (elect_one()) umma_commit(sm.p_free);
+        __syncwarp();
+      };
+      for (int i = 0; i < ntl; ++i) {
+        mbar_wait(&sm.s_free[0], (uint32_t(i) & 1u) ^ 1u);
+        tc_fence_after();
+        gemm_s(tmem_base + kBwdSCol);
+        if (elect_one()) umma_commit(&sm.s_full[0]);
+        __syncwarp();
+        if (i > 0) gemm_o(i - 1);
       }
+      if (ntl > 0) gemm_o(ntl - 1);
+      if (elect_one()) umma_commit(sm.o_full);
+      __syncwarp();
     }
   } else {
     // ===================================================================== soft-max / epilogue warps
@@ -458,21 +474,35 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 __global__ void merge_stats_kernel(const float* __restrict__ pm, const float* __restrict__ pl,
                                    const float* __restrict__ pst, const float* __restrict__ pss, int P, int B,
                                    float unit, float* m, float* l, float* st, float* ss) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per query, lanes stride over the P partials
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (b >= B) return;
-  float M = -INFINITY;
-  for (int c = 0; c < P; ++c) M = fmaxf(M, pm[size_t(c) * B + b]);
-  float L = 0.f, S = -INFINITY, SS = 0.f;
-  for (int c = 0; c < P; ++c) {
-    const float mc = pm[size_t(c) * B + b];
-    if (mc > -INFINITY) L += pl[size_t(c) * B + b] * (unit == 1.f ? expf(mc - M) : exp2f(mc - M));
+  float M = -INFINITY, S = -INFINITY, SS = 0.f;
+  for (int c = lane; c < P; c += 32) {
+    M = fmaxf(M, pm[size_t(c) * B + b]);
     S = fmaxf(S, pst[size_t(c) * B + b]);
     if (pss) SS += pss[size_t(c) * B + b];
   }
-  m[b] = M * unit;
-  l[b] = L;
-  st[b] = S * unit;
-  if (ss) ss[b] = pss ? SS * unit : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+    S = fmaxf(S, __shfl_xor_sync(0xffffffffu, S, o));
+    SS += __shfl_xor_sync(0xffffffffu, SS, o);
+  }
+  float L = 0.f;
+  for (int c = lane; c < P; c += 32) {
+    const float mc = pm[size_t(c) * B + b];
+    if (mc > -INFINITY) L += pl[size_t(c) * B + b] * (unit == 1.f ? expf(mc - M) : exp2f(mc - M));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) L += __shfl_xor_sync(0xffffffffu, L, o);
+  if (lane == 0) {
+    m[b] = M * unit;
+    l[b] = L;
+    st[b] = S * unit;
+    if (ss) ss[b] = pss ? SS * unit : 0.f;
+  }
 }
 
 __global__ void loss_kernel(const float* __restrict__ m, const float* __restrict__ l, const float* __restrict__ st,
@@ -540,6 +570,10 @@ int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan) {
   const size_t fixed = 1024 /*align slack*/ + size_t(plan->kblocks) * kBlockBytes + 256 /*barriers*/;
   int stages = int((size_t(smem_max) - fixed) / kBlockBytes);
   if (stages > 8) stages = 8;
+  if (const char* e = getenv("SPN_DEBUG_STAGES")) {  // bring-up knob: shrink the ring to probe latency sensitivity
+    const int v = atoi(e);
+    if (v >= 2 && v < stages) stages = v;
+  }
   SPN_REQUIRE(stages >= 2, SPN_ERR_BAD_SHAPE, "D=%d leaves no room for the bank ring in %d B of shared memory", D, smem_max);
   plan->stages = stages;
   plan->smem_bytes = fixed + size_t(stages) * kBlockBytes;
@@ -571,7 +605,7 @@ int bank_ce_forward(const void* q, const void* bank, const long long* labels, fl
   else        rc = extra ? launch_one<0, 32, true>(tq, tb, p, plan.grid, plan.smem_bytes, stream)
                          : launch_one<0, 32, false>(tq, tb, p, plan.grid, plan.smem_bytes, stream);
   if (rc != SPN_OK) return rc;
-  merge_stats_kernel<<<(B + 127) / 128, 128, 0, stream>>>(p.part_m, p.part_l, p.part_st, extra ? p.part_ssum : nullptr,
+  merge_stats_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p.part_m, p.part_l, p.part_st, extra ? p.part_ssum : nullptr,
                                                          plan.num_chunks, B, kLn2, m, l, s_t, s_sum);
   SPN_CUDA_CHECK(cudaGetLastError());
   return SPN_OK;
@@ -606,7 +640,7 @@ int bank_ce_backward(const void* q, const void* bank, const long long* labels, f
 int merge_stats(const float* pm, const float* pl, const float* pst, const float* pss, int P, int B, float* m,
                 float* l, float* st, float* ss, cudaStream_t stream) {
   SPN_REQUIRE(P > 0 && B > 0, SPN_ERR_BAD_SHAPE, "merge_stats needs P > 0 and B > 0");
-  merge_stats_kernel<<<(B + 127) / 128, 128, 0, stream>>>(pm, pl, pst, pss, P, B, 1.f, m, l, st, ss);
+  merge_stats_kernel<<<(B + 3) / 4, 128, 0, stream>>>(pm, pl, pst, pss, P, B, 1.f, m, l, st, ss);
   SPN_CUDA_CHECK(cudaGetLastError());
   return SPN_OK;
 }
