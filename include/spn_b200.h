@@ -153,6 +153,16 @@ int spn_sim_matrix(const float* q, const float* gallery, int Q, int G, int D, in
  * MN-major requires K == 128. */
 int spn_debug_umma_gemm(const void* a_bf16, const void* b_bf16, float* c, int N, int K, int mode, void* stream);
 
+/* Debug: raw tcgen05.mma issue-rate probe (M128 x N x K64 per iteration, SS or TS (mode bit0), optionally under
+ * concurrent TMA traffic).  b_src: bf16 [b_rows, 512] device buffer with b_rows >= grid*512.  out_cycles: device
+ * uint64[grid]. */
+int spn_debug_umma_bench(const void* b_src, int64_t b_rows, int N, int iters, int mode, int tma_on,
+                         unsigned long long* out_cycles, int grid, void* stream);
+
+/* Debug: per-CTA role cycle counters of the last bank-CE launch (16 x uint64 per CTA); only in builds made
+ * with -DSPN_TIMELINE, otherwise SPN_ERR_BAD_ARG. host_out is a HOST pointer. */
+int spn_debug_read_timeline(unsigned long long* host_out, int n);
+
 #ifdef __cplusplus
 }
 #endif

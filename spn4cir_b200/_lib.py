@@ -57,12 +57,13 @@ def _stale() -> bool:
     return any(p.stat().st_mtime > t for p in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> Path:
+def build_library(force: bool = False, verbose: bool = False, extra_flags=(), out: Path = None) -> Path:
     """Compile csrc/*.cu into spn4cir_b200/libspn_b200.so (sm_100a). Cross-compiles without a GPU."""
-    if not force and not _stale():
+    out = Path(out) if out is not None else LIB_PATH
+    if out == LIB_PATH and not force and not _stale():
         return LIB_PATH
-    tmp = LIB_PATH.with_suffix(".so.tmp%d" % os.getpid())
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(tmp), *[str(CSRC_DIR / s) for s in SOURCES]]
+    tmp = out.with_suffix(".so.tmp%d" % os.getpid())
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags, "-o", str(tmp), *[str(CSRC_DIR / s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -70,10 +71,10 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if res.returncode != 0:
         tmp.unlink(missing_ok=True)
         raise SpnError("build", -5, "nvcc failed:\n" + res.stdout + res.stderr)
-    os.replace(tmp, LIB_PATH)
+    os.replace(tmp, out)
     if verbose:
         print(res.stdout + res.stderr)
-    return LIB_PATH
+    return out
 
 
 _f32p = POINTER(c_float)
@@ -100,6 +101,8 @@ _SIGNATURES = {
     "spn_sim_rank": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                      c_int, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     "spn_sim_matrix": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "spn_debug_read_timeline": [c_void_p, c_int],
+    "spn_debug_umma_bench": [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "spn_debug_umma_gemm": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["spn_last_error"])
@@ -114,6 +117,17 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
+        override = os.environ.get("SPN_LIB_PATH")  # debug builds (e.g. -DSPN_TIMELINE) used by tools/
+        if override:
+            lib = ctypes.CDLL(override)
+            for name, args in _SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.argtypes = args
+                fn.restype = c_int
+            lib.spn_last_error.argtypes = []
+            lib.spn_last_error.restype = c_char_p
+            _lib = lib
+            return lib
         if build_if_missing and _stale():
             if shutil.which("nvcc") or Path("/usr/local/cuda/bin/nvcc").exists():
                 build_library()

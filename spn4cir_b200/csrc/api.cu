@@ -134,6 +134,17 @@ int spn_sim_matrix(const float* q, const float* gallery, int Q, int G, int D, in
   return sim_matrix(q, gallery, Q, G, D, T, out, as_stream(stream));
 }
 
+int spn_debug_read_timeline(unsigned long long* host_out, int n) {
+  SPN_REQUIRE(host_out && n > 0 && n <= 1024 * 16, SPN_ERR_BAD_ARG, "spn_debug_read_timeline: bad arguments");
+  return debug_read_timeline(host_out, n);
+}
+
+int spn_debug_umma_bench(const void* b_src, int64_t b_rows, int N, int iters, int mode, int tma_on,
+                         unsigned long long* out_cycles, int grid, void* stream) {
+  SPN_REQUIRE(b_src && out_cycles && iters > 0 && grid > 0, SPN_ERR_BAD_ARG, "spn_debug_umma_bench: bad arguments");
+  return debug_umma_bench(b_src, b_rows, N, iters, mode, tma_on, out_cycles, grid, as_stream(stream));
+}
+
 int spn_debug_umma_gemm(const void* a_bf16, const void* b_bf16, float* c, int N, int K, int mode, void* stream) {
   SPN_REQUIRE(a_bf16 && b_bf16 && c, SPN_ERR_BAD_ARG, "spn_debug_umma_gemm: NULL pointer");
   return debug_umma_gemm(a_bf16, b_bf16, c, N, K, mode, as_stream(stream));

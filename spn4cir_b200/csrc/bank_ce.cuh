@@ -18,6 +18,7 @@ struct BankCEParams {
   long long n_rows;  // N * T token rows
   int kblocks;       // D / 64
   int stages;        // ring depth
+  int bps;           // k-blocks (16 KiB) per ring stage
   int n_tiles;       // ceil(n_rows / 128)
   int q_tiles;       // ceil(B / 128)
   int num_chunks;    // bank-row chunks (grid = q_tiles * num_dsplit * num_chunks)
@@ -26,6 +27,7 @@ struct BankCEParams {
   float scale_log2;  // inv_tau * log2(e)
   long long row_base;
   const long long* labels;
+  const void* q_gmem;  // forward: bf16 [B, D] queries, staged into TMEM by the soft-max warps
   // forward partials, [num_chunks][B], log2 units
   float* part_m;
   float* part_l;
@@ -40,7 +42,7 @@ struct BankCEParams {
 };
 
 struct BankCEPlan {
-  int kblocks, q_tiles, n_tiles, num_chunks, num_dsplit, ow_blocks, stages, grid;
+  int kblocks, q_tiles, n_tiles, num_chunks, num_dsplit, ow_blocks, stages, bps, grid;
   size_t smem_bytes, ws_bytes;
 };
 
@@ -58,8 +60,13 @@ int merge_stats(const float* pm, const float* pl, const float* pst, const float*
 int bank_ce_loss(const float* m, const float* l, const float* st, const float* ss, int B, long long N_total,
                  float eps, float* lse, float* loss_q, float* loss_mean, cudaStream_t stream);
 
+int debug_read_timeline(unsigned long long* host_out, int n);
+
 // bring-up GEMM (umma_selftest.cu)
 int debug_umma_gemm(const void* a, const void* b, float* c, int N, int K, int mode, cudaStream_t stream);
+
+int debug_umma_bench(const void* b_src, long long b_rows, int N, int iters, int mode, int tma_on,
+                     unsigned long long* out_cycles, int grid, cudaStream_t stream);
 
 // prologue kernels (prologue.cu)
 int cast_to_bf16(const void* src, int src_dtype, void* dst, long long n, cudaStream_t stream);

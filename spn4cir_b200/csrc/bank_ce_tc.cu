@@ -8,10 +8,11 @@
 // CTA = 6 warps:  warp 0 lane 0  TMA producer        (bank blocks [128 rows x 64 cols] bf16, SW128)
 //                 warp 1 lane 0  tcgen05.mma issuer  (+ warp 1 owns the TMEM allocation)
 //                 warps 2..5     soft-max / epilogue (one TMEM lane quarter each, thread == query row)
-// smem:  Q tile resident (D/64 blocks of 16 KiB) + a ring of 16 KiB bank blocks.
-// TMEM:  forward   2 x S[128 x 128 f32]                         (256 columns)
-//        backward  O[128 x <=320 f32] | S[128 x 128] | P bf16   (512 columns)
-// GEMM1 (S)  : SS, A = Q block (K-major), B = bank block (K-major), M128 N128 K16 x 4 per block.
+// smem:  a ring of 16 KiB bank blocks; backward additionally keeps the Q tile resident (D/64 blocks of 16 KiB).
+// TMEM:  forward   Q[128 x D bf16] (D/2 columns) | S[128 x 128 f32]          (512 columns)
+//        backward  O[128 x <=320 f32] | S[128 x 128] | P bf16                 (512 columns)
+// GEMM1 (S)  : forward  TS, A = Q from TMEM (an SS MMA serialises a 4 KiB A read: 107 vs 74 cycles measured),
+//              backward SS, A = Q block (K-major smem); B = bank block (K-major), M128 N128 K16 x 4 per block.
 // GEMM2 (dq) : TS, A = P (TMEM, bf16), B = the same bank block bytes read MN-major, M128 N64 K16 x 8.
 #include <cuda_bf16.h>
 #include <math.h>
@@ -27,10 +28,28 @@ namespace {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-constexpr uint32_t kTmemColsFwd = 256;
+constexpr uint32_t kTmemColsFwd = 512;
 constexpr uint32_t kTmemColsBwd = 512;
 constexpr uint32_t kBwdSCol = 320;  // S tile columns [320, 448)
 constexpr uint32_t kBwdPCol = 448;  // P tile columns [448, 512): 128 bf16 = 64 x 32-bit columns
+
+// Optional cycle accounting per role (build with -DSPN_TIMELINE; read with spn_debug_read_timeline).
+#ifdef SPN_TIMELINE
+__device__ unsigned long long g_timeline[1024 * 16];
+#define TL_VARS unsigned long long tl_acc[4] = {0, 0, 0, 0}; long long tl_t0 = 0, tl_start = clock64();
+#define TL_BEGIN tl_t0 = clock64();
+#define TL_END(i) tl_acc[i] += (unsigned long long)(clock64() - tl_t0);
+#define TL_FLUSH(base)                                                                  \
+  if ((threadIdx.x & 31) == 0 && blockIdx.x < 1024) {                                   \
+    for (int _i = 0; _i < 3; ++_i) g_timeline[blockIdx.x * 16 + (base) + _i] = tl_acc[_i]; \
+    g_timeline[blockIdx.x * 16 + (base) + 3] = (unsigned long long)(clock64() - tl_start); \
+  }
+#else
+#define TL_VARS
+#define TL_BEGIN
+#define TL_END(i)
+#define TL_FLUSH(base)
+#endif
 
 struct SmemView {
   uint8_t* q;       // kblocks x 16 KiB
@@ -46,12 +65,12 @@ struct SmemView {
   uint32_t* tmem_slot;
 };
 
-__device__ __forceinline__ SmemView carve(uint8_t* raw, int kblocks, int stages) {
+__device__ __forceinline__ SmemView carve(uint8_t* raw, int q_blocks, int stages, int bps) {
   SmemView v;
   uintptr_t base = (reinterpret_cast<uintptr_t>(raw) + 1023u) & ~uintptr_t(1023u);
   v.q = reinterpret_cast<uint8_t*>(base);
-  v.ring = v.q + size_t(kblocks) * kBlockBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(v.ring + size_t(stages) * kBlockBytes);
+  v.ring = v.q + size_t(q_blocks) * kBlockBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v.ring + size_t(stages) * bps * kBlockBytes);
   v.full = bars;
   v.empty = bars + stages;
   uint64_t* rest = bars + 2 * stages;
@@ -212,7 +231,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
-  const SmemView sm = carve(smem_raw, p.kblocks, p.stages);
+  const SmemView sm = carve(smem_raw, MODE == 0 ? 0 : p.kblocks, p.stages, p.bps);
 
   // block -> (query tile, d-split, bank chunk); query tile fastest so co-resident CTAs share bank rows in L2
   int bid = blockIdx.x;
@@ -231,12 +250,12 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], 1);
     }
-    mbar_init(sm.q_full, 1);
+    mbar_init(sm.q_full, MODE == 0 ? 4 : 1);  // forward: the 4 soft-max warps stage Q into TMEM
     mbar_init(&sm.s_full[0], 1);
     mbar_init(&sm.s_full[1], 1);
     mbar_init(&sm.s_free[0], 4);
     mbar_init(&sm.s_free[1], 4);
-    mbar_init(sm.p_full, 4);
+    mbar_init(sm.p_full, MODE == 0 ? 1 : 4);  // forward: Q staging (TMA tx) barrier
     mbar_init(sm.p_free, 1);
     mbar_init(sm.o_full, 1);
     fence_barrier_init();
@@ -255,15 +274,30 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   if (warp == 0) {
     // ===================================================================== TMA producer (converged warp, one
     // elected lane issues; see elect_one())
-    if (elect_one()) {
-      mbar_arrive_expect_tx(sm.q_full, uint32_t(p.kblocks) * kBlockBytes);
-      for (int kb = 0; kb < p.kblocks; ++kb)
-        tma_load_2d(sm.q + size_t(kb) * kBlockBytes, &tmap_q, sm.q_full, kb * kBK, q0);
+    if (MODE == 1) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(sm.q_full, uint32_t(p.kblocks) * kBlockBytes);
+        for (int kb = 0; kb < p.kblocks; ++kb)
+          tma_load_2d(sm.q + size_t(kb) * kBlockBytes, &tmap_q, sm.q_full, kb * kBK, q0);
+      }
+      __syncwarp();
+    } else {
+      // forward: the Q tile passes through the (still unused) ring slots; the soft-max warps move it to TMEM
+      // and only then (q_full) may bank blocks overwrite the slots
+      if (elect_one()) {
+        mbar_arrive_expect_tx(sm.p_full, uint32_t(p.kblocks) * kBlockBytes);
+        for (int kb = 0; kb < p.kblocks; ++kb)
+          tma_load_2d(sm.ring + size_t(kb) * kBlockBytes, &tmap_q, sm.p_full, kb * kBK, q0);
+      }
+      __syncwarp();
+      mbar_wait(sm.q_full, 0);
     }
-    __syncwarp();
     Ring r(p.stages);
+    TL_VARS
     auto load_block = [&](int col_blk, int row) {
+      TL_BEGIN
       mbar_wait(&sm.empty[r.stage], r.phase ^ 1u);
+      TL_END(0)
       if (elect_one()) {
         mbar_arrive_expect_tx(&sm.full[r.stage], kBlockBytes);
         tma_load_2d(sm.ring + size_t(r.stage) * kBlockBytes, &tmap_bank, &sm.full[r.stage], col_blk * kBK, row);
@@ -271,13 +305,32 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       __syncwarp();
       r.advance();
     };
+    // forward: a stage is `bps` consecutive k-blocks (one barrier round trip per 32 KiB)
+    auto load_group = [&](int kb0, int nb, int row) {
+      TL_BEGIN
+      mbar_wait(&sm.empty[r.stage], r.phase ^ 1u);
+      TL_END(0)
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&sm.full[r.stage], uint32_t(nb) * kBlockBytes);
+        for (int b = 0; b < nb; ++b)
+          tma_load_2d(sm.ring + (size_t(r.stage) * p.bps + b) * kBlockBytes, &tmap_bank, &sm.full[r.stage],
+                      (kb0 + b) * kBK, row);
+      }
+      __syncwarp();
+      r.advance();
+    };
     for (int t = t_begin; t < t_end; ++t) {
-      for (int kb = 0; kb < p.kblocks; ++kb) load_block(kb, t * kBN);
+      if (MODE == 0) {
+        for (int kb = 0; kb < p.kblocks; kb += p.bps) load_group(kb, min(p.bps, p.kblocks - kb), t * kBN);
+      } else {
+        for (int kb = 0; kb < p.kblocks; ++kb) load_block(kb, t * kBN);
+      }
       if (MODE == 1 && t > t_begin)
         for (int j = 0; j < my_blocks; ++j) load_block(ds * p.ow_blocks + j, (t - 1) * kBN);
     }
     if (MODE == 1 && ntl > 0)
       for (int j = 0; j < my_blocks; ++j) load_block(ds * p.ow_blocks + j, (t_end - 1) * kBN);
+    TL_FLUSH(0)
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (converged warp)
     constexpr uint32_t idesc_s = make_idesc_bf16_f32(kBM, kBN, 0, 0);
@@ -289,10 +342,13 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     Ring r(p.stages);
     mbar_wait(sm.q_full, 0);
     tc_fence_after();
+    TL_VARS
 
     auto gemm_s = [&](uint32_t d_tmem) {
       for (int kb = 0; kb < p.kblocks; ++kb) {
+        TL_BEGIN
         mbar_wait(&sm.full[r.stage], r.phase);
+        TL_END(0)
         tc_fence_after();
         if (elect_one()) {
           const uint64_t adesc = q_desc0 + uint64_t(kb) * (kBlockBytes >> 4);
@@ -308,20 +364,45 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     };
 
     if (MODE == 0) {
+      const uint32_t s_tmem = tmem_base + uint32_t(p.kblocks) * 32u;  // S tile right after the Q columns
       for (int i = 0; i < ntl; ++i) {
-        const uint32_t buf = uint32_t(i) & 1u;
-        mbar_wait(&sm.s_free[buf], ((uint32_t(i) >> 1) & 1u) ^ 1u);
+        TL_BEGIN
+        mbar_wait(&sm.s_free[0], (uint32_t(i) & 1u) ^ 1u);
+        TL_END(1)
         tc_fence_after();
-        gemm_s(tmem_base + buf * kBN);
-        if (elect_one()) umma_commit(&sm.s_full[buf]);
+        for (int kb0 = 0; kb0 < p.kblocks; kb0 += p.bps) {
+          TL_BEGIN
+          mbar_wait(&sm.full[r.stage], r.phase);
+          TL_END(0)
+          tc_fence_after();
+          if (elect_one()) {
+            const int nb = min(p.bps, p.kblocks - kb0);
+            for (int b = 0; b < nb; ++b) {
+              const int kb = kb0 + b;
+              const uint64_t bdesc = ring_desc_k0 + uint64_t(r.stage * p.bps + b) * (kBlockBytes >> 4);
+#pragma unroll
+              for (int k = 0; k < kBK / kUmmaK; ++k)  // A: 8 TMEM columns (16 bf16) per K step
+                umma_ts_f16(s_tmem, tmem_base + uint32_t(kb) * 32u + uint32_t(k) * 8u, bdesc + uint64_t(k * 2),
+                            idesc_s, (kb | k) != 0);
+            }
+            umma_commit(&sm.empty[r.stage]);
+          }
+          __syncwarp();
+          r.advance();
+        }
+        if (elect_one()) umma_commit(&sm.s_full[0]);
         __syncwarp();
       }
     } else {
       auto gemm_o = [&](int u) {
+        TL_BEGIN
         mbar_wait(sm.p_full, uint32_t(u) & 1u);
+        TL_END(2)
         tc_fence_after();
         for (int j = 0; j < my_blocks; ++j) {
+          TL_BEGIN
           mbar_wait(&sm.full[r.stage], r.phase);
+          TL_END(0)
           tc_fence_after();
           if (elect_one()) {
             // the same 16 KiB block, read MN-major: rows are K (bank rows), 128 B span = 64 output columns
@@ -339,7 +420,9 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         __syncwarp();
       };
       for (int i = 0; i < ntl; ++i) {
+        TL_BEGIN
         mbar_wait(&sm.s_free[0], (uint32_t(i) & 1u) ^ 1u);
+        TL_END(1)
         tc_fence_after();
         gemm_s(tmem_base + kBwdSCol);
         if (elect_one()) umma_commit(&sm.s_full[0]);
@@ -350,6 +433,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       if (elect_one()) umma_commit(sm.o_full);
       __syncwarp();
     }
+    TL_FLUSH(4)
   } else {
     // ===================================================================== soft-max / epilogue warps
     const uint32_t quarter = warp & 3u;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
@@ -365,32 +449,57 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       if (g >= 0 && g < p.N) lbl = g;
     }
     uint32_t xr[32];
+    TL_VARS
 
     if (MODE == 0) {
+      // move this thread's query row from the TMA-staged, 128B-swizzled blocks to TMEM as the packed-bf16 A
+      // operand (columns [0, D/2)): chunk c of row r sits at r*128 + ((c ^ (r & 7)) << 4) inside a block
+      uint32_t x0[32], x1[32], x2[32], x3[32];
+      mbar_wait(sm.p_full, 0);
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        const uint8_t* blk = sm.ring + size_t(kb) * kBlockBytes + size_t(row) * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 w = *reinterpret_cast<const uint4*>(blk + ((c ^ (row & 7)) << 4));
+          x0[4 * c] = w.x; x0[4 * c + 1] = w.y; x0[4 * c + 2] = w.z; x0[4 * c + 3] = w.w;
+        }
+        tmem_st_32x32b_x32(t_row + uint32_t(kb) * 32u, x0);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.q_full);
+      const uint32_t s_col = uint32_t(p.kblocks) * 32u;
       float m_run = -INFINITY, l_run = 0.f, st = -INFINITY, ssum = 0.f;
       for (int i = 0; i < ntl; ++i) {
         const int t = t_begin + i;
-        const uint32_t buf = uint32_t(i) & 1u;
-        mbar_wait(&sm.s_full[buf], (uint32_t(i) >> 1) & 1u);
+        TL_BEGIN
+        mbar_wait(&sm.s_full[0], uint32_t(i) & 1u);
+        TL_END(0)
         tc_fence_after();
+        // drain the whole S tile to registers in one go, then hand TMEM straight back to the MMA warp
+        TL_BEGIN
+        tmem_ld_32x32b_x32(t_row + s_col, x0);
+        tmem_ld_32x32b_x32(t_row + s_col + 32u, x1);
+        tmem_ld_32x32b_x32(t_row + s_col + 64u, x2);
+        tmem_ld_32x32b_x32(t_row + s_col + 96u, x3);
+        tmem_ld_wait();
+        TL_END(1)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.s_free[0]);
         const long long row0 = (long long)t * kBN;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          tmem_ld_32x32b_x32(t_row + buf * kBN + uint32_t(c) * 32u, xr);
-          tmem_ld_wait();
-          if (c == 3) {  // S tile fully in registers: hand the buffer back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.s_free[buf]);
-          }
+          const uint32_t(&xc)[32] = c == 0 ? x0 : (c == 1 ? x1 : (c == 2 ? x2 : x3));
           const long long col0 = row0 + c * 32;
           if (T == 1) {
             const long long left = p.n_rows - col0;
             const int valid = left >= 32 ? 32 : (left > 0 ? int(left) : 0);
-            if (valid > 0) fwd_chunk_t1<EXTRA>(xr, valid, scale, col0, lbl, m_run, l_run, st, ssum);
+            if (valid > 0) fwd_chunk_t1<EXTRA>(xc, valid, scale, col0, lbl, m_run, l_run, st, ssum);
           } else {
             const long long entry = (long long)t * 4 + c;
-            fwd_chunk_t32<EXTRA>(xr, entry < p.N, scale, entry == lbl, m_run, l_run, st, ssum);
+            fwd_chunk_t32<EXTRA>(xc, entry < p.N, scale, entry == lbl, m_run, l_run, st, ssum);
           }
         }
       }
@@ -408,13 +517,17 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       uint32_t u[64];
       for (int i = 0; i < ntl; ++i) {
         const int t = t_begin + i;
+        TL_BEGIN
         mbar_wait(&sm.s_full[0], uint32_t(i) & 1u);
+        TL_END(0)
         tc_fence_after();
         const long long row0 = (long long)t * kBN;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          TL_BEGIN
           tmem_ld_32x32b_x32(t_row + kBwdSCol + uint32_t(c) * 32u, xr);
           tmem_ld_wait();
+          TL_END(1)
           if (c == 3) {
             tc_fence_before();
             __syncwarp();
@@ -433,7 +546,9 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
         }
         // P(i) -> TMEM once GEMM2 of the previous tile no longer reads the buffer
+        TL_BEGIN
         mbar_wait(sm.p_free, (uint32_t(i) & 1u) ^ 1u);
+        TL_END(2)
         tc_fence_after();
         tmem_st_32x32b_x32(t_row + kBwdPCol, *reinterpret_cast<const uint32_t(*)[32]>(&u[0]));
         tmem_st_32x32b_x32(t_row + kBwdPCol + 32u, *reinterpret_cast<const uint32_t(*)[32]>(&u[32]));
@@ -460,6 +575,9 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (EXTRA && q_ok && ds == 0) atomicAdd(&p.dlogit_dot[q], es * kLn2);
       }
     }
+#ifdef SPN_TIMELINE
+    if (warp == 2) { TL_FLUSH(8) }
+#endif
   }
 
   __syncwarp();
@@ -541,6 +659,16 @@ int launch_one(const CUtensorMap& tq, const CUtensorMap& tb, const BankCEParams&
 
 }  // namespace
 
+int debug_read_timeline(unsigned long long* host_out, int n) {
+#ifdef SPN_TIMELINE
+  SPN_CUDA_CHECK(cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(unsigned long long) * size_t(n)));
+  return SPN_OK;
+#else
+  (void)host_out; (void)n;
+  return fail(SPN_ERR_BAD_ARG, "library built without -DSPN_TIMELINE");
+#endif
+}
+
 int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan) {
   SPN_REQUIRE(B > 0 && N > 0, SPN_ERR_BAD_SHAPE, "bank-CE needs B > 0 and N > 0 (B=%d N=%lld)", B, N);
   SPN_REQUIRE(D >= 64 && D <= 768 && D % 64 == 0, SPN_ERR_BAD_SHAPE,
@@ -567,16 +695,21 @@ int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan) {
   if (chunks > plan->n_tiles) chunks = plan->n_tiles;
   plan->num_chunks = chunks;
   plan->grid = plan->q_tiles * plan->num_dsplit * chunks;
-  const size_t fixed = 1024 /*align slack*/ + size_t(plan->kblocks) * kBlockBytes + 256 /*barriers*/;
-  int stages = int((size_t(smem_max) - fixed) / kBlockBytes);
-  if (stages > 8) stages = 8;
+  // forward keeps Q in TMEM (no smem), backward keeps the Q tile in smem next to the ring
+  const size_t fixed = 1024 /*align slack*/ + (mode == 1 ? size_t(plan->kblocks) * kBlockBytes : 0) + 512 /*barriers*/;
+  const int bps = (mode == 0 && plan->kblocks >= 2) ? 2 : 1;  // k-blocks per ring stage
+  plan->bps = bps;
+  int stages = int((size_t(smem_max) - fixed) / (size_t(bps) * kBlockBytes));
+  if (stages > 12) stages = 12;
   if (const char* e = getenv("SPN_DEBUG_STAGES")) {  // bring-up knob: shrink the ring to probe latency sensitivity
     const int v = atoi(e);
     if (v >= 2 && v < stages) stages = v;
   }
+  // forward stages the Q tile through the ring before the first bank block: it must fit
+  if (mode == 0 && stages * bps < plan->kblocks) stages = (plan->kblocks + bps - 1) / bps;
   SPN_REQUIRE(stages >= 2, SPN_ERR_BAD_SHAPE, "D=%d leaves no room for the bank ring in %d B of shared memory", D, smem_max);
   plan->stages = stages;
-  plan->smem_bytes = fixed + size_t(stages) * kBlockBytes;
+  plan->smem_bytes = fixed + size_t(stages) * bps * kBlockBytes;
   plan->ws_bytes = (mode == 0) ? ((size_t(4) * chunks * B * sizeof(float) + 255) / 256) * 256 : 256;
   return SPN_OK;
 }
@@ -593,9 +726,9 @@ int bank_ce_forward(const void* q, const void* bank, const long long* labels, fl
   if ((rc = make_tmap_bf16_2d(&tq, q, uint64_t(B), uint64_t(D), kBM)) != SPN_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&tb, bank, uint64_t(N) * T, uint64_t(D), kBN)) != SPN_OK) return rc;
   BankCEParams p{};
-  p.B = B; p.D = D; p.N = N; p.n_rows = N * T; p.kblocks = plan.kblocks; p.stages = plan.stages;
+  p.B = B; p.D = D; p.N = N; p.n_rows = N * T; p.kblocks = plan.kblocks; p.stages = plan.stages; p.bps = plan.bps;
   p.n_tiles = plan.n_tiles; p.q_tiles = plan.q_tiles; p.num_chunks = plan.num_chunks; p.num_dsplit = 1;
-  p.ow_blocks = 0; p.scale_log2 = inv_tau * kLog2e; p.row_base = row_base; p.labels = labels;
+  p.ow_blocks = 0; p.scale_log2 = inv_tau * kLog2e; p.row_base = row_base; p.labels = labels; p.q_gmem = q;
   float* w = static_cast<float*>(ws);
   const size_t stride = size_t(plan.num_chunks) * B;
   p.part_m = w; p.part_l = w + stride; p.part_st = w + 2 * stride; p.part_ssum = w + 3 * stride;
@@ -623,7 +756,7 @@ int bank_ce_backward(const void* q, const void* bank, const long long* labels, f
   if ((rc = make_tmap_bf16_2d(&tq, q, uint64_t(B), uint64_t(D), kBM)) != SPN_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&tb, bank, uint64_t(N) * T, uint64_t(D), kBN)) != SPN_OK) return rc;
   BankCEParams p{};
-  p.B = B; p.D = D; p.N = N; p.n_rows = N * T; p.kblocks = plan.kblocks; p.stages = plan.stages;
+  p.B = B; p.D = D; p.N = N; p.n_rows = N * T; p.kblocks = plan.kblocks; p.stages = plan.stages; p.bps = plan.bps;
   p.n_tiles = plan.n_tiles; p.q_tiles = plan.q_tiles; p.num_chunks = plan.num_chunks;
   p.num_dsplit = plan.num_dsplit; p.ow_blocks = plan.ow_blocks; p.scale_log2 = inv_tau * kLog2e;
   p.row_base = row_base; p.labels = labels; p.lse = lse; p.gscale = gscale; p.gscale_dev = gscale_dev;

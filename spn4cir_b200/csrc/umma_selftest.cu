@@ -110,7 +110,103 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
+// ---- raw MMA issue-rate probe: every CTA issues `iters` x 4 MMAs (K=64 per iteration) back to back from a
+// resident smem tile (contents irrelevant), optionally while a second warp streams TMA boxes into a 4-deep ring.
+// mode bit0: A from TMEM.  Reports cycles per CTA.
+__global__ void __launch_bounds__(128, 1)
+umma_bench_kernel(const __grid_constant__ CUtensorMap tmap_b, int N, int iters, int mode, int tma_on,
+                  unsigned long long* __restrict__ out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t warp = threadIdx.x >> 5;
+  uintptr_t base = (reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~uintptr_t(1023u);
+  uint8_t* a_smem = reinterpret_cast<uint8_t*>(base);                // 16 KiB
+  uint8_t* b_smem = a_smem + kBlockBytes;                            // 32 KiB (N up to 256)
+  uint8_t* ring = b_smem + 2 * kBlockBytes;                          // 4 x 16 KiB TMA sink
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 4 * kBlockBytes);
+  uint64_t* done = bars;        // MMA completion
+  uint64_t* rfull = bars + 1;   // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  volatile uint32_t* stop = tmem_slot + 1;
+  if (threadIdx.x == 0) {
+    mbar_init(done, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&rfull[i], 1);
+    *stop = 0;
+    fence_barrier_init();
+  }
+  for (uint32_t i = threadIdx.x; i < 3 * kBlockBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(a_smem)[i] = 0;
+  fence_proxy_async_smem();
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16_f32(128, N, 0, 0);
+    const uint64_t adesc = make_smem_desc_sw128(smem_u32(a_smem), 16, 1024);
+    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(b_smem), 16, 1024);
+    const long long t0 = clock64();
+    if (elect_one()) {
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (mode & 1) umma_ts_f16(tmem_base, tmem_base + 256u + uint32_t(k) * 8u, bdesc + uint64_t(k * 2), idesc, 1);
+          else          umma_ss_f16(tmem_base, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, 1);
+        }
+      }
+      umma_commit(done);
+    }
+    __syncwarp();
+    mbar_wait(done, 0);
+    const long long t1 = clock64();
+    *stop = 1;
+    if ((threadIdx.x & 31) == 0) out_cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
+  } else if (warp == 2 && tma_on) {
+    uint32_t phase = 0, stage = 0;
+    const int rows = int(blockIdx.x) * 512;
+    int n = 0;
+    while (!*stop) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&rfull[stage], kBlockBytes);
+        tma_load_2d(ring + size_t(stage) * kBlockBytes, &tmap_b, &rfull[stage], ((n >> 2) % 8) * 64, rows + (n & 3) * 128);
+      }
+      __syncwarp();
+      ++n;
+      if (n >= 4) {  // keep 4 loads in flight: wait for the oldest before reusing its slot
+        const uint32_t s2 = (stage + 1) & 3u;
+        mbar_wait(&rfull[s2], (s2 == 0) ? (phase ^ 1u) : phase);
+      }
+      if (++stage == 4) { stage = 0; phase ^= 1u; }
+    }
+  }
+  __syncthreads();
+  // drain outstanding TMA (at most 4) before exit
+  if (warp == 2 && tma_on) {
+    // barriers complete on their own; give the loads time to land
+    __nanosleep(20000);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
+
+int debug_umma_bench(const void* b_src, long long b_rows, int N, int iters, int mode, int tma_on,
+                     unsigned long long* out_cycles, int grid, cudaStream_t stream) {
+  SPN_REQUIRE(N == 64 || N == 128 || N == 256, SPN_ERR_BAD_SHAPE, "bench N must be 64/128/256");
+  int rc;
+  if ((rc = require_sm100()) != SPN_OK) return rc;
+  CUtensorMap tb;
+  if ((rc = make_tmap_bf16_2d(&tb, b_src, uint64_t(b_rows), 512, 128)) != SPN_OK) return rc;
+  const size_t smem = 1024 + 7 * kBlockBytes + 128;
+  SPN_CUDA_CHECK(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  umma_bench_kernel<<<grid, 128, smem, stream>>>(tb, N, iters, mode, tma_on, out_cycles);
+  SPN_CUDA_CHECK(cudaGetLastError());
+  return SPN_OK;
+}
 
 int debug_umma_gemm(const void* a, const void* b, float* c, int N, int K, int mode, cudaStream_t stream) {
   SPN_REQUIRE(N == 64 || N == 128, SPN_ERR_BAD_SHAPE, "selftest N must be 64 or 128 (got %d)", N);

@@ -25,7 +25,7 @@ for D in (256, 512, 640, 768):
     lab = torch.randint(0, N, (B,), device="cuda")
     db = spn.DeviceBank(bank.to(torch.bfloat16).contiguous())
     q16 = cast_to_bf16(q)
-    for st in (None, 2, 3, 4, 6, 8):
+    for st in (None,):
         if st is None: os.environ.pop("SPN_DEBUG_STAGES", None)
         else: os.environ["SPN_DEBUG_STAGES"] = str(st)
         stats = _fwd_stats(q16, db, lab, 50.0, False)
