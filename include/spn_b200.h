@@ -112,6 +112,44 @@ int spn_bank_ce_bwd(const void* q_bf16, const void* bank_bf16, const int64_t* la
                     int64_t N_total, int B, int64_t N, int D, int T, int64_t row_base, float* dq_partial,
                     float* dlogit_dot, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- single-pass training path (forward statistics AND the unnormalised gradient in one sweep of the bank) ----
+ * The soft-max is taken against a STATIC per-row reference ref[b] >= (approximately) max_n s[b][n]:
+ *     ref = min( inv_tau |q_b| max_n |bank_n|  (Cauchy-Schwarz, can never overflow),  s_t + 30 )
+ * bf16 / fp32 share an 8-bit exponent, so P~ = exp(s - ref) needs no running-max rescaling and the partial
+ * sums of different CTAs / shards / ranks simply ADD (no merge pass).  Replaces, for a training step, the pair
+ * spn_bank_ce_fwd + spn_bank_ce_bwd (reference: clip4cir/models_negplus.py:150-154 + autograd, one call site
+ * clip4cir/train_negplus.py:110-121). */
+
+/* One-off per bank: maxnorm[0] = max_n |bank_n| (device float), colsum (nullable, fp32 [D]) = sum_n bank_n
+ * (only needed for label smoothing). */
+int spn_bank_stats(const void* bank_bf16, int64_t rows, int D, float* maxnorm, float* colsum, void* stream);
+
+/* Per step prologue: cast q (spn_dtype) to bf16 and compute ref[b] (natural units) for this shard.  A rank that
+ * does not own label b uses the Cauchy-Schwarz bound alone; ranks must agree on ref (min all-reduce) before
+ * spn_bank_ce_fused when the bank is sharded. */
+int spn_bank_ce_prep(const void* q_src, int src_dtype, const void* bank_bf16, const int64_t* labels, float inv_tau,
+                     const float* bank_maxnorm, int B, int64_t N, int D, int T, int64_t row_base, void* q_bf16,
+                     float* ref, void* stream);
+
+/* One sweep over the shard.  Outputs are ACCUMULATED (sum over shards / ranks; init != 0 zeroes them first):
+ *   o_acc [B, D] += sum_{n != label} exp(s - ref) bank_n        l_acc [B] += sum_{n != label} exp(s - ref)
+ *   es_acc [B] (nullable) += sum_{n != label} exp(s - ref) s    s_t [B] = s[label] (written by the owner, else -inf)
+ *   lbl_row [B] = LOCAL token row of the target (arg-max token when T = 32; -1 if not in this shard)
+ *   bank_t [B, D] (nullable) = fp32 copy of those rows (zeros when not in this shard) for spn_bank_ce_finalize. */
+int spn_bank_ce_fused(const void* q_bf16, const void* bank_bf16, const int64_t* labels, const float* ref, float inv_tau,
+                      int B, int64_t N, int D, int T, int64_t row_base, int init, float* o_acc, float* l_acc, float* s_t,
+                      int64_t* lbl_row, float* es_acc, float* bank_t, void* ws, size_t ws_bytes, void* stream);
+
+/* Combine the (globally reduced) sums:  L = l_acc + exp(s_t - ref), lse = ref + log L,
+ *   loss_b = lse - (1-eps) s_t - eps sum_n s_n / N,   loss_mean = mean_b loss_b,
+ *   dq[b]  = gscale * [ (o_acc - l_acc bank_t) / L + eps bank_t - (eps / N) colsum ]      (gscale = inv_tau / B)
+ *   dlogit_dot[b] = sum_n dlogit[b][n] s[b][n]  (nullable; needs es_acc).
+ * (1 - p_t) = l_acc / L is formed without cancellation.  dq is the gradient for an upstream gradient of 1. */
+int spn_bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, const float* bank_t, const float* ref,
+                         const float* es_acc, const void* q_bf16, const float* colsum, float inv_tau, float gscale,
+                         float label_smoothing, int64_t N_total, int B, int D, float* lse, float* loss_per_query,
+                         float* loss_mean, float* dq, float* dlogit_dot, void* stream);
+
 /* Fused cosine-similarity + per-row top-K over one gallery shard (descending score, ties -> lower
  * index first).  Replaces `distances = 1 - pred @ index.T; torch.argsort(distances)` followed by the
  * [:K] slices (clip4cir/validate.py:31-32,126-127; clip4cir/cirr_test_submission.py:91-92,106) and,

@@ -94,6 +94,14 @@ _SIGNATURES = {
                          c_void_p, c_void_p],
     "spn_bank_ce_bwd": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_float, c_void_p, c_float, c_int64,
                         c_int, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    "spn_bank_stats": [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p],
+    "spn_bank_ce_prep": [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int64, c_int, c_int, c_int64,
+                         c_void_p, c_void_p, c_void_p],
+    "spn_bank_ce_fused": [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int64, c_int, c_int, c_int64, c_int,
+                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    "spn_bank_ce_finalize": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                             c_float, c_float, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p],
     "spn_sim_topk": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int32, c_void_p,
                      c_void_p, c_void_p, c_size_t, c_void_p],
     "spn_merge_topk": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],

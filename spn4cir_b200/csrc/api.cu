@@ -91,6 +91,48 @@ int spn_bank_ce_bwd(const void* q_bf16, const void* bank_bf16, const int64_t* la
                           gscale_dev, label_smoothing, N_total, B, N, D, T, row_base, dq_partial, dlogit_dot, as_stream(stream));
 }
 
+int spn_bank_stats(const void* bank_bf16, int64_t rows, int D, float* maxnorm, float* colsum, void* stream) {
+  SPN_REQUIRE(bank_bf16 && maxnorm, SPN_ERR_BAD_ARG, "spn_bank_stats: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return bank_stats(bank_bf16, rows, D, maxnorm, colsum, as_stream(stream));
+}
+
+int spn_bank_ce_prep(const void* q_src, int src_dtype, const void* bank_bf16, const int64_t* labels, float inv_tau,
+                     const float* bank_maxnorm, int B, int64_t N, int D, int T, int64_t row_base, void* q_bf16,
+                     float* ref, void* stream) {
+  SPN_REQUIRE(q_src && bank_bf16 && labels && bank_maxnorm && q_bf16 && ref, SPN_ERR_BAD_ARG, "spn_bank_ce_prep: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return bank_ce_prep(q_src, src_dtype, bank_bf16, reinterpret_cast<const long long*>(labels), inv_tau, bank_maxnorm, B, N,
+                      D, T, row_base, q_bf16, ref, as_stream(stream));
+}
+
+int spn_bank_ce_fused(const void* q_bf16, const void* bank_bf16, const int64_t* labels, const float* ref, float inv_tau,
+                      int B, int64_t N, int D, int T, int64_t row_base, int init, float* o_acc, float* l_acc, float* s_t,
+                      int64_t* lbl_row, float* es_acc, float* bank_t, void* ws, size_t ws_bytes, void* stream) {
+  (void)ws;
+  (void)ws_bytes;
+  SPN_REQUIRE(q_bf16 && bank_bf16 && labels && ref && o_acc && l_acc && s_t && lbl_row, SPN_ERR_BAD_ARG,
+              "spn_bank_ce_fused: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return bank_ce_fused(q_bf16, bank_bf16, reinterpret_cast<const long long*>(labels), ref, inv_tau, B, N, D, T, row_base,
+                       init, o_acc, l_acc, s_t, reinterpret_cast<long long*>(lbl_row), es_acc, bank_t, as_stream(stream));
+}
+
+int spn_bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, const float* bank_t, const float* ref,
+                         const float* es_acc, const void* q_bf16, const float* colsum, float inv_tau, float gscale,
+                         float label_smoothing, int64_t N_total, int B, int D, float* lse, float* loss_per_query,
+                         float* loss_mean, float* dq, float* dlogit_dot, void* stream) {
+  SPN_REQUIRE(o_acc && l_acc && s_t && bank_t && ref && lse && loss_mean, SPN_ERR_BAD_ARG, "spn_bank_ce_finalize: NULL pointer");
+  SPN_REQUIRE(label_smoothing >= 0.f && label_smoothing < 1.f, SPN_ERR_BAD_ARG, "label_smoothing must be in [0, 1)");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return bank_ce_finalize(o_acc, l_acc, s_t, bank_t, ref, es_acc, q_bf16, colsum, inv_tau, gscale, label_smoothing, N_total,
+                          B, D, lse, loss_per_query, loss_mean, dq, dlogit_dot, as_stream(stream));
+}
+
 int spn_sim_topk(const float* q, const float* gallery, int Q, int G, int D, int T, int K, const int32_t* exclude,
                  int32_t col_base, float* out_val, int32_t* out_idx, void* ws, size_t ws_bytes, void* stream) {
   SPN_REQUIRE(q && gallery && out_val && out_idx, SPN_ERR_BAD_ARG, "spn_sim_topk: NULL pointer");

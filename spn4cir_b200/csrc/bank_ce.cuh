@@ -37,7 +37,11 @@ struct BankCEParams {
   const float* lse;  // [B] natural units, global over all shards
   float gscale, eps_over_n, one_minus_eps;
   const float* gscale_dev;  // nullable: upstream scalar gradient on the device
-  float* dq;          // [B, D] fp32, +=
+  const float* ref;   // fused: [B] static soft-max reference, natural units
+  float* l_acc;       // fused: [B] += sum_{n != label} exp(s - ref)
+  float* st_out;      // fused: [B] target logit (owner CTA writes)
+  long long* lbl_row_out;  // fused: [B] LOCAL token row of the target (arg-max token for T = 32)
+  float* dq;          // [B, D] fp32, +=  (fused: unnormalised O, label column excluded)
   float* dlogit_dot;  // [B] fp32, += (nullable)
 };
 
@@ -55,6 +59,17 @@ int bank_ce_forward(const void* q, const void* bank, const long long* labels, fl
 int bank_ce_backward(const void* q, const void* bank, const long long* labels, float inv_tau, const float* lse,
                      float gscale, const float* gscale_dev, float label_smoothing, long long N_total, int B,
                      long long N, int D, int T, long long row_base, float* dq, float* dlogit_dot, cudaStream_t stream);
+int bank_stats(const void* bank, long long rows, int D, float* maxnorm, float* colsum, cudaStream_t stream);
+int bank_ce_prep(const void* q_src, int dtype, const void* bank, const long long* labels, float inv_tau,
+                 const float* maxnorm, int B, long long N, int D, int T, long long row_base, void* q16, float* ref,
+                 cudaStream_t stream);
+int bank_ce_fused(const void* q, const void* bank, const long long* labels, const float* ref, float inv_tau, int B,
+                  long long N, int D, int T, long long row_base, int init, float* o_acc, float* l_acc, float* s_t,
+                  long long* lbl_row, float* es_acc, float* bank_t, cudaStream_t stream);
+int bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, const float* bank_t, const float* ref,
+                     const float* es_acc, const void* q16, const float* colsum, float inv_tau, float gscale, float eps,
+                     long long N_total, int B, int D, float* lse, float* loss_q, float* loss_mean, float* dq,
+                     float* dlogit_dot, cudaStream_t stream);
 int merge_stats(const float* pm, const float* pl, const float* pst, const float* pss, int P, int B, float* m,
                 float* l, float* st, float* ss, cudaStream_t stream);
 int bank_ce_loss(const float* m, const float* l, const float* st, const float* ss, int B, long long N_total,

@@ -15,6 +15,7 @@
 //              backward SS, A = Q block (K-major smem); B = bank block (K-major), M128 N128 K16 x 4 per block.
 // GEMM2 (dq) : TS, A = P (TMEM, bf16), B = the same bank block bytes read MN-major, M128 N64 K16 x 8.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -223,7 +224,82 @@ __device__ __forceinline__ void bwd_chunk_t32(const uint32_t (&xr)[32], bool ent
     u[j >> 1] = pack_bf16x2(j == ja ? pg : 0.f, (j + 1) == ja ? pg : 0.f);
 }
 
+// Fused single pass (MODE 2), T == 1: P~ = exp2(x * scale - ref2) against a STATIC per-row reference (no online
+// rescaling: bf16 and fp32 share the 8-bit exponent, so partial sums of different CTAs simply add).  The label
+// column is captured (st) and excluded from P~ and l: the finalize step applies -(1 - p_t) bank_t in fp32.
+template <bool EXTRA>
+__device__ __forceinline__ void fused_chunk_t1(const uint32_t (&xr)[32], int valid, float scale, float ref2,
+                                               long long col0, long long lbl_row, float& l_run, float& st, float& es,
+                                               uint32_t* u) {
+  float p[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float pj = ex2_approx(fmaf(__uint_as_float(xr[j]), scale, -ref2));
+    if (j >= valid) pj = 0.f;
+    p[j] = pj;
+  }
+  if (lbl_row >= col0 && lbl_row < col0 + 32) {
+    const int jj = int(lbl_row - col0);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j == jj) {
+        st = __uint_as_float(xr[j]) * scale;
+        p[j] = 0.f;
+      }
+  }
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    s0 += p[j];
+    s1 += p[j + 1];
+    s2 += p[j + 2];
+    s3 += p[j + 3];
+  }
+  l_run += (s0 + s1) + (s2 + s3);
+  if (EXTRA) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      a0 = fmaf(p[j], __uint_as_float(xr[j]), a0);
+      a1 = fmaf(p[j + 1], __uint_as_float(xr[j + 1]), a1);
+    }
+    es = fmaf(a0 + a1, scale, es);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) u[j >> 1] = pack_bf16x2(p[j], p[j + 1]);
+}
+
+// Fused, T == 32: one entry per chunk; P~ sits on the (first) arg-max token.  tok = arg-max token of the chunk.
+template <bool EXTRA>
+__device__ __forceinline__ void fused_chunk_t32(const uint32_t (&xr)[32], bool entry_ok, float scale, float ref2,
+                                                bool is_label, float& l_run, float& st, int& st_tok, float& es,
+                                                uint32_t* u) {
+  float gm = __uint_as_float(xr[0]);
+  int ja = 0;
+#pragma unroll
+  for (int j = 1; j < 32; ++j) {
+    const float v = __uint_as_float(xr[j]);
+    if (v > gm) {
+      gm = v;
+      ja = j;
+    }
+  }
+  const float y = gm * scale;
+  float pg = entry_ok ? ex2_approx(y - ref2) : 0.f;
+  if (is_label) {
+    st = y;
+    st_tok = ja;
+    pg = 0.f;
+  }
+  l_run += pg;
+  if (EXTRA) es = fmaf(pg, y, es);
+#pragma unroll
+  for (int j = 0; j < 32; j += 2)
+    u[j >> 1] = pack_bf16x2(j == ja ? pg : 0.f, (j + 1) == ja ? pg : 0.f);
+}
+
 // ------------------------------------------------------------------------------------------------
+// MODE 0: forward statistics.  MODE 1: backward from a known lse.  MODE 2: fused single pass (statistics + O).
 template <int MODE, int T, bool EXTRA>
 __global__ void __launch_bounds__(kBankCEThreads, 1)
 bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_bank,
@@ -243,7 +319,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const int t_begin = int((long long)chunk * p.n_tiles / p.num_chunks);
   const int t_end = int((long long)(chunk + 1) * p.n_tiles / p.num_chunks);
   const int ntl = t_end - t_begin;
-  const int my_blocks = (MODE == 1) ? min(p.ow_blocks, p.kblocks - ds * p.ow_blocks) : 0;
+  const int my_blocks = (MODE >= 1) ? min(p.ow_blocks, p.kblocks - ds * p.ow_blocks) : 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -274,7 +350,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   if (warp == 0) {
     // ===================================================================== TMA producer (converged warp, one
     // elected lane issues; see elect_one())
-    if (MODE == 1) {
+    if (MODE >= 1) {
       if (elect_one()) {
         mbar_arrive_expect_tx(sm.q_full, uint32_t(p.kblocks) * kBlockBytes);
         for (int kb = 0; kb < p.kblocks; ++kb)
@@ -325,10 +401,10 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       } else {
         for (int kb = 0; kb < p.kblocks; ++kb) load_block(kb, t * kBN);
       }
-      if (MODE == 1 && t > t_begin)
+      if (MODE >= 1 && t > t_begin)
         for (int j = 0; j < my_blocks; ++j) load_block(ds * p.ow_blocks + j, (t - 1) * kBN);
     }
-    if (MODE == 1 && ntl > 0)
+    if (MODE >= 1 && ntl > 0)
       for (int j = 0; j < my_blocks; ++j) load_block(ds * p.ow_blocks + j, (t_end - 1) * kBN);
     TL_FLUSH(0)
   } else if (warp == 1) {
@@ -511,9 +587,11 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (EXTRA) p.part_ssum[o] = ssum;
       }
     } else {
-      const float lse2 = q_ok ? p.lse[q] * kLog2e : INFINITY;  // padded rows: p = exp2(-inf) = 0
-      const float gscale = p.gscale_dev ? p.gscale * __ldg(p.gscale_dev) : p.gscale;
-      float es = 0.f;
+      // MODE 1: lse2 = global log-sum-exp (log2 units); MODE 2: the static per-row reference
+      const float lse2 = q_ok ? (MODE == 1 ? p.lse[q] : p.ref[q]) * kLog2e : INFINITY;  // padded rows: p = 0
+      const float gscale = (MODE == 1 && p.gscale_dev) ? p.gscale * __ldg(p.gscale_dev) : p.gscale;
+      float es = 0.f, l_run = 0.f, st = -INFINITY;
+      int st_tok = 0;
       uint32_t u[64];
       for (int i = 0; i < ntl; ++i) {
         const int t = t_begin + i;
@@ -537,12 +615,18 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           if (T == 1) {
             const long long left = p.n_rows - col0;
             const int valid = left >= 32 ? 32 : (left > 0 ? int(left) : 0);
-            bwd_chunk_t1<EXTRA>(xr, valid, scale, lse2, p.eps_over_n, p.one_minus_eps, gscale, col0, lbl, es,
-                                &u[c * 16]);
+            if (MODE == 1)
+              bwd_chunk_t1<EXTRA>(xr, valid, scale, lse2, p.eps_over_n, p.one_minus_eps, gscale, col0, lbl, es,
+                                  &u[c * 16]);
+            else
+              fused_chunk_t1<EXTRA>(xr, valid, scale, lse2, col0, lbl, l_run, st, es, &u[c * 16]);
           } else {
             const long long entry = (long long)t * 4 + c;
-            bwd_chunk_t32<EXTRA>(xr, entry < p.N, scale, lse2, p.eps_over_n, p.one_minus_eps, gscale,
-                                 entry == lbl, es, &u[c * 16]);
+            if (MODE == 1)
+              bwd_chunk_t32<EXTRA>(xr, entry < p.N, scale, lse2, p.eps_over_n, p.one_minus_eps, gscale,
+                                   entry == lbl, es, &u[c * 16]);
+            else
+              fused_chunk_t32<EXTRA>(xr, entry < p.N, scale, lse2, entry == lbl, l_run, st, st_tok, es, &u[c * 16]);
           }
         }
         // P(i) -> TMEM once GEMM2 of the previous tile no longer reads the buffer
@@ -573,6 +657,13 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
         }
         if (EXTRA && q_ok && ds == 0) atomicAdd(&p.dlogit_dot[q], es * kLn2);
+        if (MODE == 2 && q_ok && ds == 0) {
+          atomicAdd(&p.l_acc[q], l_run);
+          if (st > -INFINITY) {  // this CTA owned the label column
+            p.st_out[q] = st * kLn2;
+            p.lbl_row_out[q] = (T == 1) ? lbl : lbl * 32 + st_tok;  // LOCAL token row whose gradient is -(1 - p_t)
+          }
+        }
       }
     }
 #ifdef SPN_TIMELINE
@@ -584,6 +675,171 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, MODE == 0 ? kTmemColsFwd : kTmemColsBwd);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused-path helpers (all tiny, HBM/latency-bound).
+__global__ void fused_init_kernel(float* o_acc, long long n_o, float* l_acc, float* st, long long* lbl_row, float* es,
+                                  float* loss_mean, int B) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = i; k < n_o / 4; k += stride) reinterpret_cast<float4*>(o_acc)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < B) {
+    l_acc[i] = 0.f;
+    st[i] = -INFINITY;
+    lbl_row[i] = -1;
+    if (es) es[i] = 0.f;
+  }
+  if (i == 0 && loss_mean) *loss_mean = 0.f;
+}
+
+// max row norm (atomicMax on the float bits: norms are non-negative) and optional column sums of a bf16 bank
+__global__ void bank_stats_kernel(const __nv_bfloat16* __restrict__ bank, long long rows, int D, float* maxnorm,
+                                  float* colsum) {
+  const int lane = threadIdx.x & 31, warp_in_blk = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float best = 0.f;
+  float2 cs[12];  // this lane's columns d = 64 k + 2 lane (+1), k < 12 (D <= 768), summed over the warp's rows
+#pragma unroll
+  for (int k = 0; k < 12; ++k) cs[k] = make_float2(0.f, 0.f);
+  for (long long r = (long long)blockIdx.x * wpb + warp_in_blk; r < rows; r += (long long)gridDim.x * wpb) {
+    const __nv_bfloat16* row = bank + r * D;
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int d = k * 64 + lane * 2;
+      if (d < D) {
+        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + d));
+        ss = fmaf(v.x, v.x, fmaf(v.y, v.y, ss));
+        cs[k].x += v.x;
+        cs[k].y += v.y;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    best = fmaxf(best, ss);
+  }
+  if (lane == 0 && best > 0.f) atomicMax(reinterpret_cast<int*>(maxnorm), __float_as_int(sqrtf(best)));
+  if (colsum) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int d = k * 64 + lane * 2;
+      if (d < D) {
+        atomicAdd(&colsum[d], cs[k].x);
+        atomicAdd(&colsum[d + 1], cs[k].y);
+      }
+    }
+  }
+}
+
+template <typename SrcT>
+__device__ __forceinline__ float load_as_f32(const SrcT* p, size_t i);
+template <>
+__device__ __forceinline__ float load_as_f32<float>(const float* p, size_t i) { return p[i]; }
+template <>
+__device__ __forceinline__ float load_as_f32<__half>(const __half* p, size_t i) { return __half2float(p[i]); }
+template <>
+__device__ __forceinline__ float load_as_f32<__nv_bfloat16>(const __nv_bfloat16* p, size_t i) { return __bfloat162float(p[i]); }
+
+// one warp per query: cast to bf16, |q|, approximate target logit -> static soft-max reference (natural units)
+//   bound = inv_tau |q| max|bank|  (Cauchy-Schwarz: every logit <= bound)
+//   ref   = min(bound, max(s_t + 30, bound - 64))
+// => every exponent s - ref <= 64 (no overflow, also of the sums), the target term is exp(-30) unless the clamp is
+// active; nothing relevant underflows as long as 2 * bound <= 218 nats (tau >= 0.0092 for unit-norm features).
+template <typename SrcT>
+__global__ void prep_query_kernel(const SrcT* __restrict__ q_src, const __nv_bfloat16* __restrict__ bank,
+                                  const long long* __restrict__ labels, float inv_tau, const float* __restrict__ maxnorm,
+                                  int B, long long N, int D, int T, long long row_base, __nv_bfloat16* __restrict__ q16,
+                                  float* __restrict__ ref) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(load_as_f32<SrcT>(q_src, size_t(b) * D + d));
+    q16[size_t(b) * D + d] = h;
+    const float v = __bfloat162float(h);
+    ss = fmaf(v, v, ss);
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  float r = inv_tau * sqrtf(ss) * (*maxnorm) * 1.01f + 1e-3f;
+  const long long g = labels[b] - row_base;
+  if (g >= 0 && g < N) {
+    float best = -INFINITY;
+    for (int tok = 0; tok < T; ++tok) {
+      const __nv_bfloat16* row = bank + (g * T + tok) * D;
+      float acc = 0.f;
+      for (int d = lane; d < D; d += 32)
+        acc = fmaf(__bfloat162float(__float2bfloat16_rn(load_as_f32<SrcT>(q_src, size_t(b) * D + d))), __bfloat162float(row[d]), acc);
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      best = fmaxf(best, acc);
+    }
+    r = fminf(r, fmaxf(best * inv_tau + 30.f, r - 64.f));
+  }
+  if (lane == 0) ref[b] = r;
+}
+
+// one warp per query: combine the fused kernel's partial sums into loss, lse and the unit gradient
+//   L = l_excl + exp(s_t - ref);  p_t = exp(s_t - ref) / L;  1 - p_t = l_excl / L   (no cancellation)
+//   dq = gscale * [ (o_excl - l_excl * bank_t) / L + eps * bank_t - (eps / N) * colsum ]
+__global__ void fused_finalize_kernel(const float* __restrict__ o_acc, const float* __restrict__ l_acc,
+                                      const float* __restrict__ st, const float* __restrict__ bank_t /*[B,D] fp32*/,
+                                      const float* __restrict__ ref, const float* __restrict__ es_acc,
+                                      const __nv_bfloat16* __restrict__ q16, const float* __restrict__ colsum,
+                                      float inv_tau, float gscale, float eps, float inv_n_total, int B, int D,
+                                      float* __restrict__ lse, float* __restrict__ loss_q, float* __restrict__ loss_mean,
+                                      float* __restrict__ dq, float* __restrict__ dlogit_dot) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float r = ref[b], s_t = st[b], lx = l_acc[b];
+  const float pt_u = expf(s_t - r);  // unnormalised target term (0 if the label is outside every shard)
+  const float L = lx + pt_u;
+  const float inv_L = 1.f / L;
+  const float z = r + logf(L);
+  float s_sum_over_n = 0.f;
+  if (eps != 0.f) {  // sum_n s_n / N = inv_tau * <q, colsum> / N
+    float acc = 0.f;
+    for (int d = lane; d < D; d += 32) acc = fmaf(__bfloat162float(q16[size_t(b) * D + d]), colsum[d], acc);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    s_sum_over_n = acc * inv_tau * inv_n_total;
+  }
+  const float loss = z - (1.f - eps) * s_t - eps * s_sum_over_n;
+  if (lane == 0) {
+    lse[b] = z;
+    if (loss_q) loss_q[b] = loss;
+    atomicAdd(loss_mean, loss / float(B));
+    if (dlogit_dot) {
+      // sum_n dlogit_n s_n = (es_excl - l_excl s_t) / L + eps s_t - eps * sum_n s_n / N
+      dlogit_dot[b] = (es_acc[b] - lx * s_t) * inv_L + eps * s_t - eps * s_sum_over_n;
+    }
+  }
+  if (dq) {
+    for (int d = lane * 4; d < D; d += 128) {
+      const float4 o = *reinterpret_cast<const float4*>(o_acc + size_t(b) * D + d);
+      const float4 t = *reinterpret_cast<const float4*>(bank_t + size_t(b) * D + d);
+      float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (eps != 0.f) c = *reinterpret_cast<const float4*>(colsum + d);
+      float4 g;
+      g.x = gscale * ((o.x - lx * t.x) * inv_L + eps * t.x - eps * inv_n_total * c.x);
+      g.y = gscale * ((o.y - lx * t.y) * inv_L + eps * t.y - eps * inv_n_total * c.y);
+      g.z = gscale * ((o.z - lx * t.z) * inv_L + eps * t.z - eps * inv_n_total * c.z);
+      g.w = gscale * ((o.w - lx * t.w) * inv_L + eps * t.w - eps * inv_n_total * c.w);
+      *reinterpret_cast<float4*>(dq + size_t(b) * D + d) = g;
+    }
+  }
+}
+
+// bank_t[b] = fp32 copy of the local token row the fused kernel reported for query b (zeros if not in this shard)
+__global__ void gather_label_rows_kernel(const __nv_bfloat16* __restrict__ bank, const long long* __restrict__ lbl_row,
+                                         int B, int D, float* __restrict__ out) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const long long r = lbl_row[b];
+  for (int d = lane * 2; d < D; d += 64) {
+    float2 v = make_float2(0.f, 0.f);
+    if (r >= 0) v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(bank + r * D + d));
+    *reinterpret_cast<float2*>(out + size_t(b) * D + d) = v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -768,6 +1024,84 @@ int bank_ce_backward(const void* q, const void* bank, const long long* labels, f
   else        rc = extra ? launch_one<1, 32, true>(tq, tb, p, plan.grid, plan.smem_bytes, stream)
                          : launch_one<1, 32, false>(tq, tb, p, plan.grid, plan.smem_bytes, stream);
   return rc;
+}
+
+int bank_stats(const void* bank, long long rows, int D, float* maxnorm, float* colsum, cudaStream_t stream) {
+  SPN_REQUIRE(rows > 0 && D >= 64 && D <= 768 && D % 64 == 0, SPN_ERR_BAD_SHAPE, "bank_stats: bad shape rows=%lld D=%d", rows, D);
+  SPN_CUDA_CHECK(cudaMemsetAsync(maxnorm, 0, sizeof(float), stream));
+  if (colsum) SPN_CUDA_CHECK(cudaMemsetAsync(colsum, 0, sizeof(float) * size_t(D), stream));
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  bank_stats_kernel<<<sms * 4, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(bank), rows, D, maxnorm, colsum);
+  SPN_CUDA_CHECK(cudaGetLastError());
+  return SPN_OK;
+}
+
+int bank_ce_prep(const void* q_src, int dtype, const void* bank, const long long* labels, float inv_tau,
+                 const float* maxnorm, int B, long long N, int D, int T, long long row_base, void* q16, float* ref,
+                 cudaStream_t stream) {
+  SPN_REQUIRE(B > 0 && N > 0 && D > 0, SPN_ERR_BAD_SHAPE, "bank_ce_prep: bad shape");
+  const __nv_bfloat16* bk = static_cast<const __nv_bfloat16*>(bank);
+  __nv_bfloat16* qo = static_cast<__nv_bfloat16*>(q16);
+  const int grid = (B + 7) / 8;
+  switch (dtype) {
+    case SPN_F32: prep_query_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(q_src), bk, labels, inv_tau, maxnorm, B, N, D, T, row_base, qo, ref); break;
+    case SPN_F16: prep_query_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(q_src), bk, labels, inv_tau, maxnorm, B, N, D, T, row_base, qo, ref); break;
+    case SPN_BF16: prep_query_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(q_src), bk, labels, inv_tau, maxnorm, B, N, D, T, row_base, qo, ref); break;
+    default: return fail(SPN_ERR_BAD_DTYPE, "bank_ce_prep: unknown dtype %d", dtype);
+  }
+  SPN_CUDA_CHECK(cudaGetLastError());
+  return SPN_OK;
+}
+
+int bank_ce_fused(const void* q, const void* bank, const long long* labels, const float* ref, float inv_tau, int B,
+                  long long N, int D, int T, long long row_base, int init, float* o_acc, float* l_acc, float* s_t,
+                  long long* lbl_row, float* es_acc, float* bank_t, cudaStream_t stream) {
+  BankCEPlan plan;
+  int rc = bank_ce_plan(1, B, N, D, T, &plan);
+  if (rc != SPN_OK) return rc;
+  SPN_REQUIRE(inv_tau > 0.f && isfinite(inv_tau), SPN_ERR_BAD_ARG, "inv_tau must be positive and finite (got %g)", inv_tau);
+  SPN_REQUIRE(aligned16(o_acc), SPN_ERR_BAD_ALIGN, "bank_ce_fused: o_acc must be 16-byte aligned");
+  CUtensorMap tq, tb;
+  if ((rc = make_tmap_bf16_2d(&tq, q, uint64_t(B), uint64_t(D), kBM)) != SPN_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tb, bank, uint64_t(N) * T, uint64_t(D), kBN)) != SPN_OK) return rc;
+  if (init) {
+    fused_init_kernel<<<148, 256, 0, stream>>>(o_acc, (long long)B * D, l_acc, s_t, lbl_row, es_acc, nullptr, B);
+    SPN_CUDA_CHECK(cudaGetLastError());
+  }
+  BankCEParams p{};
+  p.B = B; p.D = D; p.N = N; p.n_rows = N * T; p.kblocks = plan.kblocks; p.stages = plan.stages; p.bps = plan.bps;
+  p.n_tiles = plan.n_tiles; p.q_tiles = plan.q_tiles; p.num_chunks = plan.num_chunks;
+  p.num_dsplit = plan.num_dsplit; p.ow_blocks = plan.ow_blocks; p.scale_log2 = inv_tau * kLog2e;
+  p.row_base = row_base; p.labels = labels; p.ref = ref; p.gscale = 1.f; p.dq = o_acc; p.dlogit_dot = es_acc;
+  p.l_acc = l_acc; p.st_out = s_t; p.lbl_row_out = lbl_row;
+  const bool extra = es_acc != nullptr;
+  if (T == 1) rc = extra ? launch_one<2, 1, true>(tq, tb, p, plan.grid, plan.smem_bytes, stream)
+                         : launch_one<2, 1, false>(tq, tb, p, plan.grid, plan.smem_bytes, stream);
+  else        rc = extra ? launch_one<2, 32, true>(tq, tb, p, plan.grid, plan.smem_bytes, stream)
+                         : launch_one<2, 32, false>(tq, tb, p, plan.grid, plan.smem_bytes, stream);
+  if (rc != SPN_OK) return rc;
+  if (bank_t) {
+    gather_label_rows_kernel<<<(B + 7) / 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(bank), lbl_row, B, D, bank_t);
+    SPN_CUDA_CHECK(cudaGetLastError());
+  }
+  return SPN_OK;
+}
+
+int bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, const float* bank_t, const float* ref,
+                     const float* es_acc, const void* q16, const float* colsum, float inv_tau, float gscale, float eps,
+                     long long N_total, int B, int D, float* lse, float* loss_q, float* loss_mean, float* dq,
+                     float* dlogit_dot, cudaStream_t stream) {
+  SPN_REQUIRE(B > 0 && D % 4 == 0 && N_total > 0, SPN_ERR_BAD_SHAPE, "bank_ce_finalize: bad shape");
+  SPN_REQUIRE(eps == 0.f || (colsum && q16), SPN_ERR_BAD_ARG, "label smoothing needs the bank column sums and q");
+  SPN_REQUIRE(!dlogit_dot || es_acc, SPN_ERR_BAD_ARG, "dlogit_dot needs es_acc");
+  SPN_REQUIRE(!dq || (aligned16(dq) && aligned16(o_acc) && aligned16(bank_t)), SPN_ERR_BAD_ALIGN, "bank_ce_finalize: 16-byte alignment");
+  SPN_CUDA_CHECK(cudaMemsetAsync(loss_mean, 0, sizeof(float), stream));
+  fused_finalize_kernel<<<(B + 7) / 8, 256, 0, stream>>>(o_acc, l_acc, s_t, bank_t, ref, es_acc,
+                                                        static_cast<const __nv_bfloat16*>(q16), colsum, inv_tau, gscale,
+                                                        eps, 1.f / float(N_total), B, D, lse, loss_q, loss_mean, dq, dlogit_dot);
+  SPN_CUDA_CHECK(cudaGetLastError());
+  return SPN_OK;
 }
 
 int merge_stats(const float* pm, const float* pl, const float* pst, const float* pss, int P, int B, float* m,

@@ -22,11 +22,14 @@ def bf16_round(x):
     return x.to(torch.bfloat16).float()
 
 
-def run_ours(q, bank, labels, tau, eps=0.0, grad_out=1.0, tau_tensor=False):
+PATHS = pytest.mark.parametrize("single_pass", [False, True], ids=["two_pass", "fused"])
+
+
+def run_ours(q, bank, labels, tau, eps=0.0, grad_out=1.0, tau_tensor=False, single_pass=None):
     qd = q.to(DEV).requires_grad_(True)
     db = spn.DeviceBank.from_tensor(bank, DEV)
     t = torch.tensor(tau, device=DEV, requires_grad=True) if tau_tensor else tau
-    loss = spn.bank_infonce(qd, db, labels.to(DEV), t, label_smoothing=eps)
+    loss = spn.bank_infonce(qd, db, labels.to(DEV), t, label_smoothing=eps, single_pass=single_pass)
     (loss * grad_out).backward()
     torch.cuda.synchronize()
     return loss.detach().cpu(), qd.grad.detach().cpu(), (t.grad.detach().cpu() if tau_tensor else None)
@@ -45,10 +48,11 @@ CASES = [
 ]
 
 
+@PATHS
 @pytest.mark.parametrize("B,N,D,mode,tau,seed", CASES)
-def test_loss_and_grad_match_oracle(B, N, D, mode, tau, seed):
+def test_loss_and_grad_match_oracle(B, N, D, mode, tau, seed, single_pass):
     q, bank, labels = synth.make_bank_case(B, N, D, 1, mode, seed)
-    loss, dq, dtau = run_ours(q, bank, labels, tau, tau_tensor=True)
+    loss, dq, dtau = run_ours(q, bank, labels, tau, tau_tensor=True, single_pass=single_pass)
     # (i) end-to-end vs the fp32 oracle on the original operands
     o_loss, o_dq, o_dtau = obank.infonce_loss_and_grads(q, bank, labels, tau, dtype=torch.float64)
     assert abs(loss.item() - o_loss.item()) <= 1e-2 * max(abs(o_loss.item()), 1e-3), (loss, o_loss)
@@ -60,11 +64,12 @@ def test_loss_and_grad_match_oracle(B, N, D, mode, tau, seed):
     assert rel_l2(dq, r_dq) < 3e-3, rel_l2(dq, r_dq)
 
 
+@PATHS
 @pytest.mark.parametrize("name", ["small_ragged", "small_uniform", "c1", "c1_uniform"])
-def test_against_reference_fixtures(golden, name):
+def test_against_reference_fixtures(golden, name, single_pass):
     g = golden(f"bank_ce_{name}")
     q, bank, labels = synth.make_bank_case(int(g["B"]), int(g["N"]), int(g["D"]), 1, str(g["mode"]), int(g["seed"]))
-    loss, dq, _ = run_ours(q, bank, labels, float(g["tau"]))
+    loss, dq, _ = run_ours(q, bank, labels, float(g["tau"]), single_pass=single_pass)
     ref_loss, ref_dq = float(g["loss"]), torch.from_numpy(g["dq"])
     assert abs(loss.item() - ref_loss) <= 1e-2 * max(abs(ref_loss), 1e-3), (loss.item(), ref_loss)
     assert rel_l2(dq, ref_dq) < 1e-2, rel_l2(dq, ref_dq)
@@ -92,22 +97,24 @@ def test_input_dtypes_fp16_bf16():
         assert abs(loss.item() - ref.item()) <= 2e-2 * abs(ref.item())
 
 
-def test_label_smoothing():
+@PATHS
+def test_label_smoothing(single_pass):
     q, bank, labels = synth.make_bank_case(40, 900, 128, 1, "U", 10)
     tau, eps = 0.05, 0.1
-    loss, dq, _ = run_ours(q, bank, labels, tau, eps=eps)
+    loss, dq, _ = run_ours(q, bank, labels, tau, eps=eps, single_pass=single_pass)
     o_loss, o_dq, _ = obank.infonce_loss_and_grads(q, bank, labels, tau, label_smoothing=eps, dtype=torch.float64)
     assert abs(loss.item() - o_loss.item()) <= 1e-2 * abs(o_loss.item())
     assert rel_l2(dq, o_dq) < 1e-2
 
 
+@PATHS
 @pytest.mark.parametrize("B,N,seed", [(6, 50, 11), (130, 1000, 12), (32, 37, 13)])
-def test_blip2_max_over_tokens(B, N, seed):
+def test_blip2_max_over_tokens(B, N, seed, single_pass):
     T, D, temp = 32, 256, 0.05
     f, bank3, labels = synth.make_bank_case(B, N, D, T, "S", seed)
     fd = f.to(DEV).requires_grad_(True)
     tp = torch.nn.Parameter(torch.tensor(temp, device=DEV))
-    out = spn.compat.forward_stage2_loss(fd, bank3.to(DEV), labels.to(DEV), tp)
+    out = {"loss_qtc": spn.bank_infonce(fd, bank3.to(DEV), labels.to(DEV), tp, single_pass=single_pass)}
     out["loss_qtc"].backward()
     o_loss, o_df, o_dt = obank.blip2_loss_and_grads(f, bank3, labels, temp, dtype=torch.float64)
     assert abs(out["loss_qtc"].item() - o_loss.item()) <= 1e-2 * max(abs(o_loss.item()), 1e-3)
@@ -182,14 +189,20 @@ def test_c3_full_size_properties():
     lab = labels.to(DEV)
     qd = q.to(DEV).requires_grad_(True)
     db = spn.DeviceBank.from_tensor(bank, DEV)
-    loss = spn.bank_infonce(qd, db, lab, tau)
+    loss = spn.bank_infonce(qd, db, lab, tau, single_pass=False)
     loss.backward()
+    qs = q.to(DEV).requires_grad_(True)
+    loss_fused = spn.bank_infonce(qs, db, lab, tau, single_pass=True)
+    loss_fused.backward()
+    assert abs(loss_fused.item() - loss.item()) <= 1e-4 * max(abs(loss.item()), 1e-3), (loss_fused.item(), loss.item())
+    assert rel_l2(qs.grad, qd.grad) < 5e-3, rel_l2(qs.grad, qd.grad)
     # (a) dense fp32 reference on the device
     qf = q.to(DEV).requires_grad_(True)
     ref = torch.nn.functional.cross_entropy((qf @ bank.to(DEV).T) / tau, lab)
     ref.backward()
     assert abs(loss.item() - ref.item()) <= 1e-2 * abs(ref.item()), (loss.item(), ref.item())
     assert rel_l2(qd.grad, qf.grad) < 1e-2, rel_l2(qd.grad, qf.grad)
+    assert rel_l2(qs.grad, qf.grad) < 1e-2, rel_l2(qs.grad, qf.grad)
     # (b) 8 shards
     from spn4cir_b200.ops import _bwd, _loss_from_stats, cast_to_bf16
     R = 8
@@ -212,3 +225,54 @@ def test_c3_full_size_properties():
     dense[torch.arange(cfg["B"], device=DEV), lab] -= 1.0
     want = (dense @ shifted.data.float()) * ((1 / tau) / cfg["B"])
     assert rel_l2(dq_a, want) < 3e-3, rel_l2(dq_a, want)
+
+
+def test_fused_static_reference_extremes():
+    """Inside its envelope (inv_tau |q| max|bank| <= 109 nats) the static reference must survive the worst rows:
+    a query anti-aligned with its target and aligned with another entry (s_max - s_t ~ 1.4 / tau)."""
+    g = torch.Generator().manual_seed(3)
+    D, N, B = 128, 700, 24
+    bank = torch.nn.functional.normalize(torch.randn((N, D), generator=g), dim=-1)
+    labels = torch.randint(0, N, (B,), generator=g)
+    q = torch.nn.functional.normalize(torch.randn((B, D), generator=g), dim=-1)
+    other = (labels + 7) % N
+    q[:8] = torch.nn.functional.normalize(-0.9 * bank[labels[:8]] + 0.9 * bank[other[:8]] + 0.05 * q[:8], dim=-1)
+    for tau in (0.01, 0.02, 0.07):
+        loss, dq, dtau = run_ours(q, bank, labels, tau, tau_tensor=True, single_pass=True)
+        o_loss, o_dq, o_dtau = obank.infonce_loss_and_grads(bf16_round(q), bf16_round(bank), labels, tau, dtype=torch.float64)
+        assert torch.isfinite(loss) and torch.isfinite(dq).all(), tau
+        assert abs(loss.item() - o_loss.item()) <= 2e-3 * max(abs(o_loss.item()), 1.0), (tau, loss, o_loss)
+        assert rel_l2(dq, o_dq) < 4e-3, (tau, rel_l2(dq, o_dq))
+        assert abs(dtau.item() - o_dtau.item()) <= 1e-2 * max(abs(o_dtau.item()), 1e-2)
+
+
+def test_cold_temperature_and_unnormalised_queries_take_the_exact_path():
+    """Outside the envelope (tau = 0.004, or |q| = 3) the default must stay correct (two-pass, running maximum)."""
+    g = torch.Generator().manual_seed(5)
+    D, N, B = 128, 900, 16
+    bank = torch.nn.functional.normalize(torch.randn((N, D), generator=g), dim=-1)
+    labels = torch.randint(0, N, (B,), generator=g)
+    q = torch.nn.functional.normalize(torch.randn((B, D), generator=g), dim=-1)
+    loss, dq, _ = run_ours(q, bank, labels, 0.004)  # default path selection
+    o_loss, o_dq, _ = obank.infonce_loss_and_grads(bf16_round(q), bf16_round(bank), labels, 0.004, dtype=torch.float64)
+    assert abs(loss.item() - o_loss.item()) <= 2e-3 * max(abs(o_loss.item()), 1.0)
+    assert rel_l2(dq, o_dq) < 4e-3
+    loss, dq, _ = run_ours(3.0 * q, bank, labels, 0.02, single_pass=False)
+    o_loss, o_dq, _ = obank.infonce_loss_and_grads(bf16_round(3.0 * q), bf16_round(bank), labels, 0.02, dtype=torch.float64)
+    assert abs(loss.item() - o_loss.item()) <= 2e-3 * max(abs(o_loss.item()), 1.0)
+    assert rel_l2(dq, o_dq) < 4e-3
+
+
+def test_peaked_softmax_has_no_cancellation():
+    """p_t -> 1 (1 - p_t ~ 1e-3): dq = -(1 - p_t) bank_t + sum_{n != t} p_n bank_n must keep its relative accuracy
+    (the one-hot never passes through the bf16 rounding of P)."""
+    g = torch.Generator().manual_seed(4)
+    D, N, B = 256, 3000, 64
+    bank = torch.nn.functional.normalize(torch.randn((N, D), generator=g), dim=-1)
+    labels = torch.randint(0, N, (B,), generator=g)
+    q = torch.nn.functional.normalize(bank[labels] + 1.55 * torch.randn((B, D), generator=g) / D ** 0.5, dim=-1)
+    for sp in (True, False):
+        loss, dq, _ = run_ours(q, bank, labels, 0.02, single_pass=sp)
+        o_loss, o_dq, _ = obank.infonce_loss_and_grads(bf16_round(q), bf16_round(bank), labels, 0.02, dtype=torch.float64)
+        assert 1e-7 < o_loss.item() < 5e-2, o_loss.item()
+        assert rel_l2(dq, o_dq) < 4e-3, (sp, rel_l2(dq, o_dq))
