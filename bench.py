@@ -158,7 +158,11 @@ def run_ours(args, cfg):
     bank_cpu = synth.make_bank(N, D, 1, seed=1234)
     labels_cpu = synth.make_labels(B, N, seed=1235 + rank)
     q_cpu = synth.make_queries(bank_cpu, labels_cpu, "S", seed=1236 + rank)
-    bank = spn.DeviceBank.from_tensor(bank_cpu, dev, shard_rank=rank, shard_world=world)
+    # N > 1, default: queries are the sharded unit (each rank scores its own B queries against a full bank replica,
+    # 128 MB of 180 GB: no collective on the path).  --bank-sharded: bank rows split across ranks, all queries scored
+    # by every rank, partial sums exchanged over NCCL.
+    sharded = world > 1 and args.bank_sharded
+    bank = spn.DeviceBank.from_tensor(bank_cpu, dev, shard_rank=rank if sharded else 0, shard_world=world if sharded else 1)
     q_dev = q_cpu.to(dev)
     labels_dev = labels_cpu.to(dev)
     q_pin = q_cpu.pin_memory()
@@ -167,7 +171,7 @@ def run_ours(args, cfg):
 
     def step(qin, lab):
         qx = qin.detach().requires_grad_(True)
-        if world > 1:
+        if sharded:
             loss = bank_infonce_sharded(qx, bank, lab, tau)
         else:
             loss = spn.bank_infonce(qx, bank, lab, tau)
@@ -232,11 +236,11 @@ def run_ours(args, cfg):
 
     # ---- dominant-kernel roofline: backward kernel (and forward kernel) timed alone, same events/stream
     from spn4cir_b200.ops import _bwd, _fwd_stats, _loss_from_stats, cast_to_bf16
-    Bt = B * world
-    q16 = cast_to_bf16(torch.cat([q_dev] * world) if world > 1 else q_dev)
-    lab_all = torch.cat([labels_dev] * world) if world > 1 else labels_dev
+    Bt = B * world if sharded else B
+    q16 = cast_to_bf16(torch.cat([q_dev] * world) if sharded else q_dev)
+    lab_all = torch.cat([labels_dev] * world) if sharded else labels_dev
     stats = _fwd_stats(q16, bank, lab_all, 1.0 / tau, False)
-    if world > 1:
+    if sharded:
         from spn4cir_b200.dist import merge_stats_across_ranks
         stats = merge_stats_across_ranks(stats)
     lse, _, _ = _loss_from_stats(stats, bank.n_total, 0.0)
@@ -246,7 +250,7 @@ def run_ours(args, cfg):
                   args.steps) / args.steps
     from spn4cir_b200.ops import _fused_sweep
     from spn4cir_b200._lib import call as _call
-    sw = _fused_sweep(torch.cat([q_dev] * world) if world > 1 else q_dev, bank, lab_all, 1.0 / tau, False)
+    sw = _fused_sweep(torch.cat([q_dev] * world) if sharded else q_dev, bank, lab_all, 1.0 / tau, False)
 
     def fused_only():
         _call("spn_bank_ce_fused", sw["q16"].data_ptr(), bank.data.data_ptr(), lab_all.data_ptr(), sw["ref"].data_ptr(),
@@ -278,7 +282,7 @@ def run_ours(args, cfg):
                                     "kernel_ms": t_bwd * 1e3},
                 "step": {"algorithmic_tflops": step_flops_rank / (t_dev / args.steps) / 1e12,
                          "frac": step_flops_rank / (t_dev / args.steps) / 1e12 / peak}}
-        prof = REPO / "profiles" / "r01_ncu_bank_ce_bwd.json"
+        prof = REPO / "profiles" / "r01_ncu_bank_ce_fused.json"
         if prof.exists():
             try:
                 roof["traffic"] = json.loads(prof.read_text()).get("dram_bytes_per_launch")
@@ -288,7 +292,9 @@ def run_ours(args, cfg):
                 "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"{args.config}: bank-CE fwd+bwd, B={B} queries/rank x N={N} x D={D} bank (bf16, fp32 accumulate), tau={tau}",
-                           "parallelism": f"bank row-sharded x{world}, queries data-parallel (all-gathered), stats all-gather + dq reduce-scatter" if world > 1 else "single GPU",
+                           "parallelism": ("single GPU" if world == 1 else
+                                           f"bank row-sharded x{world}, queries data-parallel (bf16 all-gather), reference MIN all-reduce + reduce-scatter of the additive partials" if sharded else
+                                           f"queries data-parallel x{world} (the sharded unit), bank replicated per GPU ({N * D * 2 / 1e6:.0f} MB bf16): no collective on the path"),
                            "l2": "256 MiB flush buffer written before every timed iteration",
                            "global_batch": B * world},
                 "clocks": clocks, "roofline": roof,
@@ -357,6 +363,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-retrieval", action="store_true")
     ap.add_argument("--profile", action="store_true", help="under ncu: 1 warm-up + K timed steps, nothing else")
+    ap.add_argument("--bank-sharded", action="store_true",
+                    help="N > 1: row-shard the bank across ranks (one NCCL exchange per step) instead of replicating it")
     args = ap.parse_args()
     cfg = synth.CONFIGS[args.config]
     if args.impl == "reference":

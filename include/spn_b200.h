@@ -197,6 +197,10 @@ int spn_debug_umma_gemm(const void* a_bf16, const void* b_bf16, float* c, int N,
 int spn_debug_umma_bench(const void* b_src, int64_t b_rows, int N, int iters, int mode, int tma_on,
                          unsigned long long* out_cycles, int grid, void* stream);
 
+/* Debug: distributed-shared-memory store bandwidth probe (clusters of 4 CTAs; ranks 0/1 write iters x 32 KiB to
+ * rank 2, and to rank 3 as well when ndst == 2).  out_cycles: device uint64[grid] (0 for receiver CTAs). */
+int spn_debug_dsmem_bench(int iters, int ndst, unsigned long long* out_cycles, int grid, void* stream);
+
 /* Debug: per-CTA role cycle counters of the last bank-CE launch (16 x uint64 per CTA); only in builds made
  * with -DSPN_TIMELINE, otherwise SPN_ERR_BAD_ARG. host_out is a HOST pointer. */
 int spn_debug_read_timeline(unsigned long long* host_out, int n);

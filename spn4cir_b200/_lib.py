@@ -111,6 +111,7 @@ _SIGNATURES = {
     "spn_sim_matrix": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "spn_debug_read_timeline": [c_void_p, c_int],
     "spn_debug_umma_bench": [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
+    "spn_debug_dsmem_bench": [c_int, c_int, c_void_p, c_int, c_void_p],
     "spn_debug_umma_gemm": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["spn_last_error"])

@@ -187,6 +187,11 @@ int spn_debug_umma_bench(const void* b_src, int64_t b_rows, int N, int iters, in
   return debug_umma_bench(b_src, b_rows, N, iters, mode, tma_on, out_cycles, grid, as_stream(stream));
 }
 
+int spn_debug_dsmem_bench(int iters, int ndst, unsigned long long* out_cycles, int grid, void* stream) {
+  SPN_REQUIRE(out_cycles && iters > 0, SPN_ERR_BAD_ARG, "spn_debug_dsmem_bench: bad arguments");
+  return debug_dsmem_bench(iters, ndst, out_cycles, grid, as_stream(stream));
+}
+
 int spn_debug_umma_gemm(const void* a_bf16, const void* b_bf16, float* c, int N, int K, int mode, void* stream) {
   SPN_REQUIRE(a_bf16 && b_bf16 && c, SPN_ERR_BAD_ARG, "spn_debug_umma_gemm: NULL pointer");
   return debug_umma_gemm(a_bf16, b_bf16, c, N, K, mode, as_stream(stream));

@@ -83,6 +83,8 @@ int debug_umma_gemm(const void* a, const void* b, float* c, int N, int K, int mo
 int debug_umma_bench(const void* b_src, long long b_rows, int N, int iters, int mode, int tma_on,
                      unsigned long long* out_cycles, int grid, cudaStream_t stream);
 
+int debug_dsmem_bench(int iters, int ndst, unsigned long long* out_cycles, int grid, cudaStream_t stream);
+
 // prologue kernels (prologue.cu)
 int cast_to_bf16(const void* src, int src_dtype, void* dst, long long n, cudaStream_t stream);
 int query_assemble(const float* refer_bank, const long long* refer_idx, const float* text, int B, int D, void* q_bf16,

@@ -149,11 +149,21 @@ umma_bench_kernel(const __grid_constant__ CUtensorMap tmap_b, int N, int iters, 
     const uint64_t bdesc = make_smem_desc_sw128(smem_u32(b_smem), 16, 1024);
     const long long t0 = clock64();
     if (elect_one()) {
+      const uint32_t idesc64 = make_idesc_bf16_f32(128, 64, 0, 0);
       for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (mode & 1) umma_ts_f16(tmem_base, tmem_base + 256u + uint32_t(k) * 8u, bdesc + uint64_t(k * 2), idesc, 1);
-          else          umma_ss_f16(tmem_base, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, 1);
+          // bit1: alternate between two independent accumulators; bit2: "fused" pattern = SS N into D0 followed by
+          // a TS N=64 MMA into D1 (one GEMM1 + one GEMM2 instruction)
+          const uint32_t d = (mode & 2) ? tmem_base + ((k & 1) ? 256u : 0u) : tmem_base;
+          if (mode & 4) {
+            umma_ss_f16(tmem_base, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, 1);
+            umma_ts_f16(tmem_base + 256u, tmem_base + 384u + uint32_t(k) * 8u, bdesc + uint64_t(k * 2), idesc64, 1);
+          } else if (mode & 1) {
+            umma_ts_f16(d, tmem_base + 384u + uint32_t(k) * 8u, bdesc + uint64_t(k * 2), idesc, 1);
+          } else {
+            umma_ss_f16(d, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, 1);
+          }
         }
       }
       umma_commit(done);
@@ -192,7 +202,46 @@ umma_bench_kernel(const __grid_constant__ CUtensorMap tmap_b, int N, int iters, 
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// ---- DSMEM store bandwidth probe: clusters of 4; ranks 0/1 write `iters` x 32 KiB to rank 2 (and rank 3 when
+// ndst == 2) with st.shared::cluster.v4, the way an S-CTA would ship bf16 P tiles to O-CTAs.
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(128, 1)
+dsmem_bench_kernel(int iters, int ndst, unsigned long long* __restrict__ out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t rank = cluster_ctarank();
+  uint8_t* buf = smem_raw;  // 2 x 32 KiB landing zones (one per writer) in the receivers
+  cluster_sync_all();
+  if (rank < 2) {
+    const uint32_t local = smem_u32(buf) + rank * 32768u + threadIdx.x * 256u;
+    const uint32_t d0 = mapa_shared(local, 2), d1 = mapa_shared(local, 3);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int v = 0; v < 16; ++v) {
+        st_cluster_v4(d0 + v * 16, it, v, rank, 1);
+        if (ndst == 2) st_cluster_v4(d1 + v * 16, it, v, rank, 2);
+      }
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) out_cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
+  } else if (threadIdx.x == 0) {
+    out_cycles[blockIdx.x] = 0;
+  }
+  cluster_sync_all();  // no CTA may exit while its shared memory can still be written remotely
+}
+
 }  // namespace
+
+int debug_dsmem_bench(int iters, int ndst, unsigned long long* out_cycles, int grid, cudaStream_t stream) {
+  int rc;
+  if ((rc = require_sm100()) != SPN_OK) return rc;
+  SPN_REQUIRE(grid % 4 == 0 && grid > 0, SPN_ERR_BAD_SHAPE, "dsmem bench grid must be a multiple of 4");
+  const size_t smem = 65536;
+  SPN_CUDA_CHECK(cudaFuncSetAttribute(dsmem_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  dsmem_bench_kernel<<<grid, 128, smem, stream>>>(iters, ndst, out_cycles);
+  SPN_CUDA_CHECK(cudaGetLastError());
+  return SPN_OK;
+}
 
 int debug_umma_bench(const void* b_src, long long b_rows, int N, int iters, int mode, int tma_on,
                      unsigned long long* out_cycles, int grid, cudaStream_t stream) {

@@ -3,8 +3,9 @@
 One process per GPU; torch.distributed (NCCL on GPUs, gloo in the CPU tests) is the plumbing.  Each rank
 scores ALL queries of the step against its own bank rows; one small exchange merges the partials:
 
-  bank-CE forward : all_gather of [4, B_total] statistics (m, l, s_t, s_sum) -> spn_merge_stats
-  bank-CE backward: reduce_scatter(sum) of the fp32 dq partials [B_total, D] -> each rank keeps its rows
+  bank-CE (fused single pass): MIN all-reduce of the static soft-max reference [B_total], then reduce_scatter(sum)
+                   of the additive partials o_acc / bank_t [B_total, D] and a small all_reduce of (l, s_t, es)
+  bank-CE statistics only  : all_gather of [4, B_total] (m, l, s_t, s_sum) -> spn_merge_stats
   retrieval       : all_gather of [Q, K] (value, index) lists -> spn_merge_topk; ranks are summed counts.
 
 Queries are data-parallel (each rank brings B_local queries, all-gathered as bf16 before scoring), so
@@ -50,53 +51,84 @@ def _all_gather_stacked(x: torch.Tensor, world: int, group) -> torch.Tensor:
     return flat.view(world, *x.shape)
 
 
+def global_maxnorm(bank, group=None) -> torch.Tensor:
+    """max row norm over ALL shards (device float [1]); one MAX all-reduce per bank, cached on the DeviceBank."""
+    if getattr(bank, "_maxnorm_global", None) is None:
+        mx = bank.stats()[0].clone()
+        if _world(group)[1] > 1:
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+        bank._maxnorm_global = mx
+    return bank._maxnorm_global
+
+
 class _ShardedBankCE(torch.autograd.Function):
+    """Single-pass bank-CE over a row-sharded bank.  Every rank sweeps its shard for ALL queries of the step with
+    the fused kernel (static soft-max reference agreed by one MIN all-reduce); the additive partial sums travel in
+    two reduce_scatters (o_acc, bank_t: [B_total, D] fp32) and one small all_reduce (l, s_t, es); each rank
+    finalises its own rows."""
+
     @staticmethod
     def forward(ctx, q_local, tau_t, bank, labels_local, inv_tau, eps, group):
-        from .ops import _fwd_stats, _loss_from_stats, cast_to_bf16
+        from ._lib import call
+        from .ops import _TORCH2SPN, _fused_finalize, _ptr, _stream, cast_to_bf16
         rank, world = _world(group)
-        B = q_local.shape[0]
+        B, D = q_local.shape
+        dev = q_local.device
+        tau_grad = tau_t is not None and tau_t.requires_grad
         q16 = cast_to_bf16(q_local)
         if world > 1:
-            q_all = torch.empty((world * B, q16.shape[1]), dtype=q16.dtype, device=q16.device)
+            q_all = torch.empty((world * B, D), dtype=q16.dtype, device=dev)
             dist.all_gather_into_tensor(q_all, q16, group=group)
-            lab_all = torch.empty(world * B, dtype=labels_local.dtype, device=labels_local.device)
+            lab_all = torch.empty(world * B, dtype=labels_local.dtype, device=dev)
             dist.all_gather_into_tensor(lab_all, labels_local, group=group)
         else:
             q_all, lab_all = q16, labels_local
-        stats = _fwd_stats(q_all, bank, lab_all, inv_tau, eps != 0.0)
-        stats = merge_stats_across_ranks(stats, group)
-        lse, loss_q, _ = _loss_from_stats(stats, bank.n_total, eps)
-        ctx.bank, ctx.inv_tau, ctx.eps, ctx.group = bank, inv_tau, eps, group
-        ctx.q_dtype, ctx.B, ctx.rank, ctx.world = q_local.dtype, B, rank, world
-        ctx.tau_needs_grad = tau_t is not None and tau_t.requires_grad
-        ctx.save_for_backward(q_all, lab_all, lse)
-        # each rank reports the mean over ITS OWN queries (what a DDP replica of the reference would log)
-        return loss_q[rank * B:(rank + 1) * B].mean()
+        Bt = q_all.shape[0]
+        maxnorm = global_maxnorm(bank, group)
+        ref = torch.empty(Bt, dtype=torch.float32, device=dev)
+        q16b = torch.empty_like(q_all)
+        o_acc = torch.empty((Bt, D), dtype=torch.float32, device=dev)
+        bank_t = torch.empty((Bt, D), dtype=torch.float32, device=dev)
+        vec = torch.empty((3, Bt), dtype=torch.float32, device=dev)  # l_acc, s_t, es_acc
+        lbl_row = torch.empty(Bt, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            call("spn_bank_ce_prep", _ptr(q_all), _TORCH2SPN[q_all.dtype], _ptr(bank.data), _ptr(lab_all), inv_tau,
+                 _ptr(maxnorm), Bt, bank.N, D, bank.T, bank.row_base, _ptr(q16b), _ptr(ref), st)
+            if world > 1:  # owner's clamped reference wins over the other ranks' Cauchy-Schwarz bound
+                dist.all_reduce(ref, op=dist.ReduceOp.MIN, group=group)
+            call("spn_bank_ce_fused", _ptr(q_all), _ptr(bank.data), _ptr(lab_all), _ptr(ref), inv_tau, Bt, bank.N, D,
+                 bank.T, bank.row_base, 1, _ptr(o_acc), _ptr(vec[0]), _ptr(vec[1]), _ptr(lbl_row),
+                 _ptr(vec[2]) if tau_grad else None, _ptr(bank_t), None, 0, st)
+        if world > 1:
+            # additive partials: two reduce_scatters ([Bt, D] each) + one small all_reduce ([3, Bt]); the target
+            # logit is owner-only, so non-owners contribute 0 and the sum is the value
+            vec[1] = torch.where(lbl_row >= 0, vec[1], torch.zeros_like(vec[1]))
+            if not tau_grad:
+                vec[2].zero_()
+            o_mine = torch.empty((B, D), dtype=torch.float32, device=dev)
+            t_mine = torch.empty((B, D), dtype=torch.float32, device=dev)
+            dist.reduce_scatter_tensor(o_mine, o_acc, op=dist.ReduceOp.SUM, group=group)
+            dist.reduce_scatter_tensor(t_mine, bank_t, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+            sl = slice(rank * B, (rank + 1) * B)
+            sw = dict(o_acc=o_mine, bank_t=t_mine, l_acc=vec[0, sl].contiguous(), s_t=vec[1, sl].contiguous(),
+                      es_acc=vec[2, sl].contiguous() if tau_grad else None, ref=ref[sl].contiguous(), q16=q16)
+        else:
+            sw = dict(o_acc=o_acc, bank_t=bank_t, l_acc=vec[0], es_acc=vec[2] if tau_grad else None, s_t=vec[1], ref=ref,
+                      q16=q16)
+        _, _, loss, dq_unit, ddot = _fused_finalize(sw, bank, inv_tau, B, eps, True)
+        ctx.inv_tau, ctx.B, ctx.q_dtype, ctx.tau_grad = inv_tau, B, q_local.dtype, tau_grad
+        ctx.save_for_backward(dq_unit, ddot if tau_grad else None)
+        return loss  # mean over THIS rank's queries (what a DDP replica of the reference would log)
 
     @staticmethod
     def backward(ctx, g):
-        from .ops import _bwd
-        q_all, lab_all, lse = ctx.saved_tensors
-        Bt, D = q_all.shape
-        dev = q_all.device
-        B, world, rank = ctx.B, ctx.world, ctx.rank
-        g32 = g.detach().to(torch.float32).contiguous()
-        dq = torch.zeros((Bt, D), dtype=torch.float32, device=dev)
-        ddot = torch.zeros(Bt, dtype=torch.float32, device=dev) if ctx.tau_needs_grad else None
-        _bwd(q_all, ctx.bank, lab_all, ctx.inv_tau, lse, ctx.inv_tau / B, None, ctx.eps, dq, ddot)
-        if world > 1:
-            mine = torch.empty((B, D), dtype=torch.float32, device=dev)
-            dist.reduce_scatter_tensor(mine, dq, op=dist.ReduceOp.SUM, group=ctx.group)
-            if ddot is not None:
-                dist.all_reduce(ddot, group=ctx.group)
-        else:
-            mine = dq
-        mine = mine * g32
-        dtau = None
-        if ddot is not None:
-            dtau = (-(ctx.inv_tau / B)) * ddot[rank * B:(rank + 1) * B].sum() * g32
-        return mine.to(ctx.q_dtype), dtau, None, None, None, None, None
+        dq_unit, ddot = ctx.saved_tensors
+        g32 = g.detach().to(torch.float32)
+        dq = (dq_unit * g32).to(ctx.q_dtype)
+        dtau = (-(ctx.inv_tau / ctx.B)) * ddot.sum() * g32 if ctx.tau_grad else None
+        return dq, dtau, None, None, None, None, None
 
 
 def bank_infonce_sharded(query_features: torch.Tensor, bank, labels: torch.Tensor, tau=0.01, *,
@@ -104,7 +136,10 @@ def bank_infonce_sharded(query_features: torch.Tensor, bank, labels: torch.Tenso
     """Bank-CE with the bank row-sharded over `group` (bank: this rank's DeviceBank shard with row_base /
     n_total set, labels: GLOBAL entry indices of this rank's queries).  Returns the mean loss of the local
     queries; gradients w.r.t. the local queries are exact (all shards contribute through one
-    reduce_scatter)."""
+    reduce_scatter).  Label smoothing needs the GLOBAL column sums: not supported in sharded mode yet."""
+    if label_smoothing != 0.0 and _world(group)[1] > 1:
+        from ._lib import SpnError
+        raise SpnError("bank_infonce_sharded", -7, "label_smoothing with a sharded bank is not implemented")
     from .ops import _prep_labels, _split_tau
     tau_t, tau_v = _split_tau(tau)
     lab = _prep_labels(labels, query_features.shape[0], query_features.device)

@@ -1,0 +1,69 @@
+"""Multi-GPU parity (needs >= 2 GPUs, NCCL): the row-sharded fused path must reproduce the single-GPU loss and
+gradient for every rank's queries.  Launched as a subprocess under torch.distributed.run."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+REPO = Path(__file__).resolve().parent.parent
+
+WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["SPN_REPO"])
+import spn4cir_b200 as spn
+from spn4cir_b200 import synth
+from spn4cir_b200.dist import bank_infonce_sharded, sim_topk_sharded, sim_rank_sharded, shard_bounds
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=dev)
+B, N, D, tau = 96, 5000, 256, 0.02
+bank_cpu = synth.make_bank(N, D, 1, seed=77)
+qs, labs = [], []
+for r in range(world):
+    lab = synth.make_labels(B, N, seed=100 + r)
+    qs.append(synth.make_queries(bank_cpu, lab, "S", seed=200 + r)); labs.append(lab)
+shard = spn.DeviceBank.from_tensor(bank_cpu, dev, shard_rank=rank, shard_world=world)
+tt = torch.tensor(tau, device=dev, requires_grad=True)
+q = qs[rank].to(dev).requires_grad_(True)
+loss = bank_infonce_sharded(q, shard, labs[rank].to(dev), tt)
+(loss * 3.0).backward()
+full = spn.DeviceBank.from_tensor(bank_cpu, dev)
+t2 = torch.tensor(tau, device=dev, requires_grad=True)
+q2 = qs[rank].to(dev).requires_grad_(True)
+ref = spn.bank_infonce(q2, full, labs[rank].to(dev), t2, single_pass=True)
+(ref * 3.0).backward()
+assert abs(loss.item() - ref.item()) <= 1e-5 * max(1.0, abs(ref.item())), (rank, loss.item(), ref.item())
+rel = float((q.grad - q2.grad).norm() / q2.grad.norm())
+assert rel < 1e-4, (rank, rel)
+assert abs(tt.grad.item() - t2.grad.item()) <= 1e-3 * max(abs(t2.grad.item()), 1e-3), (tt.grad, t2.grad)
+# retrieval
+qq, gal, _, refi, tgt, grp = synth.make_retrieval_case(70, 1000, 128, 1, 10, noise=6.0)
+lo, hi = shard_bounds(1000, rank, world)
+v, i = sim_topk_sharded(qq.to(dev), gal[lo:hi].to(dev), 50, lo, exclude=refi)
+v1, i1 = spn.sim_topk(qq.to(dev), gal.to(dev), 50, exclude=refi)
+assert torch.equal(i, i1) and torch.equal(v, v1)
+r, g = sim_rank_sharded(qq.to(dev), gal[lo:hi].to(dev), tgt, lo, exclude=refi, group_members=grp)
+r1, g1 = spn.sim_rank(qq.to(dev), gal.to(dev), tgt, exclude=refi, group=grp)
+assert torch.equal(r, r1) and torch.equal(g, g1)
+dist.barrier()
+if rank == 0:
+    print("DIST_OK world=%d" % world)
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_sharded_matches_single_gpu(tmp_path):
+    n = min(torch.cuda.device_count(), 8)
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, SPN_REPO=str(REPO))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29511", str(script)],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0 and "DIST_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
