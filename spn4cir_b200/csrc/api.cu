@@ -183,7 +183,7 @@ int spn_debug_read_timeline(unsigned long long* host_out, int n) {
 
 int spn_debug_umma_bench(const void* b_src, int64_t b_rows, int N, int iters, int mode, int tma_on,
                          unsigned long long* out_cycles, int grid, void* stream) {
-  SPN_REQUIRE(b_src && out_cycles && iters > 0 && grid > 0, SPN_ERR_BAD_ARG, "spn_debug_umma_bench: bad arguments");
+  SPN_REQUIRE(out_cycles && iters > 0 && grid > 0, SPN_ERR_BAD_ARG, "spn_debug_umma_bench: bad arguments");
   return debug_umma_bench(b_src, b_rows, N, iters, mode, tma_on, out_cycles, grid, as_stream(stream));
 }
 

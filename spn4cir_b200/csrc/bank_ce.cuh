@@ -47,6 +47,7 @@ struct BankCEParams {
 
 struct BankCEPlan {
   int kblocks, q_tiles, n_tiles, num_chunks, num_dsplit, ow_blocks, stages, bps, grid;
+  int cg;  // 2: CTA pairs (cta_group::2), 1: single-CTA kernel
   size_t smem_bytes, ws_bytes;
 };
 

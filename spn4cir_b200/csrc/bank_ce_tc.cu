@@ -300,22 +300,29 @@ __device__ __forceinline__ void fused_chunk_t32(const uint32_t (&xr)[32], bool e
 
 // ------------------------------------------------------------------------------------------------
 // MODE 0: forward statistics.  MODE 1: backward from a known lse.  MODE 2: fused single pass (statistics + O).
-template <int MODE, int T, bool EXTRA>
+// CG = 2 (MODE >= 1 only): two CTAs of a cluster, each with its own 128-query tile, run every MMA as one
+// tcgen05.mma.cta_group::2 (M = 256): each CTA stages only HALF of every B operand (64 of the 128 bank rows of a GEMM1
+// k-block, 64 of the 128 dq columns of a GEMM2 group), which halves both the TMA fill and the B-operand reads of the
+// shared-memory port -- the resource the 1-CTA kernel saturates (SS MMA: 8 KiB per 64 cycles = 128 B/cycle).  Rank 0
+// issues all MMAs; completions are multicast to both CTAs; both CTAs' TMA loads credit rank 0's "full" barriers.
+template <int MODE, int T, bool EXTRA, int CG>
 __global__ void __launch_bounds__(kBankCEThreads, 1)
 bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_bank,
-               const BankCEParams p) {
+               const __grid_constant__ CUtensorMap tmap_bank_half, const BankCEParams p) {
+  static_assert(CG == 1 || (CG == 2 && MODE >= 1), "the CTA-pair variant exists for the backward / fused modes only");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   const SmemView sm = carve(smem_raw, MODE == 0 ? 0 : p.kblocks, p.stages, p.bps);
 
   // block -> (query tile, d-split, bank chunk); query tile fastest so co-resident CTAs share bank rows in L2
-  int bid = blockIdx.x;
-  const int qt = bid % p.q_tiles;
+  const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;  // CG = 2: blocks (2c, 2c + 1) form cluster c
+  int bid = (CG == 2) ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int qt = bid % p.q_tiles;  // CG = 2: index of the PAIR of query tiles
   bid /= p.q_tiles;
   const int ds = bid % p.num_dsplit;
   const int chunk = bid / p.num_dsplit;
-  const int q0 = qt * kBM;
+  const int q0 = (qt * CG + int(crank)) * kBM;
   const int t_begin = int((long long)chunk * p.n_tiles / p.num_chunks);
   const int t_end = int((long long)(chunk + 1) * p.n_tiles / p.num_chunks);
   const int ntl = t_end - t_begin;
@@ -329,28 +336,43 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     mbar_init(sm.q_full, MODE == 0 ? 4 : 1);  // forward: the 4 soft-max warps stage Q into TMEM
     mbar_init(&sm.s_full[0], 1);
     mbar_init(&sm.s_full[1], 1);
-    mbar_init(&sm.s_free[0], 4);
-    mbar_init(&sm.s_free[1], 4);
-    mbar_init(sm.p_full, MODE == 0 ? 1 : 4);  // forward: Q staging (TMA tx) barrier
+    mbar_init(&sm.s_free[0], 4 * CG);  // CG = 2: the soft-max warps of both CTAs arrive on rank 0's barriers
+    mbar_init(&sm.s_free[1], 4 * CG);
+    mbar_init(sm.p_full, MODE == 0 ? 1 : 4 * CG);  // forward: Q staging (TMA tx) barrier
     mbar_init(sm.p_free, 1);
     mbar_init(sm.o_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_bank);
+    if (CG == 2) tma_prefetch_desc(&tmap_bank_half);
   }
   if (warp == 1) {
-    tmem_alloc(sm.tmem_slot, MODE == 0 ? kTmemColsFwd : kTmemColsBwd);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_cg2(sm.tmem_slot, kTmemColsBwd);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(sm.tmem_slot, MODE == 0 ? kTmemColsFwd : kTmemColsBwd);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything is signalled remotely
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *sm.tmem_slot;
 
   if (warp == 0) {
     // ===================================================================== TMA producer (converged warp, one
     // elected lane issues; see elect_one())
-    if (MODE >= 1) {
+    if (MODE >= 1 && CG == 2) {
+      const uint32_t qbar = mapa_shared(smem_u32(sm.q_full), 0);
+      if (elect_one()) {
+        if (crank == 0) mbar_arrive_expect_tx(sm.q_full, 2u * uint32_t(p.kblocks) * kBlockBytes);
+        for (int kb = 0; kb < p.kblocks; ++kb)
+          tma_load_2d_cg2(sm.q + size_t(kb) * kBlockBytes, &tmap_q, qbar, kb * kBK, q0);
+      }
+      __syncwarp();
+    } else if (MODE >= 1) {
       if (elect_one()) {
         mbar_arrive_expect_tx(sm.q_full, uint32_t(p.kblocks) * kBlockBytes);
         for (int kb = 0; kb < p.kblocks; ++kb)
@@ -395,17 +417,55 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       __syncwarp();
       r.advance();
     };
+    // CG = 2, GEMM1: a stage holds this CTA's half (64 bank rows) of two consecutive k-blocks, 8 KiB each
+    auto load_half_pair = [&](int kb0, int nb, int row) {
+      TL_BEGIN
+      mbar_wait(&sm.empty[r.stage], r.phase ^ 1u);
+      TL_END(0)
+      const uint32_t fbar = mapa_shared(smem_u32(&sm.full[r.stage]), 0);
+      if (elect_one()) {
+        if (crank == 0) mbar_arrive_expect_tx(&sm.full[r.stage], 2u * uint32_t(nb) * (kBlockBytes / 2));
+        for (int b = 0; b < nb; ++b)
+          tma_load_2d_cg2(sm.ring + size_t(r.stage) * kBlockBytes + size_t(b) * (kBlockBytes / 2), &tmap_bank_half, fbar,
+                          (kb0 + b) * kBK, row + int(crank) * (kBN / 2));
+      }
+      __syncwarp();
+      r.advance();
+    };
+    // CG = 2, GEMM2: group g of the dq split = 128 columns (64 per CTA) or, for an odd last block, 64 columns (32 per
+    // CTA: the box still spans 64 columns, of which the MMA reads the first 32)
+    auto load_ogroup = [&](int g, int row) {
+      TL_BEGIN
+      mbar_wait(&sm.empty[r.stage], r.phase ^ 1u);
+      TL_END(0)
+      const uint32_t fbar = mapa_shared(smem_u32(&sm.full[r.stage]), 0);
+      const bool wide = 2 * g + 1 < my_blocks;
+      const int col = (ds * p.ow_blocks + 2 * g) * kBK + int(crank) * (wide ? kBK : kBK / 2);
+      if (elect_one()) {
+        if (crank == 0) mbar_arrive_expect_tx(&sm.full[r.stage], 2u * kBlockBytes);
+        tma_load_2d_cg2(sm.ring + size_t(r.stage) * kBlockBytes, &tmap_bank, fbar, col, row);
+      }
+      __syncwarp();
+      r.advance();
+    };
+    const int ogroups = (my_blocks + 1) / 2;
     for (int t = t_begin; t < t_end; ++t) {
       if (MODE == 0) {
         for (int kb = 0; kb < p.kblocks; kb += p.bps) load_group(kb, min(p.bps, p.kblocks - kb), t * kBN);
+      } else if (CG == 2) {
+        for (int kb = 0; kb < p.kblocks; kb += 2) load_half_pair(kb, min(2, p.kblocks - kb), t * kBN);
       } else {
         for (int kb = 0; kb < p.kblocks; ++kb) load_block(kb, t * kBN);
       }
-      if (MODE >= 1 && t > t_begin)
-        for (int j = 0; j < my_blocks; ++j) load_block(ds * p.ow_blocks + j, (t - 1) * kBN);
+      if (MODE >= 1 && t > t_begin) {
+        if (CG == 2) for (int g = 0; g < ogroups; ++g) load_ogroup(g, (t - 1) * kBN);
+        else for (int j = 0; j < my_blocks; ++j) load_block(ds * p.ow_blocks + j, (t - 1) * kBN);
+      }
     }
-    if (MODE >= 1 && ntl > 0)
-      for (int j = 0; j < my_blocks; ++j) load_block(ds * p.ow_blocks + j, (t_end - 1) * kBN);
+    if (MODE >= 1 && ntl > 0) {
+      if (CG == 2) for (int g = 0; g < ogroups; ++g) load_ogroup(g, (t_end - 1) * kBN);
+      else for (int j = 0; j < my_blocks; ++j) load_block(ds * p.ow_blocks + j, (t_end - 1) * kBN);
+    }
     TL_FLUSH(0)
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (converged warp)
@@ -416,9 +476,78 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     const uint64_t ring_desc_k0 = make_smem_desc_sw128(smem_u32(sm.ring), 16, 1024);            // K-major view
     const uint64_t ring_desc_mn0 = make_smem_desc_sw128(smem_u32(sm.ring), kBlockBytes, 1024);  // MN-major view
     Ring r(p.stages);
+    TL_VARS
+    if (CG == 2) {
+      // ------------------------------------------------------------- CTA pair: rank 0 issues for both CTAs
+      if (crank == 0) {
+        constexpr uint32_t idesc_s2 = make_idesc_bf16_f32(2 * kBM, kBN, 0, 0);
+        constexpr uint32_t idesc_o128 = make_idesc_bf16_f32(2 * kBM, 128, 0, 1);
+        constexpr uint32_t idesc_o64 = make_idesc_bf16_f32(2 * kBM, 64, 0, 1);
+        const int ogroups = (my_blocks + 1) / 2;
+        mbar_wait_cluster(sm.q_full, 0);
+        tc_fence_after();
+        auto gemm_o2 = [&](int u) {
+          TL_BEGIN
+          mbar_wait_cluster(sm.p_full, uint32_t(u) & 1u);
+          TL_END(2)
+          tc_fence_after();
+          for (int g = 0; g < ogroups; ++g) {
+            TL_BEGIN
+            mbar_wait_cluster(&sm.full[r.stage], r.phase);
+            TL_END(0)
+            tc_fence_after();
+            if (elect_one()) {
+              // each CTA's block read MN-major supplies its half of the dq columns of this group
+              const uint64_t bdesc = ring_desc_mn0 + uint64_t(r.stage) * (kBlockBytes >> 4);
+              const uint32_t idesc = (2 * g + 1 < my_blocks) ? idesc_o128 : idesc_o64;
+#pragma unroll
+              for (int k = 0; k < kBN / kUmmaK; ++k)
+                umma_ts_f16_cg2(tmem_base + uint32_t(g) * 128u, tmem_base + kBwdPCol + uint32_t(k) * 8u,
+                                bdesc + uint64_t(k * (2048 >> 4)), idesc, (u > 0 || k > 0) ? 1u : 0u);
+              umma_commit_cg2(&sm.empty[r.stage], 3);
+            }
+            __syncwarp();
+            r.advance();
+          }
+          if (elect_one()) umma_commit_cg2(sm.p_free, 3);
+          __syncwarp();
+        };
+        for (int i = 0; i < ntl; ++i) {
+          TL_BEGIN
+          mbar_wait_cluster(&sm.s_free[0], (uint32_t(i) & 1u) ^ 1u);
+          TL_END(1)
+          tc_fence_after();
+          for (int kb0 = 0; kb0 < p.kblocks; kb0 += 2) {
+            TL_BEGIN
+            mbar_wait_cluster(&sm.full[r.stage], r.phase);
+            TL_END(0)
+            tc_fence_after();
+            if (elect_one()) {
+              const int nb = min(2, p.kblocks - kb0);
+              for (int b = 0; b < nb; ++b) {
+                const uint64_t adesc = q_desc0 + uint64_t(kb0 + b) * (kBlockBytes >> 4);
+                const uint64_t bdesc = ring_desc_k0 + uint64_t(r.stage) * (kBlockBytes >> 4) + uint64_t(b) * (kBlockBytes >> 5);
+#pragma unroll
+                for (int k = 0; k < kBK / kUmmaK; ++k)
+                  umma_ss_f16_cg2(tmem_base + kBwdSCol, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc_s2,
+                                  ((kb0 + b) | k) != 0);
+              }
+              umma_commit_cg2(&sm.empty[r.stage], 3);
+            }
+            __syncwarp();
+            r.advance();
+          }
+          if (elect_one()) umma_commit_cg2(&sm.s_full[0], 3);
+          __syncwarp();
+          if (i > 0) gemm_o2(i - 1);
+        }
+        if (ntl > 0) gemm_o2(ntl - 1);
+        if (elect_one()) umma_commit_cg2(sm.o_full, 3);
+        __syncwarp();
+      }
+    } else {
     mbar_wait(sm.q_full, 0);
     tc_fence_after();
-    TL_VARS
 
     auto gemm_s = [&](uint32_t d_tmem) {
       for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -509,6 +638,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       if (elect_one()) umma_commit(sm.o_full);
       __syncwarp();
     }
+    }  // CG == 1
     TL_FLUSH(4)
   } else {
     // ===================================================================== soft-max / epilogue warps
@@ -609,7 +739,10 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           if (c == 3) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.s_free[0]);
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&sm.s_free[0]), 0));
+              else mbar_arrive(&sm.s_free[0]);
+            }
           }
           const long long col0 = row0 + c * 32;
           if (T == 1) {
@@ -639,7 +772,10 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(sm.p_full);
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(sm.p_full), 0));
+          else mbar_arrive(sm.p_full);
+        }
       }
       // epilogue: O[128 x my_blocks*64] fp32 -> dq (+=, other chunks / shards add into the same rows)
       mbar_wait(sm.o_full, 0);
@@ -673,8 +809,13 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, MODE == 0 ? kTmemColsFwd : kTmemColsBwd);
+  if (CG == 2) {
+    cluster_sync_all();  // neither CTA may exit (or free TMEM) while the pair's MMAs / remote arrivals can still land
+    if (warp == 1) tmem_dealloc_cg2(tmem_base, kTmemColsBwd);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, MODE == 0 ? kTmemColsFwd : kTmemColsBwd);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -906,11 +1047,48 @@ __global__ void loss_kernel(const float* __restrict__ m, const float* __restrict
 template <int MODE, int T, bool EXTRA>
 int launch_one(const CUtensorMap& tq, const CUtensorMap& tb, const BankCEParams& p, int grid, size_t smem,
                cudaStream_t stream) {
-  auto kfn = bank_ce_kernel<MODE, T, EXTRA>;
+  auto kfn = bank_ce_kernel<MODE, T, EXTRA, 1>;
   SPN_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kfn<<<grid, kBankCEThreads, smem, stream>>>(tq, tb, p);
+  kfn<<<grid, kBankCEThreads, smem, stream>>>(tq, tb, tb, p);
   SPN_CUDA_CHECK(cudaGetLastError());
   return SPN_OK;
+}
+
+// CTA-pair variant: clusters of 2 along x (blocks 2c, 2c + 1); `tbh` = bank map with a 64-row box (GEMM1 halves)
+template <int MODE, int T, bool EXTRA>
+int launch_pair(const CUtensorMap& tq, const CUtensorMap& tb, const CUtensorMap& tbh, const BankCEParams& p, int grid,
+                size_t smem, cudaStream_t stream) {
+  auto kfn = bank_ce_kernel<MODE, T, EXTRA, 2>;
+  SPN_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(grid), 1, 1);
+  cfg.blockDim = dim3(kBankCEThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SPN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kfn, tq, tb, tbh, p));
+  return SPN_OK;
+}
+
+template <int MODE>
+int launch_mode(bool pair, int T, bool extra, const CUtensorMap& tq, const CUtensorMap& tb, const CUtensorMap& tbh,
+                const BankCEParams& p, int grid, size_t smem, cudaStream_t stream) {
+  if (pair) {
+    if (T == 1) return extra ? launch_pair<MODE, 1, true>(tq, tb, tbh, p, grid, smem, stream)
+                             : launch_pair<MODE, 1, false>(tq, tb, tbh, p, grid, smem, stream);
+    return extra ? launch_pair<MODE, 32, true>(tq, tb, tbh, p, grid, smem, stream)
+                 : launch_pair<MODE, 32, false>(tq, tb, tbh, p, grid, smem, stream);
+  }
+  if (T == 1) return extra ? launch_one<MODE, 1, true>(tq, tb, p, grid, smem, stream)
+                           : launch_one<MODE, 1, false>(tq, tb, p, grid, smem, stream);
+  return extra ? launch_one<MODE, 32, true>(tq, tb, p, grid, smem, stream)
+               : launch_one<MODE, 32, false>(tq, tb, p, grid, smem, stream);
 }
 
 }  // namespace
@@ -951,6 +1129,11 @@ int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan) {
   if (chunks > plan->n_tiles) chunks = plan->n_tiles;
   plan->num_chunks = chunks;
   plan->grid = plan->q_tiles * plan->num_dsplit * chunks;
+  // backward / fused: pair the query tiles (cta_group::2) whenever they come in twos -- see bank_ce_kernel<.., CG = 2>
+  plan->cg = (mode == 1 && plan->q_tiles % 2 == 0) ? 2 : 1;
+  if (const char* e = getenv("SPN_DEBUG_CG")) {
+    if (atoi(e) == 1) plan->cg = 1;
+  }
   // forward keeps Q in TMEM (no smem), backward keeps the Q tile in smem next to the ring
   const size_t fixed = 1024 /*align slack*/ + (mode == 1 ? size_t(plan->kblocks) * kBlockBytes : 0) + 512 /*barriers*/;
   const int bps = (mode == 0 && plan->kblocks >= 2) ? 2 : 1;  // k-blocks per ring stage
@@ -1008,22 +1191,18 @@ int bank_ce_backward(const void* q, const void* bank, const long long* labels, f
   if (rc != SPN_OK) return rc;
   SPN_REQUIRE(inv_tau > 0.f && isfinite(inv_tau), SPN_ERR_BAD_ARG, "inv_tau must be positive and finite (got %g)", inv_tau);
   SPN_REQUIRE(N_total >= N, SPN_ERR_BAD_ARG, "N_total=%lld smaller than the shard N=%lld", N_total, N);
-  CUtensorMap tq, tb;
+  CUtensorMap tq, tb, tbh;
   if ((rc = make_tmap_bf16_2d(&tq, q, uint64_t(B), uint64_t(D), kBM)) != SPN_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&tb, bank, uint64_t(N) * T, uint64_t(D), kBN)) != SPN_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tbh, bank, uint64_t(N) * T, uint64_t(D), kBN / 2)) != SPN_OK) return rc;
   BankCEParams p{};
   p.B = B; p.D = D; p.N = N; p.n_rows = N * T; p.kblocks = plan.kblocks; p.stages = plan.stages; p.bps = plan.bps;
-  p.n_tiles = plan.n_tiles; p.q_tiles = plan.q_tiles; p.num_chunks = plan.num_chunks;
+  p.n_tiles = plan.n_tiles; p.q_tiles = plan.q_tiles / plan.cg; p.num_chunks = plan.num_chunks;
   p.num_dsplit = plan.num_dsplit; p.ow_blocks = plan.ow_blocks; p.scale_log2 = inv_tau * kLog2e;
   p.row_base = row_base; p.labels = labels; p.lse = lse; p.gscale = gscale; p.gscale_dev = gscale_dev;
   p.eps_over_n = label_smoothing / float(N_total); p.one_minus_eps = 1.f - label_smoothing;
   p.dq = dq; p.dlogit_dot = dlogit_dot;
-  const bool extra = dlogit_dot != nullptr;
-  if (T == 1) rc = extra ? launch_one<1, 1, true>(tq, tb, p, plan.grid, plan.smem_bytes, stream)
-                         : launch_one<1, 1, false>(tq, tb, p, plan.grid, plan.smem_bytes, stream);
-  else        rc = extra ? launch_one<1, 32, true>(tq, tb, p, plan.grid, plan.smem_bytes, stream)
-                         : launch_one<1, 32, false>(tq, tb, p, plan.grid, plan.smem_bytes, stream);
-  return rc;
+  return launch_mode<1>(plan.cg == 2, T, dlogit_dot != nullptr, tq, tb, tbh, p, plan.grid, plan.smem_bytes, stream);
 }
 
 int bank_stats(const void* bank, long long rows, int D, float* maxnorm, float* colsum, cudaStream_t stream) {
@@ -1062,24 +1241,21 @@ int bank_ce_fused(const void* q, const void* bank, const long long* labels, cons
   if (rc != SPN_OK) return rc;
   SPN_REQUIRE(inv_tau > 0.f && isfinite(inv_tau), SPN_ERR_BAD_ARG, "inv_tau must be positive and finite (got %g)", inv_tau);
   SPN_REQUIRE(aligned16(o_acc), SPN_ERR_BAD_ALIGN, "bank_ce_fused: o_acc must be 16-byte aligned");
-  CUtensorMap tq, tb;
+  CUtensorMap tq, tb, tbh;
   if ((rc = make_tmap_bf16_2d(&tq, q, uint64_t(B), uint64_t(D), kBM)) != SPN_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&tb, bank, uint64_t(N) * T, uint64_t(D), kBN)) != SPN_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tbh, bank, uint64_t(N) * T, uint64_t(D), kBN / 2)) != SPN_OK) return rc;
   if (init) {
     fused_init_kernel<<<148, 256, 0, stream>>>(o_acc, (long long)B * D, l_acc, s_t, lbl_row, es_acc, nullptr, B);
     SPN_CUDA_CHECK(cudaGetLastError());
   }
   BankCEParams p{};
   p.B = B; p.D = D; p.N = N; p.n_rows = N * T; p.kblocks = plan.kblocks; p.stages = plan.stages; p.bps = plan.bps;
-  p.n_tiles = plan.n_tiles; p.q_tiles = plan.q_tiles; p.num_chunks = plan.num_chunks;
+  p.n_tiles = plan.n_tiles; p.q_tiles = plan.q_tiles / plan.cg; p.num_chunks = plan.num_chunks;
   p.num_dsplit = plan.num_dsplit; p.ow_blocks = plan.ow_blocks; p.scale_log2 = inv_tau * kLog2e;
   p.row_base = row_base; p.labels = labels; p.ref = ref; p.gscale = 1.f; p.dq = o_acc; p.dlogit_dot = es_acc;
   p.l_acc = l_acc; p.st_out = s_t; p.lbl_row_out = lbl_row;
-  const bool extra = es_acc != nullptr;
-  if (T == 1) rc = extra ? launch_one<2, 1, true>(tq, tb, p, plan.grid, plan.smem_bytes, stream)
-                         : launch_one<2, 1, false>(tq, tb, p, plan.grid, plan.smem_bytes, stream);
-  else        rc = extra ? launch_one<2, 32, true>(tq, tb, p, plan.grid, plan.smem_bytes, stream)
-                         : launch_one<2, 32, false>(tq, tb, p, plan.grid, plan.smem_bytes, stream);
+  rc = launch_mode<2>(plan.cg == 2, T, es_acc != nullptr, tq, tb, tbh, p, plan.grid, plan.smem_bytes, stream);
   if (rc != SPN_OK) return rc;
   if (bank_t) {
     gather_label_rows_kernel<<<(B + 7) / 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(bank), lbl_row, B, D, bank_t);

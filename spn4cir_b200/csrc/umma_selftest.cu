@@ -110,30 +110,26 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
-// ---- raw MMA issue-rate probe: every CTA issues `iters` x 4 MMAs (K=64 per iteration) back to back from a
-// resident smem tile (contents irrelevant), optionally while a second warp streams TMA boxes into a 4-deep ring.
-// mode bit0: A from TMEM.  Reports cycles per CTA.
+// ---- raw MMA issue-rate probe: every CTA issues `iters` x 4 k-steps of a PATTERN of up to 8 MMAs back to back from
+// resident smem tiles (contents irrelevant).  One pattern op per byte of `pattern` (0 terminates):
+//   bit0 valid | bit1 A from TMEM | bits2-3 N (0: 64, 1: 128, 2: 256) | bit4 B MN-major | bits5-6 B region (16 KiB
+//   each) | bit7 second accumulator.  `group` > 1 repeats each op `group` times (k-steps) before moving on, i.e. it
+// controls how often the instruction kind switches.  Reports cycles per CTA.
 __global__ void __launch_bounds__(128, 1)
-umma_bench_kernel(const __grid_constant__ CUtensorMap tmap_b, int N, int iters, int mode, int tma_on,
-                  unsigned long long* __restrict__ out_cycles) {
+umma_bench_kernel(unsigned long long pattern, int iters, int group, unsigned long long* __restrict__ out_cycles) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t warp = threadIdx.x >> 5;
   uintptr_t base = (reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~uintptr_t(1023u);
   uint8_t* a_smem = reinterpret_cast<uint8_t*>(base);                // 16 KiB
-  uint8_t* b_smem = a_smem + kBlockBytes;                            // 32 KiB (N up to 256)
-  uint8_t* ring = b_smem + 2 * kBlockBytes;                          // 4 x 16 KiB TMA sink
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 4 * kBlockBytes);
+  uint8_t* b_smem = a_smem + kBlockBytes;                            // 4 regions x 16 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + 4 * kBlockBytes);
   uint64_t* done = bars;        // MMA completion
-  uint64_t* rfull = bars + 1;   // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-  volatile uint32_t* stop = tmem_slot + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
   if (threadIdx.x == 0) {
     mbar_init(done, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&rfull[i], 1);
-    *stop = 0;
     fence_barrier_init();
   }
-  for (uint32_t i = threadIdx.x; i < 3 * kBlockBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(a_smem)[i] = 0;
+  for (uint32_t i = threadIdx.x; i < 5 * kBlockBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(a_smem)[i] = 0;
   fence_proxy_async_smem();
   if (warp == 0) {
     tmem_alloc(tmem_slot, 512);
@@ -144,25 +140,24 @@ umma_bench_kernel(const __grid_constant__ CUtensorMap tmap_b, int N, int iters, 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16_f32(128, N, 0, 0);
     const uint64_t adesc = make_smem_desc_sw128(smem_u32(a_smem), 16, 1024);
-    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(b_smem), 16, 1024);
+    const uint64_t bdesc_k = make_smem_desc_sw128(smem_u32(b_smem), 16, 1024);
+    const uint64_t bdesc_mn = make_smem_desc_sw128(smem_u32(b_smem), kBlockBytes, 1024);
     const long long t0 = clock64();
     if (elect_one()) {
-      const uint32_t idesc64 = make_idesc_bf16_f32(128, 64, 0, 0);
       for (int it = 0; it < iters; ++it) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // bit1: alternate between two independent accumulators; bit2: "fused" pattern = SS N into D0 followed by
-          // a TS N=64 MMA into D1 (one GEMM1 + one GEMM2 instruction)
-          const uint32_t d = (mode & 2) ? tmem_base + ((k & 1) ? 256u : 0u) : tmem_base;
-          if (mode & 4) {
-            umma_ss_f16(tmem_base, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, 1);
-            umma_ts_f16(tmem_base + 256u, tmem_base + 384u + uint32_t(k) * 8u, bdesc + uint64_t(k * 2), idesc64, 1);
-          } else if (mode & 1) {
-            umma_ts_f16(d, tmem_base + 384u + uint32_t(k) * 8u, bdesc + uint64_t(k * 2), idesc, 1);
-          } else {
-            umma_ss_f16(d, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, 1);
+        for (int o = 0; o < 8; ++o) {
+          const uint32_t op = uint32_t(pattern >> (8 * o)) & 0xffu;
+          if (!(op & 1u)) break;
+          const int n = 64 << ((op >> 2) & 3u);
+          const uint32_t mn = (op >> 4) & 1u, region = (op >> 5) & 3u;
+          const uint32_t d = tmem_base + ((op >> 7) ? 224u : 0u);  // accumulators at columns 0 / 224, A at 480
+          const uint32_t idesc = make_idesc_bf16_f32(128, n, 0, int(mn));
+          const uint64_t bd = (mn ? bdesc_mn : bdesc_k) + uint64_t(region) * (kBlockBytes >> 4);
+          for (int k = 0; k < group; ++k) {
+            const uint64_t boff = mn ? uint64_t((k & 7) * 128) : uint64_t((k & 3) * 2);
+            if (op & 2u) umma_ts_f16(d, tmem_base + 480u + uint32_t(k & 3) * 8u, bd + boff, idesc, 1);
+            else         umma_ss_f16(d, adesc + uint64_t((k & 3) * 2), bd + boff, idesc, 1);
           }
         }
       }
@@ -171,35 +166,96 @@ umma_bench_kernel(const __grid_constant__ CUtensorMap tmap_b, int N, int iters, 
     __syncwarp();
     mbar_wait(done, 0);
     const long long t1 = clock64();
-    *stop = 1;
     if ((threadIdx.x & 31) == 0) out_cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
-  } else if (warp == 2 && tma_on) {
-    uint32_t phase = 0, stage = 0;
-    const int rows = int(blockIdx.x) * 512;
-    int n = 0;
-    while (!*stop) {
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&rfull[stage], kBlockBytes);
-        tma_load_2d(ring + size_t(stage) * kBlockBytes, &tmap_b, &rfull[stage], ((n >> 2) % 8) * 64, rows + (n & 3) * 128);
-      }
-      __syncwarp();
-      ++n;
-      if (n >= 4) {  // keep 4 loads in flight: wait for the oldest before reusing its slot
-        const uint32_t s2 = (stage + 1) & 3u;
-        mbar_wait(&rfull[s2], (s2 == 0) ? (phase ^ 1u) : phase);
-      }
-      if (++stage == 4) { stage = 0; phase ^= 1u; }
-    }
-  }
-  __syncthreads();
-  // drain outstanding TMA (at most 4) before exit
-  if (warp == 2 && tma_on) {
-    // barriers complete on their own; give the loads time to land
-    __nanosleep(20000);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- compile-time MMA patterns (fully unrolled issue path, like the production kernels): one iteration = 4 k-steps.
+//  0: SS128                     1: TS64 mn                   2: SS128 + TS64 k (same B tile)   3: SS128 + TS64 k (other B)
+//  4: SS128 + TS64 mn (other B) 5: 4 x SS128 then 4 x TS64 mn 6: TS256 mn   7: TS128 mn   8: SS128 + 2 x TS64 mn
+//  9: SS256                    10: SS256 + TS64 mn          11: SS256 + 2 x TS64 mn          12: SS128 + TS128 mn
+// 13: TS128 k (A=Q-like) + TS64 mn                          14: SS64 + TS64 mn
+template <int PAT>
+__global__ void __launch_bounds__(128, 1) umma_bench2_kernel(int iters, unsigned long long* __restrict__ out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t warp = threadIdx.x >> 5;
+  uintptr_t base = (reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~uintptr_t(1023u);
+  uint8_t* a_smem = reinterpret_cast<uint8_t*>(base);  // 16 KiB
+  uint8_t* b_smem = a_smem + kBlockBytes;              // regions 0..3, 16 KiB each
+  uint64_t* done = reinterpret_cast<uint64_t*>(b_smem + 4 * kBlockBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  if (threadIdx.x == 0) {
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  for (uint32_t i = threadIdx.x; i < 5 * kBlockBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(a_smem)[i] = 0;
+  fence_proxy_async_smem();
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *tmem_slot;
+  if (warp == 1) {
+    constexpr uint32_t i_s64 = make_idesc_bf16_f32(128, 64, 0, 0), i_s128 = make_idesc_bf16_f32(128, 128, 0, 0),
+                       i_s256 = make_idesc_bf16_f32(128, 256, 0, 0), i_o64 = make_idesc_bf16_f32(128, 64, 0, 1),
+                       i_o128 = make_idesc_bf16_f32(128, 128, 0, 1), i_o256 = make_idesc_bf16_f32(128, 256, 0, 1);
+    const uint64_t ad = make_smem_desc_sw128(smem_u32(a_smem), 16, 1024);
+    const uint64_t bk = make_smem_desc_sw128(smem_u32(b_smem), 16, 1024);                      // K-major, region 0
+    const uint64_t bk2 = bk + 2 * (kBlockBytes >> 4);                                            // K-major, region 2
+    const uint64_t bm = make_smem_desc_sw128(smem_u32(b_smem), kBlockBytes, 1024);             // MN-major, region 0..
+    const uint64_t bm2 = bm + 2 * (kBlockBytes >> 4);                                            // MN-major, region 2
+    const uint32_t dS = tb, dO = tb + 256u, aP = tb + 448u;
+    const long long t0 = clock64();
+    if (elect_one()) {
+      for (int it = 0; it < iters; ++it) {
+        if (PAT == 5) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss_f16(dS, ad + uint64_t(k * 2), bk + uint64_t(k * 2), i_s128, 1);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ts_f16(dO, aP + uint32_t(k) * 8u, bm2 + uint64_t(k * 128), i_o64, 1);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ka = uint64_t(k * 2), km = uint64_t(k * 128);
+            const uint32_t pa = aP + uint32_t(k) * 8u;
+            if (PAT == 0 || PAT == 2 || PAT == 3 || PAT == 4 || PAT == 8 || PAT == 12) umma_ss_f16(dS, ad + ka, bk + ka, i_s128, 1);
+            if (PAT == 9 || PAT == 10 || PAT == 11) umma_ss_f16(dS, ad + ka, bk + ka, i_s256, 1);
+            if (PAT == 14) umma_ss_f16(dS, ad + ka, bk + ka, i_s64, 1);
+            if (PAT == 13) umma_ts_f16(dS, pa, bk + ka, i_s128, 1);
+            if (PAT == 2) umma_ts_f16(dO, pa, bk + ka, i_s64, 1);
+            if (PAT == 3) umma_ts_f16(dO, pa, bk2 + ka, i_s64, 1);
+            if (PAT == 1 || PAT == 4 || PAT == 8 || PAT == 10 || PAT == 11 || PAT == 13 || PAT == 14) umma_ts_f16(dO, pa, bm2 + km, i_o64, 1);
+            if (PAT == 8 || PAT == 11) umma_ts_f16(dO + 64u, pa, bm2 + km + (kBlockBytes >> 4), i_o64, 1);
+            if (PAT == 6) umma_ts_f16(dO, pa, bm + km, i_o256, 0);
+            if (PAT == 7 || PAT == 12) umma_ts_f16(dO, pa, bm2 + km, i_o128, 1);
+          }
+        }
+      }
+      umma_commit(done);
+    }
+    __syncwarp();
+    mbar_wait(done, 0);
+    const long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) out_cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+template <int PAT>
+int launch_bench2(int iters, unsigned long long* out, int grid, cudaStream_t stream) {
+  const size_t smem = 1024 + 5 * kBlockBytes + 128;
+  SPN_CUDA_CHECK(cudaFuncSetAttribute(umma_bench2_kernel<PAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  umma_bench2_kernel<PAT><<<grid, 128, smem, stream>>>(iters, out);
+  SPN_CUDA_CHECK(cudaGetLastError());
+  return SPN_OK;
 }
 
 // ---- DSMEM store bandwidth probe: clusters of 4; ranks 0/1 write `iters` x 32 KiB to rank 2 (and rank 3 when
@@ -245,14 +301,25 @@ int debug_dsmem_bench(int iters, int ndst, unsigned long long* out_cycles, int g
 
 int debug_umma_bench(const void* b_src, long long b_rows, int N, int iters, int mode, int tma_on,
                      unsigned long long* out_cycles, int grid, cudaStream_t stream) {
-  SPN_REQUIRE(N == 64 || N == 128 || N == 256, SPN_ERR_BAD_SHAPE, "bench N must be 64/128/256");
+  // (b_src, b_rows, N) are unused since the probe became pattern-driven: mode/tma_on carry the low/high 32 bits of the
+  // 8-op pattern, N the group length (k-steps per op before the next op is issued)
+  (void)b_src; (void)b_rows;
   int rc;
   if ((rc = require_sm100()) != SPN_OK) return rc;
-  CUtensorMap tb;
-  if ((rc = make_tmap_bf16_2d(&tb, b_src, uint64_t(b_rows), 512, 128)) != SPN_OK) return rc;
-  const size_t smem = 1024 + 7 * kBlockBytes + 128;
+  if (N == 0) {  // compile-time pattern `mode`
+    switch (mode) {
+#define SPN_B2(P) case P: return launch_bench2<P>(iters, out_cycles, grid, stream);
+      SPN_B2(0) SPN_B2(1) SPN_B2(2) SPN_B2(3) SPN_B2(4) SPN_B2(5) SPN_B2(6) SPN_B2(7) SPN_B2(8) SPN_B2(9) SPN_B2(10)
+      SPN_B2(11) SPN_B2(12) SPN_B2(13) SPN_B2(14)
+#undef SPN_B2
+      default: return fail(SPN_ERR_BAD_ARG, "unknown bench pattern %d", mode);
+    }
+  }
+  const unsigned long long pattern = (unsigned long long)(uint32_t)mode | ((unsigned long long)(uint32_t)tma_on << 32);
+  SPN_REQUIRE(N >= 1 && N <= 64, SPN_ERR_BAD_SHAPE, "bench group length must be in [1, 64]");
+  const size_t smem = 1024 + 5 * kBlockBytes + 128;
   SPN_CUDA_CHECK(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  umma_bench_kernel<<<grid, 128, smem, stream>>>(tb, N, iters, mode, tma_on, out_cycles);
+  umma_bench_kernel<<<grid, 128, smem, stream>>>(pattern, iters, N, out_cycles);
   SPN_CUDA_CHECK(cudaGetLastError());
   return SPN_OK;
 }

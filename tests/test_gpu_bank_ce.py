@@ -64,6 +64,40 @@ def test_loss_and_grad_match_oracle(B, N, D, mode, tau, seed, single_pass):
     assert rel_l2(dq, r_dq) < 3e-3, rel_l2(dq, r_dq)
 
 
+PAIR_CASES = [
+    # B (even number of 128-query tiles -> cta_group::2 pairs), N, D, T, tau, seed
+    (256, 1000, 64, 1, 0.05, 21),     # one k-block: half-filled GEMM1 stage, one narrow (2 x 32 column) dq group
+    (256, 777, 128, 1, 0.03, 22),     # one wide dq group, ragged last tile
+    (200, 3000, 256, 1, 0.03, 23),    # second tile of the pair is partly empty (B < 256)
+    (512, 2100, 320, 1, 0.02, 24),    # odd number of k-blocks and of dq blocks
+    (256, 5000, 512, 1, 0.02, 25),    # 2 d-splits of 256
+    (256, 6000, 640, 1, 0.02, 26),    # 2 d-splits of 320 = 128 + 128 + 64
+    (256, 4000, 768, 1, 0.02, 27),    # 3 d-splits of 256
+    (256, 300, 256, 32, 0.05, 28),    # BLIP-2 max over tokens
+]
+
+
+@PATHS
+@pytest.mark.parametrize("B,N,D,T,tau,seed", PAIR_CASES)
+def test_cta_pair_kernels_match_oracle_and_single_cta(B, N, D, T, tau, seed, single_pass, monkeypatch):
+    """The cta_group::2 kernels (rank 0 issues M = 256 MMAs for a pair of query tiles) against the oracle and against
+    the single-CTA kernels on the same inputs (SPN_DEBUG_CG=1 forces those)."""
+    q, bank, labels = synth.make_bank_case(B, N, D, T, "S", seed)
+    loss, dq, dtau = run_ours(q, bank, labels, tau, tau_tensor=True, single_pass=single_pass)
+    monkeypatch.setenv("SPN_DEBUG_CG", "1")
+    loss1, dq1, dtau1 = run_ours(q, bank, labels, tau, tau_tensor=True, single_pass=single_pass)
+    monkeypatch.delenv("SPN_DEBUG_CG")
+    assert abs(loss.item() - loss1.item()) <= 1e-5 * max(abs(loss1.item()), 1e-3), (loss, loss1)
+    assert rel_l2(dq, dq1) < 1e-4, rel_l2(dq, dq1)
+    assert abs(dtau.item() - dtau1.item()) <= 1e-3 * max(abs(dtau1.item()), 1e-2), (dtau, dtau1)
+    if T == 1:
+        r_loss, r_dq, _ = obank.infonce_loss_and_grads(bf16_round(q), bf16_round(bank), labels, tau, dtype=torch.float64)
+    else:
+        r_loss, r_dq, _ = obank.blip2_loss_and_grads(bf16_round(q), bf16_round(bank), labels, tau, dtype=torch.float64)
+    assert abs(loss.item() - r_loss.item()) <= 2e-4 * max(abs(r_loss.item()), 1.0), (loss, r_loss)
+    assert rel_l2(dq, r_dq) < 3e-3, rel_l2(dq, r_dq)
+
+
 @PATHS
 @pytest.mark.parametrize("name", ["small_ragged", "small_uniform", "c1", "c1_uniform"])
 def test_against_reference_fixtures(golden, name, single_pass):
