@@ -10,7 +10,7 @@ constexpr int kBN = 128;      // bank rows per S tile (UMMA N of GEMM1, K extent
 constexpr int kBK = 64;       // bf16 elements per 128-byte swizzle row
 constexpr int kUmmaK = 16;    // K per tcgen05.mma for 16-bit inputs
 constexpr uint32_t kBlockBytes = kBM * kBK * 2;  // one [128 x 64] bf16 block = 16 KiB
-constexpr int kBankCEThreads = 192;
+constexpr int kBankCEThreads = 320;  // TMA producer warp + MMA warp + 8 soft-max / epilogue warps
 
 struct BankCEParams {
   int B, D;
@@ -24,6 +24,7 @@ struct BankCEParams {
   int num_chunks;    // bank-row chunks (grid = q_tiles * num_dsplit * num_chunks)
   int num_dsplit;    // backward: splits of the output dim
   int ow_blocks;     // backward: 64-column blocks of dq per split
+  int hg;            // CTA-pair schedule knob (see the MMA issuer)
   float scale_log2;  // inv_tau * log2(e)
   long long row_base;
   const long long* labels;
@@ -47,6 +48,7 @@ struct BankCEParams {
 
 struct BankCEPlan {
   int kblocks, q_tiles, n_tiles, num_chunks, num_dsplit, ow_blocks, stages, bps, grid;
+  int hg;
   int cg;  // 2: CTA pairs (cta_group::2), 1: single-CTA kernel
   size_t smem_bytes, ws_bytes;
 };

@@ -5,9 +5,10 @@
 // Reference semantics: CIRPlus.infonce_loss (clip4cir/models_negplus.py:150-154) and, with T = 32, the
 // max-over-tokens loop of Blip2QformerCirAlignPrompt.forward_stage2 (...align_prompt.py:254-268).
 //
-// CTA = 6 warps:  warp 0 lane 0  TMA producer        (bank blocks [128 rows x 64 cols] bf16, SW128)
+// CTA = 10 warps: warp 0 lane 0  TMA producer        (bank blocks [128 rows x 64 cols] bf16, SW128)
 //                 warp 1 lane 0  tcgen05.mma issuer  (+ warp 1 owns the TMEM allocation)
-//                 warps 2..5     soft-max / epilogue (one TMEM lane quarter each, thread == query row)
+//                 warps 2..9     soft-max / epilogue (two per TMEM lane quarter, thread == query row, each warp owns
+//                                one 64-column half of the S tile)
 // smem:  a ring of 16 KiB bank blocks; backward additionally keeps the Q tile resident (D/64 blocks of 16 KiB).
 // TMEM:  forward   Q[128 x D bf16] (D/2 columns) | S[128 x 128 f32]          (512 columns)
 //        backward  O[128 x <=320 f32] | S[128 x 128] | P bf16                 (512 columns)
@@ -37,9 +38,14 @@ constexpr uint32_t kBwdPCol = 448;  // P tile columns [448, 512): 128 bf16 = 64 
 // Optional cycle accounting per role (build with -DSPN_TIMELINE; read with spn_debug_read_timeline).
 #ifdef SPN_TIMELINE
 __device__ unsigned long long g_timeline[1024 * 16];
-#define TL_VARS unsigned long long tl_acc[4] = {0, 0, 0, 0}; long long tl_t0 = 0, tl_start = clock64();
+#define TL_VARS unsigned long long tl_acc[7] = {0, 0, 0, 0, 0, 0, 0}; long long tl_t0 = 0, tl_start = clock64();
 #define TL_BEGIN tl_t0 = clock64();
 #define TL_END(i) tl_acc[i] += (unsigned long long)(clock64() - tl_t0);
+#define TL_FLUSH7(base)                                                                 \
+  if ((threadIdx.x & 31) == 0 && blockIdx.x < 1024) {                                   \
+    for (int _i = 0; _i < 7; ++_i) g_timeline[blockIdx.x * 16 + (base) + _i] = tl_acc[_i]; \
+    g_timeline[blockIdx.x * 16 + (base) + 7] = (unsigned long long)(clock64() - tl_start); \
+  }
 #define TL_FLUSH(base)                                                                  \
   if ((threadIdx.x & 31) == 0 && blockIdx.x < 1024) {                                   \
     for (int _i = 0; _i < 3; ++_i) g_timeline[blockIdx.x * 16 + (base) + _i] = tl_acc[_i]; \
@@ -50,6 +56,7 @@ __device__ unsigned long long g_timeline[1024 * 16];
 #define TL_BEGIN
 #define TL_END(i)
 #define TL_FLUSH(base)
+#define TL_FLUSH7(base)
 #endif
 
 struct SmemView {
@@ -333,12 +340,12 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], 1);
     }
-    mbar_init(sm.q_full, MODE == 0 ? 4 : 1);  // forward: the 4 soft-max warps stage Q into TMEM
+    mbar_init(sm.q_full, MODE == 0 ? 8 : 1);  // forward: the 8 soft-max warps stage Q into TMEM
     mbar_init(&sm.s_full[0], 1);
     mbar_init(&sm.s_full[1], 1);
-    mbar_init(&sm.s_free[0], 4 * CG);  // CG = 2: the soft-max warps of both CTAs arrive on rank 0's barriers
-    mbar_init(&sm.s_free[1], 4 * CG);
-    mbar_init(sm.p_full, MODE == 0 ? 1 : 4 * CG);  // forward: Q staging (TMA tx) barrier
+    mbar_init(&sm.s_free[0], 8 * CG);  // CG = 2: the soft-max warps of both CTAs arrive on rank 0's barriers
+    mbar_init(&sm.s_free[1], 8 * CG);
+    mbar_init(sm.p_full, MODE == 0 ? 1 : 8 * CG);  // forward: Q staging (TMA tx) barrier
     mbar_init(sm.p_free, 1);
     mbar_init(sm.o_full, 1);
     fence_barrier_init();
@@ -484,16 +491,16 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         constexpr uint32_t idesc_o128 = make_idesc_bf16_f32(2 * kBM, 128, 0, 1);
         constexpr uint32_t idesc_o64 = make_idesc_bf16_f32(2 * kBM, 64, 0, 1);
         const int ogroups = (my_blocks + 1) / 2;
-        mbar_wait_cluster(sm.q_full, 0);
+        mbar_wait(sm.q_full, 0);
         tc_fence_after();
         auto gemm_o2 = [&](int u) {
           TL_BEGIN
-          mbar_wait_cluster(sm.p_full, uint32_t(u) & 1u);
+          mbar_wait(sm.p_full, uint32_t(u) & 1u);
           TL_END(2)
           tc_fence_after();
           for (int g = 0; g < ogroups; ++g) {
             TL_BEGIN
-            mbar_wait_cluster(&sm.full[r.stage], r.phase);
+            mbar_wait(&sm.full[r.stage], r.phase);
             TL_END(0)
             tc_fence_after();
             if (elect_one()) {
@@ -512,14 +519,17 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           if (elect_one()) umma_commit_cg2(sm.p_free, 3);
           __syncwarp();
         };
+        const bool drain_first = p.hg != 0;
         for (int i = 0; i < ntl; ++i) {
-          TL_BEGIN
-          mbar_wait_cluster(&sm.s_free[0], (uint32_t(i) & 1u) ^ 1u);
-          TL_END(1)
-          tc_fence_after();
+          if (i == 0 || !drain_first) {
+            TL_BEGIN
+            mbar_wait(&sm.s_free[0], (uint32_t(i) & 1u) ^ 1u);
+            TL_END(1)
+            tc_fence_after();
+          }
           for (int kb0 = 0; kb0 < p.kblocks; kb0 += 2) {
             TL_BEGIN
-            mbar_wait_cluster(&sm.full[r.stage], r.phase);
+            mbar_wait(&sm.full[r.stage], r.phase);
             TL_END(0)
             tc_fence_after();
             if (elect_one()) {
@@ -539,6 +549,14 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
           if (elect_one()) umma_commit_cg2(&sm.s_full[0], 3);
           __syncwarp();
+          // tcgen05.ld of S(i) by the soft-max warps is served behind the MMAs already queued: let them drain S(i)
+          // before GEMM2(i - 1) enters the queue, so that GEMM1(i + 1) can follow GEMM2(i - 1) without a gap
+          if (drain_first && i + 1 < ntl) {
+            TL_BEGIN
+            mbar_wait(&sm.s_free[0], (uint32_t(i + 1) & 1u) ^ 1u);
+            TL_END(1)
+            tc_fence_after();
+          }
           if (i > 0) gemm_o2(i - 1);
         }
         if (ntl > 0) gemm_o2(ntl - 1);
@@ -641,8 +659,12 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }  // CG == 1
     TL_FLUSH(4)
   } else {
-    // ===================================================================== soft-max / epilogue warps
-    const uint32_t quarter = warp & 3u;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    // ===================================================================== soft-max / epilogue warps (8)
+    // Two warps per TMEM lane quarter: warp w owns lanes [32 (w & 3), +32) (thread == query row) and the 64-column
+    // half (w - 2) >> 2 of every S tile, so each SM sub-partition always has a second warp to issue while the first one
+    // waits on tcgen05.ld / MUFU / a barrier.
+    const uint32_t quarter = warp & 3u;
+    const uint32_t half = (warp - 2u) >> 2;
     const int row = int(quarter * 32u + lane);
     const int q = q0 + row;
     const bool q_ok = q < p.B;
@@ -654,15 +676,14 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       const long long g = p.labels[q] - p.row_base;
       if (g >= 0 && g < p.N) lbl = g;
     }
-    uint32_t xr[32];
+    uint32_t x0[32], x1[32];
     TL_VARS
 
     if (MODE == 0) {
       // move this thread's query row from the TMA-staged, 128B-swizzled blocks to TMEM as the packed-bf16 A
       // operand (columns [0, D/2)): chunk c of row r sits at r*128 + ((c ^ (r & 7)) << 4) inside a block
-      uint32_t x0[32], x1[32], x2[32], x3[32];
       mbar_wait(sm.p_full, 0);
-      for (int kb = 0; kb < p.kblocks; ++kb) {
+      for (int kb = int(half); kb < p.kblocks; kb += 2) {
         const uint8_t* blk = sm.ring + size_t(kb) * kBlockBytes + size_t(row) * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -675,7 +696,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sm.q_full);
-      const uint32_t s_col = uint32_t(p.kblocks) * 32u;
+      const uint32_t s_col = uint32_t(p.kblocks) * 32u + half * 64u;
       float m_run = -INFINITY, l_run = 0.f, st = -INFINITY, ssum = 0.f;
       for (int i = 0; i < ntl; ++i) {
         const int t = t_begin + i;
@@ -683,34 +704,32 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         mbar_wait(&sm.s_full[0], uint32_t(i) & 1u);
         TL_END(0)
         tc_fence_after();
-        // drain the whole S tile to registers in one go, then hand TMEM straight back to the MMA warp
+        // drain this warp's half of the S tile to registers in one go, then hand TMEM straight back to the MMA warp
         TL_BEGIN
         tmem_ld_32x32b_x32(t_row + s_col, x0);
         tmem_ld_32x32b_x32(t_row + s_col + 32u, x1);
-        tmem_ld_32x32b_x32(t_row + s_col + 64u, x2);
-        tmem_ld_32x32b_x32(t_row + s_col + 96u, x3);
         tmem_ld_wait();
         TL_END(1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.s_free[0]);
-        const long long row0 = (long long)t * kBN;
+        const long long row0 = (long long)t * kBN + half * 64;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t(&xc)[32] = c == 0 ? x0 : (c == 1 ? x1 : (c == 2 ? x2 : x3));
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t(&xc)[32] = c == 0 ? x0 : x1;
           const long long col0 = row0 + c * 32;
           if (T == 1) {
             const long long left = p.n_rows - col0;
             const int valid = left >= 32 ? 32 : (left > 0 ? int(left) : 0);
             if (valid > 0) fwd_chunk_t1<EXTRA>(xc, valid, scale, col0, lbl, m_run, l_run, st, ssum);
           } else {
-            const long long entry = (long long)t * 4 + c;
+            const long long entry = (long long)t * 4 + half * 2 + c;
             fwd_chunk_t32<EXTRA>(xc, entry < p.N, scale, entry == lbl, m_run, l_run, st, ssum);
           }
         }
       }
-      if (q_ok) {
-        const size_t o = size_t(chunk) * p.B + q;
+      if (q_ok) {  // one partial per (chunk, column half)
+        const size_t o = (size_t(chunk) * 2 + half) * p.B + q;
         p.part_m[o] = m_run;
         p.part_l[o] = l_run;
         p.part_st[o] = st;
@@ -722,80 +741,93 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       const float gscale = (MODE == 1 && p.gscale_dev) ? p.gscale * __ldg(p.gscale_dev) : p.gscale;
       float es = 0.f, l_run = 0.f, st = -INFINITY;
       int st_tok = 0;
-      uint32_t u[64];
+      uint32_t u[32];
+      const uint32_t s_col = kBwdSCol + half * 64u;
+      const uint32_t p_col = kBwdPCol + half * 32u;
+      const uint32_t sfree_bar = (CG == 2) ? mapa_shared(smem_u32(&sm.s_free[0]), 0) : 0u;
+      const uint32_t pfull_bar = (CG == 2) ? mapa_shared(smem_u32(sm.p_full), 0) : 0u;
       for (int i = 0; i < ntl; ++i) {
         const int t = t_begin + i;
         TL_BEGIN
         mbar_wait(&sm.s_full[0], uint32_t(i) & 1u);
         TL_END(0)
         tc_fence_after();
-        const long long row0 = (long long)t * kBN;
+        // drain first, release S at once: GEMM1 of the next tile must not wait for this tile's exponentials
+        TL_BEGIN
+        tmem_ld_32x32b_x32(t_row + s_col, x0);
+        tmem_ld_32x32b_x32(t_row + s_col + 32u, x1);
+        tmem_ld_wait();
+        TL_END(1)
+        TL_BEGIN
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_remote(sfree_bar);
+          else mbar_arrive(&sm.s_free[0]);
+        }
+        TL_END(5)
+        const long long row0 = (long long)t * kBN + half * 64;
+        TL_BEGIN
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          TL_BEGIN
-          tmem_ld_32x32b_x32(t_row + kBwdSCol + uint32_t(c) * 32u, xr);
-          tmem_ld_wait();
-          TL_END(1)
-          if (c == 3) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&sm.s_free[0]), 0));
-              else mbar_arrive(&sm.s_free[0]);
-            }
-          }
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t(&xc)[32] = c == 0 ? x0 : x1;
           const long long col0 = row0 + c * 32;
           if (T == 1) {
             const long long left = p.n_rows - col0;
             const int valid = left >= 32 ? 32 : (left > 0 ? int(left) : 0);
             if (MODE == 1)
-              bwd_chunk_t1<EXTRA>(xr, valid, scale, lse2, p.eps_over_n, p.one_minus_eps, gscale, col0, lbl, es,
+              bwd_chunk_t1<EXTRA>(xc, valid, scale, lse2, p.eps_over_n, p.one_minus_eps, gscale, col0, lbl, es,
                                   &u[c * 16]);
             else
-              fused_chunk_t1<EXTRA>(xr, valid, scale, lse2, col0, lbl, l_run, st, es, &u[c * 16]);
+              fused_chunk_t1<EXTRA>(xc, valid, scale, lse2, col0, lbl, l_run, st, es, &u[c * 16]);
           } else {
-            const long long entry = (long long)t * 4 + c;
+            const long long entry = (long long)t * 4 + half * 2 + c;
             if (MODE == 1)
-              bwd_chunk_t32<EXTRA>(xr, entry < p.N, scale, lse2, p.eps_over_n, p.one_minus_eps, gscale,
+              bwd_chunk_t32<EXTRA>(xc, entry < p.N, scale, lse2, p.eps_over_n, p.one_minus_eps, gscale,
                                    entry == lbl, es, &u[c * 16]);
             else
-              fused_chunk_t32<EXTRA>(xr, entry < p.N, scale, lse2, entry == lbl, l_run, st, st_tok, es, &u[c * 16]);
+              fused_chunk_t32<EXTRA>(xc, entry < p.N, scale, lse2, entry == lbl, l_run, st, st_tok, es, &u[c * 16]);
           }
         }
+        TL_END(3)
         // P(i) -> TMEM once GEMM2 of the previous tile no longer reads the buffer
         TL_BEGIN
         mbar_wait(sm.p_free, (uint32_t(i) & 1u) ^ 1u);
         TL_END(2)
+        TL_BEGIN
         tc_fence_after();
-        tmem_st_32x32b_x32(t_row + kBwdPCol, *reinterpret_cast<const uint32_t(*)[32]>(&u[0]));
-        tmem_st_32x32b_x32(t_row + kBwdPCol + 32u, *reinterpret_cast<const uint32_t(*)[32]>(&u[32]));
+        tmem_st_32x32b_x32(t_row + p_col, u);
         tmem_st_wait();
+        TL_END(4)
+        TL_BEGIN
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(sm.p_full), 0));
+          if (CG == 2) mbar_arrive_remote(pfull_bar);
           else mbar_arrive(sm.p_full);
         }
+        TL_END(6)
       }
-      // epilogue: O[128 x my_blocks*64] fp32 -> dq (+=, other chunks / shards add into the same rows)
+      // epilogue: O[128 x my_blocks*64] fp32 -> dq (+=, other chunks / shards add into the same rows); the two warps
+      // of a lane quarter take alternate 32-column chunks
       mbar_wait(sm.o_full, 0);
       tc_fence_after();
       if (ntl > 0) {
-        for (int c = 0; c < my_blocks * 2; ++c) {
-          tmem_ld_32x32b_x32(t_row + uint32_t(c) * 32u, xr);
+        for (int c = int(half); c < my_blocks * 2; c += 2) {
+          tmem_ld_32x32b_x32(t_row + uint32_t(c) * 32u, x0);
           tmem_ld_wait();
           if (q_ok) {
             float* dst = p.dq + size_t(q) * p.D + size_t(ds) * p.ow_blocks * 64 + size_t(c) * 32;
 #pragma unroll
             for (int v = 0; v < 8; ++v)
-              red_add_v4_f32(dst + v * 4, __uint_as_float(xr[4 * v]), __uint_as_float(xr[4 * v + 1]),
-                             __uint_as_float(xr[4 * v + 2]), __uint_as_float(xr[4 * v + 3]));
+              red_add_v4_f32(dst + v * 4, __uint_as_float(x0[4 * v]), __uint_as_float(x0[4 * v + 1]),
+                             __uint_as_float(x0[4 * v + 2]), __uint_as_float(x0[4 * v + 3]));
           }
         }
         if (EXTRA && q_ok && ds == 0) atomicAdd(&p.dlogit_dot[q], es * kLn2);
         if (MODE == 2 && q_ok && ds == 0) {
           atomicAdd(&p.l_acc[q], l_run);
-          if (st > -INFINITY) {  // this CTA owned the label column
+          if (st > -INFINITY) {  // this thread owned the label column
             p.st_out[q] = st * kLn2;
             p.lbl_row_out[q] = (T == 1) ? lbl : lbl * 32 + st_tok;  // LOCAL token row whose gradient is -(1 - p_t)
           }
@@ -803,7 +835,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
     }
 #ifdef SPN_TIMELINE
-    if (warp == 2) { TL_FLUSH(8) }
+    if (warp == 2) { TL_FLUSH7(8) }
 #endif
   }
 
@@ -1131,6 +1163,8 @@ int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan) {
   plan->grid = plan->q_tiles * plan->num_dsplit * chunks;
   // backward / fused: pair the query tiles (cta_group::2) whenever they come in twos -- see bank_ce_kernel<.., CG = 2>
   plan->cg = (mode == 1 && plan->q_tiles % 2 == 0) ? 2 : 1;
+  plan->hg = 0;  // 1: wait for the S drain before queueing GEMM2 of the previous tile (measured slower)
+  if (const char* e = getenv("SPN_DEBUG_HG")) plan->hg = atoi(e);
   if (const char* e = getenv("SPN_DEBUG_CG")) {
     if (atoi(e) == 1) plan->cg = 1;
   }
@@ -1149,7 +1183,7 @@ int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan) {
   SPN_REQUIRE(stages >= 2, SPN_ERR_BAD_SHAPE, "D=%d leaves no room for the bank ring in %d B of shared memory", D, smem_max);
   plan->stages = stages;
   plan->smem_bytes = fixed + size_t(stages) * bps * kBlockBytes;
-  plan->ws_bytes = (mode == 0) ? ((size_t(4) * chunks * B * sizeof(float) + 255) / 256) * 256 : 256;
+  plan->ws_bytes = (mode == 0) ? ((size_t(4) * 2 * chunks * B * sizeof(float) + 255) / 256) * 256 : 256;  // 2 column halves
   return SPN_OK;
 }
 
@@ -1169,7 +1203,7 @@ int bank_ce_forward(const void* q, const void* bank, const long long* labels, fl
   p.n_tiles = plan.n_tiles; p.q_tiles = plan.q_tiles; p.num_chunks = plan.num_chunks; p.num_dsplit = 1;
   p.ow_blocks = 0; p.scale_log2 = inv_tau * kLog2e; p.row_base = row_base; p.labels = labels; p.q_gmem = q;
   float* w = static_cast<float*>(ws);
-  const size_t stride = size_t(plan.num_chunks) * B;
+  const size_t stride = size_t(plan.num_chunks) * 2 * B;  // one partial per (chunk, column half)
   p.part_m = w; p.part_l = w + stride; p.part_st = w + 2 * stride; p.part_ssum = w + 3 * stride;
   const bool extra = s_sum != nullptr;
   if (T == 1) rc = extra ? launch_one<0, 1, true>(tq, tb, p, plan.grid, plan.smem_bytes, stream)
@@ -1178,7 +1212,7 @@ int bank_ce_forward(const void* q, const void* bank, const long long* labels, fl
                          : launch_one<0, 32, false>(tq, tb, p, plan.grid, plan.smem_bytes, stream);
   if (rc != SPN_OK) return rc;
   merge_stats_kernel<<<(B + 3) / 4, 128, 0, stream>>>(p.part_m, p.part_l, p.part_st, extra ? p.part_ssum : nullptr,
-                                                         plan.num_chunks, B, kLn2, m, l, s_t, s_sum);
+                                                         plan.num_chunks * 2, B, kLn2, m, l, s_t, s_sum);
   SPN_CUDA_CHECK(cudaGetLastError());
   return SPN_OK;
 }
@@ -1198,7 +1232,7 @@ int bank_ce_backward(const void* q, const void* bank, const long long* labels, f
   BankCEParams p{};
   p.B = B; p.D = D; p.N = N; p.n_rows = N * T; p.kblocks = plan.kblocks; p.stages = plan.stages; p.bps = plan.bps;
   p.n_tiles = plan.n_tiles; p.q_tiles = plan.q_tiles / plan.cg; p.num_chunks = plan.num_chunks;
-  p.num_dsplit = plan.num_dsplit; p.ow_blocks = plan.ow_blocks; p.scale_log2 = inv_tau * kLog2e;
+  p.num_dsplit = plan.num_dsplit; p.ow_blocks = plan.ow_blocks; p.hg = plan.hg; p.scale_log2 = inv_tau * kLog2e;
   p.row_base = row_base; p.labels = labels; p.lse = lse; p.gscale = gscale; p.gscale_dev = gscale_dev;
   p.eps_over_n = label_smoothing / float(N_total); p.one_minus_eps = 1.f - label_smoothing;
   p.dq = dq; p.dlogit_dot = dlogit_dot;
@@ -1252,7 +1286,7 @@ int bank_ce_fused(const void* q, const void* bank, const long long* labels, cons
   BankCEParams p{};
   p.B = B; p.D = D; p.N = N; p.n_rows = N * T; p.kblocks = plan.kblocks; p.stages = plan.stages; p.bps = plan.bps;
   p.n_tiles = plan.n_tiles; p.q_tiles = plan.q_tiles / plan.cg; p.num_chunks = plan.num_chunks;
-  p.num_dsplit = plan.num_dsplit; p.ow_blocks = plan.ow_blocks; p.scale_log2 = inv_tau * kLog2e;
+  p.num_dsplit = plan.num_dsplit; p.ow_blocks = plan.ow_blocks; p.hg = plan.hg; p.scale_log2 = inv_tau * kLog2e;
   p.row_base = row_base; p.labels = labels; p.ref = ref; p.gscale = 1.f; p.dq = o_acc; p.dlogit_dot = es_acc;
   p.l_acc = l_acc; p.st_out = s_t; p.lbl_row_out = lbl_row;
   rc = launch_mode<2>(plan.cg == 2, T, es_acc != nullptr, tq, tb, tbh, p, plan.grid, plan.smem_bytes, stream);

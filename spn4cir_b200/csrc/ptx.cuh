@@ -247,6 +247,12 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a,
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
+// remote arrive with the default (.release.cta) semantics, the form CUTLASS' ClusterBarrier::arrive(cta_id) uses: the
+// TMEM hand-over it signals is ordered by tcgen05.wait / tcgen05.fence, not by a cluster-scope memory release (which
+// costs on the order of a thousand cycles per arrive + acquiring try_wait, measured)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
 // wait with cluster-scope acquire: pairs with mbar_arrive_cluster after remote st.shared::cluster writes
 __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
