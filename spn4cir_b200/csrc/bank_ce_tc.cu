@@ -429,6 +429,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       TL_BEGIN
       mbar_wait(&sm.empty[r.stage], r.phase ^ 1u);
       TL_END(0)
+      TL_BEGIN
       const uint32_t fbar = mapa_shared(smem_u32(&sm.full[r.stage]), 0);
       if (elect_one()) {
         if (crank == 0) mbar_arrive_expect_tx(&sm.full[r.stage], 2u * uint32_t(nb) * (kBlockBytes / 2));
@@ -437,6 +438,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                           (kb0 + b) * kBK, row + int(crank) * (kBN / 2));
       }
       __syncwarp();
+      TL_END(1)
       r.advance();
     };
     // CG = 2, GEMM2: group g of the dq split = 128 columns (64 per CTA) or, for an odd last block, 64 columns (32 per
@@ -448,11 +450,13 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       const uint32_t fbar = mapa_shared(smem_u32(&sm.full[r.stage]), 0);
       const bool wide = 2 * g + 1 < my_blocks;
       const int col = (ds * p.ow_blocks + 2 * g) * kBK + int(crank) * (wide ? kBK : kBK / 2);
+      TL_BEGIN
       if (elect_one()) {
         if (crank == 0) mbar_arrive_expect_tx(&sm.full[r.stage], 2u * kBlockBytes);
         tma_load_2d_cg2(sm.ring + size_t(r.stage) * kBlockBytes, &tmap_bank, fbar, col, row);
       }
       __syncwarp();
+      TL_END(2)
       r.advance();
     };
     const int ogroups = (my_blocks + 1) / 2;
@@ -519,7 +523,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           if (elect_one()) umma_commit_cg2(sm.p_free, 3);
           __syncwarp();
         };
-        const bool drain_first = p.hg != 0;
+        const bool drain_first = p.hg == 1;
         for (int i = 0; i < ntl; ++i) {
           if (i == 0 || !drain_first) {
             TL_BEGIN

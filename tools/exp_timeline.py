@@ -26,7 +26,7 @@ for D in (256, 640):
         stats = _fwd_stats(q16, db, lab, 50.0, False)
         torch.cuda.synchronize()
     t = read(148)[:144]
-    names = ["prod_wait_empty", "-", "-", "prod_total", "mma_wait_full", "mma_wait_sfree", "mma_wait_pfull", "mma_total",
+    names = ["prod_wait_empty", "prod_issue_g1", "prod_issue_g2", "prod_total", "mma_wait_full", "mma_wait_sfree", "mma_wait_pfull", "mma_total",
              "sm_wait_sfull", "sm_tmem_ld", "sm_wait_pfree", "sm_math", "sm_tmem_st", "sm_arrive_sfree", "sm_arrive_pfull", "sm_total"]
     print(f"FWD D={D}:", json.dumps({n: round(float(t[:, i].mean())) for i, n in enumerate(names) if n != "-"}), flush=True)
     lse, _, _ = _loss_from_stats(stats, N, 0.0)
