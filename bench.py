@@ -178,13 +178,17 @@ def run_ours(args, cfg):
         loss.backward()
         return loss, qx.grad
 
+    dq_pin = torch.empty((B, D), dtype=torch.float32).pin_memory()
+    loss_pin = torch.empty((), dtype=torch.float32).pin_memory()
+
     def step_e2e():
+        # host (pinned) -> device, the public call, device -> host (pinned): all on the timed stream
         qd = q_pin.to(dev, non_blocking=True)
         ld = lab_pin.to(dev, non_blocking=True)
         loss, dq = step(qd, ld)
-        out = dq.to("cpu", non_blocking=True)
-        lv = loss.to("cpu", non_blocking=True)
-        return lv, out
+        dq_pin.copy_(dq, non_blocking=True)
+        loss_pin.copy_(loss, non_blocking=True)
+        return loss_pin, dq_pin
 
     def timed(fn, iters):
         """sum of per-iteration CUDA-event times (L2 flushed, untimed, before each); max over ranks."""
@@ -302,8 +306,10 @@ def run_ours(args, cfg):
                         "h2d_bytes_per_step": q_pin.numel() * 4 + lab_pin.numel() * 8,
                         "d2h_bytes_per_step": B * D * 4 + 4, "ms_per_step": t_e2e / args.steps * 1e3,
                         "note": "pinned host q/labels -> device, fwd+bwd, loss + dq back to host; the bank stays resident in HBM"},
-                "gpu_launches": 5 * args.steps,
-                "gpu_launches_detail": "per step: prep_query_kernel, fused_init_kernel, bank_ce_kernel<2>, gather_label_rows_kernel, fused_finalize_kernel"}
+                "gpu_launches": (5 if sharded else 3) * args.steps,
+                "gpu_launches_detail": ("per step: prep_query_kernel, fused_init_kernel, bank_ce_kernel<2>, gather_label_rows_kernel, fused_finalize_kernel"
+                                        if sharded else
+                                        "per step (one spn_bank_ce_step call): prep_query_kernel, bank_ce_kernel<2>, fused_finalize_kernel")}
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = time_cpu_reference(cfg, budget_s=20.0, steps=3, warmup=1)
             line["cpu_baseline"] = cb

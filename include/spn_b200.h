@@ -43,7 +43,8 @@ enum spn_op {
   SPN_OP_BANK_CE_FWD = 1,
   SPN_OP_BANK_CE_BWD = 2,
   SPN_OP_SIM_TOPK = 3,
-  SPN_OP_SIM_RANK = 4
+  SPN_OP_SIM_RANK = 4,
+  SPN_OP_BANK_CE_STEP = 5
 };
 
 enum spn_dtype { SPN_F32 = 0, SPN_F16 = 1, SPN_BF16 = 2 };
@@ -149,6 +150,18 @@ int spn_bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_
                          const float* es_acc, const void* q_bf16, const float* colsum, float inv_tau, float gscale,
                          float label_smoothing, int64_t N_total, int B, int D, float* lse, float* loss_per_query,
                          float* loss_mean, float* dq, float* dlogit_dot, void* stream);
+
+/* One whole training step on one GPU (un-sharded bank, row_base = 0) in a single call:
+ * spn_bank_ce_prep (+ zeroing of the accumulators) -> spn_bank_ce_fused -> spn_bank_ce_finalize (the target row is read
+ * from the resident bank).  Three kernel launches; every intermediate lives in `ws`
+ * (spn_workspace_bytes(SPN_OP_BANK_CE_STEP, B, N, D, T, 0), 256-byte aligned).  Replaces, per step, the forward
+ * clip4cir/models_negplus.py:150-154 and its autograd backward (clip4cir/train_negplus.py:110-121): loss_mean is the
+ * loss, dq (nullable) the gradient w.r.t. the UN-cast q for an upstream gradient of 1, dlogit_dot (nullable) gives
+ * d loss / d tau as for spn_bank_ce_finalize. */
+int spn_bank_ce_step(const void* q_src, int src_dtype, const void* bank_bf16, const int64_t* labels, float inv_tau,
+                     const float* bank_maxnorm, const float* colsum, float label_smoothing, int B, int64_t N, int D, int T,
+                     float* lse, float* loss_per_query, float* loss_mean, float* dq, float* dlogit_dot, void* ws,
+                     size_t ws_bytes, void* stream);
 
 /* Fused cosine-similarity + per-row top-K over one gallery shard (descending score, ties -> lower
  * index first).  Replaces `distances = 1 - pred @ index.T; torch.argsort(distances)` followed by the

@@ -32,7 +32,7 @@ STATUS_NAMES = {
     0: "SPN_OK", -1: "SPN_ERR_BAD_SHAPE", -2: "SPN_ERR_BAD_ALIGN", -3: "SPN_ERR_BAD_DTYPE",
     -4: "SPN_ERR_WORKSPACE", -5: "SPN_ERR_CUDA", -6: "SPN_ERR_NCCL", -7: "SPN_ERR_BAD_ARG",
 }
-OP_BANK_CE_FWD, OP_BANK_CE_BWD, OP_SIM_TOPK, OP_SIM_RANK = 1, 2, 3, 4
+OP_BANK_CE_FWD, OP_BANK_CE_BWD, OP_SIM_TOPK, OP_SIM_RANK, OP_BANK_CE_STEP = 1, 2, 3, 4, 5
 DT_F32, DT_F16, DT_BF16 = 0, 1, 2
 
 
@@ -102,6 +102,8 @@ _SIGNATURES = {
     "spn_bank_ce_finalize": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                              c_float, c_float, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p],
+    "spn_bank_ce_step": [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float, c_int, c_int64, c_int,
+                         c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     "spn_sim_topk": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int32, c_void_p,
                      c_void_p, c_void_p, c_size_t, c_void_p],
     "spn_merge_topk": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],

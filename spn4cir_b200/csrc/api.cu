@@ -27,6 +27,10 @@ int spn_workspace_bytes(int op, int B, int64_t N, int D, int T, int K, size_t* o
     case SPN_OP_SIM_RANK:
       *out_bytes = 256;
       return SPN_OK;
+    case SPN_OP_BANK_CE_STEP:
+      SPN_REQUIRE(B > 0 && D >= 64 && D <= 768 && D % 64 == 0, SPN_ERR_BAD_SHAPE, "spn_workspace_bytes(BANK_CE_STEP): bad shape B=%d D=%d", B, D);
+      *out_bytes = bank_ce_step_ws_bytes(B, D);
+      return SPN_OK;
     default:
       return fail(SPN_ERR_BAD_ARG, "spn_workspace_bytes: unknown op %d", op);
   }
@@ -129,8 +133,24 @@ int spn_bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_
   SPN_REQUIRE(label_smoothing >= 0.f && label_smoothing < 1.f, SPN_ERR_BAD_ARG, "label_smoothing must be in [0, 1)");
   int rc = require_sm100();
   if (rc != SPN_OK) return rc;
-  return bank_ce_finalize(o_acc, l_acc, s_t, bank_t, ref, es_acc, q_bf16, colsum, inv_tau, gscale, label_smoothing, N_total,
-                          B, D, lse, loss_per_query, loss_mean, dq, dlogit_dot, as_stream(stream));
+  return bank_ce_finalize(o_acc, l_acc, s_t, bank_t, nullptr, nullptr, /*zero_loss=*/1, ref, es_acc, q_bf16, colsum, inv_tau,
+                          gscale, label_smoothing, N_total, B, D, lse, loss_per_query, loss_mean, dq, dlogit_dot,
+                          as_stream(stream));
+}
+
+int spn_bank_ce_step(const void* q_src, int src_dtype, const void* bank_bf16, const int64_t* labels, float inv_tau,
+                     const float* bank_maxnorm, const float* colsum, float label_smoothing, int B, int64_t N, int D, int T,
+                     float* lse, float* loss_per_query, float* loss_mean, float* dq, float* dlogit_dot, void* ws,
+                     size_t ws_bytes, void* stream) {
+  SPN_REQUIRE(q_src && bank_bf16 && labels && bank_maxnorm && lse && loss_mean, SPN_ERR_BAD_ARG, "spn_bank_ce_step: NULL pointer");
+  SPN_REQUIRE(label_smoothing >= 0.f && label_smoothing < 1.f, SPN_ERR_BAD_ARG, "label_smoothing must be in [0, 1)");
+  SPN_REQUIRE(label_smoothing == 0.f || colsum, SPN_ERR_BAD_ARG, "label smoothing needs the bank column sums");
+  SPN_REQUIRE(!dq || aligned16(dq), SPN_ERR_BAD_ALIGN, "spn_bank_ce_step: dq must be 16-byte aligned");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return bank_ce_step(q_src, src_dtype, bank_bf16, reinterpret_cast<const long long*>(labels), inv_tau, bank_maxnorm, colsum,
+                      label_smoothing, B, N, D, T, lse, loss_per_query, loss_mean, dq, dlogit_dot, ws, ws_bytes,
+                      as_stream(stream));
 }
 
 int spn_sim_topk(const float* q, const float* gallery, int Q, int G, int D, int T, int K, const int32_t* exclude,

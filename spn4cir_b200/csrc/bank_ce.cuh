@@ -69,10 +69,15 @@ int bank_ce_prep(const void* q_src, int dtype, const void* bank, const long long
 int bank_ce_fused(const void* q, const void* bank, const long long* labels, const float* ref, float inv_tau, int B,
                   long long N, int D, int T, long long row_base, int init, float* o_acc, float* l_acc, float* s_t,
                   long long* lbl_row, float* es_acc, float* bank_t, cudaStream_t stream);
-int bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, const float* bank_t, const float* ref,
-                     const float* es_acc, const void* q16, const float* colsum, float inv_tau, float gscale, float eps,
+int bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, const float* bank_t, const void* bank,
+                     const long long* lbl_row, int zero_loss, const float* ref, const float* es_acc, const void* q16, const float* colsum, float inv_tau, float gscale, float eps,
                      long long N_total, int B, int D, float* lse, float* loss_q, float* loss_mean, float* dq,
                      float* dlogit_dot, cudaStream_t stream);
+size_t bank_ce_step_ws_bytes(int B, int D);
+int bank_ce_step(const void* q_src, int dtype, const void* bank, const long long* labels, float inv_tau,
+                 const float* maxnorm, const float* colsum, float eps, int B, long long N, int D, int T, float* lse,
+                 float* loss_q, float* loss_mean, float* dq, float* dlogit_dot, void* ws, size_t ws_bytes,
+                 cudaStream_t stream);
 int merge_stats(const float* pm, const float* pl, const float* pst, const float* pss, int P, int B, float* m,
                 float* l, float* st, float* ss, cudaStream_t stream);
 int bank_ce_loss(const float* m, const float* l, const float* st, const float* ss, int B, long long N_total,

@@ -921,20 +921,38 @@ __device__ __forceinline__ float load_as_f32<__nv_bfloat16>(const __nv_bfloat16*
 //   ref   = min(bound, max(s_t + 30, bound - 64))
 // => every exponent s - ref <= 64 (no overflow, also of the sums), the target term is exp(-30) unless the clamp is
 // active; nothing relevant underflows as long as 2 * bound <= 218 nats (tau >= 0.0092 for unit-norm features).
+// Accumulators of the fused sweep that the prologue may zero on the way (all nullable as a group via o_acc).
+struct FusedInit {
+  float* o_acc;        // [B, D]
+  float* l_acc;        // [B]
+  float* st;           // [B]  -> -inf
+  long long* lbl_row;  // [B]  -> -1
+  float* es;           // [B]  nullable
+  float* loss_mean;    // [1]  nullable
+};
+
 template <typename SrcT>
 __global__ void prep_query_kernel(const SrcT* __restrict__ q_src, const __nv_bfloat16* __restrict__ bank,
                                   const long long* __restrict__ labels, float inv_tau, const float* __restrict__ maxnorm,
                                   int B, long long N, int D, int T, long long row_base, __nv_bfloat16* __restrict__ q16,
-                                  float* __restrict__ ref) {
+                                  float* __restrict__ ref, const FusedInit init) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
+  // this lane's slice of the row, rounded to bf16 once: elements d = 2 lane + 64 k (+1), k < D / 64 <= 12
+  float2 qv[12];
   float ss = 0.f;
-  for (int d = lane; d < D; d += 32) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(load_as_f32<SrcT>(q_src, size_t(b) * D + d));
-    q16[size_t(b) * D + d] = h;
-    const float v = __bfloat162float(h);
-    ss = fmaf(v, v, ss);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    const int d = k * 64 + lane * 2;
+    qv[k] = make_float2(0.f, 0.f);
+    if (d < D) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(load_as_f32<SrcT>(q_src, size_t(b) * D + d),
+                                                     load_as_f32<SrcT>(q_src, size_t(b) * D + d + 1));
+      *reinterpret_cast<__nv_bfloat162*>(q16 + size_t(b) * D + d) = h;
+      qv[k] = __bfloat1622float2(h);
+      ss = fmaf(qv[k].x, qv[k].x, fmaf(qv[k].y, qv[k].y, ss));
+    }
   }
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   float r = inv_tau * sqrtf(ss) * (*maxnorm) * 1.01f + 1e-3f;
@@ -944,14 +962,31 @@ __global__ void prep_query_kernel(const SrcT* __restrict__ q_src, const __nv_bfl
     for (int tok = 0; tok < T; ++tok) {
       const __nv_bfloat16* row = bank + (g * T + tok) * D;
       float acc = 0.f;
-      for (int d = lane; d < D; d += 32)
-        acc = fmaf(__bfloat162float(__float2bfloat16_rn(load_as_f32<SrcT>(q_src, size_t(b) * D + d))), __bfloat162float(row[d]), acc);
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const int d = k * 64 + lane * 2;
+        if (d < D) {
+          const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + d));
+          acc = fmaf(qv[k].x, v.x, fmaf(qv[k].y, v.y, acc));
+        }
+      }
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       best = fmaxf(best, acc);
     }
     r = fminf(r, fmaxf(best * inv_tau + 30.f, r - 64.f));
   }
   if (lane == 0) ref[b] = r;
+  if (init.o_acc) {
+    float4* o = reinterpret_cast<float4*>(init.o_acc + size_t(b) * D);
+    for (int d = lane; d < D / 4; d += 32) o[d] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane == 0) {
+      init.l_acc[b] = 0.f;
+      init.st[b] = -INFINITY;
+      init.lbl_row[b] = -1;
+      if (init.es) init.es[b] = 0.f;
+      if (b == 0 && init.loss_mean) *init.loss_mean = 0.f;
+    }
+  }
 }
 
 // one warp per query: combine the fused kernel's partial sums into loss, lse and the unit gradient
@@ -959,7 +994,8 @@ __global__ void prep_query_kernel(const SrcT* __restrict__ q_src, const __nv_bfl
 //   dq = gscale * [ (o_excl - l_excl * bank_t) / L + eps * bank_t - (eps / N) * colsum ]
 __global__ void fused_finalize_kernel(const float* __restrict__ o_acc, const float* __restrict__ l_acc,
                                       const float* __restrict__ st, const float* __restrict__ bank_t /*[B,D] fp32*/,
-                                      const float* __restrict__ ref, const float* __restrict__ es_acc,
+                                      const __nv_bfloat16* __restrict__ bank /*used when bank_t == NULL*/,
+                                      const long long* __restrict__ lbl_row, const float* __restrict__ ref, const float* __restrict__ es_acc,
                                       const __nv_bfloat16* __restrict__ q16, const float* __restrict__ colsum,
                                       float inv_tau, float gscale, float eps, float inv_n_total, int B, int D,
                                       float* __restrict__ lse, float* __restrict__ loss_q, float* __restrict__ loss_mean,
@@ -992,7 +1028,15 @@ __global__ void fused_finalize_kernel(const float* __restrict__ o_acc, const flo
   if (dq) {
     for (int d = lane * 4; d < D; d += 128) {
       const float4 o = *reinterpret_cast<const float4*>(o_acc + size_t(b) * D + d);
-      const float4 t = *reinterpret_cast<const float4*>(bank_t + size_t(b) * D + d);
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bank_t) {
+        t = *reinterpret_cast<const float4*>(bank_t + size_t(b) * D + d);
+      } else if (lbl_row[b] >= 0) {  // single-GPU step: the target row straight from the resident bank
+        const uint2 raw = *reinterpret_cast<const uint2*>(bank + size_t(lbl_row[b]) * D + d);
+        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+        t = make_float4(lo.x, lo.y, hi.x, hi.y);
+      }
       float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
       if (eps != 0.f) c = *reinterpret_cast<const float4*>(colsum + d);
       float4 g;
@@ -1254,21 +1298,27 @@ int bank_stats(const void* bank, long long rows, int D, float* maxnorm, float* c
   return SPN_OK;
 }
 
-int bank_ce_prep(const void* q_src, int dtype, const void* bank, const long long* labels, float inv_tau,
-                 const float* maxnorm, int B, long long N, int D, int T, long long row_base, void* q16, float* ref,
-                 cudaStream_t stream) {
-  SPN_REQUIRE(B > 0 && N > 0 && D > 0, SPN_ERR_BAD_SHAPE, "bank_ce_prep: bad shape");
+static int launch_prep(const void* q_src, int dtype, const void* bank, const long long* labels, float inv_tau,
+                       const float* maxnorm, int B, long long N, int D, int T, long long row_base, void* q16, float* ref,
+                       const FusedInit& init, cudaStream_t stream) {
+  SPN_REQUIRE(B > 0 && N > 0 && D >= 64 && D <= 768 && D % 64 == 0, SPN_ERR_BAD_SHAPE, "bank_ce_prep: bad shape B=%d N=%lld D=%d", B, N, D);
   const __nv_bfloat16* bk = static_cast<const __nv_bfloat16*>(bank);
   __nv_bfloat16* qo = static_cast<__nv_bfloat16*>(q16);
-  const int grid = (B + 7) / 8;
+  const int grid = (B + 3) / 4;
   switch (dtype) {
-    case SPN_F32: prep_query_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(q_src), bk, labels, inv_tau, maxnorm, B, N, D, T, row_base, qo, ref); break;
-    case SPN_F16: prep_query_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(q_src), bk, labels, inv_tau, maxnorm, B, N, D, T, row_base, qo, ref); break;
-    case SPN_BF16: prep_query_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(q_src), bk, labels, inv_tau, maxnorm, B, N, D, T, row_base, qo, ref); break;
+    case SPN_F32: prep_query_kernel<float><<<grid, 128, 0, stream>>>(static_cast<const float*>(q_src), bk, labels, inv_tau, maxnorm, B, N, D, T, row_base, qo, ref, init); break;
+    case SPN_F16: prep_query_kernel<__half><<<grid, 128, 0, stream>>>(static_cast<const __half*>(q_src), bk, labels, inv_tau, maxnorm, B, N, D, T, row_base, qo, ref, init); break;
+    case SPN_BF16: prep_query_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(q_src), bk, labels, inv_tau, maxnorm, B, N, D, T, row_base, qo, ref, init); break;
     default: return fail(SPN_ERR_BAD_DTYPE, "bank_ce_prep: unknown dtype %d", dtype);
   }
   SPN_CUDA_CHECK(cudaGetLastError());
   return SPN_OK;
+}
+
+int bank_ce_prep(const void* q_src, int dtype, const void* bank, const long long* labels, float inv_tau,
+                 const float* maxnorm, int B, long long N, int D, int T, long long row_base, void* q16, float* ref,
+                 cudaStream_t stream) {
+  return launch_prep(q_src, dtype, bank, labels, inv_tau, maxnorm, B, N, D, T, row_base, q16, ref, FusedInit{}, stream);
 }
 
 int bank_ce_fused(const void* q, const void* bank, const long long* labels, const float* ref, float inv_tau, int B,
@@ -1302,20 +1352,56 @@ int bank_ce_fused(const void* q, const void* bank, const long long* labels, cons
   return SPN_OK;
 }
 
-int bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, const float* bank_t, const float* ref,
-                     const float* es_acc, const void* q16, const float* colsum, float inv_tau, float gscale, float eps,
+int bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, const float* bank_t, const void* bank,
+                     const long long* lbl_row, int zero_loss, const float* ref, const float* es_acc, const void* q16, const float* colsum, float inv_tau, float gscale, float eps,
                      long long N_total, int B, int D, float* lse, float* loss_q, float* loss_mean, float* dq,
                      float* dlogit_dot, cudaStream_t stream) {
   SPN_REQUIRE(B > 0 && D % 4 == 0 && N_total > 0, SPN_ERR_BAD_SHAPE, "bank_ce_finalize: bad shape");
   SPN_REQUIRE(eps == 0.f || (colsum && q16), SPN_ERR_BAD_ARG, "label smoothing needs the bank column sums and q");
   SPN_REQUIRE(!dlogit_dot || es_acc, SPN_ERR_BAD_ARG, "dlogit_dot needs es_acc");
   SPN_REQUIRE(!dq || (aligned16(dq) && aligned16(o_acc) && aligned16(bank_t)), SPN_ERR_BAD_ALIGN, "bank_ce_finalize: 16-byte alignment");
-  SPN_CUDA_CHECK(cudaMemsetAsync(loss_mean, 0, sizeof(float), stream));
-  fused_finalize_kernel<<<(B + 7) / 8, 256, 0, stream>>>(o_acc, l_acc, s_t, bank_t, ref, es_acc,
+  SPN_REQUIRE(bank_t || (bank && lbl_row), SPN_ERR_BAD_ARG, "bank_ce_finalize: needs bank_t or (bank, lbl_row)");
+  if (zero_loss) SPN_CUDA_CHECK(cudaMemsetAsync(loss_mean, 0, sizeof(float), stream));
+  fused_finalize_kernel<<<(B + 3) / 4, 128, 0, stream>>>(o_acc, l_acc, s_t, bank_t, static_cast<const __nv_bfloat16*>(bank),
+                                                        lbl_row, ref, es_acc,
                                                         static_cast<const __nv_bfloat16*>(q16), colsum, inv_tau, gscale,
                                                         eps, 1.f / float(N_total), B, D, lse, loss_q, loss_mean, dq, dlogit_dot);
   SPN_CUDA_CHECK(cudaGetLastError());
   return SPN_OK;
+}
+
+size_t bank_ce_step_ws_bytes(int B, int D) {
+  // q16 [B, D] bf16 | o_acc [B, D] f32 | ref, l_acc, s_t, es_acc [B] f32 | lbl_row [B] i64, each 256-byte aligned
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  return up(size_t(B) * D * 2) + up(size_t(B) * D * 4) + 4 * up(size_t(B) * 4) + up(size_t(B) * 8);
+}
+
+// One training step on one GPU in a single call: prologue (+ zeroing) -> fused sweep -> finalize (+ target-row gather).
+int bank_ce_step(const void* q_src, int dtype, const void* bank, const long long* labels, float inv_tau,
+                 const float* maxnorm, const float* colsum, float eps, int B, long long N, int D, int T, float* lse,
+                 float* loss_q, float* loss_mean, float* dq, float* dlogit_dot, void* ws, size_t ws_bytes,
+                 cudaStream_t stream) {
+  SPN_REQUIRE(ws && ws_bytes >= bank_ce_step_ws_bytes(B, D), SPN_ERR_WORKSPACE, "bank_ce_step: workspace too small: %zu < %zu",
+              ws_bytes, bank_ce_step_ws_bytes(B, D));
+  SPN_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, SPN_ERR_BAD_ALIGN, "bank_ce_step: workspace must be 256-byte aligned");
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  void* q16 = w;                                       w += up(size_t(B) * D * 2);
+  float* o_acc = reinterpret_cast<float*>(w);          w += up(size_t(B) * D * 4);
+  float* ref = reinterpret_cast<float*>(w);            w += up(size_t(B) * 4);
+  float* l_acc = reinterpret_cast<float*>(w);          w += up(size_t(B) * 4);
+  float* s_t = reinterpret_cast<float*>(w);            w += up(size_t(B) * 4);
+  float* es_acc = reinterpret_cast<float*>(w);         w += up(size_t(B) * 4);
+  long long* lbl_row = reinterpret_cast<long long*>(w);
+  if (!dlogit_dot) es_acc = nullptr;
+  int rc = launch_prep(q_src, dtype, bank, labels, inv_tau, maxnorm, B, N, D, T, 0, q16, ref,
+                       FusedInit{o_acc, l_acc, s_t, lbl_row, es_acc, loss_mean}, stream);
+  if (rc != SPN_OK) return rc;
+  rc = bank_ce_fused(q16, bank, labels, ref, inv_tau, B, N, D, T, 0, /*init=*/0, o_acc, l_acc, s_t, lbl_row, es_acc,
+                     /*bank_t=*/nullptr, stream);
+  if (rc != SPN_OK) return rc;
+  return bank_ce_finalize(o_acc, l_acc, s_t, nullptr, bank, lbl_row, /*zero_loss=*/0, ref, es_acc, q16, colsum, inv_tau,
+                          inv_tau / float(B), eps, N, B, D, lse, loss_q, loss_mean, dq, dlogit_dot, stream);
 }
 
 int merge_stats(const float* pm, const float* pl, const float* pst, const float* pss, int P, int B, float* m,

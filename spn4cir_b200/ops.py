@@ -247,6 +247,34 @@ def _fused_finalize(sw: dict, bank: DeviceBank, inv_tau: float, b_total: int, ep
     return out[0], out[1], mean, dq, ddot
 
 
+_STEP_WS = {}
+
+
+def _fused_step(q: torch.Tensor, bank: DeviceBank, labels: torch.Tensor, inv_tau: float, eps: float, want_ddot: bool):
+    """The whole single-GPU training step in ONE library call (``spn_bank_ce_step``: prologue -> fused sweep ->
+    finalize, three launches).  Returns (lse, loss_per_query, loss_mean, dq_unit, dlogit_dot | None)."""
+    B, D = q.shape
+    dev = q.device
+    qc = q.detach()
+    if qc.dtype not in _TORCH2SPN:
+        qc = qc.float()
+    qc = qc.contiguous()
+    maxnorm, colsum = bank.stats(eps != 0.0)
+    key = (B, D)
+    if key not in _STEP_WS:
+        _STEP_WS[key] = _lib.workspace_bytes(_lib.OP_BANK_CE_STEP, B, bank.N, D, bank.T)
+    ws_bytes = _STEP_WS[key]
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    out = torch.empty((3, B), dtype=torch.float32, device=dev)  # lse, loss_per_query, dlogit_dot
+    mean = torch.empty((), dtype=torch.float32, device=dev)
+    dq = torch.empty((B, D), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        call("spn_bank_ce_step", _ptr(qc), _TORCH2SPN[qc.dtype], _ptr(bank.data), _ptr(labels), inv_tau, _ptr(maxnorm),
+             _ptr(colsum) if eps != 0.0 else None, eps, B, bank.N, D, bank.T, _ptr(out[0]), _ptr(out[1]), _ptr(mean),
+             _ptr(dq), _ptr(out[2]) if want_ddot else None, _ptr(ws), ws_bytes, _stream(dev))
+    return out[0], out[1], mean, dq, out[2] if want_ddot else None
+
+
 class _BankCEFused(torch.autograd.Function):
     """Single-pass training path: forward already produces the gradient for an upstream gradient of 1
     (spn_bank_ce_prep -> spn_bank_ce_fused -> spn_bank_ce_finalize); backward only scales it."""
@@ -254,8 +282,11 @@ class _BankCEFused(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, tau_t, bank: DeviceBank, labels, inv_tau: float, eps: float):
         tau_grad = tau_t is not None and tau_t.requires_grad
-        sw = _fused_sweep(q, bank, labels, inv_tau, tau_grad)
-        _, _, loss, dq_unit, ddot = _fused_finalize(sw, bank, inv_tau, q.shape[0], eps, True)
+        if bank.row_base == 0 and bank.n_total == bank.N:
+            _, _, loss, dq_unit, ddot = _fused_step(q, bank, labels, inv_tau, eps, tau_grad)
+        else:  # one shard of a larger bank, driven piecewise (the exchange happens in dist.py)
+            sw = _fused_sweep(q, bank, labels, inv_tau, tau_grad)
+            _, _, loss, dq_unit, ddot = _fused_finalize(sw, bank, inv_tau, q.shape[0], eps, True)
         ctx.inv_tau, ctx.B, ctx.q_dtype, ctx.tau_grad = inv_tau, q.shape[0], q.dtype, tau_grad
         ctx.save_for_backward(dq_unit, ddot if tau_grad else None)
         return loss
