@@ -256,10 +256,14 @@ def run_ours(args, cfg):
     from spn4cir_b200._lib import call as _call
     sw = _fused_sweep(torch.cat([q_dev] * world) if sharded else q_dev, bank, lab_all, 1.0 / tau, False)
 
+    from spn4cir_b200.ops import fused_scratch
+    scratch, scratch_bytes = fused_scratch(Bt, bank, dev)
+
     def fused_only():
         _call("spn_bank_ce_fused", sw["q16"].data_ptr(), bank.data.data_ptr(), lab_all.data_ptr(), sw["ref"].data_ptr(),
               1.0 / tau, Bt, bank.N, D, bank.T, bank.row_base, 0, sw["o_acc"].data_ptr(), sw["l_acc"].data_ptr(),
-              sw["s_t"].data_ptr(), sw["lbl_row"].data_ptr(), None, None, None, 0, torch.cuda.current_stream().cuda_stream)
+              sw["s_t"].data_ptr(), sw["lbl_row"].data_ptr(), None, None,
+              scratch.data_ptr() if scratch is not None else None, scratch_bytes, torch.cuda.current_stream().cuda_stream)
 
     t_fused = timed(fused_only, args.steps) / args.steps
     barrier()

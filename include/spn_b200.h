@@ -44,7 +44,8 @@ enum spn_op {
   SPN_OP_BANK_CE_BWD = 2,
   SPN_OP_SIM_TOPK = 3,
   SPN_OP_SIM_RANK = 4,
-  SPN_OP_BANK_CE_STEP = 5
+  SPN_OP_BANK_CE_STEP = 5,
+  SPN_OP_BANK_CE_FUSED = 6
 };
 
 enum spn_dtype { SPN_F32 = 0, SPN_F16 = 1, SPN_BF16 = 2 };

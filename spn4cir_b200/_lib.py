@@ -32,7 +32,7 @@ STATUS_NAMES = {
     0: "SPN_OK", -1: "SPN_ERR_BAD_SHAPE", -2: "SPN_ERR_BAD_ALIGN", -3: "SPN_ERR_BAD_DTYPE",
     -4: "SPN_ERR_WORKSPACE", -5: "SPN_ERR_CUDA", -6: "SPN_ERR_NCCL", -7: "SPN_ERR_BAD_ARG",
 }
-OP_BANK_CE_FWD, OP_BANK_CE_BWD, OP_SIM_TOPK, OP_SIM_RANK, OP_BANK_CE_STEP = 1, 2, 3, 4, 5
+OP_BANK_CE_FWD, OP_BANK_CE_BWD, OP_SIM_TOPK, OP_SIM_RANK, OP_BANK_CE_STEP, OP_BANK_CE_FUSED = 1, 2, 3, 4, 5, 6
 DT_F32, DT_F16, DT_BF16 = 0, 1, 2
 
 

@@ -29,7 +29,10 @@ int spn_workspace_bytes(int op, int B, int64_t N, int D, int T, int K, size_t* o
       return SPN_OK;
     case SPN_OP_BANK_CE_STEP:
       SPN_REQUIRE(B > 0 && D >= 64 && D <= 768 && D % 64 == 0, SPN_ERR_BAD_SHAPE, "spn_workspace_bytes(BANK_CE_STEP): bad shape B=%d D=%d", B, D);
-      *out_bytes = bank_ce_step_ws_bytes(B, D);
+      *out_bytes = bank_ce_step_ws_bytes(B, N, D, T);
+      return SPN_OK;
+    case SPN_OP_BANK_CE_FUSED:
+      *out_bytes = (bank_ce_fused_ws_bytes(B, N, D, T) + 255) / 256 * 256;
       return SPN_OK;
     default:
       return fail(SPN_ERR_BAD_ARG, "spn_workspace_bytes: unknown op %d", op);
@@ -115,14 +118,13 @@ int spn_bank_ce_prep(const void* q_src, int src_dtype, const void* bank_bf16, co
 int spn_bank_ce_fused(const void* q_bf16, const void* bank_bf16, const int64_t* labels, const float* ref, float inv_tau,
                       int B, int64_t N, int D, int T, int64_t row_base, int init, float* o_acc, float* l_acc, float* s_t,
                       int64_t* lbl_row, float* es_acc, float* bank_t, void* ws, size_t ws_bytes, void* stream) {
-  (void)ws;
-  (void)ws_bytes;
   SPN_REQUIRE(q_bf16 && bank_bf16 && labels && ref && o_acc && l_acc && s_t && lbl_row, SPN_ERR_BAD_ARG,
               "spn_bank_ce_fused: NULL pointer");
   int rc = require_sm100();
   if (rc != SPN_OK) return rc;
   return bank_ce_fused(q_bf16, bank_bf16, reinterpret_cast<const long long*>(labels), ref, inv_tau, B, N, D, T, row_base,
-                       init, o_acc, l_acc, s_t, reinterpret_cast<long long*>(lbl_row), es_acc, bank_t, as_stream(stream));
+                       init, o_acc, l_acc, s_t, reinterpret_cast<long long*>(lbl_row), es_acc, bank_t, ws, ws_bytes,
+                       as_stream(stream));
 }
 
 int spn_bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, const float* bank_t, const float* ref,

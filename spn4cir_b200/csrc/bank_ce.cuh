@@ -25,6 +25,10 @@ struct BankCEParams {
   int num_dsplit;    // backward: splits of the output dim
   int ow_blocks;     // backward: 64-column blocks of dq per split
   int hg;            // CTA-pair schedule knob (see the MMA issuer)
+  int two_pass;      // fused CTA-pair kernel: second pass over the chunk for dq[:, X:D) (no S recompute)
+  int stages2;       // second-pass ring depth (stages of 2 blocks)
+  unsigned short* p_scratch;  // two-pass: bf16 global scratch for P~, tile-major [q_tile][bank tile][128][128]
+  long long p_ld;    // its row stride in elements (n_tiles * 128)
   float scale_log2;  // inv_tau * log2(e)
   long long row_base;
   const long long* labels;
@@ -50,10 +54,13 @@ struct BankCEPlan {
   int kblocks, q_tiles, n_tiles, num_chunks, num_dsplit, ow_blocks, stages, bps, grid;
   int hg;
   int cg;  // 2: CTA pairs (cta_group::2), 1: single-CTA kernel
+  int two_pass, stages2;  // mode 2 only
   size_t smem_bytes, ws_bytes;
 };
 
-// mode 0 = forward statistics, 1 = backward
+// mode 0 = forward statistics, 1 = backward / fused with the output dim split across CTAs (S recomputed per split),
+// 2 = fused two-pass (CTA pairs, D > 320: needs plan.ws_bytes of scratch for P~); falls back to the mode-1 plan when the
+// shape does not pair up
 int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan);
 
 int bank_ce_forward(const void* q, const void* bank, const long long* labels, float inv_tau, int B, long long N,
@@ -68,12 +75,13 @@ int bank_ce_prep(const void* q_src, int dtype, const void* bank, const long long
                  cudaStream_t stream);
 int bank_ce_fused(const void* q, const void* bank, const long long* labels, const float* ref, float inv_tau, int B,
                   long long N, int D, int T, long long row_base, int init, float* o_acc, float* l_acc, float* s_t,
-                  long long* lbl_row, float* es_acc, float* bank_t, cudaStream_t stream);
+                  long long* lbl_row, float* es_acc, float* bank_t, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t bank_ce_fused_ws_bytes(int B, long long N, int D, int T);
 int bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, const float* bank_t, const void* bank,
                      const long long* lbl_row, int zero_loss, const float* ref, const float* es_acc, const void* q16, const float* colsum, float inv_tau, float gscale, float eps,
                      long long N_total, int B, int D, float* lse, float* loss_q, float* loss_mean, float* dq,
                      float* dlogit_dot, cudaStream_t stream);
-size_t bank_ce_step_ws_bytes(int B, int D);
+size_t bank_ce_step_ws_bytes(int B, long long N, int D, int T);
 int bank_ce_step(const void* q_src, int dtype, const void* bank, const long long* labels, float inv_tau,
                  const float* maxnorm, const float* colsum, float eps, int B, long long N, int D, int T, float* lse,
                  float* loss_q, float* loss_mean, float* dq, float* dlogit_dot, void* ws, size_t ws_bytes,

@@ -34,6 +34,7 @@ constexpr uint32_t kTmemColsFwd = 512;
 constexpr uint32_t kTmemColsBwd = 512;
 constexpr uint32_t kBwdSCol = 320;  // S tile columns [320, 448)
 constexpr uint32_t kBwdPCol = 448;  // P tile columns [448, 512): 128 bf16 = 64 x 32-bit columns
+constexpr int kMaxStages2 = 8;       // second-pass ring: stages of 2 blocks (32 KiB)
 
 // Optional cycle accounting per role (build with -DSPN_TIMELINE; read with spn_debug_read_timeline).
 #ifdef SPN_TIMELINE
@@ -70,6 +71,12 @@ struct SmemView {
   uint64_t* p_full;
   uint64_t* p_free;
   uint64_t* o_full;
+  // two-pass fused mode (second pass: dq[:, X:] += P . bank[:, X:] with P re-read from global scratch)
+  uint64_t* full2;      // [kMaxStages2]
+  uint64_t* empty2;     // [kMaxStages2]
+  uint64_t* p2_go;      // this CTA's 8 soft-max warps have published their P tiles
+  uint64_t* tmem_free;  // (rank 0) the 16 soft-max warps of the pair have drained the pass-1 accumulator
+  uint64_t* o2_full;
   uint32_t* tmem_slot;
 };
 
@@ -88,7 +95,12 @@ __device__ __forceinline__ SmemView carve(uint8_t* raw, int q_blocks, int stages
   v.p_full = rest + 5;
   v.p_free = rest + 6;
   v.o_full = rest + 7;
-  v.tmem_slot = reinterpret_cast<uint32_t*>(rest + 8);
+  v.full2 = rest + 8;
+  v.empty2 = v.full2 + kMaxStages2;
+  v.p2_go = v.empty2 + kMaxStages2;
+  v.tmem_free = v.p2_go + 1;
+  v.o2_full = v.p2_go + 2;
+  v.tmem_slot = reinterpret_cast<uint32_t*>(v.p2_go + 3);
   return v;
 }
 
@@ -312,10 +324,24 @@ __device__ __forceinline__ void fused_chunk_t32(const uint32_t (&xr)[32], bool e
 // k-block, 64 of the 128 dq columns of a GEMM2 group), which halves both the TMA fill and the B-operand reads of the
 // shared-memory port -- the resource the 1-CTA kernel saturates (SS MMA: 8 KiB per 64 cycles = 128 B/cycle).  Rank 0
 // issues all MMAs; completions are multicast to both CTAs; both CTAs' TMA loads credit rank 0's "full" barriers.
+//
+// MODE 2, CG = 2, p.two_pass: no recompute.  O[128 x D] fp32 does not fit the 512 TMEM columns next to S and P, and
+// splitting D across CTAs makes every split recompute S (executed 6 B N D for 4 B N D of algorithmic work at D = 640).
+// Instead the sweep over this CTA pair's bank chunk is done twice:
+//   pass 1  S = Q . bank^T -> P~ (TMEM, bf16) -> O[:, 0:X) += P~ . bank[:, 0:X)   and P~ is also stored (bf16) to a
+//           global scratch [B_pad x N_pad] (one 128-byte line per thread and tile; it mostly lives in L2);
+//   pass 2  a plain tcgen05 GEMM  O[:, X:D) += P~ . bank[:, X:D)  with A = P~ tiles TMA-loaded back (K-major SS operand),
+//           B = bank blocks read MN-major, M = 256 x N = 256 instructions, accumulator = all 512 TMEM columns; the Q tile
+//           is dead by then, so its shared memory joins the ring.
+// Executed tensor work = algorithmic work; the soft-max runs once per logit instead of once per D split.
 template <int MODE, int T, bool EXTRA, int CG>
 __global__ void __launch_bounds__(kBankCEThreads, 1)
 bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_bank,
-               const __grid_constant__ CUtensorMap tmap_bank_half, const BankCEParams p) {
+               const __grid_constant__ CUtensorMap tmap_bank_half, const __grid_constant__ CUtensorMap tmap_p,
+               const BankCEParams p) {
+  constexpr bool kTP = (MODE == 2 && CG == 2);  // the only variant that carries the second pass
+  const bool do_pass2 = kTP && p.two_pass && !(p.hg & 2);   // bring-up knobs (SPN_DEBUG_HG): 2 = no second pass,
+  const bool do_pstore = kTP && p.two_pass && !(p.hg & 4);  // 4 = no P~ stores (timing experiments only)
   static_assert(CG == 1 || (CG == 2 && MODE >= 1), "the CTA-pair variant exists for the backward / fused modes only");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t warp = threadIdx.x >> 5;
@@ -348,10 +374,20 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     mbar_init(sm.p_full, MODE == 0 ? 1 : 8 * CG);  // forward: Q staging (TMA tx) barrier
     mbar_init(sm.p_free, 1);
     mbar_init(sm.o_full, 1);
+    if (kTP) {
+      for (int s2 = 0; s2 < kMaxStages2; ++s2) {
+        mbar_init(&sm.full2[s2], 1);
+        mbar_init(&sm.empty2[s2], 1);
+      }
+      mbar_init(sm.p2_go, 8);
+      mbar_init(sm.tmem_free, 8 * CG);
+      mbar_init(sm.o2_full, 1);
+    }
     fence_barrier_init();
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_bank);
     if (CG == 2) tma_prefetch_desc(&tmap_bank_half);
+    if (kTP && p.two_pass) tma_prefetch_desc(&tmap_p);
   }
   if (warp == 1) {
     if (CG == 2) {
@@ -477,6 +513,31 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       if (CG == 2) for (int g = 0; g < ogroups; ++g) load_ogroup(g, (t_end - 1) * kBN);
       else for (int j = 0; j < my_blocks; ++j) load_block(ds * p.ow_blocks + j, (t_end - 1) * kBN);
     }
+    if (do_pass2) {
+      // ------------------------------------------------------------- second pass: P~ tiles + bank column groups
+      mbar_wait(sm.o_full, 0);  // every pass-1 MMA has retired (multicast commit): Q tile and ring are free
+      mbar_wait(sm.p2_go, 0);   // this CTA's soft-max warps have written (and fenced) all of their P~ rows
+      Ring r2(p.stages2);
+      const int groups2 = (p.kblocks - my_blocks) / 4;  // pair N = 256 per group: 128 columns = 2 blocks per CTA
+      auto load_pair2 = [&](const CUtensorMap* map, int col, int row) {
+        mbar_wait(&sm.empty2[r2.stage], r2.phase ^ 1u);
+        const uint32_t fbar = mapa_shared(smem_u32(&sm.full2[r2.stage]), 0);
+        if (elect_one()) {
+          if (crank == 0) mbar_arrive_expect_tx(&sm.full2[r2.stage], 4u * kBlockBytes);  // 2 blocks from each CTA
+          uint8_t* dst = sm.q + size_t(r2.stage) * 2 * kBlockBytes;
+          tma_load_2d_cg2(dst, map, fbar, col, row);
+          tma_load_2d_cg2(dst + kBlockBytes, map, fbar, col + kBK, row);
+        }
+        __syncwarp();
+        r2.advance();
+      };
+      for (int t = t_begin; t < t_end; ++t) {
+        // A: this CTA's 128 rows of P~(t), K = 128 bank rows = 2 K-major blocks of the tile-major scratch
+        load_pair2(&tmap_p, 0, ((q0 / kBM) * p.n_tiles + t) * kBM);
+        for (int g = 0; g < groups2; ++g)
+          load_pair2(&tmap_bank, (my_blocks + 4 * g) * kBK + int(crank) * 2 * kBK, t * kBN);
+      }
+    }
     TL_FLUSH(0)
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (converged warp)
@@ -566,6 +627,42 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (ntl > 0) gemm_o2(ntl - 1);
         if (elect_one()) umma_commit_cg2(sm.o_full, 3);
         __syncwarp();
+        if (do_pass2 && ntl > 0) {
+          // ----------------------------------------------------------- second pass: O2[256 x 256 g] += P~ . bank
+          constexpr uint32_t idesc_p2 = make_idesc_bf16_f32(2 * kBM, 256, 0, 1);
+          const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(sm.q), 16, 1024);            // P~ blocks, K-major
+          const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(sm.q), kBlockBytes, 1024);   // bank blocks, MN-major
+          const int groups2 = (p.kblocks - my_blocks) / 4;
+          Ring r2(p.stages2);
+          mbar_wait(sm.tmem_free, 0);  // the pass-1 accumulator has been read out by both CTAs
+          tc_fence_after();
+          for (int i = 0; i < ntl; ++i) {
+            mbar_wait(&sm.full2[r2.stage], r2.phase);
+            const uint32_t pstage = r2.stage;
+            r2.advance();
+            for (int g = 0; g < groups2; ++g) {
+              mbar_wait(&sm.full2[r2.stage], r2.phase);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t bdesc = b_desc0 + uint64_t(r2.stage) * (2 * kBlockBytes >> 4);
+#pragma unroll
+                for (int k = 0; k < kBN / kUmmaK; ++k) {
+                  const uint64_t adesc = a_desc0 + uint64_t(pstage) * (2 * kBlockBytes >> 4) +
+                                         uint64_t(k >> 2) * (kBlockBytes >> 4) + uint64_t((k & 3) * 2);
+                  umma_ss_f16_cg2(tmem_base + uint32_t(g) * 256u, adesc, bdesc + uint64_t(k * (2048 >> 4)), idesc_p2,
+                                  (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit_cg2(&sm.empty2[r2.stage], 3);
+              }
+              __syncwarp();
+              r2.advance();
+            }
+            if (elect_one()) umma_commit_cg2(&sm.empty2[pstage], 3);
+            __syncwarp();
+          }
+          if (elect_one()) umma_commit_cg2(sm.o2_full, 3);
+          __syncwarp();
+        }
       }
     } else {
     mbar_wait(sm.q_full, 0);
@@ -811,6 +908,21 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           else mbar_arrive(sm.p_full);
         }
         TL_END(6)
+        if (do_pstore) {  // this thread's 64 bf16 of P~(t): one 128-byte line of the scratch, off the MMA critical path
+          // tile-major scratch: tile (query tile, bank tile) = 128 rows x 256 B, contiguous 32 KiB
+          unsigned short* dst = p.p_scratch + ((size_t(q0 / kBM) * p.n_tiles + size_t(t)) * kBM + row) * kBN + half * 64;
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            st_global_v8(dst + v * 16, u[8 * v], u[8 * v + 1], u[8 * v + 2], u[8 * v + 3], u[8 * v + 4], u[8 * v + 5],
+                         u[8 * v + 6], u[8 * v + 7]);
+        }
+      }
+      if (kTP && p.two_pass) {
+        // generic-proxy global writes -> visible to the TMA (async proxy) loads of pass 2 issued by warp 0
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sm.p2_go);
       }
       // epilogue: O[128 x my_blocks*64] fp32 -> dq (+=, other chunks / shards add into the same rows); the two warps
       // of a lane quarter take alternate 32-column chunks
@@ -826,6 +938,25 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             for (int v = 0; v < 8; ++v)
               red_add_v4_f32(dst + v * 4, __uint_as_float(x0[4 * v]), __uint_as_float(x0[4 * v + 1]),
                              __uint_as_float(x0[4 * v + 2]), __uint_as_float(x0[4 * v + 3]));
+          }
+        }
+        if (do_pass2) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(sm.tmem_free), 0));
+          mbar_wait(sm.o2_full, 0);
+          tc_fence_after();
+          const int cols2 = (p.kblocks - my_blocks) * 2;  // 32-column chunks of the second accumulator
+          for (int c = int(half); c < cols2; c += 2) {
+            tmem_ld_32x32b_x32(t_row + uint32_t(c) * 32u, x0);
+            tmem_ld_wait();
+            if (q_ok) {
+              float* dst = p.dq + size_t(q) * p.D + size_t(my_blocks) * 64 + size_t(c) * 32;
+#pragma unroll
+              for (int v = 0; v < 8; ++v)
+                red_add_v4_f32(dst + v * 4, __uint_as_float(x0[4 * v]), __uint_as_float(x0[4 * v + 1]),
+                               __uint_as_float(x0[4 * v + 2]), __uint_as_float(x0[4 * v + 3]));
+            }
           }
         }
         if (EXTRA && q_ok && ds == 0) atomicAdd(&p.dlogit_dot[q], es * kLn2);
@@ -1129,15 +1260,15 @@ int launch_one(const CUtensorMap& tq, const CUtensorMap& tb, const BankCEParams&
                cudaStream_t stream) {
   auto kfn = bank_ce_kernel<MODE, T, EXTRA, 1>;
   SPN_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kfn<<<grid, kBankCEThreads, smem, stream>>>(tq, tb, tb, p);
+  kfn<<<grid, kBankCEThreads, smem, stream>>>(tq, tb, tb, tb, p);
   SPN_CUDA_CHECK(cudaGetLastError());
   return SPN_OK;
 }
 
 // CTA-pair variant: clusters of 2 along x (blocks 2c, 2c + 1); `tbh` = bank map with a 64-row box (GEMM1 halves)
 template <int MODE, int T, bool EXTRA>
-int launch_pair(const CUtensorMap& tq, const CUtensorMap& tb, const CUtensorMap& tbh, const BankCEParams& p, int grid,
-                size_t smem, cudaStream_t stream) {
+int launch_pair(const CUtensorMap& tq, const CUtensorMap& tb, const CUtensorMap& tbh, const CUtensorMap& tp,
+                const BankCEParams& p, int grid, size_t smem, cudaStream_t stream) {
   auto kfn = bank_ce_kernel<MODE, T, EXTRA, 2>;
   SPN_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   cudaLaunchConfig_t cfg = {};
@@ -1152,18 +1283,18 @@ int launch_pair(const CUtensorMap& tq, const CUtensorMap& tb, const CUtensorMap&
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SPN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kfn, tq, tb, tbh, p));
+  SPN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kfn, tq, tb, tbh, tp, p));
   return SPN_OK;
 }
 
 template <int MODE>
 int launch_mode(bool pair, int T, bool extra, const CUtensorMap& tq, const CUtensorMap& tb, const CUtensorMap& tbh,
-                const BankCEParams& p, int grid, size_t smem, cudaStream_t stream) {
+                const CUtensorMap& tp, const BankCEParams& p, int grid, size_t smem, cudaStream_t stream) {
   if (pair) {
-    if (T == 1) return extra ? launch_pair<MODE, 1, true>(tq, tb, tbh, p, grid, smem, stream)
-                             : launch_pair<MODE, 1, false>(tq, tb, tbh, p, grid, smem, stream);
-    return extra ? launch_pair<MODE, 32, true>(tq, tb, tbh, p, grid, smem, stream)
-                 : launch_pair<MODE, 32, false>(tq, tb, tbh, p, grid, smem, stream);
+    if (T == 1) return extra ? launch_pair<MODE, 1, true>(tq, tb, tbh, tp, p, grid, smem, stream)
+                             : launch_pair<MODE, 1, false>(tq, tb, tbh, tp, p, grid, smem, stream);
+    return extra ? launch_pair<MODE, 32, true>(tq, tb, tbh, tp, p, grid, smem, stream)
+                 : launch_pair<MODE, 32, false>(tq, tb, tbh, tp, p, grid, smem, stream);
   }
   if (T == 1) return extra ? launch_one<MODE, 1, true>(tq, tb, p, grid, smem, stream)
                            : launch_one<MODE, 1, false>(tq, tb, p, grid, smem, stream);
@@ -1197,7 +1328,24 @@ int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan) {
   plan->q_tiles = (B + kBM - 1) / kBM;
   const long long n_rows = N * T;
   plan->n_tiles = int((n_rows + kBN - 1) / kBN);
-  if (mode == 1) {
+  plan->two_pass = 0;
+  plan->stages2 = 0;
+  bool tp = mode == 2 && plan->q_tiles % 2 == 0 && plan->kblocks > 5;
+  if (const char* e = getenv("SPN_DEBUG_TWO_PASS")) {
+    if (atoi(e) == 0) tp = false;
+  }
+  if (const char* e = getenv("SPN_DEBUG_CG")) {  // single-CTA kernels have no second pass
+    if (atoi(e) == 1) tp = false;
+  }
+  if (mode == 2) mode = 1;
+  if (tp) {
+    // pass 1 keeps X = 64 x columns of dq next to S and P in TMEM, pass 2 takes the rest in groups of 256
+    int x = plan->kblocks % 4;
+    if (x < 2) x += 4;  // 2 <= x <= 5, (kblocks - x) in {4, 8}
+    plan->num_dsplit = 1;
+    plan->ow_blocks = x;
+    plan->two_pass = 1;
+  } else if (mode == 1) {
     plan->num_dsplit = (plan->kblocks + 4) / 5;  // O tile <= 320 TMEM columns
     plan->ow_blocks = (plan->kblocks + plan->num_dsplit - 1) / plan->num_dsplit;
   } else {
@@ -1211,6 +1359,7 @@ int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan) {
   plan->grid = plan->q_tiles * plan->num_dsplit * chunks;
   // backward / fused: pair the query tiles (cta_group::2) whenever they come in twos -- see bank_ce_kernel<.., CG = 2>
   plan->cg = (mode == 1 && plan->q_tiles % 2 == 0) ? 2 : 1;
+  if (tp && plan->cg != 2) return fail(SPN_ERR_BAD_ARG, "two-pass plan needs CTA pairs");
   plan->hg = 0;  // 1: wait for the S drain before queueing GEMM2 of the previous tile (measured slower)
   if (const char* e = getenv("SPN_DEBUG_HG")) plan->hg = atoi(e);
   if (const char* e = getenv("SPN_DEBUG_CG")) {
@@ -1232,6 +1381,12 @@ int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan) {
   plan->stages = stages;
   plan->smem_bytes = fixed + size_t(stages) * bps * kBlockBytes;
   plan->ws_bytes = (mode == 0) ? ((size_t(4) * 2 * chunks * B * sizeof(float) + 255) / 256) * 256 : 256;  // 2 column halves
+  if (tp) {
+    plan->stages2 = (plan->kblocks + stages) / 2;
+    if (plan->stages2 > kMaxStages2) plan->stages2 = kMaxStages2;
+    SPN_REQUIRE(plan->stages2 >= (plan->kblocks - plan->ow_blocks) / 4 + 2, SPN_ERR_BAD_SHAPE, "two-pass ring too shallow");
+    plan->ws_bytes = size_t(plan->q_tiles) * kBM * size_t(plan->n_tiles) * kBN * 2;  // P~ scratch, bf16
+  }
   return SPN_OK;
 }
 
@@ -1284,7 +1439,7 @@ int bank_ce_backward(const void* q, const void* bank, const long long* labels, f
   p.row_base = row_base; p.labels = labels; p.lse = lse; p.gscale = gscale; p.gscale_dev = gscale_dev;
   p.eps_over_n = label_smoothing / float(N_total); p.one_minus_eps = 1.f - label_smoothing;
   p.dq = dq; p.dlogit_dot = dlogit_dot;
-  return launch_mode<1>(plan.cg == 2, T, dlogit_dot != nullptr, tq, tb, tbh, p, plan.grid, plan.smem_bytes, stream);
+  return launch_mode<1>(plan.cg == 2, T, dlogit_dot != nullptr, tq, tb, tbh, tb, p, plan.grid, plan.smem_bytes, stream);
 }
 
 int bank_stats(const void* bank, long long rows, int D, float* maxnorm, float* colsum, cudaStream_t stream) {
@@ -1321,18 +1476,33 @@ int bank_ce_prep(const void* q_src, int dtype, const void* bank, const long long
   return launch_prep(q_src, dtype, bank, labels, inv_tau, maxnorm, B, N, D, T, row_base, q16, ref, FusedInit{}, stream);
 }
 
+size_t bank_ce_fused_ws_bytes(int B, long long N, int D, int T) {
+  BankCEPlan plan;
+  if (bank_ce_plan(2, B, N, D, T, &plan) != SPN_OK) return 0;
+  return plan.two_pass ? plan.ws_bytes : 0;
+}
+
 int bank_ce_fused(const void* q, const void* bank, const long long* labels, const float* ref, float inv_tau, int B,
                   long long N, int D, int T, long long row_base, int init, float* o_acc, float* l_acc, float* s_t,
-                  long long* lbl_row, float* es_acc, float* bank_t, cudaStream_t stream) {
+                  long long* lbl_row, float* es_acc, float* bank_t, void* ws, size_t ws_bytes, cudaStream_t stream) {
   BankCEPlan plan;
-  int rc = bank_ce_plan(1, B, N, D, T, &plan);
+  int rc = bank_ce_plan(2, B, N, D, T, &plan);
   if (rc != SPN_OK) return rc;
+  if (plan.two_pass && (!ws || ws_bytes < plan.ws_bytes)) {
+    // no scratch for P~: the D-split plan (every split recomputes S) needs none
+    if ((rc = bank_ce_plan(1, B, N, D, T, &plan)) != SPN_OK) return rc;
+  }
   SPN_REQUIRE(inv_tau > 0.f && isfinite(inv_tau), SPN_ERR_BAD_ARG, "inv_tau must be positive and finite (got %g)", inv_tau);
   SPN_REQUIRE(aligned16(o_acc), SPN_ERR_BAD_ALIGN, "bank_ce_fused: o_acc must be 16-byte aligned");
-  CUtensorMap tq, tb, tbh;
+  SPN_REQUIRE(!plan.two_pass || aligned16(ws), SPN_ERR_BAD_ALIGN, "bank_ce_fused: workspace must be 16-byte aligned");
+  CUtensorMap tq, tb, tbh, tp;
   if ((rc = make_tmap_bf16_2d(&tq, q, uint64_t(B), uint64_t(D), kBM)) != SPN_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&tb, bank, uint64_t(N) * T, uint64_t(D), kBN)) != SPN_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&tbh, bank, uint64_t(N) * T, uint64_t(D), kBN / 2)) != SPN_OK) return rc;
+  tp = tb;
+  if (plan.two_pass &&
+      (rc = make_tmap_bf16_2d(&tp, ws, uint64_t(plan.q_tiles) * plan.n_tiles * kBM, uint64_t(kBN), kBM)) != SPN_OK)
+    return rc;
   if (init) {
     fused_init_kernel<<<148, 256, 0, stream>>>(o_acc, (long long)B * D, l_acc, s_t, lbl_row, es_acc, nullptr, B);
     SPN_CUDA_CHECK(cudaGetLastError());
@@ -1343,7 +1513,9 @@ int bank_ce_fused(const void* q, const void* bank, const long long* labels, cons
   p.num_dsplit = plan.num_dsplit; p.ow_blocks = plan.ow_blocks; p.hg = plan.hg; p.scale_log2 = inv_tau * kLog2e;
   p.row_base = row_base; p.labels = labels; p.ref = ref; p.gscale = 1.f; p.dq = o_acc; p.dlogit_dot = es_acc;
   p.l_acc = l_acc; p.st_out = s_t; p.lbl_row_out = lbl_row;
-  rc = launch_mode<2>(plan.cg == 2, T, es_acc != nullptr, tq, tb, tbh, p, plan.grid, plan.smem_bytes, stream);
+  p.two_pass = plan.two_pass; p.stages2 = plan.stages2; p.p_scratch = static_cast<unsigned short*>(ws);
+  p.p_ld = (long long)plan.n_tiles * kBN;
+  rc = launch_mode<2>(plan.cg == 2, T, es_acc != nullptr, tq, tb, tbh, tp, p, plan.grid, plan.smem_bytes, stream);
   if (rc != SPN_OK) return rc;
   if (bank_t) {
     gather_label_rows_kernel<<<(B + 7) / 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(bank), lbl_row, B, D, bank_t);
@@ -1370,10 +1542,14 @@ int bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, c
   return SPN_OK;
 }
 
-size_t bank_ce_step_ws_bytes(int B, int D) {
+static size_t step_fixed_ws_bytes(int B, int D) {
   // q16 [B, D] bf16 | o_acc [B, D] f32 | ref, l_acc, s_t, es_acc [B] f32 | lbl_row [B] i64, each 256-byte aligned
   auto up = [](size_t x) { return (x + 255) / 256 * 256; };
   return up(size_t(B) * D * 2) + up(size_t(B) * D * 4) + 4 * up(size_t(B) * 4) + up(size_t(B) * 8);
+}
+
+size_t bank_ce_step_ws_bytes(int B, long long N, int D, int T) {
+  return step_fixed_ws_bytes(B, D) + bank_ce_fused_ws_bytes(B, N, D, T);  // + the two-pass P~ scratch (0 if not used)
 }
 
 // One training step on one GPU in a single call: prologue (+ zeroing) -> fused sweep -> finalize (+ target-row gather).
@@ -1381,8 +1557,8 @@ int bank_ce_step(const void* q_src, int dtype, const void* bank, const long long
                  const float* maxnorm, const float* colsum, float eps, int B, long long N, int D, int T, float* lse,
                  float* loss_q, float* loss_mean, float* dq, float* dlogit_dot, void* ws, size_t ws_bytes,
                  cudaStream_t stream) {
-  SPN_REQUIRE(ws && ws_bytes >= bank_ce_step_ws_bytes(B, D), SPN_ERR_WORKSPACE, "bank_ce_step: workspace too small: %zu < %zu",
-              ws_bytes, bank_ce_step_ws_bytes(B, D));
+  SPN_REQUIRE(ws && ws_bytes >= bank_ce_step_ws_bytes(B, N, D, T), SPN_ERR_WORKSPACE,
+              "bank_ce_step: workspace too small: %zu < %zu", ws_bytes, bank_ce_step_ws_bytes(B, N, D, T));
   SPN_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, SPN_ERR_BAD_ALIGN, "bank_ce_step: workspace must be 256-byte aligned");
   auto up = [](size_t x) { return (x + 255) / 256 * 256; };
   uint8_t* w = static_cast<uint8_t*>(ws);
@@ -1392,13 +1568,15 @@ int bank_ce_step(const void* q_src, int dtype, const void* bank, const long long
   float* l_acc = reinterpret_cast<float*>(w);          w += up(size_t(B) * 4);
   float* s_t = reinterpret_cast<float*>(w);            w += up(size_t(B) * 4);
   float* es_acc = reinterpret_cast<float*>(w);         w += up(size_t(B) * 4);
-  long long* lbl_row = reinterpret_cast<long long*>(w);
+  long long* lbl_row = reinterpret_cast<long long*>(w); w += up(size_t(B) * 8);
+  void* scratch = w;
+  const size_t scratch_bytes = ws_bytes - step_fixed_ws_bytes(B, D);
   if (!dlogit_dot) es_acc = nullptr;
   int rc = launch_prep(q_src, dtype, bank, labels, inv_tau, maxnorm, B, N, D, T, 0, q16, ref,
                        FusedInit{o_acc, l_acc, s_t, lbl_row, es_acc, loss_mean}, stream);
   if (rc != SPN_OK) return rc;
   rc = bank_ce_fused(q16, bank, labels, ref, inv_tau, B, N, D, T, 0, /*init=*/0, o_acc, l_acc, s_t, lbl_row, es_acc,
-                     /*bank_t=*/nullptr, stream);
+                     /*bank_t=*/nullptr, scratch, scratch_bytes, stream);
   if (rc != SPN_OK) return rc;
   return bank_ce_finalize(o_acc, l_acc, s_t, nullptr, bank, lbl_row, /*zero_loss=*/0, ref, es_acc, q16, colsum, inv_tau,
                           inv_tau / float(B), eps, N, B, D, lse, loss_q, loss_mean, dq, dlogit_dot, stream);

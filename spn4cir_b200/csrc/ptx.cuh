@@ -352,6 +352,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 // vectorised fp32 reduction into global memory (sm_90+)
+// 256-bit global store (sm_100+): one full 32-byte sector per lane
+__device__ __forceinline__ void st_global_v8(void* gptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
+                                             uint32_t f, uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gptr), "r"(a), "r"(b), "r"(c), "r"(d),
+               "r"(e), "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
+
 __device__ __forceinline__ void red_add_v4_f32(float* gptr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");

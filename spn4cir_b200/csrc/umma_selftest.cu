@@ -33,7 +33,7 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -44,12 +44,12 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   const int row = int(warp * 32u + lane);
 
   if (a_tmem) {
-    // thread == row: pack its K bf16 (K/2 words) into TMEM columns [128, 128 + K/2)
+    // thread == row: pack its K bf16 (K/2 words) into TMEM columns [256, 256 + K/2)
     uint32_t u[32];
     for (int c = 0; c < K / 64; ++c) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) u[j] = a_gmem_u32[size_t(row) * (K / 2) + c * 32 + j];
-      tmem_st_32x32b_x32(t_row + 128u + uint32_t(c) * 32u, u);
+      tmem_st_32x32b_x32(t_row + 256u + uint32_t(c) * 32u, u);
     }
     tmem_st_wait();
     tc_fence_before();
@@ -75,10 +75,21 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         for (int k = 0; k < 4; ++k) {
           const uint32_t acc = (kb | k) != 0;
           if (a_tmem)
-            umma_ts_f16(tmem_base, tmem_base + 128u + uint32_t(kb * 4 + k) * 8u, bdesc + uint64_t(k * 2), idesc, acc);
+            umma_ts_f16(tmem_base, tmem_base + 256u + uint32_t(kb * 4 + k) * 8u, bdesc + uint64_t(k * 2), idesc, acc);
           else
             umma_ss_f16(tmem_base, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, acc);
         }
+      }
+    } else if (mode & 4) {
+      // one wide MN-major instruction: N = 64 * b_blocks columns, the 64-column atoms one block (LBO) apart
+      const uint32_t idesc = make_idesc_bf16_f32(128, N, 0, 1);
+      const uint64_t bdesc = make_smem_desc_sw128(b_addr, kBlockBytes, 1024);
+      for (int k = 0; k < 8; ++k) {
+        const uint64_t adesc = make_smem_desc_sw128(a_addr + uint32_t(k / 4) * kBlockBytes, 16, 1024) + uint64_t((k % 4) * 2);
+        if (a_tmem)
+          umma_ts_f16(tmem_base, tmem_base + 256u + uint32_t(k) * 8u, bdesc + uint64_t(k * 128), idesc, k != 0);
+        else
+          umma_ss_f16(tmem_base, adesc, bdesc + uint64_t(k * 128), idesc, k != 0);
       }
     } else {
       const uint32_t idesc = make_idesc_bf16_f32(128, 64, 0, 1);
@@ -87,7 +98,7 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         for (int k = 0; k < 8; ++k) {  // K = 128 = 8 steps of 16 rows (2048 B each)
           const uint64_t adesc = make_smem_desc_sw128(a_addr + uint32_t(k / 4) * kBlockBytes, 16, 1024) + uint64_t((k % 4) * 2);
           if (a_tmem)
-            umma_ts_f16(tmem_base + uint32_t(j) * 64u, tmem_base + 128u + uint32_t(k) * 8u, bdesc + uint64_t(k * 128), idesc, k != 0);
+            umma_ts_f16(tmem_base + uint32_t(j) * 64u, tmem_base + 256u + uint32_t(k) * 8u, bdesc + uint64_t(k * 128), idesc, k != 0);
           else
             umma_ss_f16(tmem_base + uint32_t(j) * 64u, adesc, bdesc + uint64_t(k * 128), idesc, k != 0);
         }
@@ -107,7 +118,7 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 // ---- raw MMA issue-rate probe: every CTA issues `iters` x 4 k-steps of a PATTERN of up to 8 MMAs back to back from
@@ -325,7 +336,7 @@ int debug_umma_bench(const void* b_src, long long b_rows, int N, int iters, int 
 }
 
 int debug_umma_gemm(const void* a, const void* b, float* c, int N, int K, int mode, cudaStream_t stream) {
-  SPN_REQUIRE(N == 64 || N == 128, SPN_ERR_BAD_SHAPE, "selftest N must be 64 or 128 (got %d)", N);
+  SPN_REQUIRE(N == 64 || N == 128 || (N == 256 && (mode & 4)), SPN_ERR_BAD_SHAPE, "selftest N must be 64 or 128, or 256 with the wide MN-major mode (got %d)", N);
   SPN_REQUIRE(K % 64 == 0 && K >= 64 && K <= 256, SPN_ERR_BAD_SHAPE, "selftest K must be 64..256, multiple of 64 (got %d)", K);
   const bool b_mn = mode & 2;
   SPN_REQUIRE(!b_mn || K == 128, SPN_ERR_BAD_SHAPE, "MN-major selftest needs K == 128 (got %d)", K);

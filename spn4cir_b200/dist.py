@@ -70,7 +70,7 @@ class _ShardedBankCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q_local, tau_t, bank, labels_local, inv_tau, eps, group):
         from ._lib import call
-        from .ops import _TORCH2SPN, _fused_finalize, _ptr, _stream, cast_to_bf16
+        from .ops import _TORCH2SPN, _fused_finalize, _ptr, _stream, cast_to_bf16, fused_scratch
         rank, world = _world(group)
         B, D = q_local.shape
         dev = q_local.device
@@ -97,9 +97,10 @@ class _ShardedBankCE(torch.autograd.Function):
                  _ptr(maxnorm), Bt, bank.N, D, bank.T, bank.row_base, _ptr(q16b), _ptr(ref), st)
             if world > 1:  # owner's clamped reference wins over the other ranks' Cauchy-Schwarz bound
                 dist.all_reduce(ref, op=dist.ReduceOp.MIN, group=group)
+            ws, ws_bytes = fused_scratch(Bt, bank, dev)
             call("spn_bank_ce_fused", _ptr(q_all), _ptr(bank.data), _ptr(lab_all), _ptr(ref), inv_tau, Bt, bank.N, D,
                  bank.T, bank.row_base, 1, _ptr(o_acc), _ptr(vec[0]), _ptr(vec[1]), _ptr(lbl_row),
-                 _ptr(vec[2]) if tau_grad else None, _ptr(bank_t), None, 0, st)
+                 _ptr(vec[2]) if tau_grad else None, _ptr(bank_t), _ptr(ws), ws_bytes, st)
         if world > 1:
             # additive partials: two reduce_scatters ([Bt, D] each) + one small all_reduce ([3, Bt]); the target
             # logit is owner-only, so non-owners contribute 0 and the sum is the value

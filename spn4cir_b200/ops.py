@@ -203,6 +203,19 @@ class _BankCE(torch.autograd.Function):
         return dq.to(ctx.q_dtype), dtau, None, None, None, None
 
 
+_STEP_WS = {}
+
+
+def fused_scratch(B: int, bank: DeviceBank, dev: torch.device):
+    """(buffer | None, bytes): scratch of ``spn_bank_ce_fused`` for the two-pass kernel (P~ in bf16, [B_pad, N_pad]);
+    0 bytes when the shape runs single-pass."""
+    key = ("fused", B, bank.N, bank.D, bank.T)
+    if key not in _STEP_WS:
+        _STEP_WS[key] = _lib.workspace_bytes(_lib.OP_BANK_CE_FUSED, B, bank.N, bank.D, bank.T)
+    n = _STEP_WS[key]
+    return (torch.empty(n, dtype=torch.uint8, device=dev) if n else None), n
+
+
 def _fused_sweep(q: torch.Tensor, bank: DeviceBank, labels: torch.Tensor, inv_tau: float, want_es: bool,
                  ref: Optional[torch.Tensor] = None):
     """prep (cast + reference) and one fused sweep over this shard.  Returns a dict of device buffers."""
@@ -225,9 +238,10 @@ def _fused_sweep(q: torch.Tensor, bank: DeviceBank, labels: torch.Tensor, inv_ta
              bank.N, D, bank.T, bank.row_base, _ptr(q16), _ptr(my_ref), st)
         if ref is None:
             ref = my_ref
+        ws, ws_bytes = fused_scratch(B, bank, dev)
         call("spn_bank_ce_fused", _ptr(q16), _ptr(bank.data), _ptr(labels), _ptr(ref), inv_tau, B, bank.N, D, bank.T,
              bank.row_base, 1, _ptr(o_acc), _ptr(vec[0]), _ptr(vec[1]), _ptr(lbl_row), _ptr(vec[2]) if want_es else None,
-             _ptr(bank_t), None, 0, st)
+             _ptr(bank_t), _ptr(ws), ws_bytes, st)
     return dict(q16=q16, ref=ref, my_ref=my_ref, o_acc=o_acc, bank_t=bank_t, l_acc=vec[0], s_t=vec[1],
                 es_acc=vec[2] if want_es else None, lbl_row=lbl_row)
 
@@ -247,9 +261,6 @@ def _fused_finalize(sw: dict, bank: DeviceBank, inv_tau: float, b_total: int, ep
     return out[0], out[1], mean, dq, ddot
 
 
-_STEP_WS = {}
-
-
 def _fused_step(q: torch.Tensor, bank: DeviceBank, labels: torch.Tensor, inv_tau: float, eps: float, want_ddot: bool):
     """The whole single-GPU training step in ONE library call (``spn_bank_ce_step``: prologue -> fused sweep ->
     finalize, three launches).  Returns (lse, loss_per_query, loss_mean, dq_unit, dlogit_dot | None)."""
@@ -260,7 +271,7 @@ def _fused_step(q: torch.Tensor, bank: DeviceBank, labels: torch.Tensor, inv_tau
         qc = qc.float()
     qc = qc.contiguous()
     maxnorm, colsum = bank.stats(eps != 0.0)
-    key = (B, D)
+    key = (B, bank.N, D, bank.T)
     if key not in _STEP_WS:
         _STEP_WS[key] = _lib.workspace_bytes(_lib.OP_BANK_CE_STEP, B, bank.N, D, bank.T)
     ws_bytes = _STEP_WS[key]

@@ -74,6 +74,10 @@ PAIR_CASES = [
     (256, 6000, 640, 1, 0.02, 26),    # 2 d-splits of 320 = 128 + 128 + 64
     (256, 4000, 768, 1, 0.02, 27),    # 3 d-splits of 256
     (256, 300, 256, 32, 0.05, 28),    # BLIP-2 max over tokens
+    (256, 3000, 384, 1, 0.02, 29),    # two-pass fused: X = 128, one 256-column group in pass 2
+    (512, 9000, 448, 1, 0.03, 30),    # two-pass fused: X = 192 (odd block count in pass 1)
+    (256, 2000, 576, 1, 0.02, 31),    # two-pass fused: X = 320, one group
+    (512, 20000, 704, 1, 0.02, 32),   # two-pass fused: X = 192, two groups, several tiles per CTA
 ]
 
 
@@ -94,6 +98,23 @@ def test_cta_pair_kernels_match_oracle_and_single_cta(B, N, D, T, tau, seed, sin
         r_loss, r_dq, _ = obank.infonce_loss_and_grads(bf16_round(q), bf16_round(bank), labels, tau, dtype=torch.float64)
     else:
         r_loss, r_dq, _ = obank.blip2_loss_and_grads(bf16_round(q), bf16_round(bank), labels, tau, dtype=torch.float64)
+    assert abs(loss.item() - r_loss.item()) <= 2e-4 * max(abs(r_loss.item()), 1.0), (loss, r_loss)
+    assert rel_l2(dq, r_dq) < 3e-3, rel_l2(dq, r_dq)
+
+
+@pytest.mark.parametrize("B,N,D,tau,seed", [(512, 40000, 640, 0.02, 41), (256, 30000, 768, 0.02, 42), (300, 7000, 512, 0.05, 43)])
+def test_fused_two_pass_matches_split_recompute(B, N, D, tau, seed, monkeypatch):
+    """The two-pass fused kernel (P~ through the global scratch, second pass = plain GEMM) against the D-split kernel
+    that recomputes S per split (SPN_DEBUG_TWO_PASS=0): same bf16 P~, same fp32 accumulation up to summation order."""
+    q, bank, labels = synth.make_bank_case(B, N, D, 1, "S", seed)
+    loss, dq, dtau = run_ours(q, bank, labels, tau, tau_tensor=True, single_pass=True)
+    monkeypatch.setenv("SPN_DEBUG_TWO_PASS", "0")
+    loss1, dq1, dtau1 = run_ours(q, bank, labels, tau, tau_tensor=True, single_pass=True)
+    monkeypatch.delenv("SPN_DEBUG_TWO_PASS")
+    assert abs(loss.item() - loss1.item()) <= 1e-6 * max(abs(loss1.item()), 1e-3), (loss, loss1)
+    assert rel_l2(dq, dq1) < 1e-5, rel_l2(dq, dq1)
+    assert abs(dtau.item() - dtau1.item()) <= 1e-4 * max(abs(dtau1.item()), 1e-2), (dtau, dtau1)
+    r_loss, r_dq, _ = obank.infonce_loss_and_grads(bf16_round(q), bf16_round(bank), labels, tau, dtype=torch.float64)
     assert abs(loss.item() - r_loss.item()) <= 2e-4 * max(abs(r_loss.item()), 1.0), (loss, r_loss)
     assert rel_l2(dq, r_dq) < 3e-3, rel_l2(dq, r_dq)
 

@@ -31,3 +31,16 @@ def test_umma_gemm(mode, N, K):
     c = run_gemm(a, b, N, K, mode)
     err = (c - ref).abs().max().item()
     assert err < 2e-3 * K ** 0.5, f"mode={mode} N={N} K={K}: max abs err {err}"
+
+
+@pytest.mark.parametrize("mode", [6, 7])
+@pytest.mark.parametrize("N", [128, 256])
+def test_umma_gemm_wide_mn_major(mode, N):
+    """One MN-major instruction spanning several 64-column swizzle atoms (descriptor LBO = distance between atoms):
+    the shape the second pass of the fused bank-CE kernel issues."""
+    g = torch.Generator().manual_seed(7 * mode + N)
+    a = torch.randn((128, 128), generator=g).to(torch.bfloat16).cuda()
+    b = torch.randn((128, N), generator=g).to(torch.bfloat16).cuda()
+    c = run_gemm(a, b, N, 128, mode)
+    err = (c - a.float() @ b.float()).abs().max().item()
+    assert err < 2e-3 * 128 ** 0.5, f"mode={mode} N={N}: max abs err {err}"

@@ -16,10 +16,13 @@ def time_fused(B, N, D, T, tau, iters=10):
     lab = torch.randint(0, N, (B,), device="cuda", generator=g)
     q = torch.nn.functional.normalize(bank[lab * T].float() + 3.2 * torch.randn(B, D, device="cuda", generator=g) / D ** 0.5, dim=-1)
     sw = _fused_sweep(q, db, lab, 1.0 / tau, False)
+    from spn4cir_b200.ops import fused_scratch
+    ws, ws_bytes = fused_scratch(B, db, q.device)
     def run():
         _lib.call("spn_bank_ce_fused", sw["q16"].data_ptr(), db.data.data_ptr(), lab.data_ptr(), sw["ref"].data_ptr(),
                   1.0 / tau, B, db.N, D, db.T, db.row_base, 0, sw["o_acc"].data_ptr(), sw["l_acc"].data_ptr(),
-                  sw["s_t"].data_ptr(), sw["lbl_row"].data_ptr(), None, None, None, 0, torch.cuda.current_stream().cuda_stream)
+                  sw["s_t"].data_ptr(), sw["lbl_row"].data_ptr(), None, None, ws.data_ptr() if ws is not None else None, ws_bytes,
+                  torch.cuda.current_stream().cuda_stream)
     for _ in range(3):
         run()
     torch.cuda.synchronize()
@@ -39,11 +42,16 @@ which = sys.argv[1].split(",") if len(sys.argv) > 1 and sys.argv[1] != "all" els
 for name, B, N, D, T, tau in cases:
     if which and name not in which:
         continue
-    for cg in (2, 1):
-        if cg == 1:
+    variants = os.environ.get("EXP_VARIANTS", "tp,split,cg1").split(",")
+    for var in variants:
+        for k in ("SPN_DEBUG_CG", "SPN_DEBUG_TWO_PASS", "SPN_DEBUG_HG"):
+            os.environ.pop(k, None)
+        if var == "cg1":
             os.environ["SPN_DEBUG_CG"] = "1"
-        else:
-            os.environ.pop("SPN_DEBUG_CG", None)
+        elif var == "split":
+            os.environ["SPN_DEBUG_TWO_PASS"] = "0"
+        elif var.startswith("hg"):
+            os.environ["SPN_DEBUG_HG"] = var[2:]
         t = time_fused(B, N, D, T, tau)
         fl = (2 * 32 + 2 if T == 32 else 4) * B * N * D
-        print(json.dumps(dict(case=name, B=B, N=N, D=D, T=T, cg=cg, us=round(t * 1e6, 1), alg_tflops=round(fl / t / 1e12, 1))), flush=True)
+        print(json.dumps(dict(case=name, B=B, N=N, D=D, T=T, variant=var, us=round(t * 1e6, 1), alg_tflops=round(fl / t / 1e12, 1))), flush=True)
