@@ -199,7 +199,7 @@ int spn_sim_matrix(const float* q, const float* gallery, int Q, int G, int D, in
 }
 
 int spn_debug_read_timeline(unsigned long long* host_out, int n) {
-  SPN_REQUIRE(host_out && n > 0 && n <= 1024 * 16, SPN_ERR_BAD_ARG, "spn_debug_read_timeline: bad arguments");
+  SPN_REQUIRE(host_out && n != 0 && n <= 1024 * 16 && n >= -1024 * 16, SPN_ERR_BAD_ARG, "spn_debug_read_timeline: bad arguments");
   return debug_read_timeline(host_out, n);
 }
 

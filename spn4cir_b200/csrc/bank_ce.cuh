@@ -25,6 +25,7 @@ struct BankCEParams {
   int num_dsplit;    // backward: splits of the output dim
   int ow_blocks;     // backward: 64-column blocks of dq per split
   int hg;            // CTA-pair schedule knob (see the MMA issuer)
+  int qt_blocks;     // two-pass: leading k-blocks of the Q tile that live in TMEM (TS operand) instead of shared memory
   int two_pass;      // fused CTA-pair kernel: second pass over the chunk for dq[:, X:D) (no S recompute)
   int stages2;       // second-pass ring depth (stages of 2 blocks)
   unsigned short* p_scratch;  // two-pass: bf16 global scratch for P~, tile-major [q_tile][bank tile][128][128]
@@ -54,7 +55,7 @@ struct BankCEPlan {
   int kblocks, q_tiles, n_tiles, num_chunks, num_dsplit, ow_blocks, stages, bps, grid;
   int hg;
   int cg;  // 2: CTA pairs (cta_group::2), 1: single-CTA kernel
-  int two_pass, stages2;  // mode 2 only
+  int two_pass, stages2, qt_blocks;  // mode 2 only
   size_t smem_bytes, ws_bytes;
 };
 

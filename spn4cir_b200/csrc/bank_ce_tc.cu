@@ -39,6 +39,9 @@ constexpr int kMaxStages2 = 8;       // second-pass ring: stages of 2 blocks (32
 // Optional cycle accounting per role (build with -DSPN_TIMELINE; read with spn_debug_read_timeline).
 #ifdef SPN_TIMELINE
 __device__ unsigned long long g_timeline[1024 * 16];
+__device__ unsigned long long g_events[1024 * 16];
+#define EV(i) if ((threadIdx.x & 31) == 0 && blockIdx.x < 1024) g_events[blockIdx.x * 16 + (i)] = (unsigned long long)(clock64() - ev_t0);
+#define EV_START const long long ev_t0 = clock64();
 #define TL_VARS unsigned long long tl_acc[7] = {0, 0, 0, 0, 0, 0, 0}; long long tl_t0 = 0, tl_start = clock64();
 #define TL_BEGIN tl_t0 = clock64();
 #define TL_END(i) tl_acc[i] += (unsigned long long)(clock64() - tl_t0);
@@ -53,6 +56,8 @@ __device__ unsigned long long g_timeline[1024 * 16];
     g_timeline[blockIdx.x * 16 + (base) + 3] = (unsigned long long)(clock64() - tl_start); \
   }
 #else
+#define EV(i)
+#define EV_START
 #define TL_VARS
 #define TL_BEGIN
 #define TL_END(i)
@@ -77,6 +82,9 @@ struct SmemView {
   uint64_t* p2_go;      // this CTA's 8 soft-max warps have published their P tiles
   uint64_t* tmem_free;  // (rank 0) the 16 soft-max warps of the pair have drained the pass-1 accumulator
   uint64_t* o2_full;
+  uint64_t* qt_full;   // this CTA's TMEM-bound Q blocks have landed in the ring (TMA tx)
+  uint64_t* qt_done;   // ... and have been moved to TMEM by the 8 soft-max warps: the ring is free
+  uint64_t* qt_ready;  // (rank 0) both CTAs' Q columns are in TMEM: GEMM1 may start
   uint32_t* tmem_slot;
 };
 
@@ -100,7 +108,10 @@ __device__ __forceinline__ SmemView carve(uint8_t* raw, int q_blocks, int stages
   v.p2_go = v.empty2 + kMaxStages2;
   v.tmem_free = v.p2_go + 1;
   v.o2_full = v.p2_go + 2;
-  v.tmem_slot = reinterpret_cast<uint32_t*>(v.p2_go + 3);
+  v.qt_full = v.p2_go + 3;
+  v.qt_done = v.p2_go + 4;
+  v.qt_ready = v.p2_go + 5;
+  v.tmem_slot = reinterpret_cast<uint32_t*>(v.p2_go + 6);
   return v;
 }
 
@@ -338,15 +349,19 @@ template <int MODE, int T, bool EXTRA, int CG>
 __global__ void __launch_bounds__(kBankCEThreads, 1)
 bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_bank,
                const __grid_constant__ CUtensorMap tmap_bank_half, const __grid_constant__ CUtensorMap tmap_p,
+               const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tmap_pf,
                const BankCEParams p) {
   constexpr bool kTP = (MODE == 2 && CG == 2);  // the only variant that carries the second pass
   const bool do_pass2 = kTP && p.two_pass && !(p.hg & 2);   // bring-up knobs (SPN_DEBUG_HG): 2 = no second pass,
   const bool do_pstore = kTP && p.two_pass && !(p.hg & 4);  // 4 = no P~ stores (timing experiments only)
+  const bool do_red = !(p.hg & 8);                          // 8 = no dq reductions, 16 = plain stores instead
+  const bool tma_epi = kTP && p.two_pass && !(p.hg & 32);   // 32 = per-thread red.global.add instead of TMA reduce
   static_assert(CG == 1 || (CG == 2 && MODE >= 1), "the CTA-pair variant exists for the backward / fused modes only");
   extern __shared__ uint8_t smem_raw[];
+  EV_START
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
-  const SmemView sm = carve(smem_raw, MODE == 0 ? 0 : p.kblocks, p.stages, p.bps);
+  const SmemView sm = carve(smem_raw, MODE == 0 ? 0 : p.kblocks - p.qt_blocks, p.stages, p.bps);
 
   // block -> (query tile, d-split, bank chunk); query tile fastest so co-resident CTAs share bank rows in L2
   const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;  // CG = 2: blocks (2c, 2c + 1) form cluster c
@@ -382,12 +397,18 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_init(sm.p2_go, 8);
       mbar_init(sm.tmem_free, 8 * CG);
       mbar_init(sm.o2_full, 1);
+      mbar_init(sm.qt_full, 1);
+      mbar_init(sm.qt_done, 8);
+      mbar_init(sm.qt_ready, 8 * CG);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_bank);
     if (CG == 2) tma_prefetch_desc(&tmap_bank_half);
-    if (kTP && p.two_pass) tma_prefetch_desc(&tmap_p);
+    if (kTP && p.two_pass) {
+      tma_prefetch_desc(&tmap_p);
+      tma_prefetch_desc(&tmap_dq);
+    }
   }
   if (warp == 1) {
     if (CG == 2) {
@@ -409,12 +430,18 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     // elected lane issues; see elect_one())
     if (MODE >= 1 && CG == 2) {
       const uint32_t qbar = mapa_shared(smem_u32(sm.q_full), 0);
+      const int qt = p.qt_blocks;  // leading k-blocks that go to TMEM: staged through the (still unused) ring
       if (elect_one()) {
-        if (crank == 0) mbar_arrive_expect_tx(sm.q_full, 2u * uint32_t(p.kblocks) * kBlockBytes);
-        for (int kb = 0; kb < p.kblocks; ++kb)
-          tma_load_2d_cg2(sm.q + size_t(kb) * kBlockBytes, &tmap_q, qbar, kb * kBK, q0);
+        if (qt > 0) {
+          mbar_arrive_expect_tx(sm.qt_full, uint32_t(qt) * kBlockBytes);
+          for (int kb = 0; kb < qt; ++kb) tma_load_2d(sm.ring + size_t(kb) * kBlockBytes, &tmap_q, sm.qt_full, kb * kBK, q0);
+        }
+        if (crank == 0) mbar_arrive_expect_tx(sm.q_full, 2u * uint32_t(p.kblocks - qt) * kBlockBytes);
+        for (int kb = qt; kb < p.kblocks; ++kb)
+          tma_load_2d_cg2(sm.q + size_t(kb - qt) * kBlockBytes, &tmap_q, qbar, kb * kBK, q0);
       }
       __syncwarp();
+      if (qt > 0) mbar_wait(sm.qt_done, 0);  // the soft-max warps have moved the staged blocks to TMEM
     } else if (MODE >= 1) {
       if (elect_one()) {
         mbar_arrive_expect_tx(sm.q_full, uint32_t(p.kblocks) * kBlockBytes);
@@ -531,7 +558,8 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         __syncwarp();
         r2.advance();
       };
-      for (int t = t_begin; t < t_end; ++t) {
+      // newest first: the P~ tiles written last and the bank rows streamed last are the ones still in L2
+      for (int t = t_end - 1; t >= t_begin; --t) {
         // A: this CTA's 128 rows of P~(t), K = 128 bank rows = 2 K-major blocks of the tile-major scratch
         load_pair2(&tmap_p, 0, ((q0 / kBM) * p.n_tiles + t) * kBM);
         for (int g = 0; g < groups2; ++g)
@@ -556,8 +584,12 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         constexpr uint32_t idesc_o128 = make_idesc_bf16_f32(2 * kBM, 128, 0, 1);
         constexpr uint32_t idesc_o64 = make_idesc_bf16_f32(2 * kBM, 64, 0, 1);
         const int ogroups = (my_blocks + 1) / 2;
+        EV(0)  // set-up done
         mbar_wait(sm.q_full, 0);
+        if (p.qt_blocks > 0) mbar_wait(sm.qt_ready, 0);
         tc_fence_after();
+        const uint32_t q_tmem = tmem_base + uint32_t(my_blocks) * 64u;  // Q columns right after the pass-1 accumulator
+        EV(1)  // Q tile resident
         auto gemm_o2 = [&](int u) {
           TL_BEGIN
           mbar_wait(sm.p_full, uint32_t(u) & 1u);
@@ -600,12 +632,20 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             if (elect_one()) {
               const int nb = min(2, p.kblocks - kb0);
               for (int b = 0; b < nb; ++b) {
-                const uint64_t adesc = q_desc0 + uint64_t(kb0 + b) * (kBlockBytes >> 4);
+                const int kb = kb0 + b;
                 const uint64_t bdesc = ring_desc_k0 + uint64_t(r.stage) * (kBlockBytes >> 4) + uint64_t(b) * (kBlockBytes >> 5);
+                if (kb < p.qt_blocks) {  // A = Q columns in TMEM (8 columns = 16 bf16 per K step)
 #pragma unroll
-                for (int k = 0; k < kBK / kUmmaK; ++k)
-                  umma_ss_f16_cg2(tmem_base + kBwdSCol, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc_s2,
-                                  ((kb0 + b) | k) != 0);
+                  for (int k = 0; k < kBK / kUmmaK; ++k)
+                    umma_ts_f16_cg2(tmem_base + kBwdSCol, q_tmem + uint32_t(kb) * 32u + uint32_t(k) * 8u,
+                                    bdesc + uint64_t(k * 2), idesc_s2, (kb | k) != 0);
+                } else {
+                  const uint64_t adesc = q_desc0 + uint64_t(kb - p.qt_blocks) * (kBlockBytes >> 4);
+#pragma unroll
+                  for (int k = 0; k < kBK / kUmmaK; ++k)
+                    umma_ss_f16_cg2(tmem_base + kBwdSCol, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc_s2,
+                                    (kb | k) != 0);
+                }
               }
               umma_commit_cg2(&sm.empty[r.stage], 3);
             }
@@ -627,6 +667,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (ntl > 0) gemm_o2(ntl - 1);
         if (elect_one()) umma_commit_cg2(sm.o_full, 3);
         __syncwarp();
+        EV(2)  // pass-1 MMAs issued
         if (do_pass2 && ntl > 0) {
           // ----------------------------------------------------------- second pass: O2[256 x 256 g] += P~ . bank
           constexpr uint32_t idesc_p2 = make_idesc_bf16_f32(2 * kBM, 256, 0, 1);
@@ -636,8 +677,10 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           Ring r2(p.stages2);
           mbar_wait(sm.tmem_free, 0);  // the pass-1 accumulator has been read out by both CTAs
           tc_fence_after();
+          EV(3)  // TMEM free for pass 2
           for (int i = 0; i < ntl; ++i) {
             mbar_wait(&sm.full2[r2.stage], r2.phase);
+            if (i == 0) { EV(4) }  // first P~ tile of pass 2 landed
             const uint32_t pstage = r2.stage;
             r2.advance();
             for (int g = 0; g < groups2; ++g) {
@@ -662,6 +705,22 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
           if (elect_one()) umma_commit_cg2(sm.o2_full, 3);
           __syncwarp();
+          EV(5)  // pass-2 MMAs issued
+        }
+      } else if (kTP && p.two_pass && (p.hg & 64)) {
+        // rank 1's MMA warp has nothing to issue: it pulls the pair's bank tiles into L2 kPF tiles ahead of the ring
+        // (paced by the S-tile completions, which are multicast to both CTAs), so that the 64 KiB ring only has to
+        // cover the L2 latency, not the HBM latency of the first touch
+        constexpr int kPF = 3;
+        for (int i = 0; i < ntl; ++i) {
+          if (elect_one()) {
+            const int first = (i == 0) ? 1 : kPF, last = kPF;
+            for (int j = first; j <= last; ++j)
+              if (i + j < ntl)
+                for (int c = 0; c < p.D; c += 256) tma_prefetch_l2_2d(&tmap_pf, c, (t_begin + i + j) * kBN);
+          }
+          __syncwarp();
+          mbar_wait(&sm.s_full[0], uint32_t(i) & 1u);
         }
       }
     } else {
@@ -837,6 +896,28 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (EXTRA) p.part_ssum[o] = ssum;
       }
     } else {
+      if (kTP && p.qt_blocks > 0) {
+        // move this thread's query row of the TMEM-bound Q blocks from the TMA-staged, 128B-swizzled ring slots to TMEM
+        // as packed bf16 (chunk c of row r sits at r*128 + ((c ^ (r & 7)) << 4) inside a block)
+        const uint32_t q_col = uint32_t(my_blocks) * 64u;
+        mbar_wait(sm.qt_full, 0);
+        for (int kb = int(half); kb < p.qt_blocks; kb += 2) {
+          const uint8_t* blk = sm.ring + size_t(kb) * kBlockBytes + size_t(row) * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 w = *reinterpret_cast<const uint4*>(blk + ((c ^ (row & 7)) << 4));
+            x0[4 * c] = w.x; x0[4 * c + 1] = w.y; x0[4 * c + 2] = w.z; x0[4 * c + 3] = w.w;
+          }
+          tmem_st_32x32b_x32(t_row + q_col + uint32_t(kb) * 32u, x0);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(sm.qt_done);
+          mbar_arrive_remote(mapa_shared(smem_u32(sm.qt_ready), 0));
+        }
+      }
       // MODE 1: lse2 = global log-sum-exp (log2 units); MODE 2: the static per-row reference
       const float lse2 = q_ok ? (MODE == 1 ? p.lse[q] : p.ref[q]) * kLog2e : INFINITY;  // padded rows: p = 0
       const float gscale = (MODE == 1 && p.gscale_dev) ? p.gscale * __ldg(p.gscale_dev) : p.gscale;
@@ -928,34 +1009,89 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       // of a lane quarter take alternate 32-column chunks
       mbar_wait(sm.o_full, 0);
       tc_fence_after();
-      if (ntl > 0) {
+      if (warp == 2) { EV(8) }  // pass-1 MMAs retired
+      // TMA-reduce epilogue (two-pass mode): each warp stages its [32 rows x 32 columns] fp32 piece in a 4 KiB slot
+      // (128-byte swizzle: conflict-free 16-byte stores) and one lane issues cp.reduce.async.bulk.tensor (.add): whole
+      // 128-byte lines are reduced in L2 instead of 32 scattered 16-byte reds per instruction; rows >= B are clipped.
+      auto tma_epilogue = [&](uint32_t tmem_col0, int nchunks, int d_col0, uint8_t* slots, int nslots) {
+        const bool rows_ok = q0 + int(quarter) * 32 < p.B;
+        int k = 0;
+        for (int c = int(half); c < nchunks; c += 2, ++k) {
+          tmem_ld_32x32b_x32(t_row + tmem_col0 + uint32_t(c) * 32u, x0);
+          tmem_ld_wait();
+          uint8_t* slot = slots + size_t(k % nslots) * 4096;
+          if (k >= nslots) {  // the slot's previous reduce must have read shared memory
+            if (lane == 0) {
+              if (nslots == 1) bulk_wait_group_read<0>();
+              else bulk_wait_group_read<3>();
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            *reinterpret_cast<uint4*>(slot + lane * 128u + ((uint32_t(v) ^ (lane & 7u)) << 4)) =
+                make_uint4(x0[4 * v], x0[4 * v + 1], x0[4 * v + 2], x0[4 * v + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && rows_ok && do_red) {
+            tma_reduce_add_2d(slot, &tmap_dq, d_col0 + c * 32, q0 + int(quarter) * 32);
+            bulk_commit_group();
+          }
+        }
+        if (lane == 0) bulk_wait_group<0>();
+        __syncwarp();
+      };
+      const int region_blocks = p.kblocks - p.qt_blocks + p.stages;  // [Q tile (smem part) | ring] in 16 KiB blocks
+      if (ntl > 0 && tma_epi) {
+        // pass-1 accumulator: the last 32 KiB of the region (outside the second-pass ring), one slot per warp
+        tma_epilogue(0u, my_blocks * 2, 0, sm.q + size_t(region_blocks - 2) * kBlockBytes + (warp - 2u) * 4096u, 1);
+      } else if (ntl > 0) {
         for (int c = int(half); c < my_blocks * 2; c += 2) {
           tmem_ld_32x32b_x32(t_row + uint32_t(c) * 32u, x0);
           tmem_ld_wait();
-          if (q_ok) {
+          if (q_ok && do_red) {
             float* dst = p.dq + size_t(q) * p.D + size_t(ds) * p.ow_blocks * 64 + size_t(c) * 32;
+            if (p.hg & 16) {
 #pragma unroll
-            for (int v = 0; v < 8; ++v)
-              red_add_v4_f32(dst + v * 4, __uint_as_float(x0[4 * v]), __uint_as_float(x0[4 * v + 1]),
-                             __uint_as_float(x0[4 * v + 2]), __uint_as_float(x0[4 * v + 3]));
-          }
-        }
-        if (do_pass2) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(sm.tmem_free), 0));
-          mbar_wait(sm.o2_full, 0);
-          tc_fence_after();
-          const int cols2 = (p.kblocks - my_blocks) * 2;  // 32-column chunks of the second accumulator
-          for (int c = int(half); c < cols2; c += 2) {
-            tmem_ld_32x32b_x32(t_row + uint32_t(c) * 32u, x0);
-            tmem_ld_wait();
-            if (q_ok) {
-              float* dst = p.dq + size_t(q) * p.D + size_t(my_blocks) * 64 + size_t(c) * 32;
+              for (int v = 0; v < 8; ++v)
+                reinterpret_cast<uint4*>(dst)[v] = make_uint4(x0[4 * v], x0[4 * v + 1], x0[4 * v + 2], x0[4 * v + 3]);
+            } else {
 #pragma unroll
               for (int v = 0; v < 8; ++v)
                 red_add_v4_f32(dst + v * 4, __uint_as_float(x0[4 * v]), __uint_as_float(x0[4 * v + 1]),
                                __uint_as_float(x0[4 * v + 2]), __uint_as_float(x0[4 * v + 3]));
+            }
+          }
+        }
+      }
+      if (ntl > 0) {
+        if (do_pass2) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(sm.tmem_free), 0));
+          if (warp == 2) { EV(9) }  // pass-1 epilogue done
+          mbar_wait(sm.o2_full, 0);
+          tc_fence_after();
+          if (warp == 2) { EV(10) }  // pass-2 MMAs retired
+          const int cols2 = (p.kblocks - my_blocks) * 2;  // 32-column chunks of the second accumulator
+          if (tma_epi) {  // everything in shared memory is dead now: four slots per warp from the base of the region
+            tma_epilogue(0u, cols2, my_blocks * 64, sm.q + (warp - 2u) * 16384u, 4);
+          } else
+          for (int c = int(half); c < cols2; c += 2) {
+            tmem_ld_32x32b_x32(t_row + uint32_t(c) * 32u, x0);
+            tmem_ld_wait();
+            if (q_ok && do_red) {
+              float* dst = p.dq + size_t(q) * p.D + size_t(my_blocks) * 64 + size_t(c) * 32;
+              if (p.hg & 16) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v)
+                  reinterpret_cast<uint4*>(dst)[v] = make_uint4(x0[4 * v], x0[4 * v + 1], x0[4 * v + 2], x0[4 * v + 3]);
+              } else {
+#pragma unroll
+                for (int v = 0; v < 8; ++v)
+                  red_add_v4_f32(dst + v * 4, __uint_as_float(x0[4 * v]), __uint_as_float(x0[4 * v + 1]),
+                                 __uint_as_float(x0[4 * v + 2]), __uint_as_float(x0[4 * v + 3]));
+              }
             }
           }
         }
@@ -972,6 +1108,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #ifdef SPN_TIMELINE
     if (warp == 2) { TL_FLUSH7(8) }
 #endif
+    if (warp == 2) { EV(11) }  // epilogues done
   }
 
   __syncwarp();
@@ -1260,7 +1397,7 @@ int launch_one(const CUtensorMap& tq, const CUtensorMap& tb, const BankCEParams&
                cudaStream_t stream) {
   auto kfn = bank_ce_kernel<MODE, T, EXTRA, 1>;
   SPN_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kfn<<<grid, kBankCEThreads, smem, stream>>>(tq, tb, tb, tb, p);
+  kfn<<<grid, kBankCEThreads, smem, stream>>>(tq, tb, tb, tb, tb, tb, p);
   SPN_CUDA_CHECK(cudaGetLastError());
   return SPN_OK;
 }
@@ -1268,7 +1405,8 @@ int launch_one(const CUtensorMap& tq, const CUtensorMap& tb, const BankCEParams&
 // CTA-pair variant: clusters of 2 along x (blocks 2c, 2c + 1); `tbh` = bank map with a 64-row box (GEMM1 halves)
 template <int MODE, int T, bool EXTRA>
 int launch_pair(const CUtensorMap& tq, const CUtensorMap& tb, const CUtensorMap& tbh, const CUtensorMap& tp,
-                const BankCEParams& p, int grid, size_t smem, cudaStream_t stream) {
+                const CUtensorMap& tdq, const CUtensorMap& tpf, const BankCEParams& p, int grid, size_t smem,
+                cudaStream_t stream) {
   auto kfn = bank_ce_kernel<MODE, T, EXTRA, 2>;
   SPN_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   cudaLaunchConfig_t cfg = {};
@@ -1283,18 +1421,19 @@ int launch_pair(const CUtensorMap& tq, const CUtensorMap& tb, const CUtensorMap&
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SPN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kfn, tq, tb, tbh, tp, p));
+  SPN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kfn, tq, tb, tbh, tp, tdq, tpf, p));
   return SPN_OK;
 }
 
 template <int MODE>
 int launch_mode(bool pair, int T, bool extra, const CUtensorMap& tq, const CUtensorMap& tb, const CUtensorMap& tbh,
-                const CUtensorMap& tp, const BankCEParams& p, int grid, size_t smem, cudaStream_t stream) {
+                const CUtensorMap& tp, const CUtensorMap& tdq, const CUtensorMap& tpf, const BankCEParams& p, int grid,
+                size_t smem, cudaStream_t stream) {
   if (pair) {
-    if (T == 1) return extra ? launch_pair<MODE, 1, true>(tq, tb, tbh, tp, p, grid, smem, stream)
-                             : launch_pair<MODE, 1, false>(tq, tb, tbh, tp, p, grid, smem, stream);
-    return extra ? launch_pair<MODE, 32, true>(tq, tb, tbh, tp, p, grid, smem, stream)
-                 : launch_pair<MODE, 32, false>(tq, tb, tbh, tp, p, grid, smem, stream);
+    if (T == 1) return extra ? launch_pair<MODE, 1, true>(tq, tb, tbh, tp, tdq, tpf, p, grid, smem, stream)
+                             : launch_pair<MODE, 1, false>(tq, tb, tbh, tp, tdq, tpf, p, grid, smem, stream);
+    return extra ? launch_pair<MODE, 32, true>(tq, tb, tbh, tp, tdq, tpf, p, grid, smem, stream)
+                 : launch_pair<MODE, 32, false>(tq, tb, tbh, tp, tdq, tpf, p, grid, smem, stream);
   }
   if (T == 1) return extra ? launch_one<MODE, 1, true>(tq, tb, p, grid, smem, stream)
                            : launch_one<MODE, 1, false>(tq, tb, p, grid, smem, stream);
@@ -1306,6 +1445,10 @@ int launch_mode(bool pair, int T, bool extra, const CUtensorMap& tq, const CUten
 
 int debug_read_timeline(unsigned long long* host_out, int n) {
 #ifdef SPN_TIMELINE
+  if (n < 0) {  // event stamps instead of the per-role counters
+    SPN_CUDA_CHECK(cudaMemcpyFromSymbol(host_out, g_events, sizeof(unsigned long long) * size_t(-n)));
+    return SPN_OK;
+  }
   SPN_CUDA_CHECK(cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(unsigned long long) * size_t(n)));
   return SPN_OK;
 #else
@@ -1330,6 +1473,7 @@ int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan) {
   plan->n_tiles = int((n_rows + kBN - 1) / kBN);
   plan->two_pass = 0;
   plan->stages2 = 0;
+  plan->qt_blocks = 0;
   bool tp = mode == 2 && plan->q_tiles % 2 == 0 && plan->kblocks > 5;
   if (const char* e = getenv("SPN_DEBUG_TWO_PASS")) {
     if (atoi(e) == 0) tp = false;
@@ -1345,6 +1489,14 @@ int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan) {
     plan->num_dsplit = 1;
     plan->ow_blocks = x;
     plan->two_pass = 1;
+    // TMEM in pass 1: O[0, 64 x) | Q columns | S [320, 448) | P [448, 512): the gap holds (320 - 64 x) / 32 k-blocks of Q,
+    // which frees their shared memory for the bank ring (64 KiB -> 160 KiB at D = 640)
+    plan->qt_blocks = (320 - 64 * x) / 32;
+    if (plan->qt_blocks > plan->kblocks) plan->qt_blocks = plan->kblocks;
+    if (const char* e = getenv("SPN_DEBUG_QT")) {
+      const int v = atoi(e);
+      if (v >= 0 && v < plan->qt_blocks) plan->qt_blocks = v;
+    }
   } else if (mode == 1) {
     plan->num_dsplit = (plan->kblocks + 4) / 5;  // O tile <= 320 TMEM columns
     plan->ow_blocks = (plan->kblocks + plan->num_dsplit - 1) / plan->num_dsplit;
@@ -1366,7 +1518,7 @@ int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan) {
     if (atoi(e) == 1) plan->cg = 1;
   }
   // forward keeps Q in TMEM (no smem), backward keeps the Q tile in smem next to the ring
-  const size_t fixed = 1024 /*align slack*/ + (mode == 1 ? size_t(plan->kblocks) * kBlockBytes : 0) + 512 /*barriers*/;
+  const size_t fixed = 1024 /*align slack*/ + (mode == 1 ? size_t(plan->kblocks - plan->qt_blocks) * kBlockBytes : 0) + 512 /*barriers*/;
   const int bps = (mode == 0 && plan->kblocks >= 2) ? 2 : 1;  // k-blocks per ring stage
   plan->bps = bps;
   int stages = int((size_t(smem_max) - fixed) / (size_t(bps) * kBlockBytes));
@@ -1377,12 +1529,13 @@ int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan) {
   }
   // forward stages the Q tile through the ring before the first bank block: it must fit
   if (mode == 0 && stages * bps < plan->kblocks) stages = (plan->kblocks + bps - 1) / bps;
+  if (tp && stages < plan->qt_blocks) plan->qt_blocks = stages;  // (never the case at the supported dims)
   SPN_REQUIRE(stages >= 2, SPN_ERR_BAD_SHAPE, "D=%d leaves no room for the bank ring in %d B of shared memory", D, smem_max);
   plan->stages = stages;
   plan->smem_bytes = fixed + size_t(stages) * bps * kBlockBytes;
   plan->ws_bytes = (mode == 0) ? ((size_t(4) * 2 * chunks * B * sizeof(float) + 255) / 256) * 256 : 256;  // 2 column halves
   if (tp) {
-    plan->stages2 = (plan->kblocks + stages) / 2;
+    plan->stages2 = (plan->kblocks - plan->qt_blocks + stages - 2) / 2;  // the last 32 KiB of the region stage the pass-1 epilogue
     if (plan->stages2 > kMaxStages2) plan->stages2 = kMaxStages2;
     SPN_REQUIRE(plan->stages2 >= (plan->kblocks - plan->ow_blocks) / 4 + 2, SPN_ERR_BAD_SHAPE, "two-pass ring too shallow");
     plan->ws_bytes = size_t(plan->q_tiles) * kBM * size_t(plan->n_tiles) * kBN * 2;  // P~ scratch, bf16
@@ -1439,7 +1592,7 @@ int bank_ce_backward(const void* q, const void* bank, const long long* labels, f
   p.row_base = row_base; p.labels = labels; p.lse = lse; p.gscale = gscale; p.gscale_dev = gscale_dev;
   p.eps_over_n = label_smoothing / float(N_total); p.one_minus_eps = 1.f - label_smoothing;
   p.dq = dq; p.dlogit_dot = dlogit_dot;
-  return launch_mode<1>(plan.cg == 2, T, dlogit_dot != nullptr, tq, tb, tbh, tb, p, plan.grid, plan.smem_bytes, stream);
+  return launch_mode<1>(plan.cg == 2, T, dlogit_dot != nullptr, tq, tb, tbh, tb, tb, tb, p, plan.grid, plan.smem_bytes, stream);
 }
 
 int bank_stats(const void* bank, long long rows, int D, float* maxnorm, float* colsum, cudaStream_t stream) {
@@ -1495,11 +1648,15 @@ int bank_ce_fused(const void* q, const void* bank, const long long* labels, cons
   SPN_REQUIRE(inv_tau > 0.f && isfinite(inv_tau), SPN_ERR_BAD_ARG, "inv_tau must be positive and finite (got %g)", inv_tau);
   SPN_REQUIRE(aligned16(o_acc), SPN_ERR_BAD_ALIGN, "bank_ce_fused: o_acc must be 16-byte aligned");
   SPN_REQUIRE(!plan.two_pass || aligned16(ws), SPN_ERR_BAD_ALIGN, "bank_ce_fused: workspace must be 16-byte aligned");
-  CUtensorMap tq, tb, tbh, tp;
+  CUtensorMap tq, tb, tbh, tp, tdq, tpf;
   if ((rc = make_tmap_bf16_2d(&tq, q, uint64_t(B), uint64_t(D), kBM)) != SPN_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&tb, bank, uint64_t(N) * T, uint64_t(D), kBN)) != SPN_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&tbh, bank, uint64_t(N) * T, uint64_t(D), kBN / 2)) != SPN_OK) return rc;
   tp = tb;
+  tdq = tb;
+  tpf = tb;
+  if (plan.two_pass && (rc = make_tmap_bf16_2d_prefetch(&tpf, bank, uint64_t(N) * T, uint64_t(D), kBN)) != SPN_OK) return rc;
+  if (plan.two_pass && (rc = make_tmap_f32_2d(&tdq, o_acc, uint64_t(B), uint64_t(D), 32)) != SPN_OK) return rc;
   if (plan.two_pass &&
       (rc = make_tmap_bf16_2d(&tp, ws, uint64_t(plan.q_tiles) * plan.n_tiles * kBM, uint64_t(kBN), kBM)) != SPN_OK)
     return rc;
@@ -1513,9 +1670,9 @@ int bank_ce_fused(const void* q, const void* bank, const long long* labels, cons
   p.num_dsplit = plan.num_dsplit; p.ow_blocks = plan.ow_blocks; p.hg = plan.hg; p.scale_log2 = inv_tau * kLog2e;
   p.row_base = row_base; p.labels = labels; p.ref = ref; p.gscale = 1.f; p.dq = o_acc; p.dlogit_dot = es_acc;
   p.l_acc = l_acc; p.st_out = s_t; p.lbl_row_out = lbl_row;
-  p.two_pass = plan.two_pass; p.stages2 = plan.stages2; p.p_scratch = static_cast<unsigned short*>(ws);
+  p.two_pass = plan.two_pass; p.stages2 = plan.stages2; p.qt_blocks = plan.qt_blocks; p.p_scratch = static_cast<unsigned short*>(ws);
   p.p_ld = (long long)plan.n_tiles * kBN;
-  rc = launch_mode<2>(plan.cg == 2, T, es_acc != nullptr, tq, tb, tbh, tp, p, plan.grid, plan.smem_bytes, stream);
+  rc = launch_mode<2>(plan.cg == 2, T, es_acc != nullptr, tq, tb, tbh, tp, tdq, tpf, p, plan.grid, plan.smem_bytes, stream);
   if (rc != SPN_OK) return rc;
   if (bank_t) {
     gather_label_rows_kernel<<<(B + 7) / 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(bank), lbl_row, B, D, bank_t);

@@ -99,6 +99,40 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
   return SPN_OK;
 }
 
+int make_tmap_bf16_2d_prefetch(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(SPN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {256u, box_rows};  // un-swizzled 512-byte rows: L2 prefetch only, never a shared-memory image
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SPN_ERR_CUDA, "cuTensorMapEncodeTiled(prefetch) failed (CUresult %d) rows=%llu cols=%llu", (int)r,
+                (unsigned long long)rows, (unsigned long long)cols);
+  return SPN_OK;
+}
+
+int make_tmap_f32_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(SPN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (!aligned16(gptr)) return fail(SPN_ERR_BAD_ALIGN, "TMA pointer %p is not 16-byte aligned", gptr);
+  if ((cols * 4) % 16 != 0) return fail(SPN_ERR_BAD_ALIGN, "row pitch %llu B is not a multiple of 16", (unsigned long long)(cols * 4));
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 4};
+  cuuint32_t box[2] = {32u, box_rows};  // 32 fp32 = one 128-byte swizzle row
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(gptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SPN_ERR_CUDA, "cuTensorMapEncodeTiled(f32) failed (CUresult %d) rows=%llu cols=%llu box_rows=%u", (int)r,
+                (unsigned long long)rows, (unsigned long long)cols, box_rows);
+  return SPN_OK;
+}
+
 }  // namespace spn
 
 extern "C" {

@@ -16,7 +16,7 @@ def read(ncta):
     _lib.call("spn_debug_read_timeline", ctypes.addressof(buf), ncta * 16)
     return np.frombuffer(buf, dtype=np.uint64).reshape(ncta, 16).astype(np.float64)
 
-B, N, D = 512, 100000, 640
+B, N, D = 512, int(os.environ.get("EXP_N", "100000")), 640
 bank = torch.nn.functional.normalize(torch.randn(N, D, device="cuda"), dim=-1)
 lab = torch.randint(0, N, (B,), device="cuda")
 q = torch.nn.functional.normalize(bank[lab] + 3.2 * torch.randn(B, D, device="cuda") / D ** 0.5, dim=-1)
@@ -28,6 +28,12 @@ for hg in sys.argv[1:] or ["6", "2", "0"]:
     for it in range(3):
         _fused_sweep(q, db, lab, 50.0, False)
         torch.cuda.synchronize()
+    buf = (ctypes.c_ulonglong * (148 * 16))()
+    _lib.call("spn_debug_read_timeline", ctypes.addressof(buf), -148 * 16)
+    ev = np.frombuffer(buf, dtype=np.uint64).reshape(148, 16).astype(np.float64)
+    evn = {0: "setup", 1: "q_resident", 2: "p1_issued", 3: "tmem_free", 4: "p2_first_P", 5: "p2_issued", 8: "p1_retired",
+           9: "epi1_done", 10: "p2_retired", 11: "end"}
+    print(f"hg={hg} events (rank-0 CTAs, mean cycles since kernel entry):", json.dumps({n: round(float(ev[0::2, i].mean())) for i, n in evn.items()}), flush=True)
     t = read(148)
     for rk in (0, 1):
         print(f"hg={hg} rank {rk}:", json.dumps({n: round(float(t[rk::2, i].mean())) for i, n in enumerate(names)}), flush=True)
