@@ -169,7 +169,8 @@ def run_ours(args, cfg):
     lab_pin = labels_cpu.pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def step(qin, lab):
+    def step_autograd(qin, lab):
+        """the reference call shape: loss = infonce_loss(q, bank, labels, tau); loss.backward()"""
         qx = qin.detach().requires_grad_(True)
         if sharded:
             loss = bank_infonce_sharded(qx, bank, lab, tau)
@@ -177,6 +178,14 @@ def run_ours(args, cfg):
             loss = spn.bank_infonce(qx, bank, lab, tau)
         loss.backward()
         return loss, qx.grad
+
+    def step(qin, lab):
+        """one pass of the hot path: loss + dL/dq.  Un-sharded: the step primitive (one spn_bank_ce_step C-ABI call, same
+        kernels as the autograd wrapper minus PyTorch's autograd-engine hand-off, which costs 100-200 us of host time per
+        step on these boxes and would make the measurement host-bound); the autograd wrapper is timed next to it."""
+        if sharded:
+            return step_autograd(qin, lab)
+        return spn.bank_ce_step(qin, bank, lab, tau)
 
     dq_pin = torch.empty((B, D), dtype=torch.float32).pin_memory()
     loss_pin = torch.empty((), dtype=torch.float32).pin_memory()
@@ -192,16 +201,20 @@ def run_ours(args, cfg):
 
     def timed(fn, iters):
         """sum of per-iteration CUDA-event times (L2 flushed, untimed, before each); max over ranks."""
-        evs = []
+        evs, cpu = [], 0.0
         for _ in range(iters):
             flush.zero_()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
+            t0 = time.perf_counter()
             fn()
+            cpu += time.perf_counter() - t0
             e.record()
             evs.append((s, e))
         torch.cuda.synchronize(dev)
-        return sum(s.elapsed_time(e) for s, e in evs) / 1e3
+        timed.cpu_issue_ms = cpu / iters * 1e3  # host time spent issuing one step (no sync inside)
+        timed.per_iter_ms = [s.elapsed_time(e) for s, e in evs]
+        return sum(timed.per_iter_ms) / 1e3
 
     def barrier():
         if world > 1:
@@ -230,6 +243,10 @@ def run_ours(args, cfg):
         torch.cuda.synchronize(dev)
     barrier()
     t_dev = timed(lambda: step(q_dev, labels_dev), args.steps)
+    host_issue_ms, per_iter = timed.cpu_issue_ms, list(timed.per_iter_ms)
+    barrier()
+    t_auto = timed(lambda: step_autograd(q_dev, labels_dev), args.steps)
+    auto_issue_ms = timed.cpu_issue_ms
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
@@ -280,7 +297,7 @@ def run_ours(args, cfg):
         ms_step = t_dev / args.steps * 1e3
         value = (B * world) * args.steps / t_dev
         peak = peaks["tflops"]
-        roof = {"bound": "tensor", "kernel": "bank_ce_kernel<MODE=2> (fused single pass: S = q.bank^T, P~ = exp(S - ref), O += P~.bank)",
+        roof = {"bound": "tensor", "kernel": "bank_ce_kernel<MODE=2, CG=2> (fused sweep, two passes per CTA pair: S = q.bank^T -> P~ = exp(S - ref) -> dq[:, :X] += P~.bank, P~ parked in a bf16 scratch; then dq[:, X:] += P~.bank as a plain tcgen05 GEMM; no S recompute)",
                 "achieved": step_flops_rank / t_fused / 1e12, "peak": peak, "unit": "TFLOP/s",
                 "frac": step_flops_rank / t_fused / 1e12 / peak, "traffic": None, "peak_source": peaks["src"] + " burst bf16",
                 "kernel_ms": t_fused * 1e3, "algorithmic_flops_per_launch": step_flops_rank,
@@ -306,6 +323,14 @@ def run_ours(args, cfg):
                            "l2": "256 MiB flush buffer written before every timed iteration",
                            "global_batch": B * world},
                 "clocks": clocks, "roofline": roof,
+                "host_issue_ms_per_step": host_issue_ms,
+                "api": ("spn4cir_b200.dist.bank_infonce_sharded (autograd)" if sharded else
+                        "spn4cir_b200.bank_ce_step -> spn_bank_ce_step (C ABI step primitive: loss + dL/dq)"),
+                "autograd_api": {"call": "loss = bank_infonce(q, bank, labels, tau); loss.backward()",
+                                 "value": (B * world) * args.steps / t_auto, "unit": "queries/s",
+                                 "ms_per_step": t_auto / args.steps * 1e3, "host_issue_ms_per_step": auto_issue_ms,
+                                 "note": "same kernels + the autograd engine's thread hand-off, a ones-fill and a scale kernel"},
+                "step_ms_min_median_max": [min(per_iter), statistics.median(per_iter), max(per_iter)],
                 "e2e": {"value": (B * world) * args.steps / t_e2e, "unit": "queries/s",
                         "h2d_bytes_per_step": q_pin.numel() * 4 + lab_pin.numel() * 8,
                         "d2h_bytes_per_step": B * D * 4 + 4, "ms_per_step": t_e2e / args.steps * 1e3,

@@ -26,6 +26,7 @@ struct BankCEParams {
   int ow_blocks;     // backward: 64-column blocks of dq per split
   int hg;            // CTA-pair schedule knob (see the MMA issuer)
   int qt_blocks;     // two-pass: leading k-blocks of the Q tile that live in TMEM (TS operand) instead of shared memory
+  int pdl;           // launched with programmatic stream serialization (spn_bank_ce_step chains prep -> sweep -> finalize)
   int two_pass;      // fused CTA-pair kernel: second pass over the chunk for dq[:, X:D) (no S recompute)
   int stages2;       // second-pass ring depth (stages of 2 blocks)
   unsigned short* p_scratch;  // two-pass: bf16 global scratch for P~, tile-major [q_tile][bank tile][128][128]
@@ -76,12 +77,13 @@ int bank_ce_prep(const void* q_src, int dtype, const void* bank, const long long
                  cudaStream_t stream);
 int bank_ce_fused(const void* q, const void* bank, const long long* labels, const float* ref, float inv_tau, int B,
                   long long N, int D, int T, long long row_base, int init, float* o_acc, float* l_acc, float* s_t,
-                  long long* lbl_row, float* es_acc, float* bank_t, void* ws, size_t ws_bytes, cudaStream_t stream);
+                  long long* lbl_row, float* es_acc, float* bank_t, void* ws, size_t ws_bytes, cudaStream_t stream,
+                  int pdl = 0);
 size_t bank_ce_fused_ws_bytes(int B, long long N, int D, int T);
 int bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, const float* bank_t, const void* bank,
                      const long long* lbl_row, int zero_loss, const float* ref, const float* es_acc, const void* q16, const float* colsum, float inv_tau, float gscale, float eps,
                      long long N_total, int B, int D, float* lse, float* loss_q, float* loss_mean, float* dq,
-                     float* dlogit_dot, cudaStream_t stream);
+                     float* dlogit_dot, cudaStream_t stream, int pdl = 0);
 size_t bank_ce_step_ws_bytes(int B, long long N, int D, int T);
 int bank_ce_step(const void* q_src, int dtype, const void* bank, const long long* labels, float inv_tau,
                  const float* maxnorm, const float* colsum, float eps, int B, long long N, int D, int T, float* lse,

@@ -369,7 +369,8 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const int qt = bid % p.q_tiles;  // CG = 2: index of the PAIR of query tiles
   bid /= p.q_tiles;
   const int ds = bid % p.num_dsplit;
-  const int chunk = bid / p.num_dsplit;
+  int chunk = bid / p.num_dsplit;
+  if (p.hg & 128) chunk = (chunk + (qt & 1) * (p.num_chunks / 2)) % p.num_chunks;  // experiment: no two pairs share a tile
   const int q0 = (qt * CG + int(crank)) * kBM;
   const int t_begin = int((long long)chunk * p.n_tiles / p.num_chunks);
   const int t_end = int((long long)(chunk + 1) * p.n_tiles / p.num_chunks);
@@ -424,6 +425,9 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *sm.tmem_slot;
+  // everything above touched no global memory: under programmatic dependent launch it overlapped the tail of the
+  // prologue kernel; from here on its outputs (q16, ref, zeroed accumulators) are needed
+  grid_dependency_wait();
 
   if (warp == 0) {
     // ===================================================================== TMA producer (converged warp, one
@@ -546,14 +550,18 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_wait(sm.p2_go, 0);   // this CTA's soft-max warps have written (and fenced) all of their P~ rows
       Ring r2(p.stages2);
       const int groups2 = (p.kblocks - my_blocks) / 4;  // pair N = 256 per group: 128 columns = 2 blocks per CTA
-      auto load_pair2 = [&](const CUtensorMap* map, int col, int row) {
+      auto load_pair2 = [&](const CUtensorMap* map, int col, int row, bool skip) {
         mbar_wait(&sm.empty2[r2.stage], r2.phase ^ 1u);
         const uint32_t fbar = mapa_shared(smem_u32(&sm.full2[r2.stage]), 0);
         if (elect_one()) {
-          if (crank == 0) mbar_arrive_expect_tx(&sm.full2[r2.stage], 4u * kBlockBytes);  // 2 blocks from each CTA
-          uint8_t* dst = sm.q + size_t(r2.stage) * 2 * kBlockBytes;
-          tma_load_2d_cg2(dst, map, fbar, col, row);
-          tma_load_2d_cg2(dst + kBlockBytes, map, fbar, col + kBK, row);
+          if (skip) {  // timing experiment: the stage is declared full without moving any bytes
+            if (crank == 0) mbar_arrive(&sm.full2[r2.stage]);
+          } else {
+            if (crank == 0) mbar_arrive_expect_tx(&sm.full2[r2.stage], 4u * kBlockBytes);  // 2 blocks from each CTA
+            uint8_t* dst = sm.q + size_t(r2.stage) * 2 * kBlockBytes;
+            tma_load_2d_cg2(dst, map, fbar, col, row);
+            tma_load_2d_cg2(dst + kBlockBytes, map, fbar, col + kBK, row);
+          }
         }
         __syncwarp();
         r2.advance();
@@ -561,9 +569,9 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       // newest first: the P~ tiles written last and the bank rows streamed last are the ones still in L2
       for (int t = t_end - 1; t >= t_begin; --t) {
         // A: this CTA's 128 rows of P~(t), K = 128 bank rows = 2 K-major blocks of the tile-major scratch
-        load_pair2(&tmap_p, 0, ((q0 / kBM) * p.n_tiles + t) * kBM);
+        load_pair2(&tmap_p, 0, ((q0 / kBM) * p.n_tiles + t) * kBM, (p.hg & 256) != 0);
         for (int g = 0; g < groups2; ++g)
-          load_pair2(&tmap_bank, (my_blocks + 4 * g) * kBK + int(crank) * 2 * kBK, t * kBN);
+          load_pair2(&tmap_bank, (my_blocks + 4 * g) * kBK + int(crank) * 2 * kBK, t * kBN, (p.hg & 512) != 0);
       }
     }
     TL_FLUSH(0)
@@ -679,12 +687,16 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           tc_fence_after();
           EV(3)  // TMEM free for pass 2
           for (int i = 0; i < ntl; ++i) {
+            TL_BEGIN
             mbar_wait(&sm.full2[r2.stage], r2.phase);
+            TL_END(3)
             if (i == 0) { EV(4) }  // first P~ tile of pass 2 landed
             const uint32_t pstage = r2.stage;
             r2.advance();
             for (int g = 0; g < groups2; ++g) {
+              TL_BEGIN
               mbar_wait(&sm.full2[r2.stage], r2.phase);
+              TL_END(4)
               tc_fence_after();
               if (elect_one()) {
                 const uint64_t bdesc = b_desc0 + uint64_t(r2.stage) * (2 * kBlockBytes >> 4);
@@ -706,6 +718,12 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           if (elect_one()) umma_commit_cg2(sm.o2_full, 3);
           __syncwarp();
           EV(5)  // pass-2 MMAs issued
+#ifdef SPN_TIMELINE
+          if ((threadIdx.x & 31) == 0 && blockIdx.x < 1024) {
+            g_events[blockIdx.x * 16 + 12] = tl_acc[3];  // pass 2: waiting for P~ tiles
+            g_events[blockIdx.x * 16 + 13] = tl_acc[4];  // pass 2: waiting for bank blocks
+          }
+#endif
         }
       } else if (kTP && p.two_pass && (p.hg & 64)) {
         // rank 1's MMA warp has nothing to issue: it pulls the pair's bank tiles into L2 kPF tiles ahead of the ring
@@ -1009,6 +1027,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       // of a lane quarter take alternate 32-column chunks
       mbar_wait(sm.o_full, 0);
       tc_fence_after();
+      grid_launch_dependents();  // the finalize kernel may be scheduled; it still waits for this grid to complete
       if (warp == 2) { EV(8) }  // pass-1 MMAs retired
       // TMA-reduce epilogue (two-pass mode): each warp stages its [32 rows x 32 columns] fp32 piece in a 4 KiB slot
       // (128-byte swizzle: conflict-free 16-byte stores) and one lane issues cp.reduce.async.bulk.tensor (.add): whole
@@ -1204,6 +1223,7 @@ __global__ void prep_query_kernel(const SrcT* __restrict__ q_src, const __nv_bfl
                                   const long long* __restrict__ labels, float inv_tau, const float* __restrict__ maxnorm,
                                   int B, long long N, int D, int T, long long row_base, __nv_bfloat16* __restrict__ q16,
                                   float* __restrict__ ref, const FusedInit init) {
+  grid_launch_dependents();  // the sweep kernel may start its set-up (barriers, TMEM) now
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -1268,6 +1288,7 @@ __global__ void fused_finalize_kernel(const float* __restrict__ o_acc, const flo
                                       float inv_tau, float gscale, float eps, float inv_n_total, int B, int D,
                                       float* __restrict__ lse, float* __restrict__ loss_q, float* __restrict__ loss_mean,
                                       float* __restrict__ dq, float* __restrict__ dlogit_dot) {
+  grid_dependency_wait();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -1414,13 +1435,15 @@ int launch_pair(const CUtensorMap& tq, const CUtensorMap& tb, const CUtensorMap&
   cfg.blockDim = dim3(kBankCEThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = p.pdl ? 2 : 1;
   SPN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kfn, tq, tb, tbh, tp, tdq, tpf, p));
   return SPN_OK;
 }
@@ -1637,7 +1660,8 @@ size_t bank_ce_fused_ws_bytes(int B, long long N, int D, int T) {
 
 int bank_ce_fused(const void* q, const void* bank, const long long* labels, const float* ref, float inv_tau, int B,
                   long long N, int D, int T, long long row_base, int init, float* o_acc, float* l_acc, float* s_t,
-                  long long* lbl_row, float* es_acc, float* bank_t, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                  long long* lbl_row, float* es_acc, float* bank_t, void* ws, size_t ws_bytes, cudaStream_t stream,
+                  int pdl) {
   BankCEPlan plan;
   int rc = bank_ce_plan(2, B, N, D, T, &plan);
   if (rc != SPN_OK) return rc;
@@ -1670,7 +1694,7 @@ int bank_ce_fused(const void* q, const void* bank, const long long* labels, cons
   p.num_dsplit = plan.num_dsplit; p.ow_blocks = plan.ow_blocks; p.hg = plan.hg; p.scale_log2 = inv_tau * kLog2e;
   p.row_base = row_base; p.labels = labels; p.ref = ref; p.gscale = 1.f; p.dq = o_acc; p.dlogit_dot = es_acc;
   p.l_acc = l_acc; p.st_out = s_t; p.lbl_row_out = lbl_row;
-  p.two_pass = plan.two_pass; p.stages2 = plan.stages2; p.qt_blocks = plan.qt_blocks; p.p_scratch = static_cast<unsigned short*>(ws);
+  p.two_pass = plan.two_pass; p.stages2 = plan.stages2; p.qt_blocks = plan.qt_blocks; p.pdl = pdl; p.p_scratch = static_cast<unsigned short*>(ws);
   p.p_ld = (long long)plan.n_tiles * kBN;
   rc = launch_mode<2>(plan.cg == 2, T, es_acc != nullptr, tq, tb, tbh, tp, tdq, tpf, p, plan.grid, plan.smem_bytes, stream);
   if (rc != SPN_OK) return rc;
@@ -1684,18 +1708,26 @@ int bank_ce_fused(const void* q, const void* bank, const long long* labels, cons
 int bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, const float* bank_t, const void* bank,
                      const long long* lbl_row, int zero_loss, const float* ref, const float* es_acc, const void* q16, const float* colsum, float inv_tau, float gscale, float eps,
                      long long N_total, int B, int D, float* lse, float* loss_q, float* loss_mean, float* dq,
-                     float* dlogit_dot, cudaStream_t stream) {
+                     float* dlogit_dot, cudaStream_t stream, int pdl) {
   SPN_REQUIRE(B > 0 && D % 4 == 0 && N_total > 0, SPN_ERR_BAD_SHAPE, "bank_ce_finalize: bad shape");
   SPN_REQUIRE(eps == 0.f || (colsum && q16), SPN_ERR_BAD_ARG, "label smoothing needs the bank column sums and q");
   SPN_REQUIRE(!dlogit_dot || es_acc, SPN_ERR_BAD_ARG, "dlogit_dot needs es_acc");
   SPN_REQUIRE(!dq || (aligned16(dq) && aligned16(o_acc) && aligned16(bank_t)), SPN_ERR_BAD_ALIGN, "bank_ce_finalize: 16-byte alignment");
   SPN_REQUIRE(bank_t || (bank && lbl_row), SPN_ERR_BAD_ARG, "bank_ce_finalize: needs bank_t or (bank, lbl_row)");
   if (zero_loss) SPN_CUDA_CHECK(cudaMemsetAsync(loss_mean, 0, sizeof(float), stream));
-  fused_finalize_kernel<<<(B + 3) / 4, 128, 0, stream>>>(o_acc, l_acc, s_t, bank_t, static_cast<const __nv_bfloat16*>(bank),
-                                                        lbl_row, ref, es_acc,
-                                                        static_cast<const __nv_bfloat16*>(q16), colsum, inv_tau, gscale,
-                                                        eps, 1.f / float(N_total), B, D, lse, loss_q, loss_mean, dq, dlogit_dot);
-  SPN_CUDA_CHECK(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned((B + 3) / 4), 1, 1);
+  cfg.blockDim = dim3(128, 1, 1);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  SPN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fused_finalize_kernel, o_acc, l_acc, s_t, bank_t,
+                                    static_cast<const __nv_bfloat16*>(bank), lbl_row, ref, es_acc,
+                                    static_cast<const __nv_bfloat16*>(q16), colsum, inv_tau, gscale, eps,
+                                    1.f / float(N_total), B, D, lse, loss_q, loss_mean, dq, dlogit_dot));
   return SPN_OK;
 }
 
@@ -1733,10 +1765,10 @@ int bank_ce_step(const void* q_src, int dtype, const void* bank, const long long
                        FusedInit{o_acc, l_acc, s_t, lbl_row, es_acc, loss_mean}, stream);
   if (rc != SPN_OK) return rc;
   rc = bank_ce_fused(q16, bank, labels, ref, inv_tau, B, N, D, T, 0, /*init=*/0, o_acc, l_acc, s_t, lbl_row, es_acc,
-                     /*bank_t=*/nullptr, scratch, scratch_bytes, stream);
+                     /*bank_t=*/nullptr, scratch, scratch_bytes, stream, /*pdl=*/1);
   if (rc != SPN_OK) return rc;
   return bank_ce_finalize(o_acc, l_acc, s_t, nullptr, bank, lbl_row, /*zero_loss=*/0, ref, es_acc, q16, colsum, inv_tau,
-                          inv_tau / float(B), eps, N, B, D, lse, loss_q, loss_mean, dq, dlogit_dot, stream);
+                          inv_tau / float(B), eps, N, B, D, lse, loss_q, loss_mean, dq, dlogit_dot, stream, /*pdl=*/1);
 }
 
 int merge_stats(const float* pm, const float* pl, const float* pst, const float* pss, int P, int B, float* m,

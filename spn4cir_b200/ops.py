@@ -360,6 +360,48 @@ def bank_infonce(query_features: torch.Tensor, bank: Union[DeviceBank, torch.Ten
     return fn.apply(query_features, tau_t, bank, lab, 1.0 / tau_v, float(label_smoothing))
 
 
+def bank_ce_step(query_features: torch.Tensor, bank: DeviceBank, labels: Optional[torch.Tensor] = None, tau: float = 0.01,
+                 *, label_smoothing: float = 0.0, grad_scale: float = 1.0, want_dtau: bool = False):
+    """The training-step primitive without the autograd engine: ``(loss, dq)`` or ``(loss, dq, dtau)``.
+
+    Same arithmetic as ``loss = bank_infonce(q, bank, labels, tau); (grad_scale * loss).backward()`` -- i.e. the forward of
+    /root/reference/clip4cir/models_negplus.py:150-154 and its autograd backward
+    (/root/reference/clip4cir/train_negplus.py:110-121) -- as ONE call into the C ABI (``spn_bank_ce_step``), for trainers
+    that own their backward (and for ``bench.py``, where PyTorch's autograd thread hand-off would otherwise be the
+    bottleneck: ~100-200 us of host time per step against ~130 us of GPU time).  ``bank`` must be an un-sharded
+    :class:`DeviceBank`; ``tau`` a python float.
+    """
+    _require_cuda(query_features, "query_features")
+    if not isinstance(bank, DeviceBank) or bank.row_base != 0 or bank.n_total != bank.N:
+        raise SpnError("bank_ce_step", -7, "needs an un-sharded DeviceBank (use dist.bank_infonce_sharded for shards)")
+    if query_features.dim() != 2 or query_features.shape[1] != bank.D:
+        raise SpnError("bank_ce_step", -1, f"query_features must be [B, {bank.D}], got {tuple(query_features.shape)}")
+    tau_v = float(tau)
+    if not (tau_v > 0.0 and math.isfinite(tau_v)):
+        raise SpnError("bank_ce_step", -7, f"tau must be positive and finite, got {tau_v}")
+    inv_tau = 1.0 / tau_v
+    B = query_features.shape[0]
+    lab = _prep_labels(labels, B, query_features.device)
+    eps = float(label_smoothing)
+    if inv_tau * bank.maxnorm_host() * 1.03 <= 109.0:  # the fused sweep's static soft-max reference is provably safe
+        _, _, loss, dq, ddot = _fused_step(query_features, bank, lab, inv_tau, eps, want_dtau)
+    else:  # colder temperatures: forward statistics (exact running maximum) + recompute backward
+        q16 = cast_to_bf16(query_features)
+        stats = _fwd_stats(q16, bank, lab, inv_tau, eps != 0.0)
+        lse, _, loss = _loss_from_stats(stats, bank.n_total, eps)
+        dq = torch.zeros((B, bank.D), dtype=torch.float32, device=query_features.device)
+        ddot = torch.zeros(B, dtype=torch.float32, device=query_features.device) if want_dtau else None
+        _bwd(q16, bank, lab, inv_tau, lse, inv_tau / B * grad_scale, None, eps, dq, ddot)
+        if want_dtau:
+            return loss, dq, (-(inv_tau / B) * grad_scale) * ddot.sum()
+        return loss, dq
+    if grad_scale != 1.0:
+        dq = dq * grad_scale
+    if want_dtau:
+        return loss, dq, (-(inv_tau / B) * grad_scale) * ddot.sum()
+    return loss, dq
+
+
 def bank_ce_stats(query_features: torch.Tensor, bank: DeviceBank, labels: torch.Tensor, tau: float,
                   want_ssum: bool = False) -> torch.Tensor:
     """Forward statistics only: [4, B] = (m, l, s_t, s_sum) in natural-log units (no autograd)."""

@@ -335,3 +335,21 @@ def test_peaked_softmax_has_no_cancellation():
         for sp in paths:
             loss, dq, _ = run_ours(q, bank, labels, 0.02, single_pass=sp)
             assert rel_l2(dq, o_dq) < tol, (noise, sp, rel_l2(dq, o_dq))
+
+
+@pytest.mark.parametrize("B,N,D,tau", [(512, 9000, 640, 0.02), (64, 2000, 128, 0.005), (256, 3000, 768, 0.02)])
+def test_step_primitive_equals_autograd(B, N, D, tau):
+    """spn.bank_ce_step (one C-ABI call, no autograd engine) returns the loss / gradients of the autograd path."""
+    q, bank, labels = synth.make_bank_case(B, N, D, 1, "S", 77)
+    db = spn.DeviceBank.from_tensor(bank, DEV)
+    loss, dq, dtau = spn.bank_ce_step(q.to(DEV), db, labels.to(DEV), tau, grad_scale=3.0, want_dtau=True)
+    qd = q.to(DEV).requires_grad_(True)
+    t = torch.tensor(tau, device=DEV, requires_grad=True)
+    ref = spn.bank_infonce(qd, db, labels.to(DEV), t)
+    (3.0 * ref).backward()
+    assert abs(loss.item() - ref.item()) <= 1e-6 * max(abs(ref.item()), 1e-3)
+    assert rel_l2(dq.cpu(), qd.grad.cpu()) < 1e-4
+    assert abs(dtau.item() - t.grad.item()) <= 1e-3 * max(abs(t.grad.item()), 1e-2)
+    o_loss, o_dq, _ = obank.infonce_loss_and_grads(q, bank, labels, tau, grad_out=3.0)
+    assert abs(loss.item() - o_loss.item()) <= 1e-2 * max(abs(o_loss.item()), 1e-3)
+    assert rel_l2(dq.cpu(), o_dq) < 1e-2

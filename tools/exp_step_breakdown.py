@@ -55,3 +55,22 @@ with torch.cuda.stream(s):
         out = lib_only()
 torch.cuda.synchronize()
 print(json.dumps({"graph replay of spn_bank_ce_step (flush)": measure(g.replay)}))
+# the same after 1.5 s of sustained load (what bench.py does before its timed region)
+t_end = time.perf_counter() + 1.5
+while time.perf_counter() < t_end:
+    for _ in range(20):
+        full()
+    torch.cuda.synchronize()
+print(json.dumps({"after 1.5 s load: autograd step (flush)": measure(full, iters=20), "lib only": measure(lib_only, iters=20)}))
+ev = []
+for name, fn in (("prep+main+finalize", lib_only),):
+    pass
+import spn4cir_b200.ops as ops
+from spn4cir_b200._lib import call as _call
+sw = ops._fused_sweep(q, bank, labels, 1.0 / tau, False)
+ws, wsb = ops.fused_scratch(B, bank, dev)
+def main_only():
+    _call("spn_bank_ce_fused", sw["q16"].data_ptr(), bank.data.data_ptr(), labels.data_ptr(), sw["ref"].data_ptr(), 1.0 / tau, B, bank.N, D,
+          bank.T, 0, 0, sw["o_acc"].data_ptr(), sw["l_acc"].data_ptr(), sw["s_t"].data_ptr(), sw["lbl_row"].data_ptr(), None, None,
+          ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream)
+print(json.dumps({"after load: main kernel only": measure(main_only, iters=20)}))

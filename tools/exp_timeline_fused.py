@@ -32,7 +32,7 @@ for hg in sys.argv[1:] or ["6", "2", "0"]:
     _lib.call("spn_debug_read_timeline", ctypes.addressof(buf), -148 * 16)
     ev = np.frombuffer(buf, dtype=np.uint64).reshape(148, 16).astype(np.float64)
     evn = {0: "setup", 1: "q_resident", 2: "p1_issued", 3: "tmem_free", 4: "p2_first_P", 5: "p2_issued", 8: "p1_retired",
-           9: "epi1_done", 10: "p2_retired", 11: "end"}
+           9: "epi1_done", 10: "p2_retired", 11: "end", 12: "p2_wait_P", 13: "p2_wait_bank"}
     print(f"hg={hg} events (rank-0 CTAs, mean cycles since kernel entry):", json.dumps({n: round(float(ev[0::2, i].mean())) for i, n in evn.items()}), flush=True)
     t = read(148)
     for rk in (0, 1):
