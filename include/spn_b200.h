@@ -164,6 +164,16 @@ int spn_bank_ce_step(const void* q_src, int src_dtype, const void* bank_bf16, co
                      float* lse, float* loss_per_query, float* loss_mean, float* dq, float* dlogit_dot, void* ws,
                      size_t ws_bytes, void* stream);
 
+/* Sampled-negatives loss: query b scores only its own candidate rows candidates[b][0 .. K1) of the bank
+ * (column 0 = the positive), loss_b = CE(inv_tau * <q_b, bank[cand]>, label 0), loss_mean = mean_b.  Replaces
+ * CIRPlus.part_infonce_loss (clip4cir/models.py:115-128; zscir/models_bank.py:103-122) for candidate ids drawn by the
+ * caller (the reference draws them with random.sample, models.py:109-113).  q in `src_dtype` (rounded to bf16 inside),
+ * bank bf16 [N, D], candidates int64 [B, K1] (ids outside [0, N) are masked out), dq (nullable) fp32 [B, D] =
+ * d loss_mean / d q for an upstream gradient of 1, dlogit_dot (nullable) fp32 [B] as in spn_bank_ce_bwd. */
+int spn_part_ce(const void* q_src, int src_dtype, const void* bank_bf16, const int64_t* candidates, float inv_tau, int B,
+                int K1, int D, int64_t N, float* loss_per_query, float* loss_mean, float* dq, float* dlogit_dot,
+                void* stream);
+
 /* Fused cosine-similarity + per-row top-K over one gallery shard (descending score, ties -> lower
  * index first).  Replaces `distances = 1 - pred @ index.T; torch.argsort(distances)` followed by the
  * [:K] slices (clip4cir/validate.py:31-32,126-127; clip4cir/cirr_test_submission.py:91-92,106) and,

@@ -82,3 +82,38 @@ def bank_large_step_query(refer_bank: torch.Tensor, idx: torch.Tensor, text_feat
     """Query assembly of CIRPlus.bank_large_step, /root/reference/clip4cir/models_negplus.py:133-137:
     normalize(refer_bank[idx] + text_feats)."""
     return F.normalize(refer_bank[idx] + text_feats)
+
+
+def part_infonce_loss(query_feats: torch.Tensor, target_feats_all: torch.Tensor, target_indexs: torch.Tensor,
+                      neg_num: int, tau: float, rng=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Line-faithful restatement of CIRPlus.part_infonce_loss + get_neg_id,
+    /root/reference/clip4cir/models.py:109-128 (same loop at /root/reference/zscir/models_bank.py:103-122).
+    Returns (loss, candidate ids [N, 1 + neg_num]); rng defaults to python's global `random`, as in the reference."""
+    import random as _random
+    rng = rng or _random
+    M = target_feats_all.shape[0]                                             # :116
+    N = query_feats.shape[0]                                                  # :117
+    target_loss = torch.tensor(0, dtype=torch.float)                          # :118
+    cands = []
+    for i in range(N):                                                        # :119
+        pos_id = target_indexs[i].item()                                      # :120
+        range_target = list(range(M))                                         # :110  (get_neg_id)
+        range_target.remove(pos_id)                                           # :111
+        neg_ids = rng.sample(range_target, neg_num)                           # :112
+        neg_feats = target_feats_all[neg_ids]                                 # :122
+        pos_feats = target_feats_all[pos_id].unsqueeze(0)                     # :123
+        target_feats = torch.cat([pos_feats, neg_feats])                      # :124
+        target_loss = target_loss + infonce_loss(query_feats[i], target_feats, torch.tensor(0, dtype=torch.long), tau=tau)  # :125-126
+        cands.append([pos_id] + list(neg_ids))
+    return target_loss / N, torch.tensor(cands, dtype=torch.long)             # :127-128
+
+
+def part_loss_and_grads(q: torch.Tensor, bank: torch.Tensor, cand: torch.Tensor, tau: float, grad_out: float = 1.0,
+                        dtype=torch.float64):
+    """Closed form of the loop above for given candidate ids: mean_b CE(<q_b, bank[cand_b]> / tau, 0) + autograd."""
+    qq = q.detach().to(dtype).requires_grad_(True)
+    tt = torch.tensor(float(tau), dtype=dtype, requires_grad=True)
+    logits = torch.einsum("bd,bkd->bk", qq, bank.detach().to(dtype)[cand]) / tt
+    loss = F.cross_entropy(logits, torch.zeros(q.shape[0], dtype=torch.long))
+    loss.backward(torch.tensor(float(grad_out), dtype=dtype))
+    return loss.detach(), qq.grad.detach(), tt.grad.detach()

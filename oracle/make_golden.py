@@ -83,6 +83,32 @@ def bank_cases(models_negplus):
                         input_digest=digest(q, bank))
 
 
+def part_cases():
+    """Sampled-negatives loss: the reference's CIRPlus.part_infonce_loss (clip4cir/models.py:115-128) executed with a
+    seeded python RNG; the oracle restatement must draw the same negatives and give the same loss."""
+    import random
+    import models  # /root/reference/clip4cir/models.py
+    C = models.CIRPlus
+    for name, (B, N, D, k, tau, seed, mode) in {"part_small": (12, 300, 64, 7, 0.02, 21, "S"),
+                                                 "part_640": (64, 5000, 640, 63, 0.02, 22, "U")}.items():
+        q, bank, labels = synth.make_bank_case(B, N, D, 1, mode, seed)
+        stub = types.SimpleNamespace(crossentropy_criterion=nn.CrossEntropyLoss(), device="cpu", neg_num=k, tau=tau)
+        stub.get_neg_id = lambda i, n, kk: C.get_neg_id(stub, i, n, kk)
+        stub.infonce_loss = lambda *a, **kw: C.infonce_loss(stub, *a, **kw)
+        random.seed(seed)
+        qq = q.clone().requires_grad_(True)
+        ref = C.part_infonce_loss(stub, qq, bank, labels)
+        ref.backward()
+        random.seed(seed)
+        o_loss, cand = obank.part_infonce_loss(q, bank, labels, k, tau)
+        assert torch.allclose(o_loss, ref.detach(), rtol=1e-6, atol=1e-6), (name, o_loss, ref)
+        c_loss, c_dq, c_dtau = obank.part_loss_and_grads(q, bank, cand, tau, dtype=torch.float32)
+        assert torch.allclose(c_loss, ref.detach(), rtol=1e-5, atol=1e-6) and torch.allclose(c_dq, qq.grad, rtol=1e-4, atol=1e-7), name
+        np.savez_compressed(OUT / f"{name}.npz", B=B, N=N, D=D, k=k, tau=tau, seed=seed, mode=mode, loss=ref.detach().numpy(),
+                            dq=qq.grad.numpy(), cand=cand.numpy(), dtau=c_dtau.numpy(), input_digest=digest(q, bank, labels))
+        print(f"{name}: loss={ref.item():.6f} |dq|={qq.grad.norm().item():.4e}")
+
+
 def retrieval_cases(validate):
     cases = {"cirr_small": (200, 500, 64, 0, 3.0), "cirr_c2": (4181, 2297, 640, 0, 8.0)}
     for name, (Q, G, D, seed, noise) in cases.items():
@@ -142,6 +168,10 @@ def main():
     torch.set_num_threads(os.cpu_count() or 1)
     models_negplus, validate = import_reference()
     bank_cases(models_negplus)
+    if not os.environ.get("GOLDEN_ONLY") or "part" in os.environ["GOLDEN_ONLY"]:
+        part_cases()
+    if os.environ.get("GOLDEN_ONLY"):
+        return
     blip2_cases()
     retrieval_cases(validate)
 

@@ -20,7 +20,7 @@ REPO_ROOT = PKG_DIR.parent
 LIB_PATH = PKG_DIR / "libspn_b200.so"
 HEADER_PATH = REPO_ROOT / "include" / "spn_b200.h"
 
-SOURCES = ["common.cu", "bank_ce_tc.cu", "umma_selftest.cu", "prologue.cu", "sim_rank.cu", "api.cu"]
+SOURCES = ["common.cu", "bank_ce_tc.cu", "part_ce.cu", "umma_selftest.cu", "prologue.cu", "sim_rank.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177",
@@ -104,6 +104,8 @@ _SIGNATURES = {
                              c_void_p],
     "spn_bank_ce_step": [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float, c_int, c_int64, c_int,
                          c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    "spn_part_ce": [c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
+                    c_void_p, c_void_p],
     "spn_sim_topk": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int32, c_void_p,
                      c_void_p, c_void_p, c_size_t, c_void_p],
     "spn_merge_topk": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],

@@ -6,6 +6,8 @@ Same names, argument meaning and error behaviour as the reference, so a maintain
   -- ``CIRPlus.infonce_loss`` (/root/reference/clip4cir/models_negplus.py:150-154 and its 7 copies)
 * ``BankLossMixin.bank_large_step(loss, text_feats, indexs, target_indexs, refer_indexs)``
   -- /root/reference/clip4cir/models_negplus.py:130-142
+* ``part_infonce_loss(query_feats, target_feats_all, target_indexs, neg_num, tau)`` / ``BankLossMixin.part_infonce_loss``
+  -- the sampled-negatives loss /root/reference/clip4cir/models.py:109-128 (``--neg_num > 0``), same RNG calls
 * ``forward_stage2_loss(fusion_feats, target_feats, target_indexs, temp)``
   -- the loss tail of ``Blip2QformerCirAlignPrompt.forward_stage2`` (...align_prompt.py:254-268)
 * ``inference_sim(fusion_feats, target_feats)`` -- the sim tail of ``inference`` (...align_prompt.py:311-319)
@@ -24,7 +26,9 @@ import torch
 import torch.nn.functional as F
 
 from ._lib import SpnError, call
-from .ops import DeviceBank, _ptr, _require_cuda, _stream, bank_infonce, cast_to_bf16
+import random
+
+from .ops import DeviceBank, _ptr, _require_cuda, _stream, bank_infonce, cast_to_bf16, part_infonce
 from .retrieval import _prep_gallery, names_to_ids, recall_at, sim_rank, sim_topk
 
 
@@ -33,6 +37,30 @@ def infonce_loss(query_features: torch.Tensor, target_features: Union[DeviceBank
                  labels: Optional[torch.Tensor] = None, tau=0.01, label_smoothing: float = 0.0) -> torch.Tensor:
     """``CIRPlus.infonce_loss``: ``CE((q @ bank.T) / tau, labels)``; ``labels=None`` -> ``arange(B)``."""
     return bank_infonce(query_features, target_features, labels, tau, label_smoothing=label_smoothing)
+
+
+def get_neg_id(i: int, N: int, k: int, rng=random) -> List[int]:
+    """``CIRPlus.get_neg_id`` (/root/reference/clip4cir/models.py:109-113): k distinct ids from range(N) without i,
+    drawn with the SAME calls on the SAME generator (python's global ``random`` unless ``rng`` is given), so a seeded
+    run picks the reference's negatives."""
+    range_target = list(range(N))
+    range_target.remove(i)
+    return rng.sample(range_target, k)
+
+
+def part_infonce_loss(query_feats: torch.Tensor, target_feats_all: Union[DeviceBank, torch.Tensor],
+                      target_indexs: torch.Tensor, neg_num: int, tau=0.01, rng=random,
+                      candidates: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``CIRPlus.part_infonce_loss`` (/root/reference/clip4cir/models.py:115-128): per query, CE over
+    ``[positive, neg_num sampled negatives]`` with label 0, mean over the batch.  The ids are drawn on the host in the
+    reference's order (one ``.tolist()`` instead of B ``.item()`` syncs); the arithmetic runs in ``spn_part_ce``.
+    ``candidates`` (int64 ``[B, 1 + k]``) overrides the sampling."""
+    if candidates is None:
+        M = target_feats_all.N if isinstance(target_feats_all, DeviceBank) else target_feats_all.shape[0]
+        pos = [int(v) for v in target_indexs.tolist()]
+        rows = [[p] + get_neg_id(p, M, neg_num, rng) for p in pos]                       # :120-121,124
+        candidates = torch.tensor(rows, dtype=torch.int64)
+    return part_infonce(query_feats, target_feats_all, candidates, tau)
 
 
 class BankLossMixin:
@@ -59,7 +87,13 @@ class BankLossMixin:
         reference_image_feats = self.refer_bank[idx.to(self.refer_bank.device)].detach()
         query_feats = F.normalize(self.combining_function(reference_image_feats, text_feats))
         target_indexs = target_indexs.to(self.device)
-        loss["bank_loss"] = self.infonce_loss(query_feats, self.target_bank, target_indexs, tau=self.tau)
+        if getattr(self, "neg_num", 0) > 0:  # clip4cir/models.py:140-141
+            loss["bank_loss"] = self.part_infonce_loss(query_feats, self.target_bank, target_indexs)
+        else:
+            loss["bank_loss"] = self.infonce_loss(query_feats, self.target_bank, target_indexs, tau=self.tau)
+
+    def part_infonce_loss(self, query_feats, target_feats_all, target_indexs):
+        return part_infonce_loss(query_feats, target_feats_all, target_indexs, self.neg_num, self.tau)
 
 
 def forward_stage2_loss(fusion_feats: torch.Tensor, target_feats: Union[DeviceBank, torch.Tensor],

@@ -155,6 +155,16 @@ int spn_bank_ce_step(const void* q_src, int src_dtype, const void* bank_bf16, co
                       as_stream(stream));
 }
 
+int spn_part_ce(const void* q_src, int src_dtype, const void* bank_bf16, const int64_t* candidates, float inv_tau, int B,
+                int K1, int D, int64_t N, float* loss_per_query, float* loss_mean, float* dq, float* dlogit_dot,
+                void* stream) {
+  SPN_REQUIRE(q_src && bank_bf16 && candidates && loss_mean, SPN_ERR_BAD_ARG, "spn_part_ce: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return part_ce(q_src, src_dtype, bank_bf16, reinterpret_cast<const long long*>(candidates), inv_tau, B, K1, D, N,
+                 loss_per_query, loss_mean, dq, dlogit_dot, as_stream(stream));
+}
+
 int spn_sim_topk(const float* q, const float* gallery, int Q, int G, int D, int T, int K, const int32_t* exclude,
                  int32_t col_base, float* out_val, int32_t* out_idx, void* ws, size_t ws_bytes, void* stream) {
   SPN_REQUIRE(q && gallery && out_val && out_idx, SPN_ERR_BAD_ARG, "spn_sim_topk: NULL pointer");

@@ -94,6 +94,10 @@ int merge_stats(const float* pm, const float* pl, const float* pst, const float*
 int bank_ce_loss(const float* m, const float* l, const float* st, const float* ss, int B, long long N_total,
                  float eps, float* lse, float* loss_q, float* loss_mean, cudaStream_t stream);
 
+// sampled-negatives loss (part_ce.cu)
+int part_ce(const void* q_src, int dtype, const void* bank, const long long* cand, float inv_tau, int B, int K1, int D,
+            long long N, float* loss_q, float* loss_mean, float* dq, float* dlogit_dot, cudaStream_t stream);
+
 int debug_read_timeline(unsigned long long* host_out, int n);
 
 // bring-up GEMM (umma_selftest.cu)

@@ -402,6 +402,57 @@ def bank_ce_step(query_features: torch.Tensor, bank: DeviceBank, labels: Optiona
     return loss, dq
 
 
+class _PartCE(torch.autograd.Function):
+    """mean_b CE(inv_tau * <q_b, bank[cand[b]]>, label 0): forward already holds the gradient for an upstream 1."""
+
+    @staticmethod
+    def forward(ctx, q, tau_t, bank: DeviceBank, cand, inv_tau: float):
+        B, D = q.shape
+        dev = q.device
+        qc = q.detach()
+        if qc.dtype not in _TORCH2SPN:
+            qc = qc.float()
+        qc = qc.contiguous()
+        tau_grad = tau_t is not None and tau_t.requires_grad
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        dq = torch.empty((B, D), dtype=torch.float32, device=dev)
+        ddot = torch.empty(B, dtype=torch.float32, device=dev) if tau_grad else None
+        with torch.cuda.device(dev):
+            call("spn_part_ce", _ptr(qc), _TORCH2SPN[qc.dtype], _ptr(bank.data), _ptr(cand), inv_tau, B, cand.shape[1], D,
+                 bank.data.shape[0], None, _ptr(loss), _ptr(dq), _ptr(ddot), _stream(dev))
+        ctx.inv_tau, ctx.B, ctx.q_dtype, ctx.tau_grad = inv_tau, B, q.dtype, tau_grad
+        ctx.save_for_backward(dq, ddot)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        dq_unit, ddot = ctx.saved_tensors
+        g32 = g.detach().to(torch.float32)
+        dtau = (-(ctx.inv_tau / ctx.B)) * ddot.sum() * g32 if ctx.tau_grad else None
+        return (dq_unit * g32).to(ctx.q_dtype), dtau, None, None, None
+
+
+def part_infonce(query_features: torch.Tensor, bank: Union[DeviceBank, torch.Tensor], candidates: torch.Tensor,
+                 tau=0.01) -> torch.Tensor:
+    """Sampled-negatives loss: ``candidates`` int64 ``[B, 1 + k]`` bank rows per query, column 0 the positive
+    (/root/reference/clip4cir/models.py:115-128 with the ids of ``get_neg_id`` :109-113).  Differentiable w.r.t. the
+    queries and ``tau`` (if a tensor requiring grad)."""
+    _require_cuda(query_features, "query_features")
+    if not isinstance(bank, DeviceBank):
+        bank = DeviceBank.from_tensor(bank, query_features.device)
+    if bank.T != 1 or bank.row_base != 0:
+        raise SpnError("part_infonce", -7, "needs an un-sharded single-token bank")
+    if query_features.dim() != 2 or query_features.shape[1] != bank.D:
+        raise SpnError("part_infonce", -1, f"query_features must be [B, {bank.D}], got {tuple(query_features.shape)}")
+    cand = candidates.to(device=query_features.device, dtype=torch.int64).contiguous()
+    if cand.dim() != 2 or cand.shape[0] != query_features.shape[0]:
+        raise SpnError("part_infonce", -1, f"candidates must be [B, 1 + k], got {tuple(cand.shape)}")
+    tau_t, tau_v = _split_tau(tau)
+    if not (tau_v > 0.0 and math.isfinite(tau_v)):
+        raise SpnError("part_infonce", -7, f"tau must be positive and finite, got {tau_v}")
+    return _PartCE.apply(query_features, tau_t, bank, cand, 1.0 / tau_v)
+
+
 def bank_ce_stats(query_features: torch.Tensor, bank: DeviceBank, labels: torch.Tensor, tau: float,
                   want_ssum: bool = False) -> torch.Tensor:
     """Forward statistics only: [4, B] = (m, l, s_t, s_sum) in natural-log units (no autograd)."""

@@ -353,3 +353,46 @@ def test_step_primitive_equals_autograd(B, N, D, tau):
     o_loss, o_dq, _ = obank.infonce_loss_and_grads(q, bank, labels, tau, grad_out=3.0)
     assert abs(loss.item() - o_loss.item()) <= 1e-2 * max(abs(o_loss.item()), 1e-3)
     assert rel_l2(dq.cpu(), o_dq) < 1e-2
+
+
+@pytest.mark.parametrize("name", ["part_small", "part_640"])
+def test_part_infonce_against_reference_fixture(golden, name):
+    """Sampled-negatives loss through spn_part_ce: the compat call seeded like the reference run draws the
+    same negatives (clip4cir/models.py:109-113) and reproduces its loss / gradient within the bf16 tolerance."""
+    import random
+    g = golden(name)
+    q, bank, labels = synth.make_bank_case(int(g["B"]), int(g["N"]), int(g["D"]), 1, str(g["mode"]), int(g["seed"]))
+    qd = q.to(DEV).requires_grad_(True)
+    random.seed(int(g["seed"]))
+    loss = spn.compat.part_infonce_loss(qd, spn.DeviceBank.from_tensor(bank, DEV), labels, int(g["k"]), float(g["tau"]))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-2 * max(abs(float(g["loss"])), 1e-3), (loss.item(), float(g["loss"]))
+    assert rel_l2(qd.grad.cpu(), torch.from_numpy(g["dq"])) < 1e-2
+    # kernel arithmetic against the closed form on bf16-rounded operands and the fixture's candidate ids
+    cand = torch.from_numpy(g["cand"])
+    t = torch.tensor(float(g["tau"]), device=DEV, requires_grad=True)
+    q2 = q.to(DEV).requires_grad_(True)
+    l2 = spn.part_infonce(q2, spn.DeviceBank.from_tensor(bank, DEV), cand, t)
+    (2.0 * l2).backward()
+    r_loss, r_dq, r_dtau = obank.part_loss_and_grads(bf16_round(q), bf16_round(bank), cand, float(g["tau"]), grad_out=2.0)
+    assert abs(l2.item() - r_loss.item()) <= 1e-5 * max(abs(r_loss.item()), 1.0)
+    assert rel_l2(q2.grad.cpu().double(), r_dq) < 1e-5
+    assert abs(t.grad.item() - r_dtau.item()) <= 1e-4 * max(abs(r_dtau.item()), 1e-2)
+
+
+def test_part_infonce_edge_cases():
+    """k = 0 (only the positive: loss 0, zero gradient), out-of-range ids masked, fp16 queries, a long candidate list."""
+    q, bank, labels = synth.make_bank_case(5, 4000, 128, 1, "U", 3)
+    db = spn.DeviceBank.from_tensor(bank, DEV)
+    qd = q.to(DEV).requires_grad_(True)
+    loss = spn.part_infonce(qd, db, labels.view(-1, 1), 0.05)
+    loss.backward()
+    assert abs(loss.item()) < 1e-6 and float(qd.grad.abs().max()) < 1e-6
+    g = torch.Generator().manual_seed(0)
+    cand = torch.cat([labels.view(-1, 1), torch.randint(0, 4000, (5, 3000), generator=g)], dim=1)
+    cand_masked = torch.cat([cand, torch.full((5, 2), -1), torch.full((5, 1), 4000)], dim=1)
+    a = spn.part_infonce(q.to(DEV, torch.float16), db, cand, 0.05)
+    b = spn.part_infonce(q.to(DEV, torch.float16), db, cand_masked, 0.05)
+    assert abs(a.item() - b.item()) < 1e-6
+    r_loss, _, _ = obank.part_loss_and_grads(bf16_round(q.half().float()), bf16_round(bank), cand, 0.05)
+    assert abs(a.item() - r_loss.item()) <= 1e-4 * max(1.0, abs(r_loss.item()))

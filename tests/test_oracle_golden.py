@@ -139,3 +139,18 @@ def test_blip2_inference_similarity_shape():
     assert sim.shape == (5, 20)
     ref = torch.einsum("bd,gtd->bgt", q, gallery).amax(-1)
     np.testing.assert_allclose(sim.numpy(), ref.numpy(), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["part_small", "part_640"])
+def test_part_infonce_oracle_draws_the_reference_negatives(golden, name):
+    """oracle.part_infonce_loss (restating clip4cir/models.py:109-128) against the executed reference: same python RNG
+    stream -> same negatives -> same loss; the closed form on those ids gives the same gradient."""
+    import random
+    g = golden(name)
+    q, bank, labels = synth.make_bank_case(int(g["B"]), int(g["N"]), int(g["D"]), 1, str(g["mode"]), int(g["seed"]))
+    random.seed(int(g["seed"]))
+    loss, cand = obank.part_infonce_loss(q, bank, labels, int(g["k"]), float(g["tau"]))
+    assert np.array_equal(cand.numpy(), g["cand"])
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * max(abs(float(g["loss"])), 1e-3)
+    _, dq, _ = obank.part_loss_and_grads(q, bank, cand, float(g["tau"]), dtype=torch.float32)
+    assert np.allclose(dq.numpy(), g["dq"], rtol=1e-4, atol=1e-7)
