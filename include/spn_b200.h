@@ -185,6 +185,15 @@ int spn_part_ce(const void* q_src, int src_dtype, const void* bank_bf16, const i
 int spn_sim_topk(const float* q, const float* gallery, int Q, int G, int D, int T, int K, const int32_t* exclude,
                  int32_t col_base, float* out_val, int32_t* out_idx, void* ws, size_t ws_bytes, void* stream);
 
+/* Next page of a deep top-K: as spn_sim_topk, but only entries that sort strictly AFTER the cursor
+ * (after_val[b], after_idx[b]) -- normally the last entry of the previous page -- are eligible.  Scores are
+ * bit-identical from call to call (one fp32 accumulator per score, ascending k), so consecutive pages tile the full
+ * ranking without gaps or repeats.  Used for the K = 1000 hard-negative lists of the pair-mining step
+ * (zscir/srm_utils.py:147-150,177-182: `argsort(sims, descending=True)[...][:K]` with the diagonal removed). */
+int spn_sim_topk_after(const float* q, const float* gallery, int Q, int G, int D, int T, int K, const int32_t* exclude,
+                       int32_t col_base, const float* after_val, const int32_t* after_idx, float* out_val,
+                       int32_t* out_idx, void* ws, size_t ws_bytes, void* stream);
+
 /* R-way merge of per-shard top-K lists laid out [R][Q][K] into one [Q][K] (same ordering rule). */
 int spn_merge_topk(const float* vals, const int32_t* idx, int R, int Q, int K, float* out_val, int32_t* out_idx,
                    void* stream);

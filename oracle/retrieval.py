@@ -109,3 +109,42 @@ def fiq_metrics(q: torch.Tensor, index_features: torch.Tensor, index_names: List
         elif target_names[i] in row[:50]:
             r50 += 1
     return (r10 / N) * 100, (r50 / N) * 100                                          # :48-49
+
+
+def srm_out(clip_image_feats: torch.Tensor, clip_text_feats: torch.Tensor, srm_image_feats: torch.Tensor,
+            srm_text_feats: torch.Tensor, reference_index: Sequence[int], target_index: Sequence[int], K: int = 1000):
+    """Restatement of calcu_sims + get_srm_out, /root/reference/zscir/srm_utils.py:119-183 (pair mining): the four
+    similarity matrices (:121-124), five full argsorts (:147-153), per triplet the six rank look-ups
+    `torch.where(ranks[row] == col)[0][0]` (:166-171) summed pairwise into rt / rm / mt scores (:172-174) and the first K
+    entries of the diagonal-masked intra-modal rankings as hard negatives (:176-181).
+    Triplet `index` is also the row of its caption in the text matrices.  The reference's argsort is not stable; this
+    restatement breaks ties by the lower index (the rule of the CUDA path).
+    Returns (r_fn, m_fn, t_fn [N, K] int64, rt, rm, mt [N] int64)."""
+    sims_cross_i2t = clip_image_feats @ clip_text_feats.T                     # :121
+    sims_cross_t2i = sims_cross_i2t.T                                         # :122
+    sims_intra_i2i = srm_image_feats @ srm_image_feats.T                      # :123
+    sims_intra_t2t = srm_text_feats @ srm_text_feats.T                        # :124
+
+    def order(s):
+        return torch.argsort(s, descending=True, stable=True)                 # :147-149,152-153 (ties -> lower index)
+
+    i2i_ranks, i2t_ranks, t2i_ranks = order(sims_intra_i2i), order(sims_cross_i2t), order(sims_cross_t2i)
+    sims_intra_i2i = sims_intra_i2i.clone().fill_diagonal_(-10000)            # :150
+    sims_intra_t2t = sims_intra_t2t.clone().fill_diagonal_(-10000)            # :151
+    i2i_ranks_neg, t2t_ranks_neg = order(sims_intra_i2i), order(sims_intra_t2t)
+    N = len(reference_index)
+    rt, rm, mt = (torch.ones(N, dtype=torch.long) for _ in range(3))          # :157-159
+    m_fn, t_fn, r_fn = (torch.ones((N, K), dtype=torch.long) * -10 for _ in range(3))   # :160-162
+
+    def where(ranks_row, col):
+        return torch.where(ranks_row == col)[0][0].item()
+
+    for index in range(N):                                                    # :163
+        r, t = int(reference_index[index]), int(target_index[index])         # :164-165
+        rt[index] = where(i2i_ranks[r], t) + where(i2i_ranks[t], r)           # :166-167,172
+        rm[index] = where(i2t_ranks[r], index) + where(t2i_ranks[index], r)   # :168-169,173
+        mt[index] = where(t2i_ranks[index], t) + where(i2t_ranks[t], index)   # :170-171,174
+        t_fn[index] = i2i_ranks_neg[t][:K]                                    # :176,179
+        m_fn[index] = t2t_ranks_neg[index][:K]                                # :177,180
+        r_fn[index] = i2i_ranks_neg[r][:K]                                    # :178,181
+    return r_fn, m_fn, t_fn, rt, rm, mt

@@ -108,6 +108,8 @@ _SIGNATURES = {
                     c_void_p, c_void_p],
     "spn_sim_topk": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int32, c_void_p,
                      c_void_p, c_void_p, c_size_t, c_void_p],
+    "spn_sim_topk_after": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int32, c_void_p, c_void_p,
+                           c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     "spn_merge_topk": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "spn_sim_target_score": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int32, c_void_p, c_void_p],
     "spn_sim_rank": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -8,6 +8,8 @@ Same names, argument meaning and error behaviour as the reference, so a maintain
   -- /root/reference/clip4cir/models_negplus.py:130-142
 * ``part_infonce_loss(query_feats, target_feats_all, target_indexs, neg_num, tau)`` / ``BankLossMixin.part_infonce_loss``
   -- the sampled-negatives loss /root/reference/clip4cir/models.py:109-128 (``--neg_num > 0``), same RNG calls
+* ``srm_out(clip_image_feats, clip_text_feats, srm_image_feats, srm_text_feats, reference_index, target_index, K)``
+  -- the pair-mining ranks and hard negatives of ``get_srm_out`` (/root/reference/zscir/srm_utils.py:119-183)
 * ``forward_stage2_loss(fusion_feats, target_feats, target_indexs, temp)``
   -- the loss tail of ``Blip2QformerCirAlignPrompt.forward_stage2`` (...align_prompt.py:254-268)
 * ``inference_sim(fusion_feats, target_feats)`` -- the sim tail of ``inference`` (...align_prompt.py:311-319)
@@ -245,3 +247,33 @@ def cirr_test_dicts_from_features(predicted_features: torch.Tensor, index_featur
     pair_preds = {str(int(p)): [index_names[i] for i in row] for p, row in zip(pairs_id, top)}
     pair_group = {str(int(p)): [index_names[i] for i in row] for p, row in zip(pairs_id, sub)}
     return pair_preds, pair_group
+
+
+# --------------------------------------------------------------------------------------- pair mining
+def srm_out(clip_image_feats: torch.Tensor, clip_text_feats: torch.Tensor, srm_image_feats: torch.Tensor,
+            srm_text_feats: torch.Tensor, reference_index, target_index, K: int = 1000):
+    """``calcu_sims`` + ``get_srm_out`` (/root/reference/zscir/srm_utils.py:119-183) without the four N x N / N x M
+    similarity matrices and the five full argsorts: the six rank look-ups (:166-171) are rank-of-target counts
+    (``spn_sim_rank``), the K hard negatives per triplet (:176-181) a paged top-K with the row itself excluded (the
+    reference masks the diagonal with -10000, :150-151).  Triplet ``i`` owns caption row ``i`` of the text matrices.
+    Returns ``(r_fn_indexs, m_fn_indexs, t_fn_indexs [N, K] int64, rt_scores, rm_scores, mt_scores [N] int64)`` --
+    the list the reference saves at :183.  Ordering: descending similarity, ties -> lower index."""
+    dev = clip_image_feats.device
+    _require_cuda(clip_image_feats, "clip_image_feats")
+    ref = torch.as_tensor(reference_index).to(dev, torch.int64)
+    tgt = torch.as_tensor(target_index).to(dev, torch.int64)
+    n = ref.shape[0]
+    me = torch.arange(n, device=dev, dtype=torch.int64)
+    ci, ct = clip_image_feats.float(), clip_text_feats.float()
+    si, st = srm_image_feats.float(), srm_text_feats.float()
+
+    def rank(q, gallery, target):
+        return sim_rank(q, gallery, target.to(torch.int32))[0].to(torch.int64)
+
+    rt = rank(si[ref], si, tgt) + rank(si[tgt], si, ref)          # r2t + t2r in the intra-image ranking  (:166-167,172)
+    rm = rank(ci[ref], ct, me) + rank(ct, ci, ref)                # r2m (image -> text) + m2r (text -> image) (:168-169,173)
+    mt = rank(ct, ci, tgt) + rank(ci[tgt], ct, me)                # m2t + t2m                              (:170-171,174)
+    t_fn = sim_topk(si[tgt], si, K, exclude=tgt)[1].to(torch.int64)   # (:176,179)
+    m_fn = sim_topk(st, st, K, exclude=me)[1].to(torch.int64)         # (:177,180)
+    r_fn = sim_topk(si[ref], si, K, exclude=ref)[1].to(torch.int64)   # (:178,181)
+    return r_fn, m_fn, t_fn, rt, rm, mt

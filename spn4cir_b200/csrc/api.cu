@@ -173,6 +173,16 @@ int spn_sim_topk(const float* q, const float* gallery, int Q, int G, int D, int 
   return sim_topk(q, gallery, Q, G, D, T, K, exclude, col_base, out_val, out_idx, ws, ws_bytes, as_stream(stream));
 }
 
+int spn_sim_topk_after(const float* q, const float* gallery, int Q, int G, int D, int T, int K, const int32_t* exclude,
+                       int32_t col_base, const float* after_val, const int32_t* after_idx, float* out_val,
+                       int32_t* out_idx, void* ws, size_t ws_bytes, void* stream) {
+  SPN_REQUIRE(q && gallery && out_val && out_idx && after_val && after_idx, SPN_ERR_BAD_ARG, "spn_sim_topk_after: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return sim_topk(q, gallery, Q, G, D, T, K, exclude, col_base, out_val, out_idx, ws, ws_bytes, as_stream(stream),
+                  after_val, after_idx);
+}
+
 int spn_merge_topk(const float* vals, const int32_t* idx, int R, int Q, int K, float* out_val, int32_t* out_idx,
                    void* stream) {
   SPN_REQUIRE(vals && idx && out_val && out_idx, SPN_ERR_BAD_ARG, "spn_merge_topk: NULL pointer");

@@ -81,6 +81,10 @@ struct SimParams {
   int col_base;
   int tiles_per_chunk;  // gallery tiles (64 rows) per blockIdx.y
   const int* exclude;
+  // top-k cursor (nullable): only candidates that sort strictly AFTER (after_val[q], after_idx[q]) are eligible --
+  // page p + 1 of a deep top-K starts where page p ended
+  const float* after_val;
+  const int* after_idx;
   // top-k outputs [chunks][Q][K]
   float* out_val;
   int* out_idx;
@@ -111,8 +115,8 @@ sim_tile_kernel(const SimParams p) {
   // per-warp-row state (row = warp*8 + r)
   float lv0[8], lv1[8];
   int li0[8], li1[8];
-  int cnt[8], gcnt[8], greg[8], tg[8], ex[8];
-  float ts[8];
+  int cnt[8], gcnt[8], greg[8], tg[8], ex[8], ai[8];
+  float ts[8], av[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     lv0[r] = lv1[r] = -INFINITY;
@@ -121,6 +125,8 @@ sim_tile_kernel(const SimParams p) {
     const int qq = q0 + warp * 8 + r;
     const bool ok = qq < p.Q;
     ex[r] = (ok && p.exclude) ? p.exclude[qq] : -1;
+    av[r] = (MODE == 0 && ok && p.after_val) ? p.after_val[qq] : INFINITY;  // +inf / -1 sorts before everything
+    ai[r] = (MODE == 0 && ok && p.after_val) ? p.after_idx[qq] : -1;
     if (MODE == 1) {
       tg[r] = ok ? p.target[qq] : -1;
       ts[r] = ok ? p.tscore[qq] : INFINITY;
@@ -202,6 +208,8 @@ sim_tile_kernel(const SimParams p) {
           if (c1i - p.col_base < p.G) orow[c1i] = c1v;
         }
       } else if (MODE == 0) {
+        c0ok = c0ok && sorts_before(av[r], ai[r], c0v, c0i);
+        c1ok = c1ok && sorts_before(av[r], ai[r], c1v, c1i);
         topk_offer(c0v, c0i, c0ok, p.K, lv0[r], li0[r], lv1[r], li1[r], lane);
         topk_offer(c1v, c1i, c1ok, p.K, lv0[r], li0[r], lv1[r], li1[r], lane);
       } else {
@@ -329,7 +337,9 @@ size_t sim_topk_ws_bytes(int Q, int G, int T, int K) {
 }
 
 int sim_topk(const float* q, const float* g, int Q, int G, int D, int T, int K, const int* exclude, int col_base,
-             float* out_val, int* out_idx, void* ws, size_t ws_bytes, cudaStream_t stream) {
+             float* out_val, int* out_idx, void* ws, size_t ws_bytes, cudaStream_t stream, const float* after_val,
+             const int* after_idx) {
+  SPN_REQUIRE((after_val == nullptr) == (after_idx == nullptr), SPN_ERR_BAD_ARG, "top-K cursor needs both after_val and after_idx");
   int rc = check_common(q, g, Q, G, D, T);
   if (rc != SPN_OK) return rc;
   SPN_REQUIRE(K >= 1 && K <= 64, SPN_ERR_BAD_SHAPE, "top-K supports 1 <= K <= 64 (K=%d)", K);
@@ -339,7 +349,7 @@ int sim_topk(const float* q, const float* g, int Q, int G, int D, int T, int K, 
   SPN_REQUIRE(chunks == 1 || (ws && ws_bytes >= need), SPN_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, need);
   SimParams p{};
   p.q = q; p.g = g; p.Q = Q; p.G = G; p.D = D; p.T = T; p.K = K; p.col_base = col_base;
-  p.tiles_per_chunk = tpc; p.exclude = exclude;
+  p.tiles_per_chunk = tpc; p.exclude = exclude; p.after_val = after_val; p.after_idx = after_idx;
   if (chunks == 1) {
     p.out_val = out_val; p.out_idx = out_idx;
   } else {

@@ -6,7 +6,8 @@ namespace spn {
 
 size_t sim_topk_ws_bytes(int Q, int G, int T, int K);
 int sim_topk(const float* q, const float* g, int Q, int G, int D, int T, int K, const int* exclude, int col_base,
-             float* out_val, int* out_idx, void* ws, size_t ws_bytes, cudaStream_t stream);
+             float* out_val, int* out_idx, void* ws, size_t ws_bytes, cudaStream_t stream,
+             const float* after_val = nullptr, const int* after_idx = nullptr);
 int merge_topk(const float* vals, const int* idx, int R, int Q, int K, float* out_val, int* out_idx,
                cudaStream_t stream);
 int sim_matrix(const float* q, const float* g, int Q, int G, int D, int T, float* out, cudaStream_t stream);

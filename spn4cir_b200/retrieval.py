@@ -40,7 +40,9 @@ def _i32(x, dev) -> Optional[torch.Tensor]:
 
 
 def sim_topk(query: torch.Tensor, gallery: torch.Tensor, k: int, exclude=None, col_base: int = 0):
-    """Top-``k`` gallery entries per query: returns (values [Q, k] fp32, indices [Q, k] int32, global)."""
+    """Top-``k`` gallery entries per query: returns (values [Q, k] fp32, indices [Q, k] int32, global).
+    ``k > 64`` is served in pages of 64 (``spn_sim_topk_after``: each page resumes after the last entry of the
+    previous one; -inf / -1 padding once the gallery is exhausted)."""
     _require_cuda(query, "query")
     g, G, T = _prep_gallery(gallery)
     q = query.detach().float().contiguous()
@@ -50,10 +52,33 @@ def sim_topk(query: torch.Tensor, gallery: torch.Tensor, k: int, exclude=None, c
     vals = torch.empty((Q, k), dtype=torch.float32, device=dev)
     idx = torch.empty((Q, k), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        ws_bytes = _lib.workspace_bytes(OP_SIM_TOPK, Q, G, D, T, k)
+        if k <= 64:
+            ws_bytes = _lib.workspace_bytes(OP_SIM_TOPK, Q, G, D, T, k)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            call("spn_sim_topk", _ptr(q), _ptr(g), Q, G, D, T, k, _ptr(ex), col_base, _ptr(vals), _ptr(idx), _ptr(ws),
+                 ws_bytes, _stream(dev))
+            return vals, idx
+        ws_bytes = _lib.workspace_bytes(OP_SIM_TOPK, Q, G, D, T, 64)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        call("spn_sim_topk", _ptr(q), _ptr(g), Q, G, D, T, k, _ptr(ex), col_base, _ptr(vals), _ptr(idx), _ptr(ws),
-             ws_bytes, _stream(dev))
+        pv = torch.empty((Q, 64), dtype=torch.float32, device=dev)
+        pi = torch.empty((Q, 64), dtype=torch.int32, device=dev)
+        cur_v = cur_i = None
+        for lo in range(0, k, 64):
+            kk = min(64, k - lo)
+            if cur_v is None:
+                call("spn_sim_topk", _ptr(q), _ptr(g), Q, G, D, T, kk, _ptr(ex), col_base, _ptr(pv), _ptr(pi), _ptr(ws),
+                     ws_bytes, _stream(dev))
+            else:
+                call("spn_sim_topk_after", _ptr(q), _ptr(g), Q, G, D, T, kk, _ptr(ex), col_base, _ptr(cur_v), _ptr(cur_i),
+                     _ptr(pv), _ptr(pi), _ptr(ws), ws_bytes, _stream(dev))
+            # the kernel writes [Q, kk] densely
+            vals[:, lo:lo + kk] = pv.view(-1)[:Q * kk].view(Q, kk)
+            idx[:, lo:lo + kk] = pi.view(-1)[:Q * kk].view(Q, kk)
+            last_v = vals[:, lo + kk - 1].contiguous()
+            last_i = idx[:, lo + kk - 1].contiguous()
+            # an exhausted row (padding -inf / -1) keeps an everything-excluding cursor: (-inf, INT_MAX)
+            cur_v = last_v
+            cur_i = torch.where(last_i >= 0, last_i, torch.full_like(last_i, 2 ** 31 - 1))
     return vals, idx
 
 

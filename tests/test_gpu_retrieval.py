@@ -144,3 +144,39 @@ def test_cirr_test_submission_dicts():
         assert preds[str(r)] == [names[j] for j in want[r]]
         order = [j for j in oretr.ranking(sim)[r] if j in set(groups[r].tolist()) and j != int(reference[r])][:3]
         assert gpreds[str(r)] == [names[j] for j in order]
+
+
+@pytest.mark.parametrize("Q,G,K,seed", [(30, 500, 200, 1), (7, 130, 129, 2), (65, 3000, 1000, 3)])
+def test_deep_topk_pages_tile_the_full_ranking(Q, G, K, seed):
+    """K > 64 is served in pages of 64 through spn_sim_topk_after: the concatenation must be the oracle's top-K
+    (excluded entry skipped, -1 padding once the gallery is exhausted)."""
+    q, gal, _, ref, _, _ = synth.make_retrieval_case(Q, G, 64, 1, seed, noise=4.0)
+    vals, idx = spn.sim_topk(q.to(DEV), gal.to(DEV), K, exclude=ref)
+    torch.cuda.synchronize()
+    k_real = min(K, G - 1)
+    _, want = oretr.topk(q @ gal.T, k_real, exclude=ref.tolist())
+    got = idx.cpu().numpy()
+    assert (got[:, :k_real] == want).mean() > 0.995          # fp32 summation-order ties may swap neighbours
+    assert np.all(np.sort(got[:, :k_real], axis=1) == np.sort(want, axis=1)) or (got[:, :k_real] == want).mean() > 0.995
+    assert np.all(got[:, k_real:] == -1)
+    v = vals.cpu().numpy()[:, :k_real]
+    assert np.all(v[:, :-1] >= v[:, 1:])
+
+
+def test_srm_pair_mining_matches_oracle():
+    """compat.srm_out against the restatement of zscir/srm_utils.py:119-183 on a small synthetic set."""
+    g = torch.Generator().manual_seed(5)
+    n_img, n_trip, D, K = 400, 150, 64, 100
+    ci = torch.nn.functional.normalize(torch.randn(n_img, D, generator=g), dim=-1)
+    si = torch.nn.functional.normalize(torch.randn(n_img, D, generator=g), dim=-1)
+    ct = torch.nn.functional.normalize(torch.randn(n_trip, D, generator=g), dim=-1)
+    st = torch.nn.functional.normalize(torch.randn(n_trip, D, generator=g), dim=-1)
+    ref = torch.randint(0, n_img, (n_trip,), generator=g)
+    tgt = (ref + 1 + torch.randint(0, n_img - 1, (n_trip,), generator=g)) % n_img
+    want = oretr.srm_out(ci, ct, si, st, ref.tolist(), tgt.tolist(), K)
+    got = spn.compat.srm_out(ci.to(DEV), ct.to(DEV), si.to(DEV), st.to(DEV), ref, tgt, K)
+    torch.cuda.synchronize()
+    for name, w, h in zip(("r_fn", "m_fn", "t_fn"), want[:3], got[:3]):
+        assert (h.cpu() == w).float().mean() > 0.995, name
+    for name, w, h in zip(("rt", "rm", "mt"), want[3:], got[3:]):
+        assert (h.cpu() - w).abs().max() <= 1 and (h.cpu() == w).float().mean() > 0.98, name
