@@ -1032,12 +1032,19 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       // TMA-reduce epilogue (two-pass mode): each warp stages its [32 rows x 32 columns] fp32 piece in a 4 KiB slot
       // (128-byte swizzle: conflict-free 16-byte stores) and one lane issues cp.reduce.async.bulk.tensor (.add): whole
       // 128-byte lines are reduced in L2 instead of 32 scattered 16-byte reds per instruction; rows >= B are clipped.
-      auto tma_epilogue = [&](uint32_t tmem_col0, int nchunks, int d_col0, uint8_t* slots, int nslots) {
+      auto tma_epilogue = [&](uint32_t tmem_col0, int nchunks, int d_col0, uint8_t* slots, int nslots, bool release_tmem,
+                              bool final_wait) {
         const bool rows_ok = q0 + int(quarter) * 32 < p.B;
         int k = 0;
         for (int c = int(half); c < nchunks; c += 2, ++k) {
           tmem_ld_32x32b_x32(t_row + tmem_col0 + uint32_t(c) * 32u, x0);
           tmem_ld_wait();
+          if (release_tmem && c + 2 >= nchunks) {  // last TMEM read of this warp: pass 2 may overwrite the accumulator
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(sm.tmem_free), 0));
+            release_tmem = false;
+          }
           uint8_t* slot = slots + size_t(k % nslots) * 4096;
           if (k >= nslots) {  // the slot's previous reduce must have read shared memory
             if (lane == 0) {
@@ -1057,13 +1064,22 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             bulk_commit_group();
           }
         }
-        if (lane == 0) bulk_wait_group<0>();
-        __syncwarp();
+        if (release_tmem) {  // this warp had no chunk to read
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(sm.tmem_free), 0));
+        }
+        if (final_wait) {
+          if (lane == 0) bulk_wait_group<0>();
+          __syncwarp();
+        }
       };
       const int region_blocks = p.kblocks - p.qt_blocks + p.stages;  // [Q tile (smem part) | ring] in 16 KiB blocks
       if (ntl > 0 && tma_epi) {
         // pass-1 accumulator: the last 32 KiB of the region (outside the second-pass ring), one slot per warp
-        tma_epilogue(0u, my_blocks * 2, 0, sm.q + size_t(region_blocks - 2) * kBlockBytes + (warp - 2u) * 4096u, 1);
+        // (the reductions themselves drain while pass 2 runs; TMEM is released after the last read)
+        tma_epilogue(0u, my_blocks * 2, 0, sm.q + size_t(region_blocks - 2) * kBlockBytes + (warp - 2u) * 4096u, 1, do_pass2,
+                     !do_pass2);
       } else if (ntl > 0) {
         for (int c = int(half); c < my_blocks * 2; c += 2) {
           tmem_ld_32x32b_x32(t_row + uint32_t(c) * 32u, x0);
@@ -1085,16 +1101,18 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
       if (ntl > 0) {
         if (do_pass2) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(sm.tmem_free), 0));
+          if (!tma_epi) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(sm.tmem_free), 0));
+          }
           if (warp == 2) { EV(9) }  // pass-1 epilogue done
           mbar_wait(sm.o2_full, 0);
           tc_fence_after();
           if (warp == 2) { EV(10) }  // pass-2 MMAs retired
           const int cols2 = (p.kblocks - my_blocks) * 2;  // 32-column chunks of the second accumulator
           if (tma_epi) {  // everything in shared memory is dead now: four slots per warp from the base of the region
-            tma_epilogue(0u, cols2, my_blocks * 64, sm.q + (warp - 2u) * 16384u, 4);
+            tma_epilogue(0u, cols2, my_blocks * 64, sm.q + (warp - 2u) * 16384u, 4, false, true);
           } else
           for (int c = int(half); c < cols2; c += 2) {
             tmem_ld_32x32b_x32(t_row + uint32_t(c) * 32u, x0);
