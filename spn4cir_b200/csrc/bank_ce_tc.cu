@@ -349,7 +349,7 @@ template <int MODE, int T, bool EXTRA, int CG>
 __global__ void __launch_bounds__(kBankCEThreads, 1)
 bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_bank,
                const __grid_constant__ CUtensorMap tmap_bank_half, const __grid_constant__ CUtensorMap tmap_p,
-               const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tmap_pf,
+               const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tmap_bank3,
                const BankCEParams p) {
   constexpr bool kTP = (MODE == 2 && CG == 2);  // the only variant that carries the second pass
   const bool do_pass2 = kTP && p.two_pass && !(p.hg & 2);   // bring-up knobs (SPN_DEBUG_HG): 2 = no second pass,
@@ -409,6 +409,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     if (kTP && p.two_pass) {
       tma_prefetch_desc(&tmap_p);
       tma_prefetch_desc(&tmap_dq);
+      tma_prefetch_desc(&tmap_bank3);
     }
   }
   if (warp == 1) {
@@ -499,10 +500,10 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       TL_BEGIN
       const uint32_t fbar = mapa_shared(smem_u32(&sm.full[r.stage]), 0);
       if (elect_one()) {
-        if (crank == 0) mbar_arrive_expect_tx(&sm.full[r.stage], 2u * uint32_t(nb) * (kBlockBytes / 2));
-        for (int b = 0; b < nb; ++b)
-          tma_load_2d_cg2(sm.ring + size_t(r.stage) * kBlockBytes + size_t(b) * (kBlockBytes / 2), &tmap_bank_half, fbar,
-                          (kb0 + b) * kBK, row + int(crank) * (kBN / 2));
+        // one 3-D box = this CTA's 64 rows of k-blocks kb0, kb0 + 1 (a k-block past D is zero-filled, bytes still count)
+        (void)nb;
+        if (crank == 0) mbar_arrive_expect_tx(&sm.full[r.stage], 2u * kBlockBytes);
+        tma_load_3d_cg2(sm.ring + size_t(r.stage) * kBlockBytes, &tmap_bank_half, fbar, 0, row + int(crank) * (kBN / 2), kb0);
       }
       __syncwarp();
       TL_END(1)
@@ -550,7 +551,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_wait(sm.p2_go, 0);   // this CTA's soft-max warps have written (and fenced) all of their P~ rows
       Ring r2(p.stages2);
       const int groups2 = (p.kblocks - my_blocks) / 4;  // pair N = 256 per group: 128 columns = 2 blocks per CTA
-      auto load_pair2 = [&](const CUtensorMap* map, int col, int row, bool skip) {
+      auto load_pair2 = [&](const CUtensorMap* map, int kb, int row, bool skip) {
         mbar_wait(&sm.empty2[r2.stage], r2.phase ^ 1u);
         const uint32_t fbar = mapa_shared(smem_u32(&sm.full2[r2.stage]), 0);
         if (elect_one()) {
@@ -558,9 +559,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             if (crank == 0) mbar_arrive(&sm.full2[r2.stage]);
           } else {
             if (crank == 0) mbar_arrive_expect_tx(&sm.full2[r2.stage], 4u * kBlockBytes);  // 2 blocks from each CTA
-            uint8_t* dst = sm.q + size_t(r2.stage) * 2 * kBlockBytes;
-            tma_load_2d_cg2(dst, map, fbar, col, row);
-            tma_load_2d_cg2(dst + kBlockBytes, map, fbar, col + kBK, row);
+            tma_load_3d_cg2(sm.q + size_t(r2.stage) * 2 * kBlockBytes, map, fbar, 0, row, kb);  // two blocks per box
           }
         }
         __syncwarp();
@@ -571,7 +570,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         // A: this CTA's 128 rows of P~(t), K = 128 bank rows = 2 K-major blocks of the tile-major scratch
         load_pair2(&tmap_p, 0, ((q0 / kBM) * p.n_tiles + t) * kBM, (p.hg & 256) != 0);
         for (int g = 0; g < groups2; ++g)
-          load_pair2(&tmap_bank, (my_blocks + 4 * g) * kBK + int(crank) * 2 * kBK, t * kBN, (p.hg & 512) != 0);
+          load_pair2(&tmap_bank3, my_blocks + 4 * g + int(crank) * 2, t * kBN, (p.hg & 512) != 0);
       }
     }
     TL_FLUSH(0)
@@ -724,21 +723,6 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             g_events[blockIdx.x * 16 + 13] = tl_acc[4];  // pass 2: waiting for bank blocks
           }
 #endif
-        }
-      } else if (kTP && p.two_pass && (p.hg & 64)) {
-        // rank 1's MMA warp has nothing to issue: it pulls the pair's bank tiles into L2 kPF tiles ahead of the ring
-        // (paced by the S-tile completions, which are multicast to both CTAs), so that the 64 KiB ring only has to
-        // cover the L2 latency, not the HBM latency of the first touch
-        constexpr int kPF = 3;
-        for (int i = 0; i < ntl; ++i) {
-          if (elect_one()) {
-            const int first = (i == 0) ? 1 : kPF, last = kPF;
-            for (int j = first; j <= last; ++j)
-              if (i + j < ntl)
-                for (int c = 0; c < p.D; c += 256) tma_prefetch_l2_2d(&tmap_pf, c, (t_begin + i + j) * kBN);
-          }
-          __syncwarp();
-          mbar_wait(&sm.s_full[0], uint32_t(i) & 1u);
         }
       }
     } else {
@@ -1625,7 +1609,7 @@ int bank_ce_backward(const void* q, const void* bank, const long long* labels, f
   CUtensorMap tq, tb, tbh;
   if ((rc = make_tmap_bf16_2d(&tq, q, uint64_t(B), uint64_t(D), kBM)) != SPN_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&tb, bank, uint64_t(N) * T, uint64_t(D), kBN)) != SPN_OK) return rc;
-  if ((rc = make_tmap_bf16_2d(&tbh, bank, uint64_t(N) * T, uint64_t(D), kBN / 2)) != SPN_OK) return rc;
+  if ((rc = make_tmap_bf16_3d(&tbh, bank, uint64_t(N) * T, uint64_t(D), kBN / 2)) != SPN_OK) return rc;
   BankCEParams p{};
   p.B = B; p.D = D; p.N = N; p.n_rows = N * T; p.kblocks = plan.kblocks; p.stages = plan.stages; p.bps = plan.bps;
   p.n_tiles = plan.n_tiles; p.q_tiles = plan.q_tiles / plan.cg; p.num_chunks = plan.num_chunks;
@@ -1693,14 +1677,14 @@ int bank_ce_fused(const void* q, const void* bank, const long long* labels, cons
   CUtensorMap tq, tb, tbh, tp, tdq, tpf;
   if ((rc = make_tmap_bf16_2d(&tq, q, uint64_t(B), uint64_t(D), kBM)) != SPN_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&tb, bank, uint64_t(N) * T, uint64_t(D), kBN)) != SPN_OK) return rc;
-  if ((rc = make_tmap_bf16_2d(&tbh, bank, uint64_t(N) * T, uint64_t(D), kBN / 2)) != SPN_OK) return rc;
+  if ((rc = make_tmap_bf16_3d(&tbh, bank, uint64_t(N) * T, uint64_t(D), kBN / 2)) != SPN_OK) return rc;
   tp = tb;
   tdq = tb;
   tpf = tb;
-  if (plan.two_pass && (rc = make_tmap_bf16_2d_prefetch(&tpf, bank, uint64_t(N) * T, uint64_t(D), kBN)) != SPN_OK) return rc;
+  if (plan.two_pass && (rc = make_tmap_bf16_3d(&tpf, bank, uint64_t(N) * T, uint64_t(D), kBN)) != SPN_OK) return rc;
   if (plan.two_pass && (rc = make_tmap_f32_2d(&tdq, o_acc, uint64_t(B), uint64_t(D), 32)) != SPN_OK) return rc;
   if (plan.two_pass &&
-      (rc = make_tmap_bf16_2d(&tp, ws, uint64_t(plan.q_tiles) * plan.n_tiles * kBM, uint64_t(kBN), kBM)) != SPN_OK)
+      (rc = make_tmap_bf16_3d(&tp, ws, uint64_t(plan.q_tiles) * plan.n_tiles * kBM, uint64_t(kBN), kBM)) != SPN_OK)
     return rc;
   if (init) {
     fused_init_kernel<<<148, 256, 0, stream>>>(o_acc, (long long)B * D, l_acc, s_t, lbl_row, es_acc, nullptr, B);

@@ -99,6 +99,26 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
   return SPN_OK;
 }
 
+int make_tmap_bf16_3d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(SPN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (!aligned16(gptr)) return fail(SPN_ERR_BAD_ALIGN, "TMA source pointer %p is not 16-byte aligned", gptr);
+  if (cols % 64 != 0) return fail(SPN_ERR_BAD_SHAPE, "3-D tensor map needs a multiple of 64 columns (got %llu)", (unsigned long long)cols);
+  // [rows, cols] viewed as (64-column block k, row r, column c): one box = two consecutive 64-column blocks of box_rows rows,
+  // landing in shared memory as two back-to-back [box_rows x 64] 128B-swizzled tiles (what two 2-D loads would produce)
+  cuuint64_t dims[3] = {64u, rows, cols / 64};
+  cuuint64_t strides[2] = {cols * 2, 128u};
+  cuuint32_t box[3] = {64u, box_rows, 2u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SPN_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (CUresult %d) rows=%llu cols=%llu box_rows=%u", (int)r,
+                (unsigned long long)rows, (unsigned long long)cols, box_rows);
+  return SPN_OK;
+}
+
 int make_tmap_bf16_2d_prefetch(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(SPN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");

@@ -39,6 +39,9 @@ int require_sm100();
 // 2-D bf16 row-major tensor [rows, cols] -> tensor map with box [box_rows, 64 cols], 128B swizzle.
 // Out-of-bounds rows/cols are zero-filled by the TMA unit.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+// bf16 [rows, cols] as a 3-D map (64-col block, row, column): box = [2 blocks][box_rows][64 cols], 128B swizzle -- one
+// TMA instruction fills two consecutive [box_rows x 64] operand tiles.
+int make_tmap_bf16_3d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 // bf16 [rows, cols] with an un-swizzled box [box_rows, 256 cols]: for cp.async.bulk.prefetch.tensor (L2) only.
 int make_tmap_bf16_2d_prefetch(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 // 2-D fp32 row-major tensor [rows, cols] -> tensor map with box [box_rows, 32 cols], 128B swizzle (TMA reduce-add target).

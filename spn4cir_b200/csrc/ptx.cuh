@@ -346,6 +346,14 @@ __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const void* tmap
 }
 
 // ---------------------------------------------------------------- math / misc
+__device__ __forceinline__ void tma_load_3d_cg2(void* smem_dst, const void* tmap, uint32_t cluster_bar_addr, int32_t c0,
+                                                int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(cluster_bar_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
