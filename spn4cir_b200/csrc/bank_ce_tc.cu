@@ -1494,6 +1494,11 @@ int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan) {
   if (smem_max <= 0) smem_max = 232448;
   plan->kblocks = D / 64;
   plan->q_tiles = (B + kBM - 1) / kBM;
+  // backward / fused: an odd number (>= 3) of query tiles is padded with one empty tile so that the CTA-pair kernels
+  // apply (TMA zero-fills the missing queries, nothing of them is written back): a pair with one idle half still beats
+  // two single-CTA kernels on the shared-memory port
+  if (mode >= 1 && plan->q_tiles >= 3 && plan->q_tiles % 2 == 1 && !(getenv("SPN_DEBUG_CG") && atoi(getenv("SPN_DEBUG_CG")) == 1))
+    plan->q_tiles += 1;
   const long long n_rows = N * T;
   plan->n_tiles = int((n_rows + kBN - 1) / kBN);
   plan->two_pass = 0;

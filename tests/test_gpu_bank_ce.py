@@ -78,6 +78,8 @@ PAIR_CASES = [
     (512, 9000, 448, 1, 0.03, 30),    # two-pass fused: X = 192 (odd block count in pass 1)
     (256, 2000, 576, 1, 0.02, 31),    # two-pass fused: X = 320, one group
     (512, 20000, 704, 1, 0.02, 32),   # two-pass fused: X = 192, two groups, several tiles per CTA
+    (300, 5000, 640, 1, 0.02, 33),    # 3 query tiles: padded to 2 pairs (the 4th tile is empty)
+    (600, 3000, 256, 1, 0.03, 34),    # 5 query tiles -> 3 pairs, single-pass shape
 ]
 
 
