@@ -142,7 +142,7 @@ def run_ours(args, cfg):
     import torch.distributed as dist
 
     import spn4cir_b200 as spn
-    from spn4cir_b200.dist import bank_infonce_sharded, shard_bounds
+    from spn4cir_b200.dist import bank_ce_step_sharded, bank_infonce_sharded, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -185,7 +185,7 @@ def run_ours(args, cfg):
         as long as the GPU step -- and 470 us while the nvidia-smi clock sampler's reader thread is alive, which would make
         the contract's clock-sampled measurement host-bound); the autograd wrapper is timed right after the sampler stops."""
         if sharded:
-            return step_autograd(qin, lab)
+            return bank_ce_step_sharded(qin, bank, lab, tau)
         return spn.bank_ce_step(qin, bank, lab, tau)
 
     dq_pin = torch.empty((B, D), dtype=torch.float32).pin_memory()
@@ -328,7 +328,7 @@ def run_ours(args, cfg):
                            "global_batch": B * world},
                 "clocks": clocks, "roofline": roof,
                 "host_issue_ms_per_step": host_issue_ms,
-                "api": ("spn4cir_b200.dist.bank_infonce_sharded (autograd)" if sharded else
+                "api": ("spn4cir_b200.dist.bank_ce_step_sharded (step primitive over the row-sharded bank, NCCL exchange)" if sharded else
                         "spn4cir_b200.bank_ce_step -> spn_bank_ce_step (C ABI step primitive: loss + dL/dq)"),
                 "autograd_api": {"call": "loss = bank_infonce(q, bank, labels, tau); loss.backward()",
                                  "value": (B * world) * args.steps / t_auto, "unit": "queries/s",

@@ -61,65 +61,70 @@ def global_maxnorm(bank, group=None) -> torch.Tensor:
     return bank._maxnorm_global
 
 
+def _sharded_sweep(q_local, bank, labels_local, inv_tau, eps, tau_grad, group):
+    """The sharded training step without autograd: every rank sweeps its shard for ALL queries of the step, the additive
+    partials travel in two reduce_scatters and one small all_reduce, each rank finalises its own rows.
+    Returns (loss_mean_of_local_queries, dq_unit [B, D] fp32, dlogit_dot | None)."""
+    from ._lib import call
+    from .ops import _TORCH2SPN, _fused_finalize, _ptr, _stream, cast_to_bf16, fused_scratch
+    rank, world = _world(group)
+    B, D = q_local.shape
+    dev = q_local.device
+    q16 = cast_to_bf16(q_local)
+    if world > 1:
+        q_all = torch.empty((world * B, D), dtype=q16.dtype, device=dev)
+        dist.all_gather_into_tensor(q_all, q16, group=group)
+        lab_all = torch.empty(world * B, dtype=labels_local.dtype, device=dev)
+        dist.all_gather_into_tensor(lab_all, labels_local, group=group)
+    else:
+        q_all, lab_all = q16, labels_local
+    Bt = q_all.shape[0]
+    maxnorm = global_maxnorm(bank, group)
+    ref = torch.empty(Bt, dtype=torch.float32, device=dev)
+    q16b = torch.empty_like(q_all)
+    o_acc = torch.empty((Bt, D), dtype=torch.float32, device=dev)
+    bank_t = torch.empty((Bt, D), dtype=torch.float32, device=dev)
+    vec = torch.empty((3, Bt), dtype=torch.float32, device=dev)  # l_acc, s_t, es_acc
+    lbl_row = torch.empty(Bt, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        call("spn_bank_ce_prep", _ptr(q_all), _TORCH2SPN[q_all.dtype], _ptr(bank.data), _ptr(lab_all), inv_tau,
+             _ptr(maxnorm), Bt, bank.N, D, bank.T, bank.row_base, _ptr(q16b), _ptr(ref), st)
+        if world > 1:  # owner's clamped reference wins over the other ranks' Cauchy-Schwarz bound
+            dist.all_reduce(ref, op=dist.ReduceOp.MIN, group=group)
+        ws, ws_bytes = fused_scratch(Bt, bank, dev)
+        call("spn_bank_ce_fused", _ptr(q_all), _ptr(bank.data), _ptr(lab_all), _ptr(ref), inv_tau, Bt, bank.N, D,
+             bank.T, bank.row_base, 1, _ptr(o_acc), _ptr(vec[0]), _ptr(vec[1]), _ptr(lbl_row),
+             _ptr(vec[2]) if tau_grad else None, _ptr(bank_t), _ptr(ws), ws_bytes, st)
+    if world > 1:
+        # additive partials: two reduce_scatters ([Bt, D] each) + one small all_reduce ([3, Bt]); the target
+        # logit is owner-only, so non-owners contribute 0 and the sum is the value
+        vec[1] = torch.where(lbl_row >= 0, vec[1], torch.zeros_like(vec[1]))
+        if not tau_grad:
+            vec[2].zero_()
+        o_mine = torch.empty((B, D), dtype=torch.float32, device=dev)
+        t_mine = torch.empty((B, D), dtype=torch.float32, device=dev)
+        dist.reduce_scatter_tensor(o_mine, o_acc, op=dist.ReduceOp.SUM, group=group)
+        dist.reduce_scatter_tensor(t_mine, bank_t, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+        sl = slice(rank * B, (rank + 1) * B)
+        sw = dict(o_acc=o_mine, bank_t=t_mine, l_acc=vec[0, sl].contiguous(), s_t=vec[1, sl].contiguous(),
+                  es_acc=vec[2, sl].contiguous() if tau_grad else None, ref=ref[sl].contiguous(), q16=q16)
+    else:
+        sw = dict(o_acc=o_acc, bank_t=bank_t, l_acc=vec[0], es_acc=vec[2] if tau_grad else None, s_t=vec[1], ref=ref,
+                  q16=q16)
+    _, _, loss, dq_unit, ddot = _fused_finalize(sw, bank, inv_tau, B, eps, True)
+    return loss, dq_unit, ddot
+
+
 class _ShardedBankCE(torch.autograd.Function):
-    """Single-pass bank-CE over a row-sharded bank.  Every rank sweeps its shard for ALL queries of the step with
-    the fused kernel (static soft-max reference agreed by one MIN all-reduce); the additive partial sums travel in
-    two reduce_scatters (o_acc, bank_t: [B_total, D] fp32) and one small all_reduce (l, s_t, es); each rank
-    finalises its own rows."""
+    """Single-pass bank-CE over a row-sharded bank (autograd wrapper of :func:`_sharded_sweep`)."""
 
     @staticmethod
     def forward(ctx, q_local, tau_t, bank, labels_local, inv_tau, eps, group):
-        from ._lib import call
-        from .ops import _TORCH2SPN, _fused_finalize, _ptr, _stream, cast_to_bf16, fused_scratch
-        rank, world = _world(group)
-        B, D = q_local.shape
-        dev = q_local.device
         tau_grad = tau_t is not None and tau_t.requires_grad
-        q16 = cast_to_bf16(q_local)
-        if world > 1:
-            q_all = torch.empty((world * B, D), dtype=q16.dtype, device=dev)
-            dist.all_gather_into_tensor(q_all, q16, group=group)
-            lab_all = torch.empty(world * B, dtype=labels_local.dtype, device=dev)
-            dist.all_gather_into_tensor(lab_all, labels_local, group=group)
-        else:
-            q_all, lab_all = q16, labels_local
-        Bt = q_all.shape[0]
-        maxnorm = global_maxnorm(bank, group)
-        ref = torch.empty(Bt, dtype=torch.float32, device=dev)
-        q16b = torch.empty_like(q_all)
-        o_acc = torch.empty((Bt, D), dtype=torch.float32, device=dev)
-        bank_t = torch.empty((Bt, D), dtype=torch.float32, device=dev)
-        vec = torch.empty((3, Bt), dtype=torch.float32, device=dev)  # l_acc, s_t, es_acc
-        lbl_row = torch.empty(Bt, dtype=torch.int64, device=dev)
-        with torch.cuda.device(dev):
-            st = _stream(dev)
-            call("spn_bank_ce_prep", _ptr(q_all), _TORCH2SPN[q_all.dtype], _ptr(bank.data), _ptr(lab_all), inv_tau,
-                 _ptr(maxnorm), Bt, bank.N, D, bank.T, bank.row_base, _ptr(q16b), _ptr(ref), st)
-            if world > 1:  # owner's clamped reference wins over the other ranks' Cauchy-Schwarz bound
-                dist.all_reduce(ref, op=dist.ReduceOp.MIN, group=group)
-            ws, ws_bytes = fused_scratch(Bt, bank, dev)
-            call("spn_bank_ce_fused", _ptr(q_all), _ptr(bank.data), _ptr(lab_all), _ptr(ref), inv_tau, Bt, bank.N, D,
-                 bank.T, bank.row_base, 1, _ptr(o_acc), _ptr(vec[0]), _ptr(vec[1]), _ptr(lbl_row),
-                 _ptr(vec[2]) if tau_grad else None, _ptr(bank_t), _ptr(ws), ws_bytes, st)
-        if world > 1:
-            # additive partials: two reduce_scatters ([Bt, D] each) + one small all_reduce ([3, Bt]); the target
-            # logit is owner-only, so non-owners contribute 0 and the sum is the value
-            vec[1] = torch.where(lbl_row >= 0, vec[1], torch.zeros_like(vec[1]))
-            if not tau_grad:
-                vec[2].zero_()
-            o_mine = torch.empty((B, D), dtype=torch.float32, device=dev)
-            t_mine = torch.empty((B, D), dtype=torch.float32, device=dev)
-            dist.reduce_scatter_tensor(o_mine, o_acc, op=dist.ReduceOp.SUM, group=group)
-            dist.reduce_scatter_tensor(t_mine, bank_t, op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
-            sl = slice(rank * B, (rank + 1) * B)
-            sw = dict(o_acc=o_mine, bank_t=t_mine, l_acc=vec[0, sl].contiguous(), s_t=vec[1, sl].contiguous(),
-                      es_acc=vec[2, sl].contiguous() if tau_grad else None, ref=ref[sl].contiguous(), q16=q16)
-        else:
-            sw = dict(o_acc=o_acc, bank_t=bank_t, l_acc=vec[0], es_acc=vec[2] if tau_grad else None, s_t=vec[1], ref=ref,
-                      q16=q16)
-        _, _, loss, dq_unit, ddot = _fused_finalize(sw, bank, inv_tau, B, eps, True)
-        ctx.inv_tau, ctx.B, ctx.q_dtype, ctx.tau_grad = inv_tau, B, q_local.dtype, tau_grad
+        loss, dq_unit, ddot = _sharded_sweep(q_local, bank, labels_local, inv_tau, eps, tau_grad, group)
+        ctx.inv_tau, ctx.B, ctx.q_dtype, ctx.tau_grad = inv_tau, q_local.shape[0], q_local.dtype, tau_grad
         ctx.save_for_backward(dq_unit, ddot if tau_grad else None)
         return loss  # mean over THIS rank's queries (what a DDP replica of the reference would log)
 
@@ -145,6 +150,16 @@ def bank_infonce_sharded(query_features: torch.Tensor, bank, labels: torch.Tenso
     tau_t, tau_v = _split_tau(tau)
     lab = _prep_labels(labels, query_features.shape[0], query_features.device)
     return _ShardedBankCE.apply(query_features, tau_t, bank, lab, 1.0 / tau_v, float(label_smoothing), group)
+
+
+def bank_ce_step_sharded(query_features: torch.Tensor, bank, labels: torch.Tensor, tau: float = 0.01, *, group=None):
+    """``(loss, dq)`` of this rank's queries against the row-sharded bank, without the autograd engine (the sharded
+    counterpart of :func:`spn4cir_b200.bank_ce_step`): same kernels and the same exchange as
+    :func:`bank_infonce_sharded`."""
+    from .ops import _prep_labels
+    lab = _prep_labels(labels, query_features.shape[0], query_features.device)
+    loss, dq, _ = _sharded_sweep(query_features, bank, lab, 1.0 / float(tau), 0.0, False, group)
+    return loss, dq
 
 
 def sim_topk_sharded(query: torch.Tensor, gallery_shard: torch.Tensor, k: int, col_base: int, exclude=None,
