@@ -45,7 +45,8 @@ enum spn_op {
   SPN_OP_SIM_TOPK = 3,
   SPN_OP_SIM_RANK = 4,
   SPN_OP_BANK_CE_STEP = 5,
-  SPN_OP_BANK_CE_FUSED = 6
+  SPN_OP_BANK_CE_FUSED = 6,
+  SPN_OP_SIM_TC = 7 /* spn_sim_topk_tc / spn_sim_rank_tc (K is ignored) */
 };
 
 enum spn_dtype { SPN_F32 = 0, SPN_F16 = 1, SPN_BF16 = 2 };
@@ -212,6 +213,31 @@ int spn_sim_target_score(const float* q, const float* gallery, int Q, int G, int
 int spn_sim_rank(const float* q, const float* gallery, int Q, int G, int D, int T, const int32_t* target,
                  const float* target_score, const int32_t* exclude, const int32_t* group, int M,
                  int32_t col_base, int32_t* rank, int32_t* group_rank, void* ws, size_t ws_bytes, void* stream);
+
+/* Tensor-core variants of spn_sim_topk / spn_sim_rank: SAME results (the same fp32 score bits, the same ordering rule),
+ * obtained by pruning with a tcgen05 sweep.  q and gallery (fp32) are split into bf16 hi + lo parts, the sweep
+ * accumulates S~ = Qh Gh^T + Qh Gl^T + Ql Gh^T in fp32 (|S~ - S| <= eps = 4e-5 |q| max|g|) into a [Q, G] fp32 block of the
+ * workspace, and one warp per query turns the row into the answer: the 64 best entries by S~ are rescored with the exact
+ * fp32 chain of spn_sim_topk (ascending-k fmaf) and re-sorted; a row whose 64th approximate score is within eps of its K-th
+ * exact score is completed by a second scan that rescoring every entry within eps of the boundary -- so K <= 56.  For the
+ * rank, entries farther than eps from target_score are counted from S~ and the others are rescored exactly.
+ * Replaces the same reference lines as spn_sim_topk / spn_sim_rank (clip4cir/validate.py:31-32,126-127,136-154;
+ * blip2_qformer_cir_align_prompt.py:311-319 with T = 32).  D % 64 == 0; ws from spn_workspace_bytes(SPN_OP_SIM_TC, Q, G,
+ * D, T, 0), 256-byte aligned.  n_second (nullable, device int32): number of rows that left the fast path.
+ * exact_values != 0: out_val holds the exact fp32 chain of every returned entry (bit-identical to spn_sim_topk; needed when
+ * lists of different shards are merged by value) -- K gathered gallery rows per query, L2-bandwidth bound.
+ * exact_values == 0: out_idx is STILL the exact ranking (entries S~ cannot order -- closer than 2 eps to a neighbour -- are
+ * rescored), out_val holds S~ (within eps of the exact score); this is what the reference consumes (names of the sorted
+ * indices, clip4cir/cirr_test_submission.py:94-109). */
+int spn_sim_topk_tc(const float* q, const float* gallery, int Q, int G, int D, int T, int K, const int32_t* exclude,
+                    int32_t col_base, float* out_val, int32_t* out_idx, int exact_values, int32_t* n_second, void* ws,
+                    size_t ws_bytes, void* stream);
+int spn_sim_rank_tc(const float* q, const float* gallery, int Q, int G, int D, int T, const int32_t* target,
+                    const float* target_score, const int32_t* exclude, const int32_t* group, int M, int32_t col_base,
+                    int32_t* rank, int32_t* group_rank, void* ws, size_t ws_bytes, void* stream);
+/* Debug / tests: where the last S~ block of a tensor-core call lives in its workspace (byte offset, row pitch in floats,
+ * queries per block) so that the eps bound can be checked against the exact scores. */
+int spn_debug_sim_tc_layout(int Q, int G, int D, int T, size_t* scores_offset, int* pitch, int* block_rows);
 
 /* Compatibility mode only: the dense fp32 score matrix out[Q, G] (max over T tokens), for callers that
  * still want `pred_sim` itself (blip24cir/validate.py:30,116).  The fused top-K / rank entry points

@@ -20,7 +20,7 @@ REPO_ROOT = PKG_DIR.parent
 LIB_PATH = PKG_DIR / "libspn_b200.so"
 HEADER_PATH = REPO_ROOT / "include" / "spn_b200.h"
 
-SOURCES = ["common.cu", "bank_ce_tc.cu", "part_ce.cu", "umma_selftest.cu", "prologue.cu", "sim_rank.cu", "api.cu"]
+SOURCES = ["common.cu", "bank_ce_tc.cu", "part_ce.cu", "umma_selftest.cu", "prologue.cu", "sim_rank.cu", "sim_tc.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177",
@@ -33,6 +33,7 @@ STATUS_NAMES = {
     -4: "SPN_ERR_WORKSPACE", -5: "SPN_ERR_CUDA", -6: "SPN_ERR_NCCL", -7: "SPN_ERR_BAD_ARG",
 }
 OP_BANK_CE_FWD, OP_BANK_CE_BWD, OP_SIM_TOPK, OP_SIM_RANK, OP_BANK_CE_STEP, OP_BANK_CE_FUSED = 1, 2, 3, 4, 5, 6
+OP_SIM_TC = 7
 DT_F32, DT_F16, DT_BF16 = 0, 1, 2
 
 
@@ -114,6 +115,11 @@ _SIGNATURES = {
     "spn_sim_target_score": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int32, c_void_p, c_void_p],
     "spn_sim_rank": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                      c_int, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    "spn_sim_topk_tc": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int32, c_void_p,
+                        c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
+    "spn_sim_rank_tc": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                        c_int, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    "spn_debug_sim_tc_layout": [c_int, c_int, c_int, c_int, POINTER(c_size_t), POINTER(c_int), POINTER(c_int)],
     "spn_sim_matrix": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "spn_debug_read_timeline": [c_void_p, c_int],
     "spn_debug_umma_bench": [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],

@@ -27,6 +27,11 @@ int spn_workspace_bytes(int op, int B, int64_t N, int D, int T, int K, size_t* o
     case SPN_OP_SIM_RANK:
       *out_bytes = 256;
       return SPN_OK;
+    case SPN_OP_SIM_TC:
+      SPN_REQUIRE(B > 0 && N > 0 && N * T < (1ll << 31) && D >= 64 && D % 64 == 0 && (T == 1 || T == 32), SPN_ERR_BAD_SHAPE,
+                  "spn_workspace_bytes(SIM_TC): bad shape Q=%d G=%lld D=%d T=%d", B, (long long)N, D, T);
+      *out_bytes = sim_tc_ws_bytes(B, int(N), D, T);
+      return SPN_OK;
     case SPN_OP_BANK_CE_STEP:
       SPN_REQUIRE(B > 0 && D >= 64 && D <= 768 && D % 64 == 0, SPN_ERR_BAD_SHAPE, "spn_workspace_bytes(BANK_CE_STEP): bad shape B=%d D=%d", B, D);
       *out_bytes = bank_ce_step_ws_bytes(B, N, D, T);
@@ -209,6 +214,32 @@ int spn_sim_rank(const float* q, const float* gallery, int Q, int G, int D, int 
   if (rc != SPN_OK) return rc;
   return sim_rank(q, gallery, Q, G, D, T, target, target_score, exclude, group, M, col_base, rank, group_rank,
                   as_stream(stream));
+}
+
+int spn_sim_topk_tc(const float* q, const float* gallery, int Q, int G, int D, int T, int K, const int32_t* exclude,
+                    int32_t col_base, float* out_val, int32_t* out_idx, int exact_values, int32_t* n_second, void* ws,
+                    size_t ws_bytes, void* stream) {
+  SPN_REQUIRE(q && gallery && out_val && out_idx, SPN_ERR_BAD_ARG, "spn_sim_topk_tc: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return sim_topk_tc(q, gallery, Q, G, D, T, K, exclude, col_base, out_val, out_idx, exact_values, n_second, ws, ws_bytes,
+                     as_stream(stream));
+}
+
+int spn_sim_rank_tc(const float* q, const float* gallery, int Q, int G, int D, int T, const int32_t* target,
+                    const float* target_score, const int32_t* exclude, const int32_t* group, int M, int32_t col_base,
+                    int32_t* rank, int32_t* group_rank, void* ws, size_t ws_bytes, void* stream) {
+  SPN_REQUIRE(q && gallery, SPN_ERR_BAD_ARG, "spn_sim_rank_tc: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return sim_rank_tc(q, gallery, Q, G, D, T, target, target_score, exclude, group, M, col_base, rank, group_rank, ws,
+                     ws_bytes, as_stream(stream));
+}
+
+int spn_debug_sim_tc_layout(int Q, int G, int D, int T, size_t* scores_offset, int* pitch, int* block_rows) {
+  SPN_REQUIRE(scores_offset && pitch && block_rows && Q > 0 && G > 0 && D > 0 && T > 0, SPN_ERR_BAD_ARG,
+              "spn_debug_sim_tc_layout: bad arguments");
+  return sim_tc_debug_layout(Q, G, D, T, scores_offset, pitch, block_rows);
 }
 
 int spn_sim_matrix(const float* q, const float* gallery, int Q, int G, int D, int T, float* out, void* stream) {

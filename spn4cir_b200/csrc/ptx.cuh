@@ -379,6 +379,13 @@ __device__ __forceinline__ void tma_reduce_add_2d(const void* smem_src, const vo
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// TMA store: global[box at (c0, c1)] = shared box (clipped at the tensor's bounds); bulk-group completion.
+__device__ __forceinline__ void tma_store_2d(const void* smem_src, const void* tmap, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_group_read() {

@@ -17,4 +17,16 @@ int sim_rank(const float* q, const float* g, int Q, int G, int D, int T, const i
              const int* exclude, const int* group, int M, int col_base, int* rank, int* group_rank,
              cudaStream_t stream);
 
+// tensor-core pruned variants (sim_tc.cu): same results as sim_topk / sim_rank
+size_t sim_tc_ws_bytes(int Q, int G, int D, int T);
+int sim_topk_tc(const float* q, const float* g, int Q, int G, int D, int T, int K, const int* exclude, int col_base,
+                float* out_val, int* out_idx, int exact_values, int* n_second, void* ws, size_t ws_bytes,
+                cudaStream_t stream);
+int sim_rank_tc(const float* q, const float* g, int Q, int G, int D, int T, const int* target, const float* tscore,
+                const int* exclude, const int* group, int M, int col_base, int* rank, int* group_rank, void* ws,
+                size_t ws_bytes, cudaStream_t stream);
+int sim_target_score_warp(const float* q, const float* g, int Q, int G, int D, int T, const int* target, int col_base,
+                          float* score, cudaStream_t stream);
+int sim_tc_debug_layout(int Q, int G, int D, int T, size_t* scores_offset, int* pitch, int* block_rows);
+
 }  // namespace spn

@@ -1,0 +1,934 @@
+// Retrieval scoring on the tensor cores: exact ranks / top-K from a tcgen05 score sweep + fp32 rescoring.
+// Same contract as sim_rank.cu (`distances = 1 - q @ g.T; argsort` of clip4cir/validate.py:31-32,126-127 and the
+// max-over-32-tokens similarity of blip2_qformer_cir_align_prompt.py:311-319): descending score, ties -> lower index,
+// and the scores that leave this file are the SAME fp32 bits sim_rank.cu produces (ascending-k FMA chain).
+//
+// Three kernels per call:
+//   1. split_rows_kernel      fp32 rows -> bf16 hi + bf16 lo (x = hi + lo + O(2^-18 |x|)), max row norm of the gallery
+//   2. sim_tc_gemm_kernel     persistent tcgen05 GEMM, S~ = Qh Gh^T + Qh Gl^T + Ql Gh^T accumulated in one TMEM tile
+//                             (fp32), 128 x 128 tiles, TMA-fed 3-stage ring, double-buffered accumulators, TMA-store
+//                             epilogue (T = 32: the max over each entry's 32 token columns is taken in registers)
+//                             -> S~ [Q, G] fp32 (L2-resident at validation sizes; |S~ - S| <= eps = 4e-5 |q| max|g|)
+//   3. row_topk_kernel / row_rank_kernel   one warp per query row over S~:
+//        top-K: approximate top-64 list -> the 64 candidates are rescored with the exact fp32 chain and re-sorted;
+//               the row is certified when (64th approximate score + eps) < (K-th exact score); otherwise a second scan
+//               rescoring every outside entry within eps of the K-th exact score completes it.  K <= 56.
+//        rank : entries farther than eps from the target score are counted from S~, the others are rescored exactly.
+// The tensor-core sweep decides nothing by itself: it only prunes which entries need the exact chain.
+#include <cuda_bf16.h>
+
+#include "bank_ce.cuh"
+#include "ptx.cuh"
+#include "sim_rank.cuh"
+#include "topk_list.cuh"
+
+namespace spn {
+namespace {
+
+constexpr int kTcThreads = 192;      // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int kTcStages = 3;         // ring stages of {Qh, Ql, Gh, Gl} k-blocks (4 x 16 KiB)
+constexpr uint32_t kStageBytes = 4 * kBlockBytes;
+constexpr int kSlotBytes = 4096;     // [32 rows x 32 fp32] staging slot of the TMA-store epilogue
+constexpr float kEpsRel = 4e-5f;     // bound used for |S~ - S| / (|q| max|g|): 3 * 2^-18 from the dropped split terms
+                                     // (1.1e-5) plus fp32 accumulation noise, with margin
+
+// ------------------------------------------------------------------------------------------------ split prologue
+// one warp per row: hi = bf16(x), lo = bf16(x - hi); optional max over rows of |row| (atomicMax on the float bits)
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const float* __restrict__ src, long long rows, int D, __nv_bfloat16* __restrict__ hi,
+                  __nv_bfloat16* __restrict__ lo, float* __restrict__ maxnorm) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* s4 = reinterpret_cast<const float4*>(src + row * D);
+  uint2* h2 = reinterpret_cast<uint2*>(hi + row * D);
+  uint2* l2 = reinterpret_cast<uint2*>(lo + row * D);
+  float ss = 0.f;
+  for (int c = lane; c < D / 4; c += 32) {
+    const float4 x = s4[c];
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y), h2v = __float2bfloat16_rn(x.z),
+                        h3 = __float2bfloat16_rn(x.w);
+    const float r0 = x.x - __bfloat162float(h0), r1 = x.y - __bfloat162float(h1), r2 = x.z - __bfloat162float(h2v),
+                r3 = x.w - __bfloat162float(h3);
+    uint2 ho, lw;
+    ho.x = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+    ho.y = uint32_t(__bfloat16_as_ushort(h2v)) | (uint32_t(__bfloat16_as_ushort(h3)) << 16);
+    lw.x = pack_bf16x2(r0, r1);
+    lw.y = pack_bf16x2(r2, r3);
+    h2[c] = ho;
+    l2[c] = lw;
+    ss = fmaf(x.x, x.x, ss);
+    ss = fmaf(x.y, x.y, ss);
+    ss = fmaf(x.z, x.z, ss);
+    ss = fmaf(x.w, x.w, ss);
+  }
+  if (maxnorm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFull, ss, o);
+    if (lane == 0) atomicMax(reinterpret_cast<int*>(maxnorm), __float_as_int(sqrtf(ss)));  // non-negative floats order as ints
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ tcgen05 sweep
+struct TcGemmParams {
+  int q_row0;     // first query row of this block (coordinate into the split query maps)
+  int qn;         // queries in this block
+  int G;          // gallery entries
+  int Gp;         // score row pitch (G rounded up to 4)
+  int kblocks;    // D / 64
+  int q_tiles, g_tiles;
+  int nterms;     // 3: hi*hi + hi*lo + lo*hi, 1: hi*hi only
+  float* scores;  // [qn, Gp]
+};
+
+template <bool T32>
+__global__ void __launch_bounds__(kTcThreads, 1)
+sim_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_qh, const __grid_constant__ CUtensorMap tmap_ql,
+                   const __grid_constant__ CUtensorMap tmap_gh, const __grid_constant__ CUtensorMap tmap_gl,
+                   const __grid_constant__ CUtensorMap tmap_s, const TcGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~uintptr_t(1023u));
+  uint8_t* ring = base;                                        // kTcStages x 64 KiB
+  uint8_t* slots = ring + size_t(kTcStages) * kStageBytes;     // 4 warps x 2 slots x 4 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slots + 8 * kSlotBytes);
+  uint64_t* full = bars;                    // [kTcStages] TMA -> MMA
+  uint64_t* empty = bars + kTcStages;       // [kTcStages] MMA -> TMA
+  uint64_t* acc_full = bars + 2 * kTcStages;      // [2] MMA -> epilogue
+  uint64_t* acc_empty = bars + 2 * kTcStages + 2; // [2] epilogue -> MMA (4 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 4);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_qh);
+    tma_prefetch_desc(&tmap_ql);
+    tma_prefetch_desc(&tmap_gh);
+    tma_prefetch_desc(&tmap_gl);
+    tma_prefetch_desc(&tmap_s);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_tiles = p.q_tiles * p.g_tiles;
+  const bool three = p.nterms == 3;
+
+  if (warp == 0) {
+    // ---------------- TMA producer
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int qt = tile / p.g_tiles, gt = tile % p.g_tiles;
+      const int qrow = p.q_row0 + qt * kBM, grow = gt * kBN;
+      for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+        const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        if (elect_one()) {
+          uint8_t* st = ring + size_t(s) * kStageBytes;
+          mbar_arrive_expect_tx(&full[s], three ? kStageBytes : 2 * kBlockBytes);
+          tma_load_2d(st, &tmap_qh, &full[s], kb * kBK, qrow);
+          tma_load_2d(st + 2 * kBlockBytes, &tmap_gh, &full[s], kb * kBK, grow);
+          if (three) {
+            tma_load_2d(st + kBlockBytes, &tmap_ql, &full[s], kb * kBK, qrow);
+            tma_load_2d(st + 3 * kBlockBytes, &tmap_gl, &full[s], kb * kBK, grow);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer
+    const uint32_t idesc = make_idesc_bf16_f32(kBM, kBN, 0, 0);
+    uint32_t it = 0, j = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+      const uint32_t b = j & 1u, aph = (j >> 1) & 1u;
+      mbar_wait(&acc_empty[b], aph ^ 1u);
+      tc_fence_after();
+      const uint32_t d = tmem_base + b * uint32_t(kBN);
+      for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+        const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(ring + size_t(s) * kStageBytes);
+          const uint64_t qh = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t ql = make_smem_desc_sw128(sa + kBlockBytes, 16, 1024);
+          const uint64_t gh = make_smem_desc_sw128(sa + 2 * kBlockBytes, 16, 1024);
+          const uint64_t gl = make_smem_desc_sw128(sa + 3 * kBlockBytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint64_t o = uint64_t(k * 2);
+            if (three) {  // small terms first
+              umma_ss_f16(d, qh + o, gl + o, idesc, (kb | k) != 0);
+              umma_ss_f16(d, ql + o, gh + o, idesc, 1);
+              umma_ss_f16(d, qh + o, gh + o, idesc, 1);
+            } else {
+              umma_ss_f16(d, qh + o, gh + o, idesc, (kb | k) != 0);
+            }
+          }
+          umma_commit(&empty[s]);
+          if (kb == p.kblocks - 1) umma_commit(&acc_full[b]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> (swizzled staging slot -> TMA store | max over token groups)
+    const uint32_t quarter = warp & 3u;  // the TMEM lane quarter this warp may read
+    const uint32_t t_row = tmem_base + ((quarter * 32u) << 16);
+    uint8_t* my_slots = slots + size_t(warp - 2u) * 2 * kSlotBytes;
+    uint32_t x[32];
+    uint32_t j = 0, k = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+      const int qt = tile / p.g_tiles, gt = tile % p.g_tiles;
+      const uint32_t b = j & 1u, aph = (j >> 1) & 1u;
+      const int r0 = qt * kBM + int(quarter) * 32;  // first block-relative query row of this warp
+      mbar_wait(&acc_full[b], aph);
+      tc_fence_after();
+      float mx[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld_32x32b_x32(t_row + b * uint32_t(kBN) + uint32_t(c) * 32u, x);
+        tmem_ld_wait();
+        if (c == 3) {  // accumulator drained: the MMA warp may start the tile after next
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[b]);
+        }
+        if (T32) {
+          float m = __uint_as_float(x[0]);
+#pragma unroll
+          for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(x[i]));
+          mx[c] = m;
+        } else {
+          const int col0 = gt * kBN + c * 32;
+          if (r0 < p.qn && col0 < p.Gp) {  // warp-uniform
+            uint8_t* slot = my_slots + size_t(k & 1u) * kSlotBytes;
+            if (k >= 2) {
+              if (lane == 0) bulk_wait_group_read<1>();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+              *reinterpret_cast<uint4*>(slot + lane * 128u + ((uint32_t(v) ^ (lane & 7u)) << 4)) =
+                  make_uint4(x[4 * v], x[4 * v + 1], x[4 * v + 2], x[4 * v + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(slot, &tmap_s, col0, r0);
+              bulk_commit_group();
+            }
+            ++k;
+          }
+        }
+      }
+      if (T32) {
+        const int row = r0 + int(lane);
+        if (row < p.qn) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int e = gt * 4 + c;
+            if (e < p.G) p.scores[size_t(row) * p.Gp + e] = mx[c];
+          }
+        }
+      }
+    }
+    if (!T32) {
+      if (lane == 0) bulk_wait_group<0>();
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------ exact rescoring
+// The reference chain of sim_rank.cu: one fp32 accumulator per score, fmaf in ascending k (max over T token rows).
+constexpr int kRowWarps = 4;
+constexpr int kChunkK = 32;
+constexpr int kChainPitch = kChunkK + 1;                        // conflict-free row walk
+constexpr int kChainFloats = 32 * kChainPitch + kChunkK + 32;   // staged rows | staged q chunk | row ids
+constexpr int kBins = 1024;                                     // histogram bins of the top-K threshold search
+constexpr int kCand = 128;                                      // candidates kept above the threshold bin
+constexpr int kRowSmemFloats = kBins > kChainFloats ? kBins : kChainFloats;  // the two phases share the space
+
+// Up to 32 chains at once, one per lane: returns the chain of q . g[row] for this lane's gallery row (`row` < 0: none).
+// The warp stages 32-column chunks of the <= 32 gallery rows (coalesced 128-byte reads) and of q in shared memory and
+// every lane walks its own staged row; the loads of chunk c + 1 are in flight while chunk c is walked.
+__device__ __forceinline__ float warp_chains(const float* __restrict__ qrow, const float* __restrict__ g, int D, int row,
+                                             float* sm, int lane) {
+  float acc = 0.f;
+  float* sq = sm + 32 * kChainPitch;
+  int* srows = reinterpret_cast<int*>(sq + kChunkK);
+  const unsigned have = __ballot_sync(kFull, row >= 0);
+  __syncwarp();
+  srows[lane] = row;
+  __syncwarp();
+  float t[32], tq;
+  auto load_chunk = [&](int k0) {
+#pragma unroll
+    for (int r0 = 0; r0 < 32; r0 += 8) {
+      if (((have >> r0) & 0xffu) == 0) continue;  // warp-uniform
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int rr = srows[r0 + u];
+        t[r0 + u] = rr >= 0 ? g[size_t(rr) * D + k0 + lane] : 0.f;
+      }
+    }
+    tq = qrow[k0 + lane];
+  };
+  load_chunk(0);
+  for (int k0 = 0; k0 < D; k0 += kChunkK) {
+#pragma unroll
+    for (int r0 = 0; r0 < 32; r0 += 8) {
+      if (((have >> r0) & 0xffu) == 0) continue;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) sm[(r0 + u) * kChainPitch + lane] = t[r0 + u];
+    }
+    sq[lane] = tq;
+    __syncwarp();
+    if (k0 + kChunkK < D) load_chunk(k0 + kChunkK);
+    const float* mine = sm + lane * kChainPitch;
+#pragma unroll
+    for (int k = 0; k < kChunkK; ++k) acc = fmaf(sq[k], mine[k], acc);
+    __syncwarp();
+  }
+  return acc;
+}
+
+// exact score of gallery entry `e` for every lane that asks (need), T = 1: one staged pass for the whole warp;
+// T = 32: entry by entry, the 32 lanes take the 32 token rows and the maximum is reduced across the warp
+__device__ __forceinline__ float warp_exact(const float* __restrict__ qrow, const float* __restrict__ g, int D, int T,
+                                            bool need, int e, float* sm, int lane) {
+  unsigned mask = __ballot_sync(kFull, need);
+  if (!mask) return -INFINITY;
+  if (T == 1) return warp_chains(qrow, g, D, need ? e : -1, sm, lane);
+  float out = -INFINITY;
+  while (mask) {
+    const int src = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const int ee = __shfl_sync(kFull, e, src);
+    float v = warp_chains(qrow, g, D, ee * T + lane, sm, lane);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+    if (lane == src) out = v;
+  }
+  return out;
+}
+
+// per-lane gather version for the rare paths (second scan, entries within eps of the target score)
+__device__ __forceinline__ float exact_one(const float* __restrict__ q, const float* __restrict__ g, int D, int T,
+                                           int e) {
+  float best = -INFINITY;
+  const float4* q4 = reinterpret_cast<const float4*>(q);
+  for (int tok = 0; tok < T; ++tok) {
+    const float4* a4 = reinterpret_cast<const float4*>(g + (size_t(e) * T + tok) * D);
+    float acc = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < D / 4; ++c) {
+      const float4 qq = q4[c], aa = a4[c];
+      acc = fmaf(qq.x, aa.x, acc);
+      acc = fmaf(qq.y, aa.y, acc);
+      acc = fmaf(qq.z, aa.z, acc);
+      acc = fmaf(qq.w, aa.w, acc);
+    }
+    best = fmaxf(best, acc);
+  }
+  return best;
+}
+
+struct RowParams {
+  const float* q;       // fp32 [Q, D] (row 0 = first row of this block)
+  const float* g;       // fp32 [G*T, D]
+  const float* scores;  // S~ [qn, Gp]
+  const float* gmax;    // max gallery row norm
+  int qn, G, Gp, D, T, K, col_base;
+  int exact_values;     // top-K: out_val = exact fp32 chain (else S~; the ORDER is exact either way)
+  const int* exclude;
+  // top-K
+  float* out_val;
+  int* out_idx;
+  int* n_second;        // rows that left the fast path (statistics)
+  // rank
+  const int* target;
+  const float* tscore;
+  const int* group;
+  int M;
+  int* rank;
+  int* group_rank;
+};
+
+__device__ __forceinline__ float row_eps(const float* __restrict__ qrow, int D, float gmax, int lane) {
+  float ss = 0.f;
+  for (int c = lane; c < D; c += 32) ss = fmaf(qrow[c], qrow[c], ss);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFull, ss, o);
+  return kEpsRel * sqrtf(ss) * gmax;
+}
+
+__device__ __forceinline__ void write_topk(const RowParams& p, int row, const float* srow, float x0, int j0, float x1,
+                                           int j1, int lane) {
+  const size_t o = size_t(row) * p.K;
+  if (lane < p.K) {
+    const bool real = j0 != INT_MAX;
+    p.out_val[o + lane] = real ? (p.exact_values ? x0 : srow[j0 - p.col_base]) : -INFINITY;
+    p.out_idx[o + lane] = real ? j0 : -1;
+  }
+  if (lane + 32 < p.K) {
+    const bool real = j1 != INT_MAX;
+    p.out_val[o + lane + 32] = real ? (p.exact_values ? x1 : srow[j1 - p.col_base]) : -INFINITY;
+    p.out_idx[o + lane + 32] = real ? j1 : -1;
+  }
+}
+
+// General path of a row (plateaus wider than the candidate window, lanes whose private list overflowed): shuffle-
+// insertion top-64 by S~, all 64 rescored, and a second scan over everything within eps of the K-th exact score.
+__device__ __noinline__ void row_topk_general(const RowParams& p, int row, const float* srow, const float* qrow, int ex,
+                                              float eps, int lane) {
+  float v0 = -INFINITY, v1 = -INFINITY;
+  int i0 = INT_MAX, i1 = INT_MAX;
+  for (int g0 = 0; g0 < p.G; g0 += 128) {
+    float a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int g = g0 + u * 32 + lane;
+      a[u] = g < p.G ? srow[g] : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int g = g0 + u * 32 + lane;
+      const int idx = p.col_base + g;
+      topk_offer(a[u], idx, g < p.G && idx != ex, 64, v0, i0, v1, i1, lane);
+    }
+  }
+  const float a_last = __shfl_sync(kFull, v1, 31);
+  const int i_last = __shfl_sync(kFull, i1, 31);
+  const float e0 = i0 != INT_MAX ? exact_one(qrow, p.g, p.D, p.T, i0 - p.col_base) : -INFINITY;
+  const float e1 = i1 != INT_MAX ? exact_one(qrow, p.g, p.D, p.T, i1 - p.col_base) : -INFINITY;
+  __syncwarp();
+  float x0 = -INFINITY, x1 = -INFINITY;
+  int j0 = INT_MAX, j1 = INT_MAX;
+  topk_offer(e0, i0, i0 != INT_MAX, 64, x0, j0, x1, j1, lane);
+  topk_offer(e1, i1, i1 != INT_MAX, 64, x0, j0, x1, j1, lane);
+  const int K = p.K;
+  float e_k = (K - 1 < 32) ? __shfl_sync(kFull, x0, K - 1) : __shfl_sync(kFull, x1, K - 33);
+  if (i_last != INT_MAX && !(a_last + eps < e_k)) {  // entries outside the window may still belong to the top K
+    for (int g0 = 0; g0 < p.G; g0 += 32) {
+      const int g = g0 + lane;
+      const int idx = p.col_base + g;
+      const float a = g < p.G ? srow[g] : -INFINITY;
+      const bool cand = g < p.G && idx != ex && sorts_before(a_last, i_last, a, idx) && !(a + eps < e_k);
+      if (__ballot_sync(kFull, cand)) {
+        float e = -INFINITY;
+        if (cand) e = exact_one(qrow, p.g, p.D, p.T, g);
+        __syncwarp();
+        topk_offer(e, idx, cand, K, x0, j0, x1, j1, lane);
+        e_k = (K - 1 < 32) ? __shfl_sync(kFull, x0, K - 1) : __shfl_sync(kFull, x1, K - 33);
+      }
+    }
+  }
+  write_topk(p, row, srow, x0, j0, x1, j1, lane);
+}
+
+__device__ __forceinline__ bool key_before(int ca, float va, int ia, int cb, float vb, int ib) {
+  return ca < cb || (ca == cb && sorts_before(va, ia, vb, ib));
+}
+
+// one warp per query row.  Fast path: a 1024-bin histogram of the row (linear in the score over [-|q| max|g|, +|q| max|g|],
+// shared-memory atomics) gives the bin holding the 64th best entry; a second pass compacts the entries at or above that
+// bin (<= 128, normally ~70) which one 128-element bitonic sort orders by (S~, index); exact chains run only where S~
+// cannot decide the order (entries closer than 2 eps to a neighbour; all of the first K when exact values are
+// requested), then a 64-element bitonic sort on (cluster, exact score, index).
+__global__ void __launch_bounds__(kRowWarps * 32)
+row_topk_kernel(const RowParams p) {
+  __shared__ float row_sm[kRowWarps][kRowSmemFloats];
+  __shared__ float cand_v[kRowWarps][kCand];
+  __shared__ int cand_i[kRowWarps][kCand];
+  const int wib = threadIdx.x >> 5;
+  const int row = blockIdx.x * kRowWarps + wib;
+  const int lane = threadIdx.x & 31;
+  if (row >= p.qn) return;
+  const float* srow = p.scores + size_t(row) * p.Gp;
+  const float* qrow = p.q + size_t(row) * p.D;
+  const int ex = p.exclude ? p.exclude[row] : -1;
+  const float eps = row_eps(qrow, p.D, *p.gmax, lane);
+  const int K = p.K;
+
+  // ---- pass 1: histogram
+  unsigned* hist = reinterpret_cast<unsigned*>(row_sm[wib]);
+#pragma unroll
+  for (int b = 0; b < kBins / 32; ++b) hist[b * 32 + lane] = 0u;
+  __syncwarp();
+  const float bound = fmaxf(eps * (1.001f / kEpsRel), 1e-30f);  // >= |q| max|g| >= |S~|
+  const float bscale = float(kBins / 2) / bound;
+  auto bin_of = [&](float a) {
+    const int b = __float2int_rd((a + bound) * bscale);
+    return min(kBins - 1, max(0, b));
+  };
+  for (int g0 = 0; g0 < p.G; g0 += 256) {
+    float a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int g = g0 + u * 32 + lane;
+      a[u] = g < p.G ? srow[g] : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int g = g0 + u * 32 + lane;
+      if (g < p.G && p.col_base + g != ex) atomicAdd(&hist[bin_of(a[u])], 1u);
+    }
+  }
+  __syncwarp();
+  // ---- threshold bin: lane L owns bins [32 L, 32 L + 32); walk down from the top until 64 entries are covered
+  unsigned mine = 0;
+#pragma unroll
+  for (int b = 0; b < 32; ++b) mine += hist[lane * 32 + ((b + lane) & 31)];  // staggered: conflict-free
+  unsigned above = mine;  // inclusive suffix sum over lanes >= this one
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_down_sync(kFull, above, o);
+    if (lane + o < 32) above += t;
+  }
+  const unsigned total = __shfl_sync(kFull, above, 0);
+  int tb = 0;
+  unsigned n_cand = total;
+  if (total > 64u) {
+    const unsigned owner_mask = __ballot_sync(kFull, above >= 64u && above - mine < 64u);
+    const int owner = __ffs(owner_mask) - 1;
+    if (lane == owner) {
+      unsigned c = above - mine;
+      int b = 31;
+      for (; b > 0; --b) {
+        c += hist[lane * 32 + b];
+        if (c >= 64u) break;
+      }
+      if (b == 0) c += hist[lane * 32];
+      tb = lane * 32 + b;
+      n_cand = c;
+    }
+    tb = __shfl_sync(kFull, tb, owner);
+    n_cand = __shfl_sync(kFull, n_cand, owner);
+  }
+  if (n_cand > unsigned(kCand)) {  // a plateau wider than the candidate buffer
+    if (lane == 0 && p.n_second) atomicAdd(p.n_second, 1);
+    row_topk_general(p, row, srow, qrow, ex, eps, lane);
+    return;
+  }
+  // ---- pass 2: compact the entries at or above the threshold bin
+  unsigned fill = 0;
+  for (int g0 = 0; g0 < p.G; g0 += 256) {
+    float a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int g = g0 + u * 32 + lane;
+      a[u] = g < p.G ? srow[g] : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int g = g0 + u * 32 + lane;
+      const int idx = p.col_base + g;
+      const bool take = g < p.G && idx != ex && bin_of(a[u]) >= tb;
+      const unsigned m = __ballot_sync(kFull, take);
+      if (take) {
+        const unsigned pos = fill + __popc(m & ((1u << lane) - 1u));
+        cand_v[wib][pos] = a[u];
+        cand_i[wib][pos] = idx;
+      }
+      fill += __popc(m);
+    }
+  }
+  __syncwarp();
+  // ---- 128-element bitonic sort on (S~, index), position = lane + 32 r, best first
+  float cv[4];
+  int ci[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const unsigned pos = lane + 32 * r;
+    cv[r] = pos < fill ? cand_v[wib][pos] : -INFINITY;
+    ci[r] = pos < fill ? cand_i[wib][pos] : INT_MAX;
+  }
+#pragma unroll
+  for (int k = 2; k <= 128; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {  // partner register r ^ (j / 32) of the same lane
+        const int rj = j >> 5;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if ((r & rj) == 0) {
+            const int o = r | rj;
+            const bool up = ((r * 32) & k) == 0;  // k = 64: r < 2 up, else down; k = 128: up
+            const bool r_better = sorts_before(cv[r], ci[r], cv[o], ci[o]);
+            if (r_better != up) {
+              const float tv = cv[r]; cv[r] = cv[o]; cv[o] = tv;
+              const int ti = ci[r]; ci[r] = ci[o]; ci[o] = ti;
+            }
+          }
+        }
+      } else {
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const bool up = ((lane + 32 * r) & k) == 0;
+          const float tv = __shfl_xor_sync(kFull, cv[r], j);
+          const int ti = __shfl_xor_sync(kFull, ci[r], j);
+          const bool mine_better = sorts_before(cv[r], ci[r], tv, ti);
+          if (mine_better != (lower == up)) {
+            cv[r] = tv;
+            ci[r] = ti;
+          }
+        }
+      }
+    }
+  }
+  // the window: positions 0..63 are registers 0 and 1 (the list layout used below)
+  float v0 = cv[0], v1 = cv[1];
+  int i0 = ci[0], i1 = ci[1];
+  const float a_last = __shfl_sync(kFull, v1, 31);
+  const int i_last = __shfl_sync(kFull, i1, 31);
+  const float a_k1 = (K - 1 < 32) ? __shfl_sync(kFull, v0, K - 1) : __shfl_sync(kFull, v1, K - 33);
+  // a window whose last entry is within 2 eps of the K-th cannot exclude the entries outside it
+  if (i_last != INT_MAX && !(a_last + 2.f * eps < a_k1)) {
+    if (lane == 0 && p.n_second) atomicAdd(p.n_second, 1);
+    row_topk_general(p, row, srow, qrow, ex, eps, lane);
+    return;
+  }
+
+  // ---- which window entries can still be in the top K, and which of them S~ cannot order
+  const bool rel0 = i0 != INT_MAX && (lane < K || !(v0 + 2.f * eps < a_k1));
+  const bool rel1 = i1 != INT_MAX && (lane + 32 < K || !(v1 + 2.f * eps < a_k1));
+  int c0 = 0, c1 = 0;
+  bool need0 = rel0, need1 = rel1;
+  if (!p.exact_values) {
+    float pv0 = __shfl_up_sync(kFull, v0, 1);
+    float pv1 = __shfl_up_sync(kFull, v1, 1);
+    const float v0_last = __shfl_sync(kFull, v0, 31);
+    if (lane == 0) pv1 = v0_last;
+    const bool head0 = lane == 0 || (pv0 - v0 > 2.f * eps);
+    const bool head1 = pv1 - v1 > 2.f * eps;
+    const unsigned long long heads =
+        (unsigned long long)__ballot_sync(kFull, head0) | ((unsigned long long)__ballot_sync(kFull, head1) << 32);
+    const int p0 = lane, p1 = lane + 32;
+    c0 = 63 - __clzll(heads & ((2ull << p0) - 1ull));
+    c1 = 63 - __clzll(heads & (p1 == 63 ? ~0ull : ((2ull << p1) - 1ull)));
+    const bool next_head0 = (heads >> (p0 + 1)) & 1ull;
+    const bool next_head1 = p1 == 63 ? true : ((heads >> (p1 + 1)) & 1ull);
+    need0 = rel0 && !(head0 && next_head0);  // singleton clusters keep their place without a chain
+    need1 = rel1 && !(head1 && next_head1);
+  }
+  if (!rel0) c0 = INT_MAX;
+  if (!rel1) c1 = INT_MAX;
+  const float e0 = warp_exact(qrow, p.g, p.D, p.T, need0, i0 - p.col_base, row_sm[wib], lane);
+  const float e1 = warp_exact(qrow, p.g, p.D, p.T, need1, i1 - p.col_base, row_sm[wib], lane);
+  float x0 = need0 ? e0 : v0, x1 = need1 ? e1 : v1;
+  int j0 = i0, j1 = i1;
+
+  // ---- 64-element bitonic sort on (cluster, score, index); position = lane + 32 * r
+#pragma unroll
+  for (int k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j == 32) {  // k == 64: register 0 against register 1 of the same lane, best first
+        if (key_before(c1, x1, j1, c0, x0, j0)) {
+          const int tc = c0; c0 = c1; c1 = tc;
+          const float tv = x0; x0 = x1; x1 = tv;
+          const int ti = j0; j0 = j1; j1 = ti;
+        }
+      } else {
+        const bool lower = (lane & j) == 0;
+        const bool up0 = k == 64 ? true : (k == 32 ? true : (lane & k) == 0);
+        const bool up1 = k == 64 ? true : (k == 32 ? false : (lane & k) == 0);
+        {
+          const int tc = __shfl_xor_sync(kFull, c0, j);
+          const float tv = __shfl_xor_sync(kFull, x0, j);
+          const int ti = __shfl_xor_sync(kFull, j0, j);
+          const bool mine_better = key_before(c0, x0, j0, tc, tv, ti);
+          if (mine_better != (lower == up0)) { c0 = tc; x0 = tv; j0 = ti; }
+        }
+        {
+          const int tc = __shfl_xor_sync(kFull, c1, j);
+          const float tv = __shfl_xor_sync(kFull, x1, j);
+          const int ti = __shfl_xor_sync(kFull, j1, j);
+          const bool mine_better = key_before(c1, x1, j1, tc, tv, ti);
+          if (mine_better != (lower == up1)) { c1 = tc; x1 = tv; j1 = ti; }
+        }
+      }
+    }
+  }
+  if (c0 == INT_MAX) j0 = INT_MAX;
+  if (c1 == INT_MAX) j1 = INT_MAX;
+  write_topk(p, row, srow, x0, j0, x1, j1, lane);
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32)
+row_rank_kernel(const RowParams p) {
+  __shared__ float chain_sm[kRowWarps][kChainFloats];
+  __shared__ int unsure_g[kRowWarps][64];
+  const int wib = threadIdx.x >> 5;
+  const int row = blockIdx.x * kRowWarps + wib;
+  const int lane = threadIdx.x & 31;
+  if (row >= p.qn) return;
+  const float* srow = p.scores + size_t(row) * p.Gp;
+  const float* qrow = p.q + size_t(row) * p.D;
+  const int ex = p.exclude ? p.exclude[row] : -1;
+  const int tg = p.target[row];
+  const float ts = p.tscore[row];
+  const float eps = row_eps(qrow, p.D, *p.gmax, lane);
+  const int greg = (p.group && lane < p.M) ? p.group[size_t(row) * p.M + lane] : -2;
+  int cnt = 0, gcnt = 0;
+  unsigned n_unsure = 0;
+  auto in_group = [&](int idx) {
+    bool in = false;
+    for (int mm = 0; mm < p.M; ++mm) in |= (__shfl_sync(kFull, greg, mm) == idx);
+    return in;
+  };
+  // entries within eps of the target score wait in a list and are rescored (up to 32 at a time) with the exact chain
+  auto flush = [&](unsigned n) {
+    const bool have = unsigned(lane) < n;
+    const int g = have ? unsure_g[wib][lane] : 0;
+    __syncwarp();
+    const float e = warp_exact(qrow, p.g, p.D, p.T, have, g, chain_sm[wib], lane);
+    const int idx = p.col_base + g;
+    const bool before = have && sorts_before(e, idx, ts, tg);
+    cnt += __popc(__ballot_sync(kFull, before));
+    if (p.group) {
+      const bool in = in_group(idx);  // every lane takes part in the shuffles
+      gcnt += __popc(__ballot_sync(kFull, before && in));
+    }
+  };
+  for (int g0 = 0; g0 < p.G; g0 += 256) {
+    float av[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int g = g0 + u * 32 + lane;
+      av[u] = g < p.G ? srow[g] : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int g = g0 + u * 32 + lane;
+      const int idx = p.col_base + g;
+      const bool ok = g < p.G && idx != ex && idx != tg;
+      const float a = av[u];
+      const bool before = ok && a > ts + eps;
+      const bool unsure = ok && !before && !(a < ts - eps);
+      const unsigned um = __ballot_sync(kFull, unsure);
+      if (um) {
+        if (unsure) unsure_g[wib][n_unsure + __popc(um & ((1u << lane) - 1u))] = g;
+        n_unsure += __popc(um);
+        __syncwarp();
+        if (n_unsure >= 32u) {
+          flush(32u);
+          n_unsure -= 32u;
+          const int carry = unsigned(lane) < n_unsure ? unsure_g[wib][32 + lane] : 0;
+          __syncwarp();
+          if (unsigned(lane) < n_unsure) unsure_g[wib][lane] = carry;
+          __syncwarp();
+        }
+      }
+      const unsigned bm = __ballot_sync(kFull, before);
+      cnt += __popc(bm);
+      if (p.group && bm) {
+        const bool in = in_group(idx);
+        gcnt += __popc(__ballot_sync(kFull, before && in));
+      }
+    }
+  }
+  if (n_unsure) flush(n_unsure);
+  if (lane == 0) {
+    if (cnt) atomicAdd(&p.rank[row], cnt);
+    if (p.group_rank && gcnt) atomicAdd(&p.group_rank[row], gcnt);
+  }
+}
+
+// score[b] of the target entry with the exact chain (same bits as target_score_kernel of sim_rank.cu), one warp per query
+__global__ void __launch_bounds__(kRowWarps * 32)
+target_score_warp_kernel(const float* __restrict__ q, const float* __restrict__ g, int Q, int G, int D, int T,
+                         const int* __restrict__ target, int col_base, float* __restrict__ score) {
+  __shared__ float chain_sm[kRowWarps][kChainFloats];
+  const int wib = threadIdx.x >> 5;
+  const int row = blockIdx.x * kRowWarps + wib;
+  const int lane = threadIdx.x & 31;
+  if (row >= Q) return;
+  const int t = target[row] - col_base;
+  float v = -INFINITY;
+  if (t >= 0 && t < G) {  // warp-uniform
+    v = warp_chains(q + size_t(row) * D, g, D, T == 1 ? (lane == 0 ? t : -1) : t * T + lane, chain_sm[wib], lane);
+    if (T != 1) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+    }
+  }
+  if (lane == 0) score[row] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct TcLayout {
+  size_t qh, ql, gh, gl, scores, misc, total;
+  int qb;  // queries per block (multiple of 128)
+  int Gp;
+};
+
+TcLayout tc_layout(int Q, int G, int D, int T) {
+  TcLayout L{};
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  L.Gp = (G + 3) / 4 * 4;
+  const size_t budget = size_t(512) << 20;  // score block budget
+  long long qb = (long long)(budget / (size_t(L.Gp) * 4)) / 128 * 128;
+  if (qb < 128) qb = 128;
+  const long long qpad = (long long)(Q + 127) / 128 * 128;
+  if (qb > qpad) qb = qpad;
+  L.qb = int(qb);
+  size_t o = 0;
+  L.qh = o; o += up(size_t(Q) * D * 2);
+  L.ql = o; o += up(size_t(Q) * D * 2);
+  L.gh = o; o += up(size_t(G) * T * D * 2);
+  L.gl = o; o += up(size_t(G) * T * D * 2);
+  L.scores = o; o += up(size_t(L.qb) * L.Gp * 4);
+  L.misc = o; o += 256;
+  L.total = o;
+  return L;
+}
+
+int tc_check(const float* q, const float* g, int Q, int G, int D, int T) {
+  SPN_REQUIRE(Q > 0 && G > 0, SPN_ERR_BAD_SHAPE, "retrieval needs Q > 0 and G > 0 (Q=%d G=%d)", Q, G);
+  SPN_REQUIRE(D >= 64 && D % 64 == 0, SPN_ERR_BAD_SHAPE, "tensor-core retrieval needs D %% 64 == 0 (D=%d)", D);
+  SPN_REQUIRE(T == 1 || T == 32, SPN_ERR_BAD_SHAPE, "tokens per entry T=%d unsupported (1 or 32)", T);
+  SPN_REQUIRE((long long)G * T < (1ll << 31), SPN_ERR_BAD_SHAPE, "gallery too large: G*T=%lld", (long long)G * T);
+  SPN_REQUIRE(aligned16(q) && aligned16(g), SPN_ERR_BAD_ALIGN, "retrieval operands must be 16-byte aligned");
+  return SPN_OK;
+}
+
+size_t tc_gemm_smem() { return 1024 + size_t(kTcStages) * kStageBytes + 8 * kSlotBytes + 256; }
+
+// split both operands, then per query block: tensor-core sweep + row kernel (`rank_mode` selects which)
+int tc_run(bool rank_mode, const float* q, const float* g, int Q, int G, int D, int T, RowParams rp, int* n_second_out,
+           void* ws, size_t ws_bytes, cudaStream_t stream) {
+  int rc = tc_check(q, g, Q, G, D, T);
+  if (rc != SPN_OK) return rc;
+  const TcLayout L = tc_layout(Q, G, D, T);
+  SPN_REQUIRE(ws && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0 && ws_bytes >= L.total, SPN_ERR_WORKSPACE,
+              "tensor-core retrieval workspace too small or misaligned: %zu < %zu", ws_bytes, L.total);
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  auto* qh = reinterpret_cast<__nv_bfloat16*>(w + L.qh);
+  auto* ql = reinterpret_cast<__nv_bfloat16*>(w + L.ql);
+  auto* gh = reinterpret_cast<__nv_bfloat16*>(w + L.gh);
+  auto* gl = reinterpret_cast<__nv_bfloat16*>(w + L.gl);
+  float* scores = reinterpret_cast<float*>(w + L.scores);
+  float* gmax = reinterpret_cast<float*>(w + L.misc);
+  int* n_second = reinterpret_cast<int*>(w + L.misc + 16);
+  SPN_CUDA_CHECK(cudaMemsetAsync(w + L.misc, 0, 256, stream));
+  const long long grows = (long long)G * T;
+  split_rows_kernel<<<unsigned((Q + 7) / 8), 256, 0, stream>>>(q, Q, D, qh, ql, nullptr);
+  split_rows_kernel<<<unsigned((grows + 7) / 8), 256, 0, stream>>>(g, grows, D, gh, gl, gmax);
+  SPN_CUDA_CHECK(cudaGetLastError());
+
+  CUtensorMap tqh, tql, tgh, tgl, ts;
+  if ((rc = make_tmap_bf16_2d(&tqh, qh, uint64_t(Q), uint64_t(D), kBM)) != SPN_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tql, ql, uint64_t(Q), uint64_t(D), kBM)) != SPN_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tgh, gh, uint64_t(grows), uint64_t(D), kBN)) != SPN_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tgl, gl, uint64_t(grows), uint64_t(D), kBN)) != SPN_OK) return rc;
+
+  const size_t smem = tc_gemm_smem();
+  static bool attr_done = false;
+  if (!attr_done) {
+    SPN_REQUIRE(size_t(device_max_smem_optin()) >= smem, SPN_ERR_CUDA, "device offers %d B of shared memory, %zu needed",
+                device_max_smem_optin(), smem);
+    SPN_CUDA_CHECK(cudaFuncSetAttribute(sim_tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    SPN_CUDA_CHECK(cudaFuncSetAttribute(sim_tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    attr_done = true;
+  }
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+
+  for (int qb0 = 0; qb0 < Q; qb0 += L.qb) {
+    const int qn = (Q - qb0 < L.qb) ? Q - qb0 : L.qb;
+    if ((rc = make_tmap_f32_2d(&ts, scores, uint64_t(qn), uint64_t(L.Gp), 32)) != SPN_OK) return rc;
+    TcGemmParams gp{};
+    gp.q_row0 = qb0; gp.qn = qn; gp.G = G; gp.Gp = L.Gp; gp.kblocks = D / kBK;
+    gp.q_tiles = (qn + kBM - 1) / kBM;
+    gp.g_tiles = int((grows + kBN - 1) / kBN);
+    gp.nterms = 3;
+    gp.scores = scores;
+    const long long n_tiles = (long long)gp.q_tiles * gp.g_tiles;
+    const int grid = int(n_tiles < sms ? n_tiles : sms);
+    if (T == 1) sim_tc_gemm_kernel<false><<<grid, kTcThreads, smem, stream>>>(tqh, tql, tgh, tgl, ts, gp);
+    else        sim_tc_gemm_kernel<true><<<grid, kTcThreads, smem, stream>>>(tqh, tql, tgh, tgl, ts, gp);
+    SPN_CUDA_CHECK(cudaGetLastError());
+
+    RowParams r = rp;
+    r.q = q + size_t(qb0) * D; r.g = g; r.scores = scores; r.gmax = gmax; r.qn = qn; r.G = G; r.Gp = L.Gp; r.D = D; r.T = T;
+    r.n_second = n_second;
+    if (r.exclude) r.exclude += qb0;
+    if (rank_mode) {
+      r.target += qb0; r.tscore += qb0;
+      if (r.group) r.group += size_t(qb0) * r.M;
+      r.rank += qb0;
+      if (r.group_rank) r.group_rank += qb0;
+      row_rank_kernel<<<(qn + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, stream>>>(r);
+    } else {
+      r.out_val += size_t(qb0) * r.K; r.out_idx += size_t(qb0) * r.K;
+      row_topk_kernel<<<(qn + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, stream>>>(r);
+    }
+    SPN_CUDA_CHECK(cudaGetLastError());
+  }
+  if (n_second_out)
+    SPN_CUDA_CHECK(cudaMemcpyAsync(n_second_out, n_second, sizeof(int), cudaMemcpyDeviceToDevice, stream));
+  return SPN_OK;
+}
+
+}  // namespace
+
+size_t sim_tc_ws_bytes(int Q, int G, int D, int T) { return tc_layout(Q, G, D, T).total; }
+
+int sim_tc_debug_layout(int Q, int G, int D, int T, size_t* scores_offset, int* pitch, int* block_rows) {
+  const TcLayout L = tc_layout(Q, G, D, T);
+  *scores_offset = L.scores;
+  *pitch = L.Gp;
+  *block_rows = L.qb;
+  return SPN_OK;
+}
+
+int sim_topk_tc(const float* q, const float* g, int Q, int G, int D, int T, int K, const int* exclude, int col_base,
+                float* out_val, int* out_idx, int exact_values, int* n_second, void* ws, size_t ws_bytes,
+                cudaStream_t stream) {
+  SPN_REQUIRE(K >= 1 && K <= 56, SPN_ERR_BAD_SHAPE, "tensor-core top-K supports 1 <= K <= 56 (K=%d): 64 candidates are rescored", K);
+  RowParams rp{};
+  rp.K = K; rp.col_base = col_base; rp.exclude = exclude; rp.out_val = out_val; rp.out_idx = out_idx;
+  rp.exact_values = exact_values;
+  return tc_run(false, q, g, Q, G, D, T, rp, n_second, ws, ws_bytes, stream);
+}
+
+int sim_rank_tc(const float* q, const float* g, int Q, int G, int D, int T, const int* target, const float* tscore,
+                const int* exclude, const int* group, int M, int col_base, int* rank, int* group_rank, void* ws,
+                size_t ws_bytes, cudaStream_t stream) {
+  SPN_REQUIRE(target && tscore && rank, SPN_ERR_BAD_ARG, "sim_rank needs target, target_score and rank");
+  SPN_REQUIRE(!group || (M >= 1 && M <= 32 && group_rank), SPN_ERR_BAD_SHAPE, "sim_rank: group needs 1 <= M <= 32 and group_rank");
+  RowParams rp{};
+  rp.K = 1; rp.col_base = col_base; rp.exclude = exclude; rp.target = target; rp.tscore = tscore; rp.group = group; rp.M = M;
+  rp.rank = rank; rp.group_rank = group_rank;
+  return tc_run(true, q, g, Q, G, D, T, rp, nullptr, ws, ws_bytes, stream);
+}
+
+int sim_target_score_warp(const float* q, const float* g, int Q, int G, int D, int T, const int* target, int col_base,
+                          float* score, cudaStream_t stream) {
+  SPN_REQUIRE(Q > 0 && G > 0 && D >= 64 && D % 64 == 0 && (T == 1 || T == 32), SPN_ERR_BAD_SHAPE,
+              "sim_target_score_warp: bad shape Q=%d G=%d D=%d T=%d", Q, G, D, T);
+  target_score_warp_kernel<<<(Q + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, stream>>>(q, g, Q, G, D, T, target, col_base,
+                                                                                       score);
+  SPN_CUDA_CHECK(cudaGetLastError());
+  return SPN_OK;
+}
+
+}  // namespace spn

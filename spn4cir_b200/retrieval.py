@@ -17,7 +17,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import OP_SIM_TOPK, SpnError, call
+from ._lib import OP_SIM_TC, OP_SIM_TOPK, SpnError, call
 from .ops import _ptr, _require_cuda, _stream
 
 
@@ -39,10 +39,46 @@ def _i32(x, dev) -> Optional[torch.Tensor]:
     return torch.as_tensor(x).to(device=dev, dtype=torch.int32).contiguous()
 
 
-def sim_topk(query: torch.Tensor, gallery: torch.Tensor, k: int, exclude=None, col_base: int = 0):
+TC_MAX_K = 56          # spn_sim_topk_tc rescoring window: 64 candidates, K <= 56
+TC_MIN_SCORES = 1 << 18  # below this many (query, token-row) pairs the fp32 tile kernel is launch-bound anyway
+
+
+def _use_tc(mode: str, Q: int, G: int, D: int, T: int, k: int = 1) -> bool:
+    """``mode``: "fp32" = the fp32 tile kernel, "tc" = tcgen05 sweep + exact rescoring (same results), "auto"."""
+    if mode == "fp32":
+        return False
+    ok = D % 64 == 0 and k <= TC_MAX_K
+    if mode == "tc":
+        if not ok:
+            raise SpnError("retrieval", -1, f"tensor-core retrieval needs D % 64 == 0 and K <= {TC_MAX_K} (D={D}, K={k})")
+        return True
+    if mode != "auto":
+        raise SpnError("retrieval", -7, f"unknown mode {mode!r} (fp32 | tc | auto)")
+    return ok and Q * G * T >= TC_MIN_SCORES
+
+
+_ws_cache = {}
+
+
+def _tc_workspace(Q: int, G: int, D: int, T: int, dev) -> torch.Tensor:
+    """Workspace of the tensor-core path (split operands + one S~ block), kept per device and grown on demand."""
+    need = _lib.workspace_bytes(OP_SIM_TC, Q, G, D, T, 0)
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        _ws_cache[key] = ws
+    return ws
+
+
+def sim_topk(query: torch.Tensor, gallery: torch.Tensor, k: int, exclude=None, col_base: int = 0, mode: str = "auto",
+             exact_values: bool = True, n_second_out: Optional[torch.Tensor] = None):
     """Top-``k`` gallery entries per query: returns (values [Q, k] fp32, indices [Q, k] int32, global).
-    ``k > 64`` is served in pages of 64 (``spn_sim_topk_after``: each page resumes after the last entry of the
-    previous one; -inf / -1 padding once the gallery is exhausted)."""
+    ``mode``: "fp32" (tile kernel), "tc" (``spn_sim_topk_tc``: tcgen05 sweep prunes, exact fp32 rescoring decides --
+    identical output) or "auto".  ``exact_values=False`` (tensor-core path only): the indices are still the exact
+    ranking, the values are the sweep's S~ (within 4e-5 |q| max|g| of the exact score) -- enough for every consumer that
+    only maps indices to names, and ~2x faster at CIRR size; keep True when lists are merged by value.  ``k > 64`` is served in pages of 64 (``spn_sim_topk_after``: each page resumes after
+    the last entry of the previous one; -inf / -1 padding once the gallery is exhausted)."""
     _require_cuda(query, "query")
     g, G, T = _prep_gallery(gallery)
     q = query.detach().float().contiguous()
@@ -52,6 +88,11 @@ def sim_topk(query: torch.Tensor, gallery: torch.Tensor, k: int, exclude=None, c
     vals = torch.empty((Q, k), dtype=torch.float32, device=dev)
     idx = torch.empty((Q, k), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
+        if _use_tc(mode, Q, G, D, T, k):
+            ws = _tc_workspace(Q, G, D, T, dev)
+            call("spn_sim_topk_tc", _ptr(q), _ptr(g), Q, G, D, T, k, _ptr(ex), col_base, _ptr(vals), _ptr(idx),
+                 1 if exact_values else 0, _ptr(n_second_out), _ptr(ws), ws.numel(), _stream(dev))
+            return vals, idx
         if k <= 64:
             ws_bytes = _lib.workspace_bytes(OP_SIM_TOPK, Q, G, D, T, k)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -109,7 +150,8 @@ def sim_target_score(query: torch.Tensor, gallery: torch.Tensor, target, col_bas
 
 
 def sim_rank(query: torch.Tensor, gallery: torch.Tensor, target, exclude=None, group=None, *,
-             target_score: Optional[torch.Tensor] = None, col_base: int = 0, rank_out=None, group_rank_out=None):
+             target_score: Optional[torch.Tensor] = None, col_base: int = 0, rank_out=None, group_rank_out=None,
+             mode: str = "auto"):
     """Rank of ``target`` per query (0 = best) after dropping ``exclude``; with ``group`` [Q, M] also the
     rank restricted to the group members.  Returns (rank [Q] int32, group_rank [Q] int32 | None)."""
     _require_cuda(query, "query")
@@ -128,8 +170,13 @@ def sim_rank(query: torch.Tensor, gallery: torch.Tensor, target, exclude=None, g
         grank = None
         if gr is not None:
             grank = group_rank_out if group_rank_out is not None else torch.zeros(Q, dtype=torch.int32, device=dev)
-        call("spn_sim_rank", _ptr(q), _ptr(g), Q, G, D, T, _ptr(tg), _ptr(target_score), _ptr(ex), _ptr(gr), M,
-             col_base, _ptr(rank), _ptr(grank), None, 0, _stream(dev))
+        if _use_tc(mode, Q, G, D, T):
+            ws = _tc_workspace(Q, G, D, T, dev)
+            call("spn_sim_rank_tc", _ptr(q), _ptr(g), Q, G, D, T, _ptr(tg), _ptr(target_score), _ptr(ex), _ptr(gr), M,
+                 col_base, _ptr(rank), _ptr(grank), _ptr(ws), ws.numel(), _stream(dev))
+        else:
+            call("spn_sim_rank", _ptr(q), _ptr(g), Q, G, D, T, _ptr(tg), _ptr(target_score), _ptr(ex), _ptr(gr), M,
+                 col_base, _ptr(rank), _ptr(grank), None, 0, _stream(dev))
     return rank, grank
 
 

@@ -22,9 +22,18 @@ def t(fn, iters=20):
     for _ in range(iters): fn()
     e.record(); torch.cuda.synchronize()
     return round(s.elapsed_time(e) / iters * 1e3, 1)
-out = {"topk50_us": t(lambda: spn.sim_topk(qd, gd, 50, exclude=refd)),
-       "topk10_us": t(lambda: spn.sim_topk(qd, gd, 10, exclude=refd)),
-       "rank_us": t(lambda: spn.sim_rank(qd, gd, tgtd, exclude=refd, group=grpd)),
+out = {}
+for mode in ("fp32", "tc"):
+    out.update({f"topk50_{mode}_us": t(lambda: spn.sim_topk(qd, gd, 50, exclude=refd, mode=mode)),
+                f"topk10_{mode}_us": t(lambda: spn.sim_topk(qd, gd, 10, exclude=refd, mode=mode)),
+                f"rank_{mode}_us": t(lambda: spn.sim_rank(qd, gd, tgtd, exclude=refd, group=grpd, mode=mode))})
+out["topk50_tc_index_exact_us"] = t(lambda: spn.sim_topk(qd, gd, 50, exclude=refd, mode="tc", exact_values=False))
+out["topk10_tc_index_exact_us"] = t(lambda: spn.sim_topk(qd, gd, 10, exclude=refd, mode="tc", exact_values=False))
+n2 = torch.zeros(1, dtype=torch.int32, device=dev)
+spn.sim_topk(qd, gd, 50, exclude=refd, mode="tc", n_second_out=n2)
+out["topk50_tc_rows_second_scan"] = int(n2)
+# the three kernels of the tensor-core path, timed one by one through the profiler-free event pairs of a CUDA graph-less loop
+out.update({
        "matrix_us": t(lambda: dense(qd, gd)),
-       "torch_matmul_fp32_us": t(lambda: qd @ gd.T)}
+       "torch_matmul_fp32_us": t(lambda: qd @ gd.T)})
 print(json.dumps(out))
