@@ -232,6 +232,8 @@ int spn_sim_rank(const float* q, const float* gallery, int Q, int G, int D, int 
 int spn_sim_topk_tc(const float* q, const float* gallery, int Q, int G, int D, int T, int K, const int32_t* exclude,
                     int32_t col_base, float* out_val, int32_t* out_idx, int exact_values, int32_t* n_second, void* ws,
                     size_t ws_bytes, void* stream);
+/* spn_sim_rank_tc: target_score may be NULL when the gallery is not sharded (every target row is in `gallery`): the kernel
+ * then computes the target's exact score itself (same chain as spn_sim_target_score) and one launch is saved. */
 int spn_sim_rank_tc(const float* q, const float* gallery, int Q, int G, int D, int T, const int32_t* target,
                     const float* target_score, const int32_t* exclude, const int32_t* group, int M, int32_t col_base,
                     int32_t* rank, int32_t* group_rank, void* ws, size_t ws_bytes, void* stream);

@@ -258,15 +258,18 @@ sim_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_qh, const __grid_con
 // The reference chain of sim_rank.cu: one fp32 accumulator per score, fmaf in ascending k (max over T token rows).
 constexpr int kRowWarps = 4;
 constexpr int kChunkK = 32;
-constexpr int kChainPitch = kChunkK + 1;                        // conflict-free row walk
-constexpr int kChainFloats = 32 * kChainPitch + kChunkK + 32;   // staged rows | staged q chunk | row ids
+constexpr int kChainPitch = kChunkK + 4;                        // 16-byte aligned rows, float4 walk
+constexpr int kFewW = 128;                                      // columns per step of the <= 8-row variant
+constexpr int kFewPitch = kFewW + 4;                            // 8 rows x 4 banks: conflict-free float4 walk
+constexpr int kChainFloats = 8 * kFewPitch + kFewW + 32;        // >= 32 * kChainPitch + kChunkK + 32: rows | q | row ids
 constexpr int kBins = 1024;                                     // histogram bins of the top-K threshold search
 constexpr int kCand = 128;                                      // candidates kept above the threshold bin
 constexpr int kRowSmemFloats = kBins > kChainFloats ? kBins : kChainFloats;  // the two phases share the space
 
 // Up to 32 chains at once, one per lane: returns the chain of q . g[row] for this lane's gallery row (`row` < 0: none).
-// The warp stages 32-column chunks of the <= 32 gallery rows (coalesced 128-byte reads) and of q in shared memory and
-// every lane walks its own staged row; the loads of chunk c + 1 are in flight while chunk c is walked.
+// The warp stages 32-column chunks of the <= 32 gallery rows (16-byte loads: one instruction fetches 128 bytes of four
+// rows) and of q in shared memory and every lane walks its own staged row; the loads of chunk c + 1 are in flight while
+// chunk c is walked.
 __device__ __forceinline__ float warp_chains(const float* __restrict__ qrow, const float* __restrict__ g, int D, int row,
                                              float* sm, int lane) {
   float acc = 0.f;
@@ -276,56 +279,145 @@ __device__ __forceinline__ float warp_chains(const float* __restrict__ qrow, con
   __syncwarp();
   srows[lane] = row;
   __syncwarp();
-  float t[32], tq;
+  const int sub = lane >> 3, c4 = (lane & 7) * 4;
+  float4 t[8], tq;
+  int my_rows[8];
+#pragma unroll
+  for (int h = 0; h < 8; ++h) my_rows[h] = srows[h * 4 + sub];
   auto load_chunk = [&](int k0) {
 #pragma unroll
-    for (int r0 = 0; r0 < 32; r0 += 8) {
-      if (((have >> r0) & 0xffu) == 0) continue;  // warp-uniform
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int rr = srows[r0 + u];
-        t[r0 + u] = rr >= 0 ? g[size_t(rr) * D + k0 + lane] : 0.f;
-      }
+    for (int h = 0; h < 8; ++h) {
+      if (((have >> (h * 4)) & 0xfu) == 0) continue;  // warp-uniform
+      const int rr = my_rows[h];
+      t[h] = rr >= 0 ? *reinterpret_cast<const float4*>(g + size_t(rr) * D + k0 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    tq = qrow[k0 + lane];
+    if (lane < 8) tq = *reinterpret_cast<const float4*>(qrow + k0 + c4);
   };
   load_chunk(0);
   for (int k0 = 0; k0 < D; k0 += kChunkK) {
 #pragma unroll
-    for (int r0 = 0; r0 < 32; r0 += 8) {
-      if (((have >> r0) & 0xffu) == 0) continue;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) sm[(r0 + u) * kChainPitch + lane] = t[r0 + u];
+    for (int h = 0; h < 8; ++h) {
+      if (((have >> (h * 4)) & 0xfu) == 0) continue;
+      *reinterpret_cast<float4*>(sm + (h * 4 + sub) * kChainPitch + c4) = t[h];
     }
-    sq[lane] = tq;
+    if (lane < 8) *reinterpret_cast<float4*>(sq + c4) = tq;
     __syncwarp();
     if (k0 + kChunkK < D) load_chunk(k0 + kChunkK);
-    const float* mine = sm + lane * kChainPitch;
+    const float4* mine4 = reinterpret_cast<const float4*>(sm + lane * kChainPitch);
+    const float4* sq4 = reinterpret_cast<const float4*>(sq);
 #pragma unroll
-    for (int k = 0; k < kChunkK; ++k) acc = fmaf(sq[k], mine[k], acc);
+    for (int k = 0; k < kChunkK / 4; ++k) {
+      const float4 a = sq4[k], b = mine4[k];
+      acc = fmaf(a.x, b.x, acc);
+      acc = fmaf(a.y, b.y, acc);
+      acc = fmaf(a.z, b.z, acc);
+      acc = fmaf(a.w, b.w, acc);
+    }
     __syncwarp();
   }
   return acc;
 }
 
-// exact score of gallery entry `e` for every lane that asks (need), T = 1: one staged pass for the whole warp;
-// T = 32: entry by entry, the 32 lanes take the 32 token rows and the maximum is reduced across the warp
+// Same chains for at most 8 rows, held by lanes 0..7: 128 columns per step (one 512-byte load instruction per row, nine
+// loads in flight, a quarter of the dependent L2 round trips) -- the common case: a near-tie cluster, the target row, a
+// few unsure entries.
+__device__ __forceinline__ float warp_chains_few(const float* __restrict__ qrow, const float* __restrict__ g, int D, int row,
+                                                 float* sm, int lane) {
+  float acc = 0.f;
+  float* sq = sm + 8 * kFewPitch;
+  int* srows = reinterpret_cast<int*>(sq + kFewW);
+  __syncwarp();
+  srows[lane] = lane < 8 ? row : -1;
+  __syncwarp();
+  int rows8[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) rows8[u] = srows[u];
+  float4 t[8], tq;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load_step = [&](int k0) {
+    const bool in = k0 + lane * 4 < D;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      t[u] = (in && rows8[u] >= 0) ? *reinterpret_cast<const float4*>(g + size_t(rows8[u]) * D + k0 + lane * 4) : zero4;
+    tq = in ? *reinterpret_cast<const float4*>(qrow + k0 + lane * 4) : zero4;
+  };
+  load_step(0);
+  const float* mine = sm + (lane & 7) * kFewPitch;
+  for (int k0 = 0; k0 < D; k0 += kFewW) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) *reinterpret_cast<float4*>(sm + u * kFewPitch + lane * 4) = t[u];
+    *reinterpret_cast<float4*>(sq + lane * 4) = tq;
+    __syncwarp();
+    if (k0 + kFewW < D) load_step(k0 + kFewW);
+    const int n4 = min(kFewW, D - k0) / 4;
+    if (lane < 8 && row >= 0) {  // only the lanes that own a row walk it (a quarter of the shared-memory wavefronts)
+      const float4* mine4 = reinterpret_cast<const float4*>(mine);
+      const float4* sq4 = reinterpret_cast<const float4*>(sq);
+#pragma unroll 8
+      for (int k = 0; k < n4; ++k) {
+        const float4 a = sq4[k], b = mine4[k];
+        acc = fmaf(a.x, b.x, acc);
+        acc = fmaf(a.y, b.y, acc);
+        acc = fmaf(a.z, b.z, acc);
+        acc = fmaf(a.w, b.w, acc);
+      }
+    }
+    __syncwarp();
+  }
+  return acc;
+}
+
+// Exact scores of gallery entries for the lanes that ask: (need0, e0) and (need1, e1) are two independent requests per
+// lane (the two list positions a lane owns).  T = 1: the requests are compacted to the low lanes and served by one staged
+// pass when they fit (<= 8: the few-row variant); T = 32: entry by entry, the 32 lanes take the 32 token rows and the
+// maximum is reduced across the warp.
+__device__ __forceinline__ void warp_exact2(const float* __restrict__ qrow, const float* __restrict__ g, int D, int T,
+                                            bool need0, int e0, bool need1, int e1, float* sm, int lane, float& out0,
+                                            float& out1) {
+  out0 = out1 = -INFINITY;
+  const unsigned m0 = __ballot_sync(kFull, need0), m1 = __ballot_sync(kFull, need1);
+  const int n0 = __popc(m0), n1 = __popc(m1);
+  if (n0 + n1 == 0) return;
+  if (T == 1) {
+    if (n0 + n1 <= 32) {
+      // lane j serves request j: the j-th set bit of m0, then of m1
+      const unsigned src0 = __fns(m0, 0, lane + 1), src1 = __fns(m1, 0, lane - n0 + 1);
+      const int a = __shfl_sync(kFull, e0, src0 & 31u), b = __shfl_sync(kFull, e1, src1 & 31u);
+      const int mine = lane < n0 ? a : (lane < n0 + n1 ? b : -1);
+      const float acc = (n0 + n1 <= 8) ? warp_chains_few(qrow, g, D, mine, sm, lane) : warp_chains(qrow, g, D, mine, sm, lane);
+      const float r0 = __shfl_sync(kFull, acc, __popc(m0 & ((1u << lane) - 1u)) & 31);
+      const float r1 = __shfl_sync(kFull, acc, (n0 + __popc(m1 & ((1u << lane) - 1u))) & 31);
+      if (need0) out0 = r0;
+      if (need1) out1 = r1;
+    } else {
+      const float r0 = warp_chains(qrow, g, D, need0 ? e0 : -1, sm, lane);
+      const float r1 = warp_chains(qrow, g, D, need1 ? e1 : -1, sm, lane);
+      if (need0) out0 = r0;
+      if (need1) out1 = r1;
+    }
+    return;
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    unsigned mask = pass ? m1 : m0;
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int ee = __shfl_sync(kFull, pass ? e1 : e0, src);
+      float v = warp_chains(qrow, g, D, ee * T + lane, sm, lane);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+      if (lane == src) {
+        if (pass) out1 = v;
+        else out0 = v;
+      }
+    }
+  }
+}
 __device__ __forceinline__ float warp_exact(const float* __restrict__ qrow, const float* __restrict__ g, int D, int T,
                                             bool need, int e, float* sm, int lane) {
-  unsigned mask = __ballot_sync(kFull, need);
-  if (!mask) return -INFINITY;
-  if (T == 1) return warp_chains(qrow, g, D, need ? e : -1, sm, lane);
-  float out = -INFINITY;
-  while (mask) {
-    const int src = __ffs(mask) - 1;
-    mask &= mask - 1;
-    const int ee = __shfl_sync(kFull, e, src);
-    float v = warp_chains(qrow, g, D, ee * T + lane, sm, lane);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
-    if (lane == src) out = v;
-  }
-  return out;
+  float a, b;
+  warp_exact2(qrow, g, D, T, need, e, false, 0, sm, lane, a, b);
+  return a;
 }
 
 // per-lane gather version for the rare paths (second scan, entries within eps of the target score)
@@ -451,7 +543,7 @@ __device__ __forceinline__ bool key_before(int ca, float va, int ia, int cb, flo
 // bin (<= 128, normally ~70) which one 128-element bitonic sort orders by (S~, index); exact chains run only where S~
 // cannot decide the order (entries closer than 2 eps to a neighbour; all of the first K when exact values are
 // requested), then a 64-element bitonic sort on (cluster, exact score, index).
-__global__ void __launch_bounds__(kRowWarps * 32)
+__global__ void __launch_bounds__(kRowWarps * 32, 6)
 row_topk_kernel(const RowParams p) {
   __shared__ float row_sm[kRowWarps][kRowSmemFloats];
   __shared__ float cand_v[kRowWarps][kCand];
@@ -630,8 +722,8 @@ row_topk_kernel(const RowParams p) {
   }
   if (!rel0) c0 = INT_MAX;
   if (!rel1) c1 = INT_MAX;
-  const float e0 = warp_exact(qrow, p.g, p.D, p.T, need0, i0 - p.col_base, row_sm[wib], lane);
-  const float e1 = warp_exact(qrow, p.g, p.D, p.T, need1, i1 - p.col_base, row_sm[wib], lane);
+  float e0, e1;
+  warp_exact2(qrow, p.g, p.D, p.T, need0, i0 - p.col_base, need1, i1 - p.col_base, row_sm[wib], lane, e0, e1);
   float x0 = need0 ? e0 : v0, x1 = need1 ? e1 : v1;
   int j0 = i0, j1 = i1;
 
@@ -672,10 +764,10 @@ row_topk_kernel(const RowParams p) {
   write_topk(p, row, srow, x0, j0, x1, j1, lane);
 }
 
-__global__ void __launch_bounds__(kRowWarps * 32)
+__global__ void __launch_bounds__(kRowWarps * 32, 5)
 row_rank_kernel(const RowParams p) {
   __shared__ float chain_sm[kRowWarps][kChainFloats];
-  __shared__ int unsure_g[kRowWarps][64];
+  __shared__ int unsure_g[kRowWarps][352];  // < 64 carried (members + entries) + up to 256 per group
   const int wib = threadIdx.x >> 5;
   const int row = blockIdx.x * kRowWarps + wib;
   const int lane = threadIdx.x & 31;
@@ -684,30 +776,45 @@ row_rank_kernel(const RowParams p) {
   const float* qrow = p.q + size_t(row) * p.D;
   const int ex = p.exclude ? p.exclude[row] : -1;
   const int tg = p.target[row];
-  const float ts = p.tscore[row];
+  float ts;
+  if (p.tscore) {
+    ts = p.tscore[row];
+  } else {  // un-sharded call: the target row is here, its exact score is one more chain of this warp
+    const int t = tg - p.col_base;
+    ts = -INFINITY;
+    if (t >= 0 && t < p.G) {  // warp-uniform
+      float v = p.T == 1 ? warp_chains_few(qrow, p.g, p.D, lane == 0 ? t : -1, chain_sm[wib], lane)
+                         : warp_chains(qrow, p.g, p.D, t * p.T + lane, chain_sm[wib], lane);
+      if (p.T != 1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+      }
+      ts = __shfl_sync(kFull, v, 0);
+    }
+  }
   const float eps = row_eps(qrow, p.D, *p.gmax, lane);
   const int greg = (p.group && lane < p.M) ? p.group[size_t(row) * p.M + lane] : -2;
   int cnt = 0, gcnt = 0;
   unsigned n_unsure = 0;
-  auto in_group = [&](int idx) {
-    bool in = false;
-    for (int mm = 0; mm < p.M; ++mm) in |= (__shfl_sync(kFull, greg, mm) == idx);
-    return in;
-  };
-  // entries within eps of the target score wait in a list and are rescored (up to 32 at a time) with the exact chain
-  auto flush = [&](unsigned n) {
-    const bool have = unsigned(lane) < n;
-    const int g = have ? unsure_g[wib][lane] : 0;
-    __syncwarp();
-    const float e = warp_exact(qrow, p.g, p.D, p.T, have, g, chain_sm[wib], lane);
-    const int idx = p.col_base + g;
-    const bool before = have && sorts_before(e, idx, ts, tg);
-    cnt += __popc(__ballot_sync(kFull, before));
-    if (p.group) {
-      const bool in = in_group(idx);  // every lane takes part in the shuffles
-      gcnt += __popc(__ballot_sync(kFull, before && in));
+  // entries within eps of the target score wait in a list (a stack) and are rescored, up to 32 at a time, with the
+  // exact chain -- one call site, after each group of 256 entries.  Group members (the CIRR subset, validate.py:140-142)
+  // are looked up directly, one per lane, instead of testing every gallery entry for membership; an unsure member goes
+  // on the same list, tagged (~g).
+  if (p.group) {
+    const int ml = greg - p.col_base;
+    bool valid = lane < p.M && ml >= 0 && ml < p.G && greg != ex && greg != tg;
+    for (int mm = 0; mm < p.M; ++mm) {  // a member listed twice counts once
+      const int o = __shfl_sync(kFull, greg, mm);
+      if (mm < lane && o == greg) valid = false;
     }
-  };
+    const float a = valid ? srow[ml] : -INFINITY;
+    const bool before = valid && a > ts + eps;
+    const bool unsure = valid && !before && !(a < ts - eps);
+    gcnt = __popc(__ballot_sync(kFull, before));
+    const unsigned um = __ballot_sync(kFull, unsure);
+    if (unsure) unsure_g[wib][__popc(um & ((1u << lane) - 1u))] = ~ml;
+    n_unsure = __popc(um);
+  }
   for (int g0 = 0; g0 < p.G; g0 += 256) {
     float av[8];
 #pragma unroll
@@ -727,25 +834,24 @@ row_rank_kernel(const RowParams p) {
       if (um) {
         if (unsure) unsure_g[wib][n_unsure + __popc(um & ((1u << lane) - 1u))] = g;
         n_unsure += __popc(um);
-        __syncwarp();
-        if (n_unsure >= 32u) {
-          flush(32u);
-          n_unsure -= 32u;
-          const int carry = unsigned(lane) < n_unsure ? unsure_g[wib][32 + lane] : 0;
-          __syncwarp();
-          if (unsigned(lane) < n_unsure) unsure_g[wib][lane] = carry;
-          __syncwarp();
-        }
       }
-      const unsigned bm = __ballot_sync(kFull, before);
-      cnt += __popc(bm);
-      if (p.group && bm) {
-        const bool in = in_group(idx);
-        gcnt += __popc(__ballot_sync(kFull, before && in));
-      }
+      cnt += __popc(__ballot_sync(kFull, before));
+    }
+    const bool last = g0 + 256 >= p.G;
+    while (n_unsure >= 32u || (last && n_unsure > 0u)) {
+      const unsigned take = n_unsure < 32u ? n_unsure : 32u;
+      __syncwarp();
+      const bool have = unsigned(lane) < take;
+      const int raw = have ? unsure_g[wib][n_unsure - take + lane] : 0;
+      const bool member = raw < 0;
+      const int g = member ? ~raw : raw;
+      n_unsure -= take;
+      const float e = warp_exact(qrow, p.g, p.D, p.T, have, g, chain_sm[wib], lane);
+      const bool before = have && sorts_before(e, p.col_base + g, ts, tg);
+      cnt += __popc(__ballot_sync(kFull, before && !member));
+      gcnt += __popc(__ballot_sync(kFull, before && member));
     }
   }
-  if (n_unsure) flush(n_unsure);
   if (lane == 0) {
     if (cnt) atomicAdd(&p.rank[row], cnt);
     if (p.group_rank && gcnt) atomicAdd(&p.group_rank[row], gcnt);
@@ -764,7 +870,8 @@ target_score_warp_kernel(const float* __restrict__ q, const float* __restrict__ 
   const int t = target[row] - col_base;
   float v = -INFINITY;
   if (t >= 0 && t < G) {  // warp-uniform
-    v = warp_chains(q + size_t(row) * D, g, D, T == 1 ? (lane == 0 ? t : -1) : t * T + lane, chain_sm[wib], lane);
+    v = T == 1 ? warp_chains_few(q + size_t(row) * D, g, D, lane == 0 ? t : -1, chain_sm[wib], lane)
+               : warp_chains(q + size_t(row) * D, g, D, t * T + lane, chain_sm[wib], lane);
     if (T != 1) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
@@ -872,7 +979,8 @@ int tc_run(bool rank_mode, const float* q, const float* g, int Q, int G, int D, 
     r.n_second = n_second;
     if (r.exclude) r.exclude += qb0;
     if (rank_mode) {
-      r.target += qb0; r.tscore += qb0;
+      r.target += qb0;
+      if (r.tscore) r.tscore += qb0;
       if (r.group) r.group += size_t(qb0) * r.M;
       r.rank += qb0;
       if (r.group_rank) r.group_rank += qb0;
@@ -913,7 +1021,7 @@ int sim_topk_tc(const float* q, const float* g, int Q, int G, int D, int T, int 
 int sim_rank_tc(const float* q, const float* g, int Q, int G, int D, int T, const int* target, const float* tscore,
                 const int* exclude, const int* group, int M, int col_base, int* rank, int* group_rank, void* ws,
                 size_t ws_bytes, cudaStream_t stream) {
-  SPN_REQUIRE(target && tscore && rank, SPN_ERR_BAD_ARG, "sim_rank needs target, target_score and rank");
+  SPN_REQUIRE(target && rank, SPN_ERR_BAD_ARG, "sim_rank_tc needs target and rank");
   SPN_REQUIRE(!group || (M >= 1 && M <= 32 && group_rank), SPN_ERR_BAD_SHAPE, "sim_rank: group needs 1 <= M <= 32 and group_rank");
   RowParams rp{};
   rp.K = 1; rp.col_base = col_base; rp.exclude = exclude; rp.target = target; rp.tscore = tscore; rp.group = group; rp.M = M;

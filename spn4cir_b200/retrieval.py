@@ -162,7 +162,8 @@ def sim_rank(query: torch.Tensor, gallery: torch.Tensor, target, exclude=None, g
     tg, ex, gr = _i32(target, dev), _i32(exclude, dev), _i32(group, dev)
     M = 0 if gr is None else gr.shape[1]
     with torch.cuda.device(dev):
-        if target_score is None:
+        use_tc = _use_tc(mode, Q, G, D, T)
+        if target_score is None and not use_tc:  # (the tensor-core kernel scores the target row itself)
             target_score = torch.empty(Q, dtype=torch.float32, device=dev)
             call("spn_sim_target_score", _ptr(q), _ptr(g), Q, G, D, T, _ptr(tg), col_base, _ptr(target_score),
                  _stream(dev))
@@ -170,7 +171,7 @@ def sim_rank(query: torch.Tensor, gallery: torch.Tensor, target, exclude=None, g
         grank = None
         if gr is not None:
             grank = group_rank_out if group_rank_out is not None else torch.zeros(Q, dtype=torch.int32, device=dev)
-        if _use_tc(mode, Q, G, D, T):
+        if use_tc:
             ws = _tc_workspace(Q, G, D, T, dev)
             call("spn_sim_rank_tc", _ptr(q), _ptr(g), Q, G, D, T, _ptr(tg), _ptr(target_score), _ptr(ex), _ptr(gr), M,
                  col_base, _ptr(rank), _ptr(grank), _ptr(ws), ws.numel(), _stream(dev))
