@@ -233,7 +233,7 @@ def cirr_test_dicts_from_features(predicted_features: torch.Tensor, index_featur
     lut = {n: i for i, n in enumerate(index_names)}
     gallery = _normalize_gallery(index_features)
     k = min(50, len(index_names) - 1)
-    _, top = sim_topk(predicted_features, gallery, k, exclude=ref_ids)
+    _, top = sim_topk(predicted_features, gallery, k, exclude=ref_ids, exact_values=False)  # only the names are used
     top = top.cpu().tolist()
     # subset ranking: the (<= 6)-member groups are scored as tiny per-query galleries on the device
     grp_ids = torch.tensor([[lut[m] for m in row] for row in group_members], dtype=torch.int64,
