@@ -16,6 +16,7 @@
 //        rank : entries farther than eps from the target score are counted from S~, the others are rescored exactly.
 // The tensor-core sweep decides nothing by itself: it only prunes which entries need the exact chain.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "bank_ce.cuh"
 #include "ptx.cuh"
@@ -891,7 +892,11 @@ TcLayout tc_layout(int Q, int G, int D, int T) {
   TcLayout L{};
   auto up = [](size_t x) { return (x + 255) / 256 * 256; };
   L.Gp = (G + 3) / 4 * 4;
-  const size_t budget = size_t(512) << 20;  // score block budget
+  size_t budget = size_t(512) << 20;  // score block budget (SPN_TC_SCORE_BLOCK_MB overrides: tests force several blocks)
+  if (const char* e = getenv("SPN_TC_SCORE_BLOCK_MB")) {
+    const long v = atol(e);
+    if (v >= 1 && v <= 65536) budget = size_t(v) << 20;
+  }
   long long qb = (long long)(budget / (size_t(L.Gp) * 4)) / 128 * 128;
   if (qb < 128) qb = 128;
   const long long qpad = (long long)(Q + 127) / 128 * 128;

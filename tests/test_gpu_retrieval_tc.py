@@ -190,3 +190,29 @@ def test_tc_mode_rejects_unsupported_shapes():
     # auto quietly keeps the fp32 kernel for them
     v, i = spn.sim_topk(q, g, 57, mode="auto")
     assert i.shape == (10, 57)
+
+
+def test_query_blocks(monkeypatch):
+    """S~ is produced in query blocks when [Q, G] fp32 would exceed the block budget (pair-mining sizes); force 1 MiB
+    blocks (128 queries at G = 2000) and compare with the fp32 kernels across the block boundaries."""
+    monkeypatch.setenv("SPN_TC_SCORE_BLOCK_MB", "1")
+    Q, G, D = 300, 2000, 128
+    q, g, reference, target, groups = _case(Q, G, D, 1, 60)
+    v0, i0 = spn.sim_topk(q, g, 20, exclude=reference, mode="fp32")
+    v1, i1 = spn.sim_topk(q, g, 20, exclude=reference, mode="tc")
+    assert torch.equal(i0, i1) and _same_bits(v0, v1)
+    r0, g0 = spn.sim_rank(q, g, target, exclude=reference, group=groups, mode="fp32")
+    r1, g1 = spn.sim_rank(q, g, target, exclude=reference, group=groups, mode="tc")
+    assert torch.equal(r0, r1) and torch.equal(g0, g1)
+    torch.cuda.synchronize()
+
+
+def test_pair_mining_shape():
+    """N x N similarities with the diagonal excluded (zscir/srm_utils.py:147-150 shape, scaled down): 6000 x 6000 x 768."""
+    N, D, K = 6000, 768, 50
+    gen = torch.Generator().manual_seed(61)
+    x = F.normalize(torch.randn(N, D, generator=gen), dim=-1).to(DEV)
+    me = torch.arange(N, dtype=torch.int32)
+    v0, i0 = spn.sim_topk(x, x, K, exclude=me, mode="fp32")
+    v1, i1 = spn.sim_topk(x, x, K, exclude=me, mode="tc")
+    assert torch.equal(i0, i1) and _same_bits(v0, v1)
