@@ -953,14 +953,13 @@ int tc_run(bool rank_mode, const float* q, const float* g, int Q, int G, int D, 
   if ((rc = make_tmap_bf16_2d(&tgl, gl, uint64_t(grows), uint64_t(D), kBN)) != SPN_OK) return rc;
 
   const size_t smem = tc_gemm_smem();
-  static bool attr_done = false;
-  if (!attr_done) {
-    SPN_REQUIRE(size_t(device_max_smem_optin()) >= smem, SPN_ERR_CUDA, "device offers %d B of shared memory, %zu needed",
-                device_max_smem_optin(), smem);
+  // per launch, like the bank-CE kernels: the attribute is per device and the call costs a few microseconds of host time
+  SPN_REQUIRE(size_t(device_max_smem_optin()) >= smem, SPN_ERR_CUDA, "device offers %d B of shared memory, %zu needed",
+              device_max_smem_optin(), smem);
+  if (T == 1)
     SPN_CUDA_CHECK(cudaFuncSetAttribute(sim_tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  else
     SPN_CUDA_CHECK(cudaFuncSetAttribute(sim_tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    attr_done = true;
-  }
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
 
