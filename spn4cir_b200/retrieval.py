@@ -71,6 +71,11 @@ def _tc_workspace(Q: int, G: int, D: int, T: int, dev) -> torch.Tensor:
     return ws
 
 
+def release_workspaces() -> None:
+    """Drop the cached tensor-core workspaces (they grow to the largest problem seen: ~0.6 GB at pair-mining sizes)."""
+    _ws_cache.clear()
+
+
 def sim_topk(query: torch.Tensor, gallery: torch.Tensor, k: int, exclude=None, col_base: int = 0, mode: str = "auto",
              exact_values: bool = True, n_second_out: Optional[torch.Tensor] = None):
     """Top-``k`` gallery entries per query: returns (values [Q, k] fp32, indices [Q, k] int32, global).
