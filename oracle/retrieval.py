@@ -148,3 +148,30 @@ def srm_out(clip_image_feats: torch.Tensor, clip_text_feats: torch.Tensor, srm_i
         m_fn[index] = t2t_ranks_neg[index][:K]                                # :177,180
         r_fn[index] = i2i_ranks_neg[r][:K]                                    # :178,181
     return r_fn, m_fn, t_fn, rt, rm, mt
+
+
+def i2i_rank_window(image_feats: torch.Tensor, rank_lo: int, rank_hi=None) -> torch.Tensor:
+    """Restatement of /root/reference/zscir/get_cir_data.py:33-34 + :60-64 (CIRR twin :119-123):
+    `i2i_ranks = torch.argsort(sims_intra_i2i, descending=True)` with `sims_intra_i2i = feats @ feats.T`
+    (zscir/srm_utils.py:123), then `i2i_ranks[i].tolist()[rank:rank_max]` (or `[rank:]` when rank_max <= rank) for every
+    row.  The reference's argsort is not stable; ties are broken by the lower index here (the rule of the CUDA path)."""
+    sims = image_feats @ image_feats.T
+    ranks = torch.argsort(sims, descending=True, stable=True)                  # :34
+    if rank_hi is not None and rank_hi > rank_lo:                              # :60-61
+        return ranks[:, rank_lo:rank_hi]
+    return ranks[:, rank_lo:]                                                  # :62-64
+
+
+def get_diff_id(i: int, N: int, k: int, i2i_ranks_row=None, rank_lo: int = -1, rank_hi: int = -1, rng=None):
+    """get_diff_id, /root/reference/zscir/get_cir_data.py:58-68, with the module globals passed in."""
+    import random as _random
+    rng = rng or _random
+    if rank_lo >= 0:                                                           # :59
+        if rank_hi > rank_lo:
+            range_target = i2i_ranks_row.tolist()[rank_lo:rank_hi]             # :61
+        else:
+            range_target = i2i_ranks_row.tolist()[rank_lo:]                    # :63
+    else:
+        range_target = list(range(N))                                          # :65
+        range_target.remove(i)                                                 # :66
+    return rng.sample(range_target, k)                                         # :67

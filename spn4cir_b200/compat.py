@@ -277,3 +277,38 @@ def srm_out(clip_image_feats: torch.Tensor, clip_text_feats: torch.Tensor, srm_i
     m_fn = sim_topk(st, st, K, exclude=me)[1].to(torch.int64)         # (:177,180)
     r_fn = sim_topk(si[ref], si, K, exclude=ref)[1].to(torch.int64)   # (:178,181)
     return r_fn, m_fn, t_fn, rt, rm, mt
+
+
+def i2i_rank_window(image_feats: torch.Tensor, rank_lo: int, rank_hi: Optional[int] = None, *, block_rows: int = 2048):
+    """Rows ``[rank_lo:rank_hi]`` of ``i2i_ranks = torch.argsort(sims_intra_i2i, descending=True)``
+    (/root/reference/zscir/get_cir_data.py:33-34 and the slices of ``get_diff_id`` :60-64; the CIRR twin :119-123):
+    for every image the gallery indices whose similarity rank falls in the window (``rank_hi=None`` or
+    ``rank_hi <= rank_lo``: to the end, as :61-64 do).  The N x N matrix never exists: blocks of ``block_rows`` rows of
+    exact fp32 scores (``spn_sim_matrix``) are ordered on the device (descending, ties -> lower index) and only the
+    window is kept.  One-off preprocessing; the ordering itself is torch's stable sort.  Returns int64 ``[N, width]``."""
+    _require_cuda(image_feats, "image_feats")
+    f = image_feats.detach().float().contiguous()
+    n = f.shape[0]
+    hi = n if (rank_hi is None or rank_hi <= rank_lo) else min(int(rank_hi), n)
+    lo = min(max(int(rank_lo), 0), hi)
+    out = torch.empty((n, hi - lo), dtype=torch.int64, device=f.device)
+    for r0 in range(0, n, block_rows):
+        blk = f[r0:r0 + block_rows]
+        sim = inference_sim(blk, f)
+        if sim.dim() == 1:
+            sim = sim[None, :]
+        out[r0:r0 + blk.shape[0]] = torch.sort(sim, dim=1, descending=True, stable=True).indices[:, lo:hi]
+    return out
+
+
+def get_diff_id(i: int, N: int, k: int, rank_window_row=None, rng=random) -> List[int]:
+    """``get_diff_id`` of /root/reference/zscir/get_cir_data.py:58-68: k distinct partner images for image ``i`` --
+    from its rank window (a row of :func:`i2i_rank_window`) when one is given (``--i2i_rank >= 0``), else from
+    ``range(N)`` without ``i``; the SAME ``random.sample`` call on the same list, so a seeded run draws the reference's
+    pairs."""
+    if rank_window_row is not None:
+        range_target = rank_window_row.tolist() if hasattr(rank_window_row, "tolist") else list(rank_window_row)
+    else:
+        range_target = list(range(N))
+        range_target.remove(i)
+    return rng.sample(range_target, k)

@@ -180,3 +180,33 @@ def test_srm_pair_mining_matches_oracle():
         assert (h.cpu() == w).float().mean() > 0.995, name
     for name, w, h in zip(("rt", "rm", "mt"), want[3:], got[3:]):
         assert (h.cpu() - w).abs().max() <= 1 and (h.cpu() == w).float().mean() > 0.98, name
+
+
+def test_rank_window_matches_oracle():
+    """compat.i2i_rank_window (zscir/get_cir_data.py:33-34,58-68): the [lo:hi] slice of every row of the full
+    descending ranking.  Exact against a stable argsort of the device's own scores; against the CPU restatement (whose
+    matmul sums in another order) up to near-ties; and the seeded partner draw picks the same images."""
+    import random
+    g = torch.Generator().manual_seed(9)
+    n, D, lo, hi = 1500, 128, 400, 700
+    f = torch.nn.functional.normalize(torch.randn(n, D, generator=g), dim=-1)
+    got = compat.i2i_rank_window(f.to(DEV), lo, hi, block_rows=512)
+    sim_dev = compat.inference_sim(f.to(DEV), f.to(DEV)).cpu()
+    want_dev = torch.argsort(sim_dev, descending=True, stable=True)[:, lo:hi]
+    assert got.shape == (n, hi - lo) and torch.equal(got.cpu(), want_dev)
+    want = oretr.i2i_rank_window(f, lo, hi)
+    sim = (f @ f.T).numpy()
+    assert_same_up_to_ties(got.cpu().numpy(), want.numpy(), sim)
+    tail = compat.i2i_rank_window(f.to(DEV), 1400, 0)           # rank_max <= rank: to the end (:62-64)
+    assert tail.shape == (n, 100) and torch.equal(tail.cpu(), torch.argsort(sim_dev, descending=True, stable=True)[:, 1400:])
+    ranks_full = torch.argsort(sim_dev, descending=True, stable=True)
+    for i in (0, 7, 1499):
+        random.seed(123 + i)
+        a = compat.get_diff_id(i, n, 5, got[i].cpu())
+        random.seed(123 + i)
+        b = oretr.get_diff_id(i, n, 5, ranks_full[i], lo, hi)
+        assert a == b
+    random.seed(5)
+    a = compat.get_diff_id(3, n, 4)
+    random.seed(5)
+    assert a == oretr.get_diff_id(3, n, 4) and 3 not in a

@@ -48,3 +48,26 @@ def test_shard_bounds_cover_the_bank_once():
         assert all(spans[k][1] == spans[k + 1][0] or spans[k + 1][0] == spans[k + 1][1] for k in range(r - 1))
         if covered is not None:
             assert covered == list(range(n))
+
+
+def test_rank_window_draw_matches_restated_reference():
+    """get_diff_id (zscir/get_cir_data.py:58-68): the compat draw from a rank-window row uses the same random.sample call
+    on the same list as the restated reference, with and without a window."""
+    import random
+    from oracle import retrieval as oretr
+    from spn4cir_b200 import compat
+    g = torch.Generator().manual_seed(1)
+    f = torch.nn.functional.normalize(torch.randn(50, 16, generator=g), dim=-1)
+    w = oretr.i2i_rank_window(f, 10, 20)
+    assert w.shape == (50, 10) and oretr.i2i_rank_window(f, 45, 0).shape == (50, 5)
+    full = torch.argsort(f @ f.T, descending=True, stable=True)
+    assert torch.equal(w, full[:, 10:20])
+    for i in (0, 4, 49):
+        random.seed(10 + i)
+        a = compat.get_diff_id(i, 50, 3, w[i])
+        random.seed(10 + i)
+        assert a == oretr.get_diff_id(i, 50, 3, full[i], 10, 20) and set(a) <= set(w[i].tolist())
+    random.seed(2)
+    a = compat.get_diff_id(4, 50, 3)
+    random.seed(2)
+    assert a == oretr.get_diff_id(4, 50, 3) and 4 not in a
