@@ -151,7 +151,7 @@ def srm_out(clip_image_feats: torch.Tensor, clip_text_feats: torch.Tensor, srm_i
 
 
 def i2i_rank_window(image_feats: torch.Tensor, rank_lo: int, rank_hi=None) -> torch.Tensor:
-    """Restatement of /root/reference/zscir/get_cir_data.py:33-34 + :60-64 (CIRR twin :119-123):
+    """Restatement of /root/reference/zscir/get_cir_data.py:33-34 + :60-64 (CIRR twin :106-109,131-141):
     `i2i_ranks = torch.argsort(sims_intra_i2i, descending=True)` with `sims_intra_i2i = feats @ feats.T`
     (zscir/srm_utils.py:123), then `i2i_ranks[i].tolist()[rank:rank_max]` (or `[rank:]` when rank_max <= rank) for every
     row.  The reference's argsort is not stable; ties are broken by the lower index here (the rule of the CUDA path)."""

@@ -281,7 +281,7 @@ def srm_out(clip_image_feats: torch.Tensor, clip_text_feats: torch.Tensor, srm_i
 
 def i2i_rank_window(image_feats: torch.Tensor, rank_lo: int, rank_hi: Optional[int] = None, *, block_rows: int = 2048):
     """Rows ``[rank_lo:rank_hi]`` of ``i2i_ranks = torch.argsort(sims_intra_i2i, descending=True)``
-    (/root/reference/zscir/get_cir_data.py:33-34 and the slices of ``get_diff_id`` :60-64; the CIRR twin :119-123):
+    (/root/reference/zscir/get_cir_data.py:33-34 and the slices of ``get_diff_id`` :60-64; the CIRR twin :106-109,131-141):
     for every image the gallery indices whose similarity rank falls in the window (``rank_hi=None`` or
     ``rank_hi <= rank_lo``: to the end, as :61-64 do).  The N x N matrix never exists: blocks of ``block_rows`` rows of
     exact fp32 scores (``spn_sim_matrix``) are ordered on the device (descending, ties -> lower index) and only the
