@@ -10,10 +10,16 @@
 //                             epilogue (T = 32: the max over each entry's 32 token columns is taken in registers)
 //                             -> S~ [Q, G] fp32 (L2-resident at validation sizes; |S~ - S| <= eps = 4e-5 |q| max|g|)
 //   3. row_topk_kernel / row_rank_kernel   one warp per query row over S~:
-//        top-K: approximate top-64 list -> the 64 candidates are rescored with the exact fp32 chain and re-sorted;
-//               the row is certified when (64th approximate score + eps) < (K-th exact score); otherwise a second scan
-//               rescoring every outside entry within eps of the K-th exact score completes it.  K <= 56.
-//        rank : entries farther than eps from the target score are counted from S~, the others are rescored exactly.
+//        top-K: shared-memory histogram of the row -> bin of the 64th best -> the <= 128 entries at or above it are
+//               compacted and bitonic-sorted by (S~, index) -> window of 64.  Entries closer than 2 eps to a neighbour
+//               (S~ cannot order them) are rescored with the exact fp32 chain -- all K returned entries when exact
+//               values are requested -- and a 64-element bitonic sort on (cluster, exact score, index) finishes.  The
+//               row is certified when (64th S~ + 2 eps) < (K-th S~); otherwise (plateaus wider than the window) it
+//               takes the general path: all 64 rescored and a second scan rescoring every outside entry within eps of
+//               the K-th exact score.  K <= 56.
+//        rank : the target's exact score (one chain, or the caller's value when the gallery is sharded); entries
+//               farther than eps from it are counted from S~, the others are rescored exactly.
+//      The decision rules are restated and fuzzed on the CPU in tests/test_tc_decision_model.py.
 // The tensor-core sweep decides nothing by itself: it only prunes which entries need the exact chain.
 #include <cuda_bf16.h>
 #include <stdlib.h>
