@@ -61,9 +61,10 @@ _ws_cache = {}
 
 
 def _tc_workspace(Q: int, G: int, D: int, T: int, dev) -> torch.Tensor:
-    """Workspace of the tensor-core path (split operands + one S~ block), kept per device and grown on demand."""
+    """Workspace of the tensor-core path (split operands + one S~ block), kept per device and stream, grown on demand."""
     need = _lib.workspace_bytes(OP_SIM_TC, Q, G, D, T, 0)
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    # one workspace per (device, stream): calls issued on different streams may overlap on the GPU
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream(dev))
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.uint8, device=dev)
