@@ -392,7 +392,7 @@ def run_ours(args, cfg):
                         "loss_read_back": loss_e2e, "mode": e2e_mode,
                         "note": "pinned host q/labels -> device, fwd+bwd through the public call, loss + dq back to pinned host memory, every step; "
                                 "copy-in / compute / copy-out of neighbouring steps overlap on three event-chained streams (3 slots); one event pair around the K steps, no L2 flush "
-                                "(working set 230 MB > 126 MB L2); the bank stays resident in HBM",
+                                "(working set 230 MB > 126 MB L2: `value` above pays a fully cold L2 before every step, this loop does not); the bank stays resident in HBM",
                         "serial": {"value": (B * world) * args.steps / t_e2e_serial, "ms_per_step": t_e2e_serial / args.steps * 1e3,
                                    "note": "the same step with its copies serialised on one stream, L2 flushed before each (latency of one isolated step)"}},
                 "gpu_launches": (5 if sharded else 3) * args.steps,
