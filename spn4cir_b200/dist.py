@@ -61,16 +61,74 @@ def global_maxnorm(bank, group=None) -> torch.Tensor:
     return bank._maxnorm_global
 
 
-def _sharded_sweep(q_local, bank, labels_local, inv_tau, eps, tau_grad, group):
+class _CudaShardCompute:
+    """The per-rank compute of the sharded step: the C-ABI calls of the fused path (spn_cast_to_bf16, spn_bank_ce_prep,
+    spn_bank_ce_fused, spn_bank_ce_finalize).  ``tests/test_dist_gloo.py`` swaps in a CPU emulation of the same sums so
+    that the exchange below runs over gloo without a GPU."""
+
+    def cast(self, q_local):
+        from .ops import cast_to_bf16
+        return cast_to_bf16(q_local)
+
+    def maxnorm(self, bank, group):
+        return global_maxnorm(bank, group)
+
+    def prep(self, q_all, lab_all, bank, inv_tau, maxnorm):
+        """-> ref [Bt]: this shard's static soft-max reference (owner rows clamped around the target logit)."""
+        from ._lib import call
+        from .ops import _TORCH2SPN, _ptr, _stream
+        dev = q_all.device
+        ref = torch.empty(q_all.shape[0], dtype=torch.float32, device=dev)
+        q16b = torch.empty_like(q_all)
+        with torch.cuda.device(dev):
+            call("spn_bank_ce_prep", _ptr(q_all), _TORCH2SPN[q_all.dtype], _ptr(bank.data), _ptr(lab_all), inv_tau,
+                 _ptr(maxnorm), q_all.shape[0], bank.N, q_all.shape[1], bank.T, bank.row_base, _ptr(q16b), _ptr(ref),
+                 _stream(dev))
+        return ref
+
+    def fused(self, q_all, lab_all, ref, bank, inv_tau, tau_grad):
+        """-> o_acc [Bt, D], bank_t [Bt, D], vec [3, Bt] (l_acc, s_t, es_acc), lbl_row [Bt] for this shard."""
+        from ._lib import call
+        from .ops import _ptr, _stream, fused_scratch
+        Bt, D = q_all.shape
+        dev = q_all.device
+        o_acc = torch.empty((Bt, D), dtype=torch.float32, device=dev)
+        bank_t = torch.empty((Bt, D), dtype=torch.float32, device=dev)
+        vec = torch.empty((3, Bt), dtype=torch.float32, device=dev)  # l_acc, s_t, es_acc
+        lbl_row = torch.empty(Bt, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            ws, ws_bytes = fused_scratch(Bt, bank, dev)
+            call("spn_bank_ce_fused", _ptr(q_all), _ptr(bank.data), _ptr(lab_all), _ptr(ref), inv_tau, Bt, bank.N, D,
+                 bank.T, bank.row_base, 1, _ptr(o_acc), _ptr(vec[0]), _ptr(vec[1]), _ptr(lbl_row),
+                 _ptr(vec[2]) if tau_grad else None, _ptr(bank_t), _ptr(ws), ws_bytes, _stream(dev))
+        return o_acc, bank_t, vec, lbl_row
+
+    def finalize(self, sw, bank, inv_tau, B, eps):
+        from .ops import _fused_finalize
+        _, _, loss, dq_unit, ddot = _fused_finalize(sw, bank, inv_tau, B, eps, True)
+        return loss, dq_unit, ddot
+
+
+def _reduce_scatter_sum(out: torch.Tensor, inp: torch.Tensor, rank: int, group) -> None:
+    """out = rows [rank * B, (rank + 1) * B) of the sum of `inp` over the group.  NCCL: one reduce_scatter; gloo (CPU tests)
+    has no reduce_scatter: all_reduce + slice."""
+    if dist.get_backend(group) == "gloo":
+        tmp = inp.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+        out.copy_(tmp[rank * out.shape[0]:(rank + 1) * out.shape[0]])
+    else:
+        dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
+
+
+def _sharded_sweep(q_local, bank, labels_local, inv_tau, eps, tau_grad, group, compute=None):
     """The sharded training step without autograd: every rank sweeps its shard for ALL queries of the step, the additive
     partials travel in two reduce_scatters and one small all_reduce, each rank finalises its own rows.
     Returns (loss_mean_of_local_queries, dq_unit [B, D] fp32, dlogit_dot | None)."""
-    from ._lib import call
-    from .ops import _TORCH2SPN, _fused_finalize, _ptr, _stream, cast_to_bf16, fused_scratch
+    compute = compute or _CudaShardCompute()
     rank, world = _world(group)
     B, D = q_local.shape
     dev = q_local.device
-    q16 = cast_to_bf16(q_local)
+    q16 = compute.cast(q_local)
     if world > 1:
         q_all = torch.empty((world * B, D), dtype=q16.dtype, device=dev)
         dist.all_gather_into_tensor(q_all, q16, group=group)
@@ -78,34 +136,21 @@ def _sharded_sweep(q_local, bank, labels_local, inv_tau, eps, tau_grad, group):
         dist.all_gather_into_tensor(lab_all, labels_local, group=group)
     else:
         q_all, lab_all = q16, labels_local
-    Bt = q_all.shape[0]
-    maxnorm = global_maxnorm(bank, group)
-    ref = torch.empty(Bt, dtype=torch.float32, device=dev)
-    q16b = torch.empty_like(q_all)
-    o_acc = torch.empty((Bt, D), dtype=torch.float32, device=dev)
-    bank_t = torch.empty((Bt, D), dtype=torch.float32, device=dev)
-    vec = torch.empty((3, Bt), dtype=torch.float32, device=dev)  # l_acc, s_t, es_acc
-    lbl_row = torch.empty(Bt, dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
-        st = _stream(dev)
-        call("spn_bank_ce_prep", _ptr(q_all), _TORCH2SPN[q_all.dtype], _ptr(bank.data), _ptr(lab_all), inv_tau,
-             _ptr(maxnorm), Bt, bank.N, D, bank.T, bank.row_base, _ptr(q16b), _ptr(ref), st)
-        if world > 1:  # owner's clamped reference wins over the other ranks' Cauchy-Schwarz bound
-            dist.all_reduce(ref, op=dist.ReduceOp.MIN, group=group)
-        ws, ws_bytes = fused_scratch(Bt, bank, dev)
-        call("spn_bank_ce_fused", _ptr(q_all), _ptr(bank.data), _ptr(lab_all), _ptr(ref), inv_tau, Bt, bank.N, D,
-             bank.T, bank.row_base, 1, _ptr(o_acc), _ptr(vec[0]), _ptr(vec[1]), _ptr(lbl_row),
-             _ptr(vec[2]) if tau_grad else None, _ptr(bank_t), _ptr(ws), ws_bytes, st)
+    maxnorm = compute.maxnorm(bank, group)
+    ref = compute.prep(q_all, lab_all, bank, inv_tau, maxnorm)
+    if world > 1:  # owner's clamped reference wins over the other ranks' Cauchy-Schwarz bound
+        dist.all_reduce(ref, op=dist.ReduceOp.MIN, group=group)
+    o_acc, bank_t, vec, lbl_row = compute.fused(q_all, lab_all, ref, bank, inv_tau, tau_grad)
     if world > 1:
         # additive partials: two reduce_scatters ([Bt, D] each) + one small all_reduce ([3, Bt]); the target
         # logit is owner-only, so non-owners contribute 0 and the sum is the value
         vec[1] = torch.where(lbl_row >= 0, vec[1], torch.zeros_like(vec[1]))
         if not tau_grad:
             vec[2].zero_()
-        o_mine = torch.empty((B, D), dtype=torch.float32, device=dev)
-        t_mine = torch.empty((B, D), dtype=torch.float32, device=dev)
-        dist.reduce_scatter_tensor(o_mine, o_acc, op=dist.ReduceOp.SUM, group=group)
-        dist.reduce_scatter_tensor(t_mine, bank_t, op=dist.ReduceOp.SUM, group=group)
+        o_mine = torch.empty((B, D), dtype=o_acc.dtype, device=dev)
+        t_mine = torch.empty((B, D), dtype=bank_t.dtype, device=dev)
+        _reduce_scatter_sum(o_mine, o_acc, rank, group)
+        _reduce_scatter_sum(t_mine, bank_t, rank, group)
         dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
         sl = slice(rank * B, (rank + 1) * B)
         sw = dict(o_acc=o_mine, bank_t=t_mine, l_acc=vec[0, sl].contiguous(), s_t=vec[1, sl].contiguous(),
@@ -113,8 +158,7 @@ def _sharded_sweep(q_local, bank, labels_local, inv_tau, eps, tau_grad, group):
     else:
         sw = dict(o_acc=o_acc, bank_t=bank_t, l_acc=vec[0], es_acc=vec[2] if tau_grad else None, s_t=vec[1], ref=ref,
                   q16=q16)
-    _, _, loss, dq_unit, ddot = _fused_finalize(sw, bank, inv_tau, B, eps, True)
-    return loss, dq_unit, ddot
+    return compute.finalize(sw, bank, inv_tau, B, eps)
 
 
 class _ShardedBankCE(torch.autograd.Function):

@@ -74,3 +74,98 @@ def test_two_rank_merge_over_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert out.get(timeout=5) == "ok"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The fused sharded training step (spn4cir_b200.dist._sharded_sweep: what `bench.py --bank-sharded` and
+# bank_infonce_sharded run): the exchange -- all_gather of the queries, MIN all-reduce of the static soft-max reference,
+# reduce_scatter of the additive partials, all_reduce of the row sums, per-rank finalize -- is product code and runs here
+# over gloo; the per-rank CUDA calls are replaced by a CPU emulation of the SAME sums (include/spn_b200.h:
+# spn_bank_ce_prep / spn_bank_ce_fused / spn_bank_ce_finalize) in fp64.
+class CpuShardCompute:
+    def cast(self, q_local):
+        return q_local.to(torch.bfloat16).double()  # the kernels score the bf16-rounded query
+
+    def maxnorm(self, bank, group):
+        mx = bank.data.norm(dim=-1).max().reshape(1).clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+        return mx
+
+    def prep(self, q_all, lab_all, bank, inv_tau, maxnorm):
+        # prep_query_kernel: Cauchy-Schwarz bound, clamped around the target logit by the rank that owns the label
+        r = inv_tau * q_all.norm(dim=-1) * maxnorm * 1.01 + 1e-3
+        g = lab_all - bank.row_base
+        own = (g >= 0) & (g < bank.N)
+        s_t = inv_tau * (q_all[own] * bank.data[g[own]]).sum(-1)
+        r[own] = torch.minimum(r[own], torch.maximum(s_t + 30.0, r[own] - 64.0))
+        return r
+
+    def fused(self, q_all, lab_all, ref, bank, inv_tau, tau_grad):
+        s = inv_tau * q_all @ bank.data.T                                   # [Bt, N_shard]
+        g = lab_all - bank.row_base
+        own = (g >= 0) & (g < bank.N)
+        p = torch.exp(s - ref[:, None])
+        rows = torch.nonzero(own).squeeze(1)
+        p[rows, g[own]] = 0.0                                               # the label column is excluded from P~
+        o_acc = p @ bank.data
+        l_acc = p.sum(-1)
+        es = (p * s).sum(-1)
+        s_t = torch.full_like(l_acc, -float("inf"))
+        s_t[own] = s[rows, g[own]]
+        bank_t = torch.zeros_like(o_acc)
+        bank_t[own] = bank.data[g[own]]
+        lbl_row = torch.where(own, g, torch.full_like(g, -1))
+        return o_acc, bank_t, torch.stack([l_acc, s_t, es]), lbl_row
+
+    def finalize(self, sw, bank, inv_tau, B, eps):
+        L = sw["l_acc"] + torch.exp(sw["s_t"] - sw["ref"])
+        lse = sw["ref"] + torch.log(L)
+        loss = (lse - sw["s_t"]).mean()
+        dq = (inv_tau / B) * (sw["o_acc"] - sw["l_acc"][:, None] * sw["bank_t"]) / L[:, None]
+        return loss, dq, None
+
+
+class _Shard:  # the attributes of DeviceBank the exchange reads
+    def __init__(self, data, row_base, n_total):
+        self.data, self.N, self.T, self.row_base, self.n_total = data, data.shape[0], 1, row_base, n_total
+
+
+def _worker_fused(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from spn4cir_b200.dist import _sharded_sweep
+        B, N, D, tau = 6, 333, 64, 0.02
+        _, bank, _ = synth.make_bank_case(B, N, D, 1, "S", 41)
+        bank = bank.to(torch.bfloat16).double()                              # the resident bank is bf16
+        labels = synth.make_labels(B, N, seed=50 + rank)                     # every rank brings its own queries
+        q = synth.make_queries(bank.float(), labels, "S", seed=60 + rank)
+        lo, hi = shard_bounds(N, rank, world)
+        shard = _Shard(bank[lo:hi].contiguous(), lo, N)
+        loss, dq, _ = _sharded_sweep(q, shard, labels, 1.0 / tau, 0.0, False, None, compute=CpuShardCompute())
+        # dense fp64 oracle on this rank's queries (bf16-rounded, as the kernels see them)
+        qd = q.to(torch.bfloat16).double().requires_grad_(True)
+        dense = obank.infonce_loss(qd, bank, labels, tau)
+        dense.backward()
+        assert abs(loss.item() - dense.item()) < 1e-9 * max(1.0, abs(dense.item())), (rank, loss.item(), dense.item())
+        err = (dq - qd.grad).abs().max().item() / qd.grad.abs().max().item()
+        assert err < 1e-9, (rank, err)
+        labels_elsewhere = ((labels < lo) | (labels >= hi)).sum().item()
+        out.put(("ok", rank, labels_elsewhere))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_fused_exchange_over_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_fused, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    got = sorted(out.get(timeout=5) for _ in range(2))
+    assert [g[0] for g in got] == ["ok", "ok"]
+    assert sum(g[2] for g in got) > 0  # some targets live on the other rank: the owner-only terms really travelled
