@@ -162,6 +162,85 @@ def blip2_cases():
     print(f"blip2_small: loop={loop.item():.6f} closed={closed.item():.6f} dtemp={dtemp.item():.4e}")
 
 
+BLIP2_SRC = Path("/root/reference/blip24cir/lavis/models/blip2_models/blip2_qformer_cir_align_prompt.py")
+
+
+def exec_reference_lines(path: Path, first: int, last: int, env: dict) -> dict:
+    """Execute lines [first, last] (1-based, inclusive) of a reference source file VERBATIM in `env`.  blip24cir cannot be
+    imported offline (omegaconf / timm / iopath are absent), but the tails of the hot path are straight-line tensor code
+    inside the methods: running those very lines on prepared locals is the reference executing, not a restatement."""
+    import textwrap
+    lines = path.read_text().splitlines()[first - 1:last]
+    code = compile(textwrap.dedent("\n".join(lines)), f"{path}:{first}-{last}", "exec")
+    exec(code, env)
+    return env
+
+
+def blip2_reference_exec_cases():
+    """forward_stage2 loss tail (:254-265) and inference similarity tail (:314-318) executed from the reference file."""
+    import torch.nn.functional as F
+    cases = {"blip2_ref_small": (6, 50, 0.05, 11), "blip2_ref_ragged": (5, 131, 0.07, 12)}
+    for name, (B, N, temp, seed) in cases.items():
+        T, D = 32, 256
+        f, bank3, labels = synth.make_bank_case(B, N, D, T, "S", seed)
+        ff = f.clone().requires_grad_(True)
+        stub = types.SimpleNamespace(device="cpu", temp=torch.tensor(temp, requires_grad=True))
+        env = exec_reference_lines(BLIP2_SRC, 254, 265, dict(torch=torch, F=F, self=stub, bs=B, fusion_feats=ff,
+                                                             target_feats=bank3, target_indexs=labels))
+        loss = env["loss_qtc"]
+        loss.backward()
+        # the restatement and the closed form must reproduce the executed lines
+        loop = obank.blip2_stage2_loss_loop(f, bank3, labels, torch.tensor(temp))
+        closed, df, dtemp = obank.blip2_loss_and_grads(f, bank3, labels, temp)
+        assert torch.allclose(loss.detach(), loop, atol=1e-6) and torch.allclose(loss.detach(), closed, atol=1e-6)
+        assert torch.allclose(ff.grad, df, atol=1e-6, rtol=1e-4) and torch.allclose(stub.temp.grad, dtemp, rtol=1e-4)
+        # inference tail on the same features: sim_i2t [B, N]
+        env2 = exec_reference_lines(BLIP2_SRC, 314, 318, dict(torch=torch, fusion_feats=f, target_feats=bank3))
+        sim = env2["sim_i2t"]
+        assert sim.shape == (B, N)
+        np.savez_compressed(OUT / f"{name}.npz", B=B, N=N, T=T, D=D, temp=temp, seed=seed, loss=loss.detach().numpy(),
+                            df=ff.grad.numpy(), dtemp=stub.temp.grad.numpy(), sim_i2t=sim.numpy(),
+                            input_digest=digest(f, bank3, labels))
+        print(f"{name}: executed reference lines loss={loss.item():.6f} dtemp={stub.temp.grad.item():.4e}")
+
+
+SRM_SRC = Path("/root/reference/zscir/srm_utils.py")
+
+
+def srm_reference_exec_case():
+    """calcu_sims (:121-124) and the body of get_srm_out (:145-180) executed from zscir/srm_utils.py -- a script around
+    module globals and dataset files, so the globals are prepared here and the dataset line (:143-144) is replaced by a
+    stub carrying `triplets` / `imagename2id`."""
+    ci, ct, si, st, ref, tgt = synth.make_srm_case(21)
+    env = dict(torch=torch, clip_image_feats=ci, clip_text_feats=ct, srm_image_feats=si, srm_text_feats=st)
+    exec_reference_lines(SRM_SRC, 121, 124, env)
+    names = [f"img{i:05d}" for i in range(ci.shape[0])]
+    env["triplets"] = [{"reference_name": names[int(r)], "target_name": names[int(t)]} for r, t in zip(ref, tgt)]
+    env["cirDataset"] = types.SimpleNamespace(imagename2id={n: i for i, n in enumerate(names)})
+    env["tqdm"] = lambda it, **kw: it
+    exec_reference_lines(SRM_SRC, 145, 180, env)
+    got = [env[k] for k in ("r_fn_indexs", "m_fn_indexs", "t_fn_indexs", "rt_scores", "rm_scores", "mt_scores")]
+    want = oretr.srm_out(ci, ct, si, st, ref.tolist(), tgt.tolist(), 1000)
+    # identical, except that the reference's unstable argsort may order EXACTLY equal scores either way (the oracle and
+    # the CUDA path put the lower index first): every differing position must be such a tie
+    s_ii, s_tt = si @ si.T, st @ st.T
+    rows = {"r_fn": s_ii[ref], "m_fn": s_tt, "t_fn": s_ii[tgt]}
+    n_ties = 0
+    for name, a, b in zip(("r_fn", "m_fn", "t_fn"), got[:3], want[:3]):
+        for r, c in (a != b).nonzero().tolist():
+            assert rows[name][r, a[r, c]] == rows[name][r, b[r, c]], f"{name}[{r},{c}] differs beyond an exact tie"
+            n_ties += 1
+    for name, a, b in zip(("rt", "rm", "mt"), got[3:], want[3:]):
+        assert torch.equal(a, b), f"oracle restatement differs from the executed reference lines: {name}"
+    np.savez_compressed(OUT / "srm_ref.npz", seed=21, n_img=ci.shape[0], n_trip=ct.shape[0], D=ci.shape[1], K=1000,
+                        rt=got[3].numpy(), rm=got[4].numpy(), mt=got[5].numpy(),
+                        r_fn_head=want[0][:, :24].numpy().astype(np.int32), m_fn_head=want[1][:, :24].numpy().astype(np.int32),
+                        t_fn_head=want[2][:, :24].numpy().astype(np.int32),
+                        fn_digest_oracle_order=digest(want[0], want[1], want[2]), exact_tie_positions=n_ties,
+                        input_digest=digest(ci, ct, si, st, ref, tgt))
+    print("srm_ref: executed reference lines, rt mean", got[3].float().mean().item(), "exact-tie positions", n_ties)
+
+
 def main():
     assert REF.exists(), "run in the build container: /root/reference is required"
     OUT.mkdir(parents=True, exist_ok=True)
@@ -173,6 +252,8 @@ def main():
     if os.environ.get("GOLDEN_ONLY"):
         return
     blip2_cases()
+    blip2_reference_exec_cases()
+    srm_reference_exec_case()
     retrieval_cases(validate)
 
 

@@ -116,3 +116,17 @@ class FakeModel:
     @staticmethod
     def combining_function(a, b):
         return a + b
+
+
+def make_srm_case(seed: int = 21, n_img: int = 1100, n_trip: int = 1050, D: int = 64):
+    """Seeded pair-mining inputs (zscir/srm_utils.py:119-183 shape): CLIP / SRM image features [n_img, D], caption features
+    [n_trip, D] (triplet i owns caption row i), reference / target image ids per triplet.  K = 1000 is hard-coded in the
+    reference (:155), so both sides need more than 1000 rows."""
+    g = _gen(seed)
+    ci = F.normalize(torch.randn(n_img, D, generator=g), dim=-1)
+    si = F.normalize(torch.randn(n_img, D, generator=g), dim=-1)
+    ct = F.normalize(torch.randn(n_trip, D, generator=g), dim=-1)
+    st = F.normalize(torch.randn(n_trip, D, generator=g), dim=-1)
+    ref = torch.randint(0, n_img, (n_trip,), generator=g)
+    tgt = (ref + 1 + torch.randint(0, n_img - 1, (n_trip,), generator=g)) % n_img
+    return ci, ct, si, st, ref, tgt

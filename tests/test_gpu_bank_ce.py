@@ -192,6 +192,24 @@ def test_blip2_fixture(golden):
     assert rel_l2(fd.grad.cpu(), torch.from_numpy(g["df"])) < 1.5e-2
 
 
+@pytest.mark.parametrize("name", ["blip2_ref_small", "blip2_ref_ragged"])
+def test_blip2_against_executed_reference_lines(golden, name):
+    """The CUDA path (T = 32: max over token rows, learnable temp) against the fixtures produced by executing the
+    reference's own loss loop (blip2_qformer_cir_align_prompt.py:254-265) and inference tail (:314-318)."""
+    from spn4cir_b200 import compat
+    g = golden(name)
+    f, bank3, labels = synth.make_bank_case(int(g["B"]), int(g["N"]), int(g["D"]), int(g["T"]), "S", int(g["seed"]))
+    fd = f.to(DEV).requires_grad_(True)
+    tp = torch.tensor(float(g["temp"]), device=DEV, requires_grad=True)
+    out = compat.forward_stage2_loss(fd, bank3.to(DEV), labels.to(DEV), tp)
+    out["loss_qtc"].backward()
+    assert abs(out["loss_qtc"].item() - float(g["loss"])) <= 1e-2 * abs(float(g["loss"]))          # bf16 vs the reference's fp32
+    assert rel_l2(fd.grad.cpu(), torch.from_numpy(g["df"])) < 1.5e-2
+    assert abs(tp.grad.item() - float(g["dtemp"])) <= 3e-2 * max(abs(float(g["dtemp"])), 1e-2)
+    sim = compat.inference_sim(f.to(DEV), bank3.to(DEV)).cpu().numpy()                               # exact fp32 chain
+    np.testing.assert_allclose(sim, g["sim_i2t"], rtol=1e-5, atol=2e-6)
+
+
 def test_shards_merge_to_the_unsharded_result():
     """8 'fake ranks' on one GPU: per-shard statistics merged by spn_merge_stats, dq accumulated shard by shard."""
     q, bank, labels = synth.make_bank_case(96, 4000, 128, 1, "S", 14)

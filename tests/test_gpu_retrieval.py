@@ -210,3 +210,20 @@ def test_rank_window_matches_oracle():
     a = compat.get_diff_id(3, n, 4)
     random.seed(5)
     assert a == oretr.get_diff_id(3, n, 4) and 3 not in a
+
+
+def test_srm_pair_mining_against_executed_reference_lines(golden):
+    """compat.srm_out (K = 1000, the reference's hard-coded value) against the fixture written by executing
+    zscir/srm_utils.py:121-124,145-180: rank sums exact up to near-ties of the fp32 scores, hard-negative lists equal at
+    (almost) every position."""
+    g = golden("srm_ref")
+    ci, ct, si, st, ref, tgt = synth.make_srm_case(int(g["seed"]), int(g["n_img"]), int(g["n_trip"]), int(g["D"]))
+    got = spn.compat.srm_out(ci.to(DEV), ct.to(DEV), si.to(DEV), st.to(DEV), ref, tgt, int(g["K"]))
+    torch.cuda.synchronize()
+    for name, h in zip(("r_fn", "m_fn", "t_fn"), got[:3]):
+        assert h.shape == (int(g["n_trip"]), int(g["K"]))
+        assert (h[:, :24].cpu().numpy() == g[name + "_head"]).mean() > 0.995, name
+        assert int(h.min()) >= 0                      # > 1000 candidates everywhere: no padding
+    for name, h in zip(("rt", "rm", "mt"), got[3:]):
+        d = np.abs(h.cpu().numpy() - g[name])
+        assert d.max() <= 2 and (d == 0).mean() > 0.98, name

@@ -88,6 +88,27 @@ def test_blip2_loop_equals_closed_form(golden):
     np.testing.assert_allclose(temp.grad.item(), g["dtemp"], rtol=1e-4)
 
 
+@pytest.mark.parametrize("name", ["blip2_ref_small", "blip2_ref_ragged"])
+def test_blip2_restatement_matches_executed_reference_lines(golden, name):
+    """Fixtures written by oracle/make_golden.py EXECUTING lines 254-265 (stage-2 loss loop) and 314-318 (inference
+    similarity) of the reference's blip2_qformer_cir_align_prompt.py on prepared locals: the oracle's loop, its closed
+    form and its max-over-tokens similarity must reproduce them."""
+    g = golden(name)
+    f, bank3, labels = synth.make_bank_case(int(g["B"]), int(g["N"]), int(g["D"]), int(g["T"]), "S", int(g["seed"]))
+    assert digest(f, bank3, labels) == str(g["input_digest"])
+    temp = torch.tensor(float(g["temp"]), requires_grad=True)
+    ff = f.clone().requires_grad_(True)
+    loop = obank.blip2_stage2_loss_loop(ff, bank3, labels, temp)
+    loop.backward()
+    np.testing.assert_allclose(loop.item(), g["loss"], rtol=1e-6)
+    np.testing.assert_allclose(ff.grad.numpy(), g["df"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(temp.grad.item(), g["dtemp"], rtol=1e-4)
+    closed, df, dtemp = obank.blip2_loss_and_grads(f, bank3, labels, float(g["temp"]))
+    np.testing.assert_allclose(closed.item(), g["loss"], rtol=1e-6)
+    np.testing.assert_allclose(df.numpy(), g["df"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(oretr.similarity(f, bank3).numpy(), g["sim_i2t"], rtol=1e-6, atol=1e-7)
+
+
 @pytest.mark.parametrize("name", ["cirr_small", "cirr_c2"])
 def test_cirr_metrics_match_reference_outputs(golden, name):
     g = golden(name)
@@ -154,3 +175,20 @@ def test_part_infonce_oracle_draws_the_reference_negatives(golden, name):
     assert abs(loss.item() - float(g["loss"])) <= 1e-5 * max(abs(float(g["loss"])), 1e-3)
     _, dq, _ = obank.part_loss_and_grads(q, bank, cand, float(g["tau"]), dtype=torch.float32)
     assert np.allclose(dq.numpy(), g["dq"], rtol=1e-4, atol=1e-7)
+
+
+def test_pair_mining_restatement_matches_executed_reference_lines(golden):
+    """tests/golden/srm_ref.npz was written by oracle/make_golden.py EXECUTING zscir/srm_utils.py:121-124 and :145-180
+    (calcu_sims + the body of get_srm_out) on these seeded inputs and checking that oracle.retrieval.srm_out reproduces
+    them -- identically, except that the reference's unstable argsort may order exactly equal scores either way (the fixture
+    counts those positions and stores the lists in the oracle's order: ties -> lower index)."""
+    g = golden("srm_ref")
+    ci, ct, si, st, ref, tgt = synth.make_srm_case(int(g["seed"]), int(g["n_img"]), int(g["n_trip"]), int(g["D"]))
+    assert digest(ci, ct, si, st, ref, tgt) == str(g["input_digest"])
+    r_fn, m_fn, t_fn, rt, rm, mt = oretr.srm_out(ci, ct, si, st, ref.tolist(), tgt.tolist(), int(g["K"]))
+    np.testing.assert_array_equal(rt.numpy(), g["rt"])
+    np.testing.assert_array_equal(rm.numpy(), g["rm"])
+    np.testing.assert_array_equal(mt.numpy(), g["mt"])
+    assert digest(r_fn, m_fn, t_fn) == str(g["fn_digest_oracle_order"])
+    np.testing.assert_array_equal(r_fn[:, :24].numpy(), g["r_fn_head"])
+    assert int(g["exact_tie_positions"]) < 100
