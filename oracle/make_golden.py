@@ -151,7 +151,7 @@ def retrieval_cases(validate):
 
 
 def blip2_cases():
-    # not importable offline -> line-faithful loop vs closed form only (parity unpinned, see oracle/__init__.py)
+    # loop restatement vs closed form (the executed-reference fixtures are written by blip2_reference_exec_cases below)
     B, N, T, D, temp = 6, 50, 32, 256, 0.05
     f, bank3, labels = synth.make_bank_case(B, N, D, T, "S", 11)
     loop = obank.blip2_stage2_loss_loop(f, bank3, labels, torch.tensor(temp))
