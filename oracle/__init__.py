@@ -11,6 +11,7 @@ against the reference's own code executed in the build container (oracle/make_go
 tests/golden/.  Two parts of the path live in files that cannot be imported offline -- the BLIP-2 tails (blip24cir
 needs omegaconf / timm / iopath) and the pair-mining script zscir/srm_utils.py (module globals + dataset files).  Their
 hot-path lines are straight-line tensor code, so make_golden.py EXECUTES THOSE SOURCE LINES VERBATIM
-(exec_reference_lines: blip2_qformer_cir_align_prompt.py:254-265 and :314-318, srm_utils.py:121-124 and :145-180) on
-prepared locals, checks the restatements against the result and commits it as fixtures (blip2_ref_*.npz, srm_ref.npz).
+(exec_reference_lines: blip2_qformer_cir_align_prompt.py:254-265 and :314-318, srm_utils.py:121-124 and :145-180, and the
+submission writer clip4cir/cirr_test_submission.py:84-109) on prepared locals, checks the restatements against the result
+and commits it as fixtures (blip2_ref_*.npz, srm_ref.npz, cirr_submit_ref.npz).
 """

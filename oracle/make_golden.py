@@ -241,6 +241,33 @@ def srm_reference_exec_case():
     print("srm_ref: executed reference lines, rt mean", got[3].float().mean().item(), "exact-tie positions", n_ties)
 
 
+CIRR_SUBMIT_SRC = Path("/root/reference/clip4cir/cirr_test_submission.py")
+
+
+def cirr_test_submission_exec_case():
+    """generate_cirr_test_dicts after the model pass (clip4cir/cirr_test_submission.py:84-109: normalise the index, `1 - q @
+    g.T`, argsort, drop the reference, subset mask, top-50 / top-3 name lists) executed verbatim on prepared locals."""
+    import torch.nn.functional as F
+    Q, G, D, seed = 60, 400, 64, 31
+    q, gallery, names, reference, target, groups = synth.make_retrieval_case(Q, G, D, 1, seed, noise=6.0)
+    env = dict(torch=torch, F=F, np=np, predicted_features=q, index_features=gallery * 1.7,   # un-normalised index (:87)
+               index_names=names, reference_names=[names[int(i)] for i in reference],
+               group_members=[[names[int(j)] for j in row] for row in groups], pairs_id=list(range(100, 100 + Q)))
+    exec_reference_lines(CIRR_SUBMIT_SRC, 84, 109, env)
+    lut = {n: i for i, n in enumerate(names)}
+    top50 = np.array([[lut[n] for n in env["pairid_to_predictions"][str(100 + r)]] for r in range(Q)], dtype=np.int32)
+    top3 = np.array([[lut[n] for n in env["pairid_to_group_predictions"][str(100 + r)]] for r in range(Q)], dtype=np.int32)
+    # the restatement: top-K of the exact scores with the reference excluded, subset = ranking restricted to the group
+    sim = q @ F.normalize(gallery * 1.7, dim=-1).T
+    _, want = oretr.topk(sim, 50, exclude=reference.tolist())
+    bad = np.argwhere(top50 != want)
+    for r, c in bad:   # `1 - s` rounds away low bits and the argsort is unstable: only near-ties may differ
+        assert abs(float(sim[r, top50[r, c]]) - float(sim[r, want[r, c]])) < 1e-6, (r, c)
+    np.savez_compressed(OUT / "cirr_submit_ref.npz", Q=Q, G=G, D=D, seed=seed, noise=6.0, scale=1.7, top50=top50, top3=top3,
+                        input_digest=digest(q, gallery, reference, groups))
+    print(f"cirr_submit_ref: executed reference lines; {len(bad)} near-tie positions differ from the exact-score order")
+
+
 def main():
     assert REF.exists(), "run in the build container: /root/reference is required"
     OUT.mkdir(parents=True, exist_ok=True)
@@ -254,6 +281,7 @@ def main():
     blip2_cases()
     blip2_reference_exec_cases()
     srm_reference_exec_case()
+    cirr_test_submission_exec_case()
     retrieval_cases(validate)
 
 

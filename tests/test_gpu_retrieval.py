@@ -227,3 +227,19 @@ def test_srm_pair_mining_against_executed_reference_lines(golden):
     for name, h in zip(("rt", "rm", "mt"), got[3:]):
         d = np.abs(h.cpu().numpy() - g[name])
         assert d.max() <= 2 and (d == 0).mean() > 0.98, name
+
+
+def test_cirr_submission_against_executed_reference_lines(golden):
+    """compat.cirr_test_dicts_from_features against the lists produced by executing clip4cir/cirr_test_submission.py:84-109."""
+    g = golden("cirr_submit_ref")
+    Q, G, D = int(g["Q"]), int(g["G"]), int(g["D"])
+    q, gallery, names, reference, target, groups = synth.make_retrieval_case(Q, G, D, 1, int(g["seed"]), noise=float(g["noise"]))
+    preds, gpreds = compat.cirr_test_dicts_from_features(
+        q.to(DEV), (gallery * float(g["scale"])).to(DEV), names, [names[int(i)] for i in reference],
+        [[names[int(j)] for j in row] for row in groups], list(range(100, 100 + Q)))
+    lut = {n: i for i, n in enumerate(names)}
+    got50 = np.array([[lut[n] for n in preds[str(100 + r)]] for r in range(Q)])
+    got3 = np.array([[lut[n] for n in gpreds[str(100 + r)]] for r in range(Q)])
+    sim = (q @ F.normalize(gallery * float(g["scale"]), dim=-1).T).numpy()
+    assert_same_up_to_ties(got50, g["top50"].astype(np.int64), sim)
+    assert_same_up_to_ties(got3, g["top3"].astype(np.int64), sim)

@@ -192,3 +192,19 @@ def test_pair_mining_restatement_matches_executed_reference_lines(golden):
     assert digest(r_fn, m_fn, t_fn) == str(g["fn_digest_oracle_order"])
     np.testing.assert_array_equal(r_fn[:, :24].numpy(), g["r_fn_head"])
     assert int(g["exact_tie_positions"]) < 100
+
+
+def test_cirr_submission_restatement_matches_executed_reference_lines(golden):
+    """tests/golden/cirr_submit_ref.npz: clip4cir/cirr_test_submission.py:84-109 executed verbatim (top-50 names and top-3
+    in-subset names per pair id).  The oracle's top-K / restricted ranking of the exact scores must give the same lists."""
+    g = golden("cirr_submit_ref")
+    Q, G, D = int(g["Q"]), int(g["G"]), int(g["D"])
+    q, gallery, names, reference, target, groups = synth.make_retrieval_case(Q, G, D, 1, int(g["seed"]), noise=float(g["noise"]))
+    assert digest(q, gallery, reference, groups) == str(g["input_digest"])
+    sim = q @ F.normalize(gallery * float(g["scale"]), dim=-1).T
+    _, top = oretr.topk(sim, 50, exclude=reference.tolist())
+    np.testing.assert_array_equal(top, g["top50"])
+    full = oretr.ranking(sim)
+    for r in range(Q):
+        members = set(groups[r].tolist()) - {int(reference[r])}
+        assert [j for j in full[r] if j in members][:3] == g["top3"][r].tolist()
