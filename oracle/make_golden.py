@@ -241,6 +241,30 @@ def srm_reference_exec_case():
     print("srm_ref: executed reference lines, rt mean", got[3].float().mean().item(), "exact-tie positions", n_ties)
 
 
+def bank_large_step_cases(models_negplus):
+    """CIRPlus.bank_large_step (clip4cir/models_negplus.py:130-142) called unbound on a stub that carries the banks: the
+    query assembly (refer_bank gather + element_wise_sum + F.normalize), the loss and autograd down to text_feats."""
+    C = models_negplus.CIRPlus
+    for name, (B, R, N, D, tau, plus, seed) in {"bank_step_plus": (24, 60, 300, 64, 0.02, True, 41),
+                                                "bank_step_noplus": (16, 40, 257, 128, 0.05, False, 42)}.items():
+        refer_bank, target_bank, text, indexs, refer_indexs, target_indexs = synth.make_bank_step_case(seed, B, R, N, D)
+        stub = types.SimpleNamespace(plus=plus, refer_bank=refer_bank, target_bank=target_bank, device="cpu", tau=tau,
+                                     crossentropy_criterion=nn.CrossEntropyLoss())
+        stub.combining_function = lambda a, b: C.element_wise_sum(stub, a, b)                  # :26, :48-50
+        stub.infonce_loss = lambda *a, **k: C.infonce_loss(stub, *a, **k)                      # :150-154
+        tt = text.clone().requires_grad_(True)
+        loss = {}
+        C.bank_large_step(stub, loss, tt, indexs, target_indexs, refer_indexs)
+        loss["bank_loss"].backward()
+        q = obank.bank_large_step_query(refer_bank, refer_indexs if plus else indexs, text)
+        o_loss = obank.infonce_loss(q, target_bank, target_indexs, tau)
+        assert torch.allclose(o_loss, loss["bank_loss"].detach(), rtol=1e-5)
+        np.savez_compressed(OUT / f"{name}.npz", B=B, R=R, N=N, D=D, tau=tau, plus=int(plus), seed=seed,
+                            loss=loss["bank_loss"].detach().numpy(), dtext=tt.grad.numpy(),
+                            input_digest=digest(refer_bank, target_bank, text, indexs, refer_indexs, target_indexs))
+        print(f"{name}: executed reference loss {loss['bank_loss'].item():.6f}")
+
+
 CIRR_SUBMIT_SRC = Path("/root/reference/clip4cir/cirr_test_submission.py")
 
 
@@ -274,6 +298,7 @@ def main():
     torch.set_num_threads(os.cpu_count() or 1)
     models_negplus, validate = import_reference()
     bank_cases(models_negplus)
+    bank_large_step_cases(models_negplus)
     if not os.environ.get("GOLDEN_ONLY") or "part" in os.environ["GOLDEN_ONLY"]:
         part_cases()
     if os.environ.get("GOLDEN_ONLY"):

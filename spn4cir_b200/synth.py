@@ -130,3 +130,16 @@ def make_srm_case(seed: int = 21, n_img: int = 1100, n_trip: int = 1050, D: int 
     ref = torch.randint(0, n_img, (n_trip,), generator=g)
     tgt = (ref + 1 + torch.randint(0, n_img - 1, (n_trip,), generator=g)) % n_img
     return ci, ct, si, st, ref, tgt
+
+
+def make_bank_step_case(seed: int, B: int, R: int, N: int, D: int):
+    """Inputs of CIRPlus.bank_large_step (clip4cir/models_negplus.py:130-142): row-normalised refer / target banks (built as
+    :76-77 do), un-normalised text features, the three index vectors."""
+    g = _gen(seed)
+    refer_bank = F.normalize(torch.randn(R, D, generator=g), dim=-1)
+    target_bank = F.normalize(torch.randn(N, D, generator=g), dim=-1)
+    text = 0.7 * torch.randn(B, D, generator=g)
+    indexs = torch.randint(0, R, (B,), generator=g)
+    refer_indexs = torch.randint(0, R, (B,), generator=g)
+    target_indexs = torch.randint(0, N, (B,), generator=g)
+    return refer_bank, target_bank, text, indexs, refer_indexs, target_indexs

@@ -240,6 +240,27 @@ def test_shards_merge_to_the_unsharded_result():
     assert rel_l2(dq_sh, o_dq) < 1e-2
 
 
+@pytest.mark.parametrize("name", ["bank_step_plus", "bank_step_noplus"])
+def test_bank_large_step_mixin_against_executed_reference(golden, name):
+    """compat.BankLossMixin.bank_large_step (the drop-in for clip4cir/models_negplus.py:130-142: resident bf16 bank, no per-step
+    upload) against the fixtures written by executing the reference method: loss and the gradient w.r.t. text_feats."""
+    from spn4cir_b200.compat import BankLossMixin
+    g = golden(name)
+    rb, tb, text, ix, rix, tix = synth.make_bank_step_case(int(g["seed"]), int(g["B"]), int(g["R"]), int(g["N"]), int(g["D"]))
+
+    class Model(BankLossMixin):
+        device, tau, plus = torch.device(DEV), float(g["tau"]), bool(int(g["plus"]))
+
+    m = Model()
+    m.set_banks(rb, tb)
+    tt = text.to(DEV).requires_grad_(True)
+    loss = {}
+    m.bank_large_step(loss, tt, ix.to(DEV), tix.to(DEV), rix.to(DEV))
+    loss["bank_loss"].backward()
+    assert abs(loss["bank_loss"].item() - float(g["loss"])) <= 1e-2 * abs(float(g["loss"]))
+    assert rel_l2(tt.grad.cpu(), torch.from_numpy(g["dtext"])) < 2e-2, rel_l2(tt.grad.cpu(), torch.from_numpy(g["dtext"]))
+
+
 def test_query_assemble_prologue():
     g = torch.Generator().manual_seed(5)
     refer = torch.randn((50, 640), generator=g)

@@ -208,3 +208,18 @@ def test_cirr_submission_restatement_matches_executed_reference_lines(golden):
     for r in range(Q):
         members = set(groups[r].tolist()) - {int(reference[r])}
         assert [j for j in full[r] if j in members][:3] == g["top3"][r].tolist()
+
+
+@pytest.mark.parametrize("name", ["bank_step_plus", "bank_step_noplus"])
+def test_bank_large_step_restatement_matches_executed_reference(golden, name):
+    """tests/golden/bank_step_*.npz: CIRPlus.bank_large_step (clip4cir/models_negplus.py:130-142) called unbound on a stub
+    (refer-bank gather, element_wise_sum, F.normalize, infonce_loss) with autograd down to text_feats."""
+    g = golden(name)
+    rb, tb, text, ix, rix, tix = synth.make_bank_step_case(int(g["seed"]), int(g["B"]), int(g["R"]), int(g["N"]), int(g["D"]))
+    assert digest(rb, tb, text, ix, rix, tix) == str(g["input_digest"])
+    tt = text.clone().requires_grad_(True)
+    q = obank.bank_large_step_query(rb, rix if int(g["plus"]) else ix, tt)
+    loss = obank.infonce_loss(q, tb, tix, float(g["tau"]))
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-5)
+    np.testing.assert_allclose(tt.grad.numpy(), g["dtext"], rtol=1e-3, atol=1e-6)
