@@ -13,6 +13,7 @@ per-rank work stays B_total * N / R and the job's throughput scales with the ran
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -148,10 +149,19 @@ def _sharded_sweep(q_local, bank, labels_local, inv_tau, eps, tau_grad, group, c
         if not tau_grad:
             vec[2].zero_()
         o_mine = torch.empty((B, D), dtype=o_acc.dtype, device=dev)
-        t_mine = torch.empty((B, D), dtype=bank_t.dtype, device=dev)
-        _reduce_scatter_sum(o_mine, o_acc, rank, group)
-        _reduce_scatter_sum(t_mine, bank_t, rank, group)
-        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+        if os.environ.get("SPN_SHARD_FOLD", "0") == "1":
+            # experimental (off by default, not yet measured on GPUs): the row sums travel first, then the rank that owns
+            # a label folds the target-row term into its partial -- sum_r (o_r - [r owns b] l_b bank_t[b]) = o - l bank_t --
+            # so the second [Bt, D] reduce_scatter (a mostly-zero fp32 matrix) disappears; finalize sees bank_t = 0
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+            o_acc.addcmul_(bank_t, vec[0][:, None], value=-1.0)
+            _reduce_scatter_sum(o_mine, o_acc, rank, group)
+            t_mine = torch.zeros((B, D), dtype=bank_t.dtype, device=dev)
+        else:
+            t_mine = torch.empty((B, D), dtype=bank_t.dtype, device=dev)
+            _reduce_scatter_sum(o_mine, o_acc, rank, group)
+            _reduce_scatter_sum(t_mine, bank_t, rank, group)
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
         sl = slice(rank * B, (rank + 1) * B)
         sw = dict(o_acc=o_mine, bank_t=t_mine, l_acc=vec[0, sl].contiguous(), s_t=vec[1, sl].contiguous(),
                   es_acc=vec[2, sl].contiguous() if tau_grad else None, ref=ref[sl].contiguous(), q16=q16)

@@ -142,14 +142,17 @@ def _worker_fused(rank, world, port, out):
         q = synth.make_queries(bank.float(), labels, "S", seed=60 + rank)
         lo, hi = shard_bounds(N, rank, world)
         shard = _Shard(bank[lo:hi].contiguous(), lo, N)
-        loss, dq, _ = _sharded_sweep(q, shard, labels, 1.0 / tau, 0.0, False, None, compute=CpuShardCompute())
         # dense fp64 oracle on this rank's queries (bf16-rounded, as the kernels see them)
         qd = q.to(torch.bfloat16).double().requires_grad_(True)
         dense = obank.infonce_loss(qd, bank, labels, tau)
         dense.backward()
-        assert abs(loss.item() - dense.item()) < 1e-9 * max(1.0, abs(dense.item())), (rank, loss.item(), dense.item())
-        err = (dq - qd.grad).abs().max().item() / qd.grad.abs().max().item()
-        assert err < 1e-9, (rank, err)
+        for fold in ("0", "1"):  # the shipped exchange and the experimental one-reduce_scatter variant
+            os.environ["SPN_SHARD_FOLD"] = fold
+            loss, dq, _ = _sharded_sweep(q, shard, labels, 1.0 / tau, 0.0, False, None, compute=CpuShardCompute())
+            assert abs(loss.item() - dense.item()) < 1e-9 * max(1.0, abs(dense.item())), (rank, fold, loss.item(), dense.item())
+            err = (dq - qd.grad).abs().max().item() / qd.grad.abs().max().item()
+            assert err < 1e-9, (rank, fold, err)
+        os.environ.pop("SPN_SHARD_FOLD")
         labels_elsewhere = ((labels < lo) | (labels >= hi)).sum().item()
         out.put(("ok", rank, labels_elsewhere))
     finally:
