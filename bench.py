@@ -1,12 +1,17 @@
 #!/usr/bin/env python
 """bench.py -- bank-CE forward+backward throughput of the B200-native path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C5]
 
-One "step" = one pass of the hot path over one batch of synthetic queries: forward statistics + loss and
-the backward dL/dq against the device-resident bank (config C3: 512 queries x 100k x 640-d bank, bf16).
-Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, L2 flushed between timed
-iterations, max over ranks, clocks sampled with nvidia-smi during the timed region.
+Headline workload at every N: BASELINE config 5 -- 1024 queries per rank against the 1 M x 768 bf16 bank (the largest
+configuration that fits one GPU).  N = 1: the whole bank on one GPU.  N > 1: the bank is ROW-SHARDED over the ranks
+(N / R rows each), every rank scores all R * 1024 queries of the step against its rows (same FLOPs per rank as N = 1) and
+the partials are merged over NCCL (spn4cir_b200/dist.py) -- weak scaling, `value` = all queries of the job / step time.
+
+One "step" = one pass of the hot path over one batch of synthetic queries: loss + dL/dq against the device-resident bank.
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, L2 flushed between timed iterations, max
+over ranks, clocks sampled with nvidia-smi during the timed region.  At N = 1 the line also carries the secondary
+workloads (C3, the 1 M x 640 north-star shape, C4 / BLIP-2, small batches, C2 retrieval).
 `--impl reference` times the reference's CPU torch path (the oracle restatement of
 clip4cir/models_negplus.py:150-154 + backward) on the host cores.
 """
@@ -30,6 +35,7 @@ sys.path.insert(0, str(REPO))
 from spn4cir_b200 import synth  # noqa: E402
 
 METRIC = "bank_ce_fwd_bwd_queries_per_sec"
+L2_FLUSH_BYTES = 256 * 1024 * 1024  # > 126 MB L2
 
 
 def measured_peaks():
@@ -67,23 +73,24 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for l in self.lines:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])), mx.append(float(f[2]))
+                sm.append(float(f[1])), mx.append(float(f[2])), pw.append(float(f[3]))
             except ValueError:
                 continue
             for n, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_median": statistics.median(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
 def cpu_reference_step(q, bank, labels, tau):
     """The reference's CPU path: oracle restatement of infonce_loss + autograd backward, fp32, all host threads."""
     from oracle import bank_ce as obank
@@ -106,8 +113,7 @@ def time_cpu_reference(cfg, budget_s: float, steps: int, warmup: int):
     t_probe = time.perf_counter() - t0
     est_full = t_probe * N / n_probe
     frac = min(1.0, budget_s / max(1e-9, est_full * (steps + warmup)))
-    n_s = max(1024, int(N * frac))
-    n_s = min(N, n_s)
+    n_s = min(N, 262144, max(1024, int(N * frac)))  # <= 2^18 rows: [B, N'] fp32 logits + their gradient stay ~1 GB each
     q, bank, labels = synth.make_bank_case(B, n_s, D, 1, "S", 0)
     for _ in range(warmup):
         cpu_reference_step(q, bank, labels, tau)
@@ -122,27 +128,122 @@ def time_cpu_reference(cfg, budget_s: float, steps: int, warmup: int):
                        f"scaled linearly to N={N}; torch {torch.__version__} CPU, {torch.get_num_threads()} threads"), t_step_full
 
 
+def workload_name(tag, cfg):
+    return (f"{tag}: bank-CE fwd+bwd, B={cfg['B']} queries/rank x N={cfg['N']} x D={cfg['D']}"
+            + (f" x T={cfg['T']} tokens (max over tokens)" if cfg.get("T", 1) > 1 else "") + " bank")
+
+
 def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if cfg.get("T", 1) != 1:
+        raise SystemExit("--impl reference times the single-token bank loss (C1/C3/C5)")
     cb, t_step = time_cpu_reference(cfg, budget_s=150.0, steps=max(1, args.steps), warmup=max(0, args.warmup))
     line = {"metric": METRIC, "value": cb["value"], "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"{args.config}: bank-CE fwd+bwd, B={cfg['B']} queries x N={cfg['N']} x D={cfg['D']} "
-                                   "bank, reference CPU torch path (oracle port of clip4cir/models_negplus.py:150-154)"},
+            "config": {"workload": workload_name(args.config, cfg) + f", tau={cfg['tau']}",
+                       "arm": "reference CPU torch path (oracle port of clip4cir/models_negplus.py:150-154 + autograd backward), fp32"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------ GPU helpers
+class Timer:
+    """CUDA-event timing on the current stream with an untimed L2 flush before every timed iteration."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def run(self, fn, iters, flush=True):
+        """-> seconds per iteration (mean); also .per_iter_ms, .cpu_issue_ms"""
+        evs, cpu = [], 0.0
+        for _ in range(iters):
+            if flush:
+                self.flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            t0 = time.perf_counter()
+            fn()
+            cpu += time.perf_counter() - t0
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize(self.dev)
+        self.cpu_issue_ms = cpu / iters * 1e3  # host time spent issuing one step (no sync inside)
+        self.per_iter_ms = [s.elapsed_time(e) for s, e in evs]
+        return sum(self.per_iter_ms) / 1e3 / iters
+
+
+def algorithmic_flops(B, N, D, T):
+    """fwd+bwd 4 N D FLOP per query; BLIP-2 (T = 32): (2 * 32 + 2) N D."""
+    return (4.0 if T == 1 else 2.0 * T + 2.0) * B * N * D
+
+
+def fused_kernel_closure(spn, q_dev, bank, labels_dev, tau):
+    """zero-argument launcher of ONLY the dominant kernel (spn_bank_ce_fused, accumulating) for the roofline timing"""
+    from spn4cir_b200._lib import call as _call
+    from spn4cir_b200.ops import _fused_sweep, fused_scratch
+    sw = _fused_sweep(q_dev, bank, labels_dev, 1.0 / tau, False)
+    Bt, D = q_dev.shape
+    scratch, scratch_bytes = fused_scratch(Bt, bank, q_dev.device)
+
+    def fused_only():
+        _call("spn_bank_ce_fused", sw["q16"].data_ptr(), bank.data.data_ptr(), labels_dev.data_ptr(), sw["ref"].data_ptr(),
+              1.0 / tau, Bt, bank.N, D, bank.T, bank.row_base, 0, sw["o_acc"].data_ptr(), sw["l_acc"].data_ptr(),
+              sw["s_t"].data_ptr(), sw["lbl_row"].data_ptr(), None, None,
+              scratch.data_ptr() if scratch is not None else None, scratch_bytes, torch.cuda.current_stream().cuda_stream)
+    return fused_only
+
+
+def bench_shape(spn, timer, dev, peaks, tag, B, N, D, T, tau, steps, kernel_split=False):
+    """One secondary bank-CE workload on one GPU: step primitive + the fused kernel alone, fractions of measured peak."""
+    rows, _, q, lab = synth.make_device_case(B, N, D, T, dev, seed=3)
+    bank = spn.DeviceBank(rows, T)
+    step = lambda: spn.bank_ce_step(q, bank, lab, tau)  # noqa: E731
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    t = timer.run(step, steps)
+    per = list(timer.per_iter_ms)
+    fk = fused_kernel_closure(spn, q, bank, lab, tau)
+    fk()
+    t_k = timer.run(fk, steps)
+    fl = algorithmic_flops(B, N, D, T)
+    bank_bytes = float(bank.data.numel() * 2)
+    out = {"workload": tag, "B": B, "N": N, "D": D, "T": T, "tau": tau, "value": B / t, "unit": "queries/s",
+           "ms_per_step": t * 1e3, "step_ms_min_median_max": [min(per), statistics.median(per), max(per)],
+           "step_frac_of_bf16_peak": fl / t / 1e12 / peaks["tflops"], "kernel_ms": t_k * 1e3,
+           "kernel_tflops": fl / t_k / 1e12, "kernel_frac_of_bf16_peak": fl / t_k / 1e12 / peaks["tflops"],
+           "bank_stream_gbs": bank_bytes / t_k / 1e9, "kernel_frac_of_hbm_peak": bank_bytes / t_k / 1e9 / peaks["hbm"]}
+    if kernel_split:
+        from spn4cir_b200.ops import _bwd, _fwd_stats, _loss_from_stats, cast_to_bf16
+        q16 = cast_to_bf16(q)
+        stats = _fwd_stats(q16, bank, lab, 1.0 / tau, False)
+        lse, _, _ = _loss_from_stats(stats, bank.n_total, 0.0)
+        dq_acc = torch.zeros((B, D), dtype=torch.float32, device=dev)
+        t_f = timer.run(lambda: _fwd_stats(q16, bank, lab, 1.0 / tau, False), steps)
+        t_b = timer.run(lambda: _bwd(q16, bank, lab, 1.0 / tau, lse, (1.0 / tau) / B, None, 0.0, dq_acc, None), steps)
+        half = fl / 2.0 if T == 1 else 2.0 * T * B * N * D
+        out["forward_kernel"] = {"kernel_ms": t_f * 1e3, "frac": half / t_f / 1e12 / peaks["tflops"],
+                                 "note": "MODE 0 statistics kernel (inference / cold temperatures)"}
+        out["backward_kernel"] = {"kernel_ms": t_b * 1e3, "frac": (fl - half) / t_b / 1e12 / peaks["tflops"],
+                                  "note": "MODE 1 recompute backward from the global lse (S recompute not credited)"}
+    del bank, rows
+    spn.ops.release_scratch()
+    torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args, cfg):
     import torch.distributed as dist
 
     import spn4cir_b200 as spn
-    from spn4cir_b200.dist import bank_ce_step_sharded, bank_infonce_sharded, shard_bounds
+    from spn4cir_b200.dist import bank_ce_step_sharded
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -151,42 +252,35 @@ def run_ours(args, cfg):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B, N, D, tau = cfg["B"], cfg["N"], cfg["D"], cfg["tau"]
+    B, N, D, T, tau = cfg["B"], cfg["N"], cfg["D"], cfg.get("T", 1), cfg["tau"]
     peaks = measured_peaks()
+    steps = args.steps
+    warm = max(3, args.warmup)
 
-    # ---- synthetic inputs (same generator as the tests); bank row-sharded when world > 1
-    bank_cpu = synth.make_bank(N, D, 1, seed=1234)
-    labels_cpu = synth.make_labels(B, N, seed=1235 + rank)
-    q_cpu = synth.make_queries(bank_cpu, labels_cpu, "S", seed=1236 + rank)
-    # N > 1, default: queries are the sharded unit (each rank scores its own B queries against a full bank replica,
-    # 128 MB of 180 GB: no collective on the path).  --bank-sharded: bank rows split across ranks, all queries scored
-    # by every rank, partial sums exchanged over NCCL.
-    sharded = world > 1 and args.bank_sharded
-    bank = spn.DeviceBank.from_tensor(bank_cpu, dev, shard_rank=rank if sharded else 0, shard_world=world if sharded else 1)
-    q_dev = q_cpu.to(dev)
-    labels_dev = labels_cpu.to(dev)
-    q_pin = q_cpu.pin_memory()
-    lab_pin = labels_cpu.pin_memory()
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    # ---- synthetic inputs, generated on the device; N > 1: bank row-sharded (default) or replicated (--bank-replicated)
+    sharded = world > 1 and not args.bank_replicated
+    rows, row_base, q_dev, labels_dev = synth.make_device_case(B, N, D, T, dev, rank=rank, world=world, sharded=sharded)
+    bank = spn.DeviceBank(rows, T, row_base=row_base if sharded else 0, n_total=N)
+    q_pin = q_dev.cpu().pin_memory()
+    lab_pin = labels_dev.cpu().pin_memory()
+    timer = Timer(dev)
+
+    def step(qin, lab):
+        """one pass of the hot path: loss + dL/dq.  N = 1: the step primitive (one spn_bank_ce_step C-ABI call);
+        N > 1: the same sweep over this rank's bank rows for all ranks' queries + the NCCL exchange."""
+        if sharded:
+            return bank_ce_step_sharded(qin, bank, lab, tau)
+        return spn.bank_ce_step(qin, bank, lab, tau)
 
     def step_autograd(qin, lab):
         """the reference call shape: loss = infonce_loss(q, bank, labels, tau); loss.backward()"""
         qx = qin.detach().requires_grad_(True)
         if sharded:
-            loss = bank_infonce_sharded(qx, bank, lab, tau)
+            loss = spn.dist.bank_infonce_sharded(qx, bank, lab, tau)
         else:
             loss = spn.bank_infonce(qx, bank, lab, tau)
         loss.backward()
         return loss, qx.grad
-
-    def step(qin, lab):
-        """one pass of the hot path: loss + dL/dq.  Un-sharded: the step primitive (one spn_bank_ce_step C-ABI call, same
-        kernels as the autograd wrapper minus PyTorch's autograd-engine hand-off: ~135 us of host time per step at best --
-        as long as the GPU step -- and 470 us while the nvidia-smi clock sampler's reader thread is alive, which would make
-        the contract's clock-sampled measurement host-bound); the autograd wrapper is timed right after the sampler stops."""
-        if sharded:
-            return bank_ce_step_sharded(qin, bank, lab, tau)
-        return spn.bank_ce_step(qin, bank, lab, tau)
 
     dq_pin = torch.empty((B, D), dtype=torch.float32).pin_memory()
     loss_pin = torch.empty((), dtype=torch.float32).pin_memory()
@@ -204,8 +298,8 @@ def run_ours(args, cfg):
         """K steps through the public call with the copies of neighbouring steps overlapped (what a trainer with a
         prefetching loader does): every step still copies ITS inputs from pinned host memory and ITS loss + dq back into
         pinned host memory inside the timed region; copy-in / compute / copy-out run on three streams chained by events.
-        One start/end event pair around the K steps (no L2 flush in between: the step's working set -- 128 MB bank +
-        102 MB P~ scratch, written and re-read -- exceeds the 126 MB L2 by itself)."""
+        One start/end event pair around the K steps (no L2 flush in between: the step's working set -- bank + P~ scratch
+        -- exceeds the 126 MB L2 many times over)."""
         s_comp = torch.cuda.current_stream(dev)
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         slots = [{"q": torch.empty_like(q_dev), "lab": torch.empty_like(labels_dev),
@@ -214,7 +308,7 @@ def run_ours(args, cfg):
                   "ev_in": torch.cuda.Event(), "ev_comp": torch.cuda.Event(), "ev_out": torch.cuda.Event()}
                  for _ in range(depth)]
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        flush.zero_()
+        timer.flush.zero_()
         start.record(s_comp)
         s_in.wait_event(start)
         s_out.wait_event(start)
@@ -242,177 +336,220 @@ def run_ours(args, cfg):
         torch.cuda.synchronize(dev)
         return start.elapsed_time(end) / 1e3, float(slots[(iters - 1) % depth]["loss_pin"])
 
-    def timed(fn, iters):
-        """sum of per-iteration CUDA-event times (L2 flushed, untimed, before each); max over ranks."""
-        evs, cpu = [], 0.0
-        for _ in range(iters):
-            flush.zero_()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            t0 = time.perf_counter()
-            fn()
-            cpu += time.perf_counter() - t0
-            e.record()
-            evs.append((s, e))
-        torch.cuda.synchronize(dev)
-        timed.cpu_issue_ms = cpu / iters * 1e3  # host time spent issuing one step (no sync inside)
-        timed.per_iter_ms = [s.elapsed_time(e) for s, e in evs]
-        return sum(timed.per_iter_ms) / 1e3
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def agree_max(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     if args.profile:
         step(q_dev, labels_dev)
         barrier()
-        t = timed(lambda: step(q_dev, labels_dev), args.steps)
+        t = timer.run(lambda: step(q_dev, labels_dev), steps)
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": t / args.steps * 1e3}))
+            print(json.dumps({"profile_run": True, "ms_per_step": t * 1e3}))
         return
-    for _ in range(max(3, args.warmup)):
+    for _ in range(warm):
         step(q_dev, labels_dev)
     barrier()
-    # clocks: nvidia-smi samples every 100 ms, a K-step timed region lasts milliseconds -> keep the GPU under the
-    # same load for ~1.5 s (untimed) right before and sample through both regions
+    # clocks: nvidia-smi samples every 100 ms, a K-step timed region lasts milliseconds -> keep the GPU under the same
+    # load for ~1.5 s (untimed) right before and sample through both regions.  The number of load steps is FIXED and
+    # agreed across ranks (a wall-clock loop would issue a different number of collectives on every rank).
+    t_est = agree_max(timer.run(lambda: step(q_dev, labels_dev), 5, flush=False))
+    n_load = max(10, min(20000, int(1.5 / max(t_est, 1e-5))))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    t_end_load = time.perf_counter() + 1.5
-    while time.perf_counter() < t_end_load:
-        for _ in range(20):
-            step(q_dev, labels_dev)
-        torch.cuda.synchronize(dev)
+    for i in range(n_load):
+        step(q_dev, labels_dev)
+        if i % 50 == 49:
+            torch.cuda.synchronize(dev)
     barrier()
-    t_dev = timed(lambda: step(q_dev, labels_dev), args.steps)
-    host_issue_ms, per_iter = timed.cpu_issue_ms, list(timed.per_iter_ms)
+    t_dev = timer.run(lambda: step(q_dev, labels_dev), steps)
+    host_issue_ms, per_iter = timer.cpu_issue_ms, list(timer.per_iter_ms)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(3):
         step_autograd(q_dev, labels_dev)
     barrier()
-    t_auto = timed(lambda: step_autograd(q_dev, labels_dev), args.steps)
-    auto_issue_ms = timed.cpu_issue_ms
+    t_auto = timer.run(lambda: step_autograd(q_dev, labels_dev), steps)
+    auto_issue_ms = timer.cpu_issue_ms
     barrier()
     for _ in range(2):
         step_e2e()
     barrier()
-    t_e2e_serial = timed(step_e2e, args.steps)
+    t_e2e_serial = timer.run(step_e2e, steps)
     barrier()
     e2e_mode = "pipelined"
     try:
-        e2e_pipelined(max(3, args.warmup))
+        e2e_pipelined(warm)
         barrier()
-        t_e2e, loss_e2e = e2e_pipelined(args.steps)
+        t_e2e, loss_e2e = e2e_pipelined(steps)
+        t_e2e /= steps
     except Exception as exc:  # never lose the bench line over the overlapped variant: report the serial measurement
         print(f"bench: pipelined e2e failed ({exc!r}); reporting the serial e2e", file=sys.stderr)
         e2e_mode, t_e2e, loss_e2e = "serial", t_e2e_serial, None
     barrier()
 
-    # ---- dominant-kernel roofline: backward kernel (and forward kernel) timed alone, same events/stream
-    from spn4cir_b200.ops import _bwd, _fwd_stats, _loss_from_stats, cast_to_bf16
+    # ---- dominant kernel alone (same events / stream): the fused sweep over this rank's rows for all queries of the step
     Bt = B * world if sharded else B
-    q16 = cast_to_bf16(torch.cat([q_dev] * world) if sharded else q_dev)
-    lab_all = torch.cat([labels_dev] * world) if sharded else labels_dev
-    stats = _fwd_stats(q16, bank, lab_all, 1.0 / tau, False)
     if sharded:
-        from spn4cir_b200.dist import merge_stats_across_ranks
-        stats = merge_stats_across_ranks(stats)
-    lse, _, _ = _loss_from_stats(stats, bank.n_total, 0.0)
-    dq_acc = torch.zeros((Bt, D), dtype=torch.float32, device=dev)
-    t_fwd = timed(lambda: _fwd_stats(q16, bank, lab_all, 1.0 / tau, False), args.steps) / args.steps
-    t_bwd = timed(lambda: _bwd(q16, bank, lab_all, 1.0 / tau, lse, (1.0 / tau) / B, None, 0.0, dq_acc, None),
-                  args.steps) / args.steps
-    from spn4cir_b200.ops import _fused_sweep
-    from spn4cir_b200._lib import call as _call
-    sw = _fused_sweep(torch.cat([q_dev] * world) if sharded else q_dev, bank, lab_all, 1.0 / tau, False)
-
-    from spn4cir_b200.ops import fused_scratch
-    scratch, scratch_bytes = fused_scratch(Bt, bank, dev)
-
-    def fused_only():
-        _call("spn_bank_ce_fused", sw["q16"].data_ptr(), bank.data.data_ptr(), lab_all.data_ptr(), sw["ref"].data_ptr(),
-              1.0 / tau, Bt, bank.N, D, bank.T, bank.row_base, 0, sw["o_acc"].data_ptr(), sw["l_acc"].data_ptr(),
-              sw["s_t"].data_ptr(), sw["lbl_row"].data_ptr(), None, None,
-              scratch.data_ptr() if scratch is not None else None, scratch_bytes, torch.cuda.current_stream().cuda_stream)
-
-    t_fused = timed(fused_only, args.steps) / args.steps
+        q_all = torch.empty((Bt, D), dtype=q_dev.dtype, device=dev)
+        dist.all_gather_into_tensor(q_all, q_dev)
+        lab_all = torch.empty(Bt, dtype=labels_dev.dtype, device=dev)
+        dist.all_gather_into_tensor(lab_all, labels_dev)
+    else:
+        q_all, lab_all = q_dev, labels_dev
+    fused_only = fused_kernel_closure(spn, q_all, bank, lab_all, tau)
+    fused_only()
+    t_fused = timer.run(fused_only, steps)
     barrier()
 
-    red = torch.tensor([t_dev, t_e2e, t_fwd, t_bwd, t_fused, t_e2e_serial], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e, t_fwd, t_bwd, t_fused, t_e2e_serial = red.tolist()
+    # ---- self check (untimed): the fused single sweep against the two-pass path (forward statistics kernel with an exact
+    # running maximum + recompute backward: different kernels, same mathematics), on this rank's queries
+    from spn4cir_b200.ops import _bwd, _fwd_stats, _loss_from_stats, cast_to_bf16
+    loss_f, dq_f = step(q_dev, labels_dev)
+    q16 = cast_to_bf16(q_all)
+    stats = _fwd_stats(q16, bank, lab_all, 1.0 / tau, False)
+    if sharded:
+        stats = spn.dist.merge_stats_across_ranks(stats)
+    lse, loss_q, _ = _loss_from_stats(stats, bank.n_total, 0.0)
+    dq2 = torch.zeros((Bt, D), dtype=torch.float32, device=dev)
+    _bwd(q16, bank, lab_all, 1.0 / tau, lse, (1.0 / tau) / B, None, 0.0, dq2, None)
+    if sharded:
+        dist.all_reduce(dq2)
+    sl = slice(rank * B, (rank + 1) * B) if sharded else slice(0, B)
+    loss_2 = float(loss_q[sl].mean().item())
+    dq_rel = float(((dq_f - dq2[sl]).norm() / dq2[sl].norm()).item())
+    self_check = {"loss_fused_sweep": float(loss_f.item()), "loss_two_pass": loss_2, "dq_rel_l2_diff": dq_rel,
+                  "ok": bool(abs(float(loss_f.item()) - loss_2) <= 1e-3 * max(1.0, abs(loss_2)) and dq_rel < 5e-3)}
+    del dq2, stats, q16
+    barrier()
+
+    # ---- exchange breakdown (N > 1): every collective of the step alone, same buffers' shapes, CUDA events, max over ranks
+    exchange = None
+    if sharded:
+        o_full = torch.zeros((Bt, D), dtype=torch.float32, device=dev)
+        o_mine = torch.empty((B, D), dtype=torch.float32, device=dev)
+        q16l = cast_to_bf16(q_dev)
+        q16a = torch.empty((Bt, D), dtype=torch.bfloat16, device=dev)
+        refv = torch.zeros(Bt, dtype=torch.float32, device=dev)
+        vec = torch.zeros((4, Bt), dtype=torch.float32, device=dev)
+        parts = {
+            "all_gather_q_bf16": (lambda: dist.all_gather_into_tensor(q16a, q16l), Bt * D * 2),
+            "all_gather_labels": (lambda: dist.all_gather_into_tensor(lab_all, labels_dev), Bt * 8),
+            "all_reduce_min_ref": (lambda: dist.all_reduce(refv, op=dist.ReduceOp.MIN), Bt * 4),
+            "all_reduce_sum_vec": (lambda: dist.all_reduce(vec), 4 * Bt * 4),
+            "reduce_scatter_o_fp32": (lambda: dist.reduce_scatter_tensor(o_mine, o_full), Bt * D * 4),
+        }
+        exchange = {}
+        for name, (fn, nbytes) in parts.items():
+            for _ in range(3):
+                fn()
+            barrier()
+            ms = agree_max(timer.run(fn, steps, flush=False)) * 1e3
+            exchange[name] = {"ms": ms, "bytes": nbytes}
+        exchange["sum_ms"] = sum(v["ms"] for v in exchange.values())
+        del o_full, o_mine, q16a
+    barrier()
+
+    t_dev, t_e2e, t_fused, t_e2e_serial, t_auto = (agree_max(x) for x in (t_dev, t_e2e, t_fused, t_e2e_serial, t_auto))
 
     if rank == 0:
-        n_local = bank.N
-        flops_alg_kernel = 2.0 * Bt * n_local * D  # per launch, per rank (dq = P . bank; the S recompute is not credited)
-        step_flops_rank = 4.0 * Bt * n_local * D
-        ms_step = t_dev / args.steps * 1e3
-        value = (B * world) * args.steps / t_dev
+        fl = algorithmic_flops(Bt, bank.N, D, T)  # per launch = per rank per step
+        value = (B * world) / t_dev
         peak = peaks["tflops"]
-        roof = {"bound": "tensor", "kernel": "bank_ce_kernel<MODE=2, CG=2> (fused sweep, two passes per CTA pair: S = q.bank^T -> P~ = exp(S - ref) -> dq[:, :X] += P~.bank, P~ parked in a bf16 scratch; then dq[:, X:] += P~.bank as a plain tcgen05 GEMM; no S recompute)",
-                "achieved": step_flops_rank / t_fused / 1e12, "peak": peak, "unit": "TFLOP/s",
-                "frac": step_flops_rank / t_fused / 1e12 / peak, "traffic": None, "peak_source": peaks["src"] + " burst bf16",
-                "kernel_ms": t_fused * 1e3, "algorithmic_flops_per_launch": step_flops_rank,
-                "forward_kernel": {"achieved": flops_alg_kernel / t_fwd / 1e12, "frac": flops_alg_kernel / t_fwd / 1e12 / peak,
-                                   "kernel_ms": t_fwd * 1e3},
-                "backward_kernel": {"achieved": flops_alg_kernel / t_bwd / 1e12, "frac": flops_alg_kernel / t_bwd / 1e12 / peak,
-                                    "kernel_ms": t_bwd * 1e3},
-                "step": {"algorithmic_tflops": step_flops_rank / (t_dev / args.steps) / 1e12,
-                         "frac": step_flops_rank / (t_dev / args.steps) / 1e12 / peak}}
-        prof = REPO / "profiles" / "r01_ncu_bank_ce_fused.json"
+        roof = {"bound": "tensor",
+                "kernel": "bank_ce_kernel<MODE=2, CG=2> (fused sweep, two passes per CTA pair: S = q.bank^T -> P~ = exp(S - ref) -> "
+                          "dq[:, :X] += P~.bank, P~ parked in a bf16 scratch; then dq[:, X:] += P~.bank as a plain tcgen05 GEMM; no S recompute)",
+                "achieved": fl / t_fused / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": fl / t_fused / 1e12 / peak,
+                "traffic": None, "peak_source": peaks["src"] + " burst bf16 (kernel timed alone)", "kernel_ms": t_fused * 1e3,
+                "algorithmic_flops_per_launch": fl,
+                "units_per_launch": f"{Bt} queries x {bank.N} bank rows of this rank, 4 D = {4 * D} FLOP per (query, row)",
+                "step": {"algorithmic_tflops": fl / t_dev / 1e12, "frac": fl / t_dev / 1e12 / peak,
+                         "frac_of_sustained_peak": fl / t_dev / 1e12 / peaks["tflops_sustained"]}}
+        prof = REPO / "profiles" / "r02_ncu_bank_ce_fused_c5.json"
         if prof.exists():
             try:
                 roof["traffic"] = json.loads(prof.read_text()).get("dram_bytes_per_launch")
             except Exception:
                 pass
-        line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        par = ("single GPU, whole bank resident" if world == 1 else
+               f"bank row-sharded x{world} ({bank.N} rows/rank), queries data-parallel: all_gather(q bf16, labels) -> MIN all_reduce(ref) "
+               f"-> fused sweep -> SUM all_reduce([4, {Bt}]) -> owner folds the target rows -> reduce_scatter(o fp32 [{Bt}, {D}]) over NCCL"
+               if sharded else
+               f"queries data-parallel x{world}, bank replicated per GPU ({N * T * D * 2 / 1e6:.0f} MB bf16): no collective on the path")
+        line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps,
+                "warmup": warm, "ms_per_step": t_dev * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"{args.config}: bank-CE fwd+bwd, B={B} queries/rank x N={N} x D={D} bank (bf16, fp32 accumulate), tau={tau}",
-                           "parallelism": ("single GPU" if world == 1 else
-                                           f"bank row-sharded x{world}, queries data-parallel (bf16 all-gather), reference MIN all-reduce + reduce-scatter of the additive partials" if sharded else
-                                           f"queries data-parallel x{world} (the sharded unit), bank replicated per GPU ({N * D * 2 / 1e6:.0f} MB bf16): no collective on the path"),
-                           "l2": "256 MiB flush buffer written before every timed iteration",
-                           "global_batch": B * world},
-                "clocks": clocks, "roofline": roof,
+                "config": {"workload": workload_name(args.config, cfg) + f", tau={tau}",
+                           "arm": "B200 path: bf16 operands, fp32 accumulate (tcgen05)", "parallelism": par, "l2": "256 MiB flush buffer written before every timed iteration",
+                           "global_batch": B * world, "per_rank_flops_per_step": fl},
+                "clocks": clocks, "roofline": roof, "self_check": self_check,
                 "host_issue_ms_per_step": host_issue_ms,
                 "api": ("spn4cir_b200.dist.bank_ce_step_sharded (step primitive over the row-sharded bank, NCCL exchange)" if sharded else
                         "spn4cir_b200.bank_ce_step -> spn_bank_ce_step (C ABI step primitive: loss + dL/dq)"),
                 "autograd_api": {"call": "loss = bank_infonce(q, bank, labels, tau); loss.backward()",
-                                 "value": (B * world) * args.steps / t_auto, "unit": "queries/s",
-                                 "ms_per_step": t_auto / args.steps * 1e3, "host_issue_ms_per_step": auto_issue_ms,
-                                 "note": "same kernels + the autograd engine's thread hand-off, a ones-fill and a scale kernel; timed after the clock sampler stopped (with its reader thread alive the hand-off costs ~470 us of host time per step)"},
+                                 "value": (B * world) / t_auto, "unit": "queries/s",
+                                 "ms_per_step": t_auto * 1e3, "host_issue_ms_per_step": auto_issue_ms},
                 "step_ms_min_median_max": [min(per_iter), statistics.median(per_iter), max(per_iter)],
-                "e2e": {"value": (B * world) * args.steps / t_e2e, "unit": "queries/s",
+                "e2e": {"value": (B * world) / t_e2e, "unit": "queries/s",
                         "h2d_bytes_per_step": q_pin.numel() * 4 + lab_pin.numel() * 8,
-                        "d2h_bytes_per_step": B * D * 4 + 4, "ms_per_step": t_e2e / args.steps * 1e3,
+                        "d2h_bytes_per_step": B * D * 4 + 4, "ms_per_step": t_e2e * 1e3,
                         "loss_read_back": loss_e2e, "mode": e2e_mode,
                         "note": "pinned host q/labels -> device, fwd+bwd through the public call, loss + dq back to pinned host memory, every step; "
-                                "copy-in / compute / copy-out of neighbouring steps overlap on three event-chained streams (3 slots); one event pair around the K steps, no L2 flush "
-                                "(working set 230 MB > 126 MB L2: `value` above pays a fully cold L2 before every step, this loop does not); the bank stays resident in HBM",
-                        "serial": {"value": (B * world) * args.steps / t_e2e_serial, "ms_per_step": t_e2e_serial / args.steps * 1e3,
+                                "copy-in / compute / copy-out of neighbouring steps overlap on three event-chained streams (3 slots); one event pair "
+                                "around the K steps; the bank stays resident in HBM",
+                        "serial": {"value": (B * world) / t_e2e_serial, "ms_per_step": t_e2e_serial * 1e3,
                                    "note": "the same step with its copies serialised on one stream, L2 flushed before each (latency of one isolated step)"}},
-                "gpu_launches": (5 if sharded else 3) * args.steps,
-                "gpu_launches_detail": ("per step: prep_query_kernel, fused_init_kernel, bank_ce_kernel<2>, gather_label_rows_kernel, fused_finalize_kernel"
+                "gpu_launches": (7 if sharded else 3) * steps,
+                "gpu_launches_detail": ("per step: cast_bf16_kernel, prep_query_kernel, fused_init_kernel, bank_ce_kernel<2>, shard_pack_kernel, "
+                                        "shard_fold_kernel, fused_finalize_kernel (+ 5 NCCL collectives)"
                                         if sharded else
                                         "per step (one spn_bank_ce_step call): prep_query_kernel, bank_ce_kernel<2>, fused_finalize_kernel")}
+        if exchange is not None:
+            exchange["step_minus_sweep_ms"] = (t_dev - t_fused) * 1e3
+            line["exchange"] = exchange
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = time_cpu_reference(cfg, budget_s=20.0, steps=3, warmup=1)
             line["cpu_baseline"] = cb
-        if world == 1 and not args.no_retrieval:
+        if world == 1 and not args.no_secondary:
+            del bank, rows, fused_only
+            spn.ops.release_scratch()
+            torch.cuda.empty_cache()
+            sec = {}
+            shapes = [
+                ("c3", "C3: FashionIQ-shaped stage-2 step, 512 x 100k x 640", 512, 100000, 640, 1, 0.02, True),
+                ("north_star_1m_640", "north-star target shape: 1024 x 1M x 640 fwd+bwd on 1 B200", 1024, 1000000, 640, 1, 0.02, False),
+                ("c4_blip2", "C4: BLIP-2 stage-2, 256 x 200k entries x 32 tokens x 256 (max over tokens)", 256, 200000, 256, 32, 0.05, False),
+                ("b256_100k_640", "reference batch 256 (README :236): 256 x 100k x 640", 256, 100000, 640, 1, 0.02, False),
+                ("b128_100k_640", "reference batch 128 (README :330): 128 x 100k x 640", 128, 100000, 640, 1, 0.02, False),
+                ("b512_100k_256", "512 x 100k x 256", 512, 100000, 256, 1, 0.02, False),
+                ("b32_t32_256", "BLIP-2 batch 32 (README :377): 32 x 50k entries x 32 tokens x 256", 32, 50000, 256, 32, 0.05, False),
+            ]
+            for key, tag, b, n, d, t, ta, split in shapes:
+                try:
+                    sec[key] = bench_shape(spn, timer, dev, peaks, tag, b, n, d, t, ta, min(steps, 20), kernel_split=split)
+                except Exception as exc:  # the headline line must survive a failure of a secondary workload
+                    sec[key] = {"workload": tag, "error": repr(exc)}
+            line["secondary"] = sec
             try:
-                line["retrieval"] = bench_retrieval(dev, args)
-            except Exception as exc:  # the headline line must survive a failure of the secondary workload
+                line["retrieval"] = bench_retrieval(dev, args, peaks, timer)
+            except Exception as exc:
                 line["retrieval"] = {"error": repr(exc)}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
-def bench_retrieval(dev, args):
+def bench_retrieval(dev, args, peaks, timer):
     """C2: CIRR-shaped validation retrieval, 4181 queries x 2297 gallery x 640-d on one GPU: the ranking the reference's
     validate.py consumes (sorted indices -> top-50 names, rank of the target + subset rank -> Recall@K)."""
     import spn4cir_b200 as spn
@@ -423,6 +560,7 @@ def bench_retrieval(dev, args):
     iters = max(3, min(args.steps, 20))
 
     def timed(fn):
+        """(warm-L2 seconds: back-to-back launches; cold-L2 seconds: 256 MiB flush before each, per-iteration events)"""
         for _ in range(3):
             fn()
         torch.cuda.synchronize(dev)
@@ -432,14 +570,14 @@ def bench_retrieval(dev, args):
             fn()
         e.record()
         torch.cuda.synchronize(dev)
-        return s.elapsed_time(e) / 1e3 / iters
+        return s.elapsed_time(e) / 1e3 / iters, timer.run(fn, iters)
 
     # headline: exact top-K indices (what the reference keeps of its argsort), tcgen05 sweep + fp32 rescoring of near-ties
-    t = timed(lambda: spn.sim_topk(qd, gd, c["K"], exclude=refd, mode="tc", exact_values=False))
-    t_vals = timed(lambda: spn.sim_topk(qd, gd, c["K"], exclude=refd, mode="tc", exact_values=True))
-    t_fp32 = timed(lambda: spn.sim_topk(qd, gd, c["K"], exclude=refd, mode="fp32"))
-    t_rank = timed(lambda: spn.sim_rank(qd, gd, tgtd, exclude=refd, group=grpd, mode="tc"))
-    t_rank_fp32 = timed(lambda: spn.sim_rank(qd, gd, tgtd, exclude=refd, group=grpd, mode="fp32"))
+    t, t_cold = timed(lambda: spn.sim_topk(qd, gd, c["K"], exclude=refd, mode="tc", exact_values=False))
+    t_vals, _ = timed(lambda: spn.sim_topk(qd, gd, c["K"], exclude=refd, mode="tc", exact_values=True))
+    t_fp32, _ = timed(lambda: spn.sim_topk(qd, gd, c["K"], exclude=refd, mode="fp32"))
+    t_rank, t_rank_cold = timed(lambda: spn.sim_rank(qd, gd, tgtd, exclude=refd, group=grpd, mode="tc"))
+    t_rank_fp32, _ = timed(lambda: spn.sim_rank(qd, gd, tgtd, exclude=refd, group=grpd, mode="fp32"))
     # the two paths must agree before either number means anything
     i_tc = spn.sim_topk(qd, gd, c["K"], exclude=refd, mode="tc", exact_values=False)[1]
     i_fp = spn.sim_topk(qd, gd, c["K"], exclude=refd, mode="fp32")[1]
@@ -463,14 +601,22 @@ def bench_retrieval(dev, args):
     oretr.reference_style_sorted_indices(q, gal)
     t_cpu = time.perf_counter() - t0
     flop = 2.0 * c["Q"] * c["G"] * c["D"]
+    nbytes = 4.0 * (c["Q"] + c["G"]) * c["D"] + 8.0 * c["Q"] * c["K"]  # fp32 operands once + the [Q, K] (value, index) lists
+
+    def roof(sec):
+        return {"tensor_frac": flop / sec / 1e12 / peaks["tflops"], "hbm_frac": nbytes / sec / 1e9 / peaks["hbm"],
+                "algorithmic_tflops": flop / sec / 1e12, "algorithmic_gbs": nbytes / sec / 1e9}
+
     return {"workload": f"C2: {c['Q']} queries x {c['G']} gallery x {c['D']}-d fp32 features, exact top-{c['K']} indices "
                         "(spn_sim_topk_tc: bf16 hi/lo tcgen05 sweep + fp32 rescoring of near-ties; indices identical to the fp32 kernel, checked in this run)",
-            "value": c["Q"] / t, "unit": "queries/s", "ms": t * 1e3, "e2e_value": c["Q"] / t_e2e,
+            "value": c["Q"] / t, "unit": "queries/s", "ms": t * 1e3, "ms_cold_l2": t_cold * 1e3, "e2e_value": c["Q"] / t_e2e,
             "exact_values_ms": t_vals * 1e3, "fp32_kernel_ms": t_fp32 * 1e3,
+            "roofline": {"bound": "launch/latency class (12.3 GFLOP = 7 us of tensor time, 17.5 MB = 2.7 us of HBM time): both fractions reported, neither near 1",
+                         "algorithmic_flops": flop, "algorithmic_bytes": nbytes, "peak_tflops": peaks["tflops"], "peak_gbs": peaks["hbm"],
+                         "topk_warm_l2": roof(t), "topk_cold_l2": roof(t_cold), "rank_warm_l2": roof(t_rank), "rank_cold_l2": roof(t_rank_cold)},
             "rank_of_target": {"call": "spn_sim_rank_tc (rank + CIRR subset rank -> Recall@K)", "value": c["Q"] / t_rank,
-                               "ms": t_rank * 1e3, "fp32_kernel_ms": t_rank_fp32 * 1e3},
-            "cpu_reference_value": c["Q"] / t_cpu, "cpu_cores": os.cpu_count(),
-            "algorithmic_tflops": flop / t / 1e12}
+                               "ms": t_rank * 1e3, "ms_cold_l2": t_rank_cold * 1e3, "fp32_kernel_ms": t_rank_fp32 * 1e3},
+            "cpu_reference_value": c["Q"] / t_cpu, "cpu_cores": os.cpu_count()}
 
 
 def main():
@@ -479,12 +625,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="C3", choices=["C1", "C3", "C5"])
+    ap.add_argument("--config", default="C5", choices=["C1", "C3", "C4", "C5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="N = 1: skip the secondary workloads (C3, 1M x 640, C4, small batches, C2)")
     ap.add_argument("--profile", action="store_true", help="under ncu: 1 warm-up + K timed steps, nothing else")
-    ap.add_argument("--bank-sharded", action="store_true",
-                    help="N > 1: row-shard the bank across ranks (one NCCL exchange per step) instead of replicating it")
+    ap.add_argument("--bank-replicated", action="store_true",
+                    help="N > 1: replicate the bank on every GPU (no collective) instead of row-sharding it")
     args = ap.parse_args()
     cfg = synth.CONFIGS[args.config]
     if args.impl == "reference":

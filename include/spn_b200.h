@@ -147,11 +147,26 @@ int spn_bank_ce_fused(const void* q_bf16, const void* bank_bf16, const int64_t* 
  *   loss_b = lse - (1-eps) s_t - eps sum_n s_n / N,   loss_mean = mean_b loss_b,
  *   dq[b]  = gscale * [ (o_acc - l_acc bank_t) / L + eps bank_t - (eps / N) colsum ]      (gscale = inv_tau / B)
  *   dlogit_dot[b] = sum_n dlogit[b][n] s[b][n]  (nullable; needs es_acc).
- * (1 - p_t) = l_acc / L is formed without cancellation.  dq is the gradient for an upstream gradient of 1. */
+ * (1 - p_t) = l_acc / L is formed without cancellation.  dq is the gradient for an upstream gradient of 1.
+ * bank_t == NULL: the target-row terms were already folded into o_acc by spn_shard_fold (row-sharded bank). */
 int spn_bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, const float* bank_t, const float* ref,
                          const float* es_acc, const void* q_bf16, const float* colsum, float inv_tau, float gscale,
                          float label_smoothing, int64_t N_total, int B, int D, float* lse, float* loss_per_query,
                          float* loss_mean, float* dq, float* dlogit_dot, void* stream);
+
+/* ---- row-sharded bank (reference loss over ALL rows: zscir/models_bank.py:90-101,130-134) ----
+ * Every rank sweeps its N / R rows for all Bt = R * B queries of the step (spn_bank_ce_fused with row_base); the partial
+ * sums are additive.  spn_shard_pack lays the per-query scalars out as vec [4, Bt] = (l_acc, s_t of the owner else 0,
+ * es_acc or 0, owned in {0, 1}) so that ONE sum all-reduce merges them.  After it, spn_shard_fold lets the rank that owns
+ * label b add the target-row terms of the gradient to its partial,
+ *     o_acc[b] += (-l_b + eps L_b) bank[lbl_row[b]],   L_b = l_b + exp(s_t - ref_b)      (vec = the all-reduced values)
+ * and writes s_t_out[b] = s_t (or -inf when no rank owns the label: the loss is +inf, as on one GPU).  One
+ * reduce-scatter(sum) of o_acc then gives every rank the rows of its own queries; spn_bank_ce_finalize(bank_t = NULL)
+ * finishes them.  Host plumbing (torch.distributed / NCCL): spn4cir_b200/dist.py. */
+int spn_shard_pack(const float* l_acc, const float* s_t, const float* es_acc, const int64_t* lbl_row, int Bt, float* vec,
+                   void* stream);
+int spn_shard_fold(float* o_acc, const float* vec, const float* ref, const int64_t* lbl_row, const void* bank_bf16, int Bt,
+                   int D, float label_smoothing, float* s_t_out, void* stream);
 
 /* One whole training step on one GPU (un-sharded bank, row_base = 0) in a single call:
  * spn_bank_ce_prep (+ zeroing of the accumulators) -> spn_bank_ce_fused -> spn_bank_ce_finalize (the target row is read

@@ -20,7 +20,7 @@ REPO_ROOT = PKG_DIR.parent
 LIB_PATH = PKG_DIR / "libspn_b200.so"
 HEADER_PATH = REPO_ROOT / "include" / "spn_b200.h"
 
-SOURCES = ["common.cu", "bank_ce_tc.cu", "part_ce.cu", "umma_selftest.cu", "prologue.cu", "sim_rank.cu", "sim_tc.cu", "api.cu"]
+SOURCES = ["common.cu", "bank_ce_tc.cu", "shard.cu", "part_ce.cu", "umma_selftest.cu", "prologue.cu", "sim_rank.cu", "sim_tc.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177",
@@ -59,22 +59,41 @@ def _stale() -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False, extra_flags=(), out: Path = None) -> Path:
-    """Compile csrc/*.cu into spn4cir_b200/libspn_b200.so (sm_100a). Cross-compiles without a GPU."""
+    """Compile csrc/*.cu into spn4cir_b200/libspn_b200.so (sm_100a). Cross-compiles without a GPU.
+    One nvcc -c per source (in parallel, objects cached under build/ by mtime), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
     out = Path(out) if out is not None else LIB_PATH
     if out == LIB_PATH and not force and not _stale():
         return LIB_PATH
+    nvcc = _nvcc()
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags)
+    tag = "obj" if not extra_flags else "obj_" + "".join(c if c.isalnum() else "_" for c in "".join(extra_flags))
+    objdir = REPO_ROOT / "build" / tag
+    objdir.mkdir(parents=True, exist_ok=True)
+    hdr_t = max(p.stat().st_mtime for p in list(CSRC_DIR.glob("*.cuh")) + [HEADER_PATH])
+
+    def compile_one(src: str):
+        s, o = CSRC_DIR / src, objdir / (Path(src).stem + ".o")
+        if not force and o.exists() and o.stat().st_mtime > max(s.stat().st_mtime, hdr_t):
+            return o, ""
+        cmd = [nvcc, *flags, *(["-Xptxas", "-v"] if verbose else []), "-c", str(s), "-o", str(o)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            o.unlink(missing_ok=True)
+            raise SpnError("build", -5, f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        return o, res.stdout + res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        done = list(ex.map(compile_one, SOURCES))
     tmp = out.with_suffix(".so.tmp%d" % os.getpid())
-    cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags, "-o", str(tmp), *[str(CSRC_DIR / s) for s in SOURCES]]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp),
+                          *[str(o) for o, _ in done]], capture_output=True, text=True)
     if res.returncode != 0:
         tmp.unlink(missing_ok=True)
-        raise SpnError("build", -5, "nvcc failed:\n" + res.stdout + res.stderr)
+        raise SpnError("build", -5, "link failed:\n" + res.stdout + res.stderr)
     os.replace(tmp, out)
     if verbose:
-        print(res.stdout + res.stderr)
+        print("".join(log for _, log in done))
     return out
 
 
@@ -103,6 +122,8 @@ _SIGNATURES = {
     "spn_bank_ce_finalize": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                              c_float, c_float, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p],
+    "spn_shard_pack": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    "spn_shard_fold": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p],
     "spn_bank_ce_step": [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float, c_int, c_int64, c_int,
                          c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     "spn_part_ce": [c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,

@@ -37,7 +37,20 @@ from .retrieval import _prep_gallery, names_to_ids, recall_at, sim_rank, sim_top
 # --------------------------------------------------------------------------------------- bank-CE
 def infonce_loss(query_features: torch.Tensor, target_features: Union[DeviceBank, torch.Tensor],
                  labels: Optional[torch.Tensor] = None, tau=0.01, label_smoothing: float = 0.0) -> torch.Tensor:
-    """``CIRPlus.infonce_loss``: ``CE((q @ bank.T) / tau, labels)``; ``labels=None`` -> ``arange(B)``."""
+    """``CIRPlus.infonce_loss``: ``CE((q @ bank.T) / tau, labels)``; ``labels=None`` -> ``arange(B)``.
+
+    The accelerated path treats ``target_features`` as a CONSTANT bank (the reference detaches it at the bank call
+    sites, models_negplus.py:138).  The same method is also called by the reference with in-batch targets that carry
+    gradient (``bbc_loss`` clip4cir/models.py:160, zscir/models.py:168, the symmetric losses models_negtype.py:84-107):
+    those sites are outside the path (they need image-tower gradients) and keep the reference's dense
+    formula here, so that rebinding the method never drops a gradient silently."""
+    if query_features.dim() == 1:  # clip4cir/models.py:125 scores one query at a time
+        query_features = query_features.unsqueeze(0)
+    if isinstance(target_features, torch.Tensor) and target_features.requires_grad and torch.is_grad_enabled():
+        logits = (query_features @ target_features.T) / tau
+        if labels is None:
+            labels = torch.arange(query_features.shape[0], dtype=torch.long, device=query_features.device)
+        return F.cross_entropy(logits, labels.to(query_features.device), label_smoothing=label_smoothing)
     return bank_infonce(query_features, target_features, labels, tau, label_smoothing=label_smoothing)
 
 

@@ -136,13 +136,31 @@ int spn_bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_
                          const float* es_acc, const void* q_bf16, const float* colsum, float inv_tau, float gscale,
                          float label_smoothing, int64_t N_total, int B, int D, float* lse, float* loss_per_query,
                          float* loss_mean, float* dq, float* dlogit_dot, void* stream) {
-  SPN_REQUIRE(o_acc && l_acc && s_t && bank_t && ref && lse && loss_mean, SPN_ERR_BAD_ARG, "spn_bank_ce_finalize: NULL pointer");
+  SPN_REQUIRE(o_acc && l_acc && s_t && ref && lse && loss_mean, SPN_ERR_BAD_ARG, "spn_bank_ce_finalize: NULL pointer");
   SPN_REQUIRE(label_smoothing >= 0.f && label_smoothing < 1.f, SPN_ERR_BAD_ARG, "label_smoothing must be in [0, 1)");
   int rc = require_sm100();
   if (rc != SPN_OK) return rc;
   return bank_ce_finalize(o_acc, l_acc, s_t, bank_t, nullptr, nullptr, /*zero_loss=*/1, ref, es_acc, q_bf16, colsum, inv_tau,
                           gscale, label_smoothing, N_total, B, D, lse, loss_per_query, loss_mean, dq, dlogit_dot,
                           as_stream(stream));
+}
+
+int spn_shard_pack(const float* l_acc, const float* s_t, const float* es_acc, const int64_t* lbl_row, int Bt, float* vec,
+                   void* stream) {
+  SPN_REQUIRE(l_acc && s_t && lbl_row && vec, SPN_ERR_BAD_ARG, "spn_shard_pack: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return shard_pack(l_acc, s_t, es_acc, reinterpret_cast<const long long*>(lbl_row), Bt, vec, as_stream(stream));
+}
+
+int spn_shard_fold(float* o_acc, const float* vec, const float* ref, const int64_t* lbl_row, const void* bank_bf16, int Bt,
+                   int D, float label_smoothing, float* s_t_out, void* stream) {
+  SPN_REQUIRE(o_acc && vec && ref && lbl_row && bank_bf16 && s_t_out, SPN_ERR_BAD_ARG, "spn_shard_fold: NULL pointer");
+  SPN_REQUIRE(label_smoothing >= 0.f && label_smoothing < 1.f, SPN_ERR_BAD_ARG, "label_smoothing must be in [0, 1)");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return shard_fold(o_acc, vec, ref, reinterpret_cast<const long long*>(lbl_row), bank_bf16, Bt, D, label_smoothing,
+                    s_t_out, as_stream(stream));
 }
 
 int spn_bank_ce_step(const void* q_src, int src_dtype, const void* bank_bf16, const int64_t* labels, float inv_tau,

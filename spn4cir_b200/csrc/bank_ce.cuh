@@ -94,6 +94,12 @@ int merge_stats(const float* pm, const float* pl, const float* pst, const float*
 int bank_ce_loss(const float* m, const float* l, const float* st, const float* ss, int B, long long N_total,
                  float eps, float* lse, float* loss_q, float* loss_mean, cudaStream_t stream);
 
+// row-sharded bank: pack / fold kernels around the exchange (shard.cu)
+int shard_pack(const float* l_acc, const float* s_t, const float* es_acc, const long long* lbl_row, int Bt, float* vec,
+               cudaStream_t stream);
+int shard_fold(float* o_acc, const float* vec, const float* ref, const long long* lbl_row, const void* bank, int Bt,
+               int D, float eps, float* s_t_out, cudaStream_t stream);
+
 // sampled-negatives loss (part_ce.cu)
 int part_ce(const void* q_src, int dtype, const void* bank, const long long* cand, float inv_tau, int B, int K1, int D,
             long long N, float* loss_q, float* loss_mean, float* dq, float* dlogit_dot, cudaStream_t stream);

@@ -1322,7 +1322,7 @@ __global__ void fused_finalize_kernel(const float* __restrict__ o_acc, const flo
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
       if (bank_t) {
         t = *reinterpret_cast<const float4*>(bank_t + size_t(b) * D + d);
-      } else if (lbl_row[b] >= 0) {  // single-GPU step: the target row straight from the resident bank
+      } else if (lbl_row && lbl_row[b] >= 0) {  // single-GPU step: the target row straight from the resident bank
         const uint2 raw = *reinterpret_cast<const uint2*>(bank + size_t(lbl_row[b]) * D + d);
         const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
         const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
@@ -1720,7 +1720,7 @@ int bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, c
   SPN_REQUIRE(eps == 0.f || (colsum && q16), SPN_ERR_BAD_ARG, "label smoothing needs the bank column sums and q");
   SPN_REQUIRE(!dlogit_dot || es_acc, SPN_ERR_BAD_ARG, "dlogit_dot needs es_acc");
   SPN_REQUIRE(!dq || (aligned16(dq) && aligned16(o_acc) && aligned16(bank_t)), SPN_ERR_BAD_ALIGN, "bank_ce_finalize: 16-byte alignment");
-  SPN_REQUIRE(bank_t || (bank && lbl_row), SPN_ERR_BAD_ARG, "bank_ce_finalize: needs bank_t or (bank, lbl_row)");
+  // bank_t == NULL and lbl_row == NULL: the target-row terms are already folded into o_acc (shard_fold)
   if (zero_loss) SPN_CUDA_CHECK(cudaMemsetAsync(loss_mean, 0, sizeof(float), stream));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(unsigned((B + 3) / 4), 1, 1);

@@ -3,8 +3,9 @@
 One process per GPU; torch.distributed (NCCL on GPUs, gloo in the CPU tests) is the plumbing.  Each rank
 scores ALL queries of the step against its own bank rows; one small exchange merges the partials:
 
-  bank-CE (fused single pass): MIN all-reduce of the static soft-max reference [B_total], then reduce_scatter(sum)
-                   of the additive partials o_acc / bank_t [B_total, D] and a small all_reduce of (l, s_t, es)
+  bank-CE (fused single pass): MIN all-reduce of the static soft-max reference [B_total]; after the sweep a small
+                   SUM all_reduce of (l, s_t, es, owned) [4, B_total], the owner folds the target-row terms into its
+                   partial, and ONE reduce_scatter(sum) of o_acc [B_total, D] fp32 brings every rank its own rows
   bank-CE statistics only  : all_gather of [4, B_total] (m, l, s_t, s_sum) -> spn_merge_stats
   retrieval       : all_gather of [Q, K] (value, index) lists -> spn_merge_topk; ranks are summed counts.
 
@@ -13,7 +14,6 @@ per-rank work stays B_total * N / R and the job's throughput scales with the ran
 """
 from __future__ import annotations
 
-import os
 from typing import Optional, Tuple
 
 import torch
@@ -64,8 +64,8 @@ def global_maxnorm(bank, group=None) -> torch.Tensor:
 
 class _CudaShardCompute:
     """The per-rank compute of the sharded step: the C-ABI calls of the fused path (spn_cast_to_bf16, spn_bank_ce_prep,
-    spn_bank_ce_fused, spn_bank_ce_finalize).  ``tests/test_dist_gloo.py`` swaps in a CPU emulation of the same sums so
-    that the exchange below runs over gloo without a GPU."""
+    spn_bank_ce_fused, spn_shard_pack, spn_shard_fold, spn_bank_ce_finalize).  ``tests/test_dist_gloo.py`` swaps in a CPU
+    emulation of the same sums so that the exchange below runs over gloo without a GPU."""
 
     def cast(self, q_local):
         from .ops import cast_to_bf16
@@ -73,6 +73,20 @@ class _CudaShardCompute:
 
     def maxnorm(self, bank, group):
         return global_maxnorm(bank, group)
+
+    def colsum(self, bank, group):
+        return global_colsum(bank, group)
+
+    def check_tau(self, bank, inv_tau, group):
+        """The fused sweep's static soft-max reference is provably safe while inv_tau |q| max|bank| <= 109 nats (same
+        guard as ops.bank_infonce; one cached host read of the GLOBAL max row norm)."""
+        from ._lib import SpnError
+        if getattr(bank, "_maxnorm_global_host", None) is None:
+            bank._maxnorm_global_host = float(global_maxnorm(bank, group).item())
+        if inv_tau * bank._maxnorm_global_host * 1.03 > 109.0:
+            raise SpnError("bank_infonce_sharded", -7,
+                           f"tau = {1.0 / inv_tau:.5g} is too cold for the single-sweep sharded path (needs inv_tau * max|bank| "
+                           f"<= 105; got {inv_tau * bank._maxnorm_global_host:.1f}): use tau >= 0.0095 for unit-norm features")
 
     def prep(self, q_all, lab_all, bank, inv_tau, maxnorm):
         """-> ref [Bt]: this shard's static soft-max reference (owner rows clamped around the target logit)."""
@@ -88,26 +102,69 @@ class _CudaShardCompute:
         return ref
 
     def fused(self, q_all, lab_all, ref, bank, inv_tau, tau_grad):
-        """-> o_acc [Bt, D], bank_t [Bt, D], vec [3, Bt] (l_acc, s_t, es_acc), lbl_row [Bt] for this shard."""
+        """-> o_acc [Bt, D], (l_acc, s_t, es_acc | None) [Bt] each, lbl_row [Bt] (LOCAL target row, -1 if not owned)."""
         from ._lib import call
         from .ops import _ptr, _stream, fused_scratch
         Bt, D = q_all.shape
         dev = q_all.device
         o_acc = torch.empty((Bt, D), dtype=torch.float32, device=dev)
-        bank_t = torch.empty((Bt, D), dtype=torch.float32, device=dev)
-        vec = torch.empty((3, Bt), dtype=torch.float32, device=dev)  # l_acc, s_t, es_acc
+        part = torch.empty((3, Bt), dtype=torch.float32, device=dev)  # l_acc, s_t, es_acc
         lbl_row = torch.empty(Bt, dtype=torch.int64, device=dev)
         with torch.cuda.device(dev):
             ws, ws_bytes = fused_scratch(Bt, bank, dev)
             call("spn_bank_ce_fused", _ptr(q_all), _ptr(bank.data), _ptr(lab_all), _ptr(ref), inv_tau, Bt, bank.N, D,
-                 bank.T, bank.row_base, 1, _ptr(o_acc), _ptr(vec[0]), _ptr(vec[1]), _ptr(lbl_row),
-                 _ptr(vec[2]) if tau_grad else None, _ptr(bank_t), _ptr(ws), ws_bytes, _stream(dev))
-        return o_acc, bank_t, vec, lbl_row
+                 bank.T, bank.row_base, 1, _ptr(o_acc), _ptr(part[0]), _ptr(part[1]), _ptr(lbl_row),
+                 _ptr(part[2]) if tau_grad else None, None, _ptr(ws), ws_bytes, _stream(dev))
+        return o_acc, part[0], part[1], (part[2] if tau_grad else None), lbl_row
 
-    def finalize(self, sw, bank, inv_tau, B, eps):
-        from .ops import _fused_finalize
-        _, _, loss, dq_unit, ddot = _fused_finalize(sw, bank, inv_tau, B, eps, True)
-        return loss, dq_unit, ddot
+    def pack(self, l_acc, s_t, es_acc, lbl_row):
+        """-> vec [4, Bt] = (l_acc, owner's s_t else 0, es_acc or 0, owned): what the sum all-reduce carries."""
+        from ._lib import call
+        from .ops import _ptr, _stream
+        Bt = l_acc.shape[0]
+        dev = l_acc.device
+        vec = torch.empty((4, Bt), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            call("spn_shard_pack", _ptr(l_acc), _ptr(s_t), _ptr(es_acc), _ptr(lbl_row), Bt, _ptr(vec), _stream(dev))
+        return vec
+
+    def fold(self, o_acc, vec, ref, lbl_row, bank, eps):
+        """o_acc[b] += (-l + eps L) bank[target row] on the rank that owns label b (vec = all-reduced); -> s_t [Bt]."""
+        from ._lib import call
+        from .ops import _ptr, _stream
+        Bt, D = o_acc.shape
+        dev = o_acc.device
+        s_t = torch.empty(Bt, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            call("spn_shard_fold", _ptr(o_acc), _ptr(vec), _ptr(ref), _ptr(lbl_row), _ptr(bank.data), Bt, D, eps, _ptr(s_t),
+                 _stream(dev))
+        return s_t
+
+    def finalize(self, o_mine, l_mine, st_mine, ref_mine, es_mine, q16, colsum, bank, inv_tau, B, eps):
+        """This rank's B queries: (loss_mean, dq_unit [B, D], dlogit_dot | None) from the globally reduced sums."""
+        from ._lib import call
+        from .ops import _ptr, _stream
+        D = o_mine.shape[1]
+        dev = o_mine.device
+        out = torch.empty((2, B), dtype=torch.float32, device=dev)  # lse, loss_per_query
+        mean = torch.empty((), dtype=torch.float32, device=dev)
+        dq = torch.empty((B, D), dtype=torch.float32, device=dev)
+        ddot = torch.empty(B, dtype=torch.float32, device=dev) if es_mine is not None else None
+        with torch.cuda.device(dev):
+            call("spn_bank_ce_finalize", _ptr(o_mine), _ptr(l_mine), _ptr(st_mine), None, _ptr(ref_mine), _ptr(es_mine),
+                 _ptr(q16), _ptr(colsum), inv_tau, inv_tau / B, eps, bank.n_total, B, D, _ptr(out[0]), _ptr(out[1]),
+                 _ptr(mean), _ptr(dq), _ptr(ddot), _stream(dev))
+        return mean, dq, ddot
+
+
+def global_colsum(bank, group=None) -> torch.Tensor:
+    """column sums over ALL shards (device float [D], label smoothing only); one SUM all-reduce per bank, cached."""
+    if getattr(bank, "_colsum_global", None) is None:
+        cs = bank.stats(True)[1].clone()
+        if _world(group)[1] > 1:
+            dist.all_reduce(cs, op=dist.ReduceOp.SUM, group=group)
+        bank._colsum_global = cs
+    return bank._colsum_global
 
 
 def _reduce_scatter_sum(out: torch.Tensor, inp: torch.Tensor, rank: int, group) -> None:
@@ -121,16 +178,41 @@ def _reduce_scatter_sum(out: torch.Tensor, inp: torch.Tensor, rank: int, group) 
         dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
 
 
+_checked_batch = set()
+
+
+def _check_uniform_batch(B: int, dev, group) -> None:
+    """all_gather_into_tensor / reduce_scatter_tensor need the same B on every rank (a ragged last batch would hang or
+    corrupt the exchange): verified once per (group, B) with one tiny all-reduce."""
+    key = (id(group), B)
+    if key in _checked_batch:
+        return
+    t = torch.tensor([B, -B], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    lo, hi = -int(t[1].item()), int(t[0].item())
+    if lo != hi:
+        from ._lib import SpnError
+        raise SpnError("bank_infonce_sharded", -1,
+                       f"every rank must bring the same number of queries per step (got between {lo} and {hi}): pad or drop the ragged last batch")
+    _checked_batch.add(key)
+
+
 def _sharded_sweep(q_local, bank, labels_local, inv_tau, eps, tau_grad, group, compute=None):
-    """The sharded training step without autograd: every rank sweeps its shard for ALL queries of the step, the additive
-    partials travel in two reduce_scatters and one small all_reduce, each rank finalises its own rows.
+    """The sharded training step without autograd: every rank sweeps its shard for ALL queries of the step; the exchange
+    is  all_gather(q bf16), all_gather(labels)  ->  MIN all_reduce(ref [Bt])  ->  [sweep]  ->  SUM all_reduce(vec [4, Bt])
+    ->  [fold target rows]  ->  reduce_scatter(o_acc [Bt, D] fp32);  each rank finalises its own rows.
     Returns (loss_mean_of_local_queries, dq_unit [B, D] fp32, dlogit_dot | None)."""
     compute = compute or _CudaShardCompute()
     rank, world = _world(group)
     B, D = q_local.shape
     dev = q_local.device
+    if eps != 0.0 and bank.T > 1:
+        from ._lib import SpnError
+        raise SpnError("bank_infonce_sharded", -7, "label smoothing over a multi-token (T > 1) sharded bank is not implemented")
+    compute.check_tau(bank, inv_tau, group)
     q16 = compute.cast(q_local)
     if world > 1:
+        _check_uniform_batch(B, dev, group)
         q_all = torch.empty((world * B, D), dtype=q16.dtype, device=dev)
         dist.all_gather_into_tensor(q_all, q16, group=group)
         lab_all = torch.empty(world * B, dtype=labels_local.dtype, device=dev)
@@ -138,37 +220,23 @@ def _sharded_sweep(q_local, bank, labels_local, inv_tau, eps, tau_grad, group, c
     else:
         q_all, lab_all = q16, labels_local
     maxnorm = compute.maxnorm(bank, group)
+    colsum = compute.colsum(bank, group) if eps != 0.0 else None
     ref = compute.prep(q_all, lab_all, bank, inv_tau, maxnorm)
     if world > 1:  # owner's clamped reference wins over the other ranks' Cauchy-Schwarz bound
         dist.all_reduce(ref, op=dist.ReduceOp.MIN, group=group)
-    o_acc, bank_t, vec, lbl_row = compute.fused(q_all, lab_all, ref, bank, inv_tau, tau_grad)
+    o_acc, l_acc, s_t, es_acc, lbl_row = compute.fused(q_all, lab_all, ref, bank, inv_tau, tau_grad)
+    vec = compute.pack(l_acc, s_t, es_acc, lbl_row)
     if world > 1:
-        # additive partials: two reduce_scatters ([Bt, D] each) + one small all_reduce ([3, Bt]); the target
-        # logit is owner-only, so non-owners contribute 0 and the sum is the value
-        vec[1] = torch.where(lbl_row >= 0, vec[1], torch.zeros_like(vec[1]))
-        if not tau_grad:
-            vec[2].zero_()
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+    st_all = compute.fold(o_acc, vec, ref, lbl_row, bank, eps)
+    if world > 1:
         o_mine = torch.empty((B, D), dtype=o_acc.dtype, device=dev)
-        if os.environ.get("SPN_SHARD_FOLD", "0") == "1":
-            # experimental (off by default, not yet measured on GPUs): the row sums travel first, then the rank that owns
-            # a label folds the target-row term into its partial -- sum_r (o_r - [r owns b] l_b bank_t[b]) = o - l bank_t --
-            # so the second [Bt, D] reduce_scatter (a mostly-zero fp32 matrix) disappears; finalize sees bank_t = 0
-            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
-            o_acc.addcmul_(bank_t, vec[0][:, None], value=-1.0)
-            _reduce_scatter_sum(o_mine, o_acc, rank, group)
-            t_mine = torch.zeros((B, D), dtype=bank_t.dtype, device=dev)
-        else:
-            t_mine = torch.empty((B, D), dtype=bank_t.dtype, device=dev)
-            _reduce_scatter_sum(o_mine, o_acc, rank, group)
-            _reduce_scatter_sum(t_mine, bank_t, rank, group)
-            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
-        sl = slice(rank * B, (rank + 1) * B)
-        sw = dict(o_acc=o_mine, bank_t=t_mine, l_acc=vec[0, sl].contiguous(), s_t=vec[1, sl].contiguous(),
-                  es_acc=vec[2, sl].contiguous() if tau_grad else None, ref=ref[sl].contiguous(), q16=q16)
+        _reduce_scatter_sum(o_mine, o_acc, rank, group)
     else:
-        sw = dict(o_acc=o_acc, bank_t=bank_t, l_acc=vec[0], es_acc=vec[2] if tau_grad else None, s_t=vec[1], ref=ref,
-                  q16=q16)
-    return compute.finalize(sw, bank, inv_tau, B, eps)
+        o_mine = o_acc
+    sl = slice(rank * B, (rank + 1) * B)
+    return compute.finalize(o_mine, vec[0, sl], st_all[sl], ref[sl], vec[2, sl] if tau_grad else None, q16, colsum, bank,
+                            inv_tau, B, eps)
 
 
 class _ShardedBankCE(torch.autograd.Function):
@@ -191,28 +259,36 @@ class _ShardedBankCE(torch.autograd.Function):
         return dq, dtau, None, None, None, None, None
 
 
+def _check_tau(tau_v: float, fn: str) -> None:
+    import math
+    if not (tau_v > 0.0 and math.isfinite(tau_v)):
+        from ._lib import SpnError
+        raise SpnError(fn, -7, f"tau must be positive and finite, got {tau_v}")
+
+
 def bank_infonce_sharded(query_features: torch.Tensor, bank, labels: torch.Tensor, tau=0.01, *,
                          label_smoothing: float = 0.0, group=None) -> torch.Tensor:
     """Bank-CE with the bank row-sharded over `group` (bank: this rank's DeviceBank shard with row_base /
-    n_total set, labels: GLOBAL entry indices of this rank's queries).  Returns the mean loss of the local
-    queries; gradients w.r.t. the local queries are exact (all shards contribute through one
-    reduce_scatter).  Label smoothing needs the GLOBAL column sums: not supported in sharded mode yet."""
-    if label_smoothing != 0.0 and _world(group)[1] > 1:
-        from ._lib import SpnError
-        raise SpnError("bank_infonce_sharded", -7, "label_smoothing with a sharded bank is not implemented")
+    n_total set, labels: GLOBAL entry indices of this rank's queries; every rank brings the same number of queries).
+    Returns the mean loss of the local queries; gradients w.r.t. the local queries are exact (all shards contribute
+    through one reduce_scatter).  Label smoothing (zscir/models_bank.py:35) uses the all-reduced column sums of the bank.
+    A label no rank owns gives loss = +inf (as the single-GPU path does)."""
     from .ops import _prep_labels, _split_tau
     tau_t, tau_v = _split_tau(tau)
+    _check_tau(tau_v, "bank_infonce_sharded")
     lab = _prep_labels(labels, query_features.shape[0], query_features.device)
     return _ShardedBankCE.apply(query_features, tau_t, bank, lab, 1.0 / tau_v, float(label_smoothing), group)
 
 
-def bank_ce_step_sharded(query_features: torch.Tensor, bank, labels: torch.Tensor, tau: float = 0.01, *, group=None):
+def bank_ce_step_sharded(query_features: torch.Tensor, bank, labels: torch.Tensor, tau: float = 0.01, *,
+                         label_smoothing: float = 0.0, group=None):
     """``(loss, dq)`` of this rank's queries against the row-sharded bank, without the autograd engine (the sharded
     counterpart of :func:`spn4cir_b200.bank_ce_step`): same kernels and the same exchange as
     :func:`bank_infonce_sharded`."""
     from .ops import _prep_labels
+    _check_tau(float(tau), "bank_ce_step_sharded")
     lab = _prep_labels(labels, query_features.shape[0], query_features.device)
-    loss, dq, _ = _sharded_sweep(query_features, bank, lab, 1.0 / float(tau), 0.0, False, group)
+    loss, dq, _ = _sharded_sweep(query_features, bank, lab, 1.0 / float(tau), float(label_smoothing), False, group)
     return loss, dq
 
 

@@ -213,7 +213,28 @@ def fused_scratch(B: int, bank: DeviceBank, dev: torch.device):
     if key not in _STEP_WS:
         _STEP_WS[key] = _lib.workspace_bytes(_lib.OP_BANK_CE_FUSED, B, bank.N, bank.D, bank.T)
     n = _STEP_WS[key]
-    return (torch.empty(n, dtype=torch.uint8, device=dev) if n else None), n
+    return (_scratch_buffer(n, dev) if n else None), n
+
+
+_SCRATCH = {}
+
+
+def _scratch_buffer(nbytes: int, dev: torch.device) -> torch.Tensor:
+    """One scratch buffer per (device, stream), grown on demand and reused by every step (the P~ scratch is 2 GB at
+    1024 x 1 M: it is write-before-read inside one launch, so successive steps on a stream may share it)."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream(dev))
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _SCRATCH.pop(key, None)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _SCRATCH[key] = buf
+    return buf
+
+
+def release_scratch() -> None:
+    """Drop the cached step scratch buffers."""
+    _SCRATCH.clear()
 
 
 def _fused_sweep(q: torch.Tensor, bank: DeviceBank, labels: torch.Tensor, inv_tau: float, want_es: bool,
@@ -275,7 +296,7 @@ def _fused_step(q: torch.Tensor, bank: DeviceBank, labels: torch.Tensor, inv_tau
     if key not in _STEP_WS:
         _STEP_WS[key] = _lib.workspace_bytes(_lib.OP_BANK_CE_STEP, B, bank.N, D, bank.T)
     ws_bytes = _STEP_WS[key]
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ws = _scratch_buffer(ws_bytes, dev)
     out = torch.empty((3, B), dtype=torch.float32, device=dev)  # lse, loss_per_query, dlogit_dot
     mean = torch.empty((), dtype=torch.float32, device=dev)
     dq = torch.empty((B, D), dtype=torch.float32, device=dev)
@@ -356,6 +377,10 @@ def bank_infonce(query_features: torch.Tensor, bank: Union[DeviceBank, torch.Ten
         # provably safe while inv_tau * |q| * max|bank| <= 109 nats (unit-norm q: tau >= 0.0092, every setting the
         # reference uses); colder temperatures take the two-pass path (exact running maximum).
         single_pass = needs_grad and (1.0 / tau_v) * bank.maxnorm_host() * 1.03 <= 109.0
+    if label_smoothing != 0.0 and bank.T > 1:
+        # the fused finalize forms sum_n s_n from the bank's column sums, which for a multi-token bank would sum every
+        # token row instead of the per-entry max: the two-pass path accumulates it on the entry max
+        single_pass = False
     fn = _BankCEFused if single_pass else _BankCE
     return fn.apply(query_features, tau_t, bank, lab, 1.0 / tau_v, float(label_smoothing))
 
@@ -383,7 +408,9 @@ def bank_ce_step(query_features: torch.Tensor, bank: DeviceBank, labels: Optiona
     B = query_features.shape[0]
     lab = _prep_labels(labels, B, query_features.device)
     eps = float(label_smoothing)
-    if inv_tau * bank.maxnorm_host() * 1.03 <= 109.0:  # the fused sweep's static soft-max reference is provably safe
+    # the fused sweep's static soft-max reference is provably safe; multi-token banks with label smoothing take the
+    # two-pass path (see bank_infonce)
+    if inv_tau * bank.maxnorm_host() * 1.03 <= 109.0 and not (eps != 0.0 and bank.T > 1):
         _, _, loss, dq, ddot = _fused_step(query_features, bank, lab, inv_tau, eps, want_dtau)
     else:  # colder temperatures: forward statistics (exact running maximum) + recompute backward
         q16 = cast_to_bf16(query_features)

@@ -143,3 +143,52 @@ def make_bank_step_case(seed: int, B: int, R: int, N: int, D: int):
     refer_indexs = torch.randint(0, R, (B,), generator=g)
     target_indexs = torch.randint(0, N, (B,), generator=g)
     return refer_bank, target_bank, text, indexs, refer_indexs, target_indexs
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Full-size synthetic banks generated ON THE DEVICE (bench.py and the full-size property tests): a 1 M x 768 bank is
+# 3 GB of fp32 on the host, seconds of CPU time per process; on the GPU it is milliseconds.  The bank is defined chunk by
+# chunk (fixed chunk count, one seed per chunk), so every rank of an N-GPU job can build exactly its own rows and any rank
+# can regenerate the rows its labels point at -- the global bank is the same for every world size.
+DEVICE_CHUNKS = 8
+
+
+def device_bank_chunk(c: int, N: int, D: int, T: int, dev, seed: int = 1234) -> Tuple[int, int, torch.Tensor]:
+    """Chunk c of DEVICE_CHUNKS: (lo, hi, rows) with rows = normalize(randn) fp32 [(hi - lo) * T, D] on `dev`."""
+    per = (N + DEVICE_CHUNKS - 1) // DEVICE_CHUNKS
+    lo, hi = min(N, c * per), min(N, (c + 1) * per)
+    g = torch.Generator(device=dev).manual_seed(seed + 7919 * c)
+    rows = torch.randn(((hi - lo) * T, D), generator=g, device=dev, dtype=torch.float32)
+    return lo, hi, F.normalize(rows, dim=-1)
+
+
+def make_device_case(B: int, N: int, D: int, T: int, dev, *, rank: int = 0, world: int = 1, sharded: bool = False,
+                     seed: int = 0, noise: float = 3.2):
+    """(bank_rows_bf16 [n_local * T, D], row_base, q fp32 [B, D], labels int64 [B]) on `dev`.  Labels are uniform over
+    the WHOLE bank (they mostly live on other ranks when sharded); q = normalize(bank[label] (mean over tokens) +
+    noise * randn / sqrt(D)) like make_queries('S').  `sharded`: keep only the chunks of this rank (world must divide
+    DEVICE_CHUNKS)."""
+    if sharded and DEVICE_CHUNKS % world != 0:
+        raise ValueError(f"world size {world} must divide {DEVICE_CHUNKS}")
+    g = torch.Generator(device=dev).manual_seed(99991 + 31 * seed + rank)
+    labels = torch.randint(0, N, (B,), generator=g, device=dev, dtype=torch.int64)
+    if B >= 2:
+        labels[1] = labels[0]
+    tgt = torch.zeros((B, D), dtype=torch.float32, device=dev)
+    keep, row_base = [], None
+    cpr = DEVICE_CHUNKS // world if sharded else DEVICE_CHUNKS
+    for c in range(DEVICE_CHUNKS):
+        lo, hi, rows = device_bank_chunk(c, N, D, T, dev, seed=1234 + seed)
+        if hi <= lo:
+            continue
+        m = (labels >= lo) & (labels < hi)
+        if bool(m.any()):
+            sel = (labels[m] - lo)
+            tgt[m] = rows.view(hi - lo, T, D)[sel].mean(dim=1)
+        if (not sharded) or (rank * cpr <= c < (rank + 1) * cpr):
+            if row_base is None:
+                row_base = lo
+            keep.append(rows.to(torch.bfloat16))
+        del rows
+    q = F.normalize(tgt + noise * torch.randn((B, D), generator=g, device=dev) / D ** 0.5, dim=-1)
+    return torch.cat(keep), row_base, q, labels

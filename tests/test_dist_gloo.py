@@ -77,19 +77,28 @@ def test_two_rank_merge_over_gloo():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# The fused sharded training step (spn4cir_b200.dist._sharded_sweep: what `bench.py --bank-sharded` and
+# The fused sharded training step (spn4cir_b200.dist._sharded_sweep: what `bench.py --gpus N` and
 # bank_infonce_sharded run): the exchange -- all_gather of the queries, MIN all-reduce of the static soft-max reference,
-# reduce_scatter of the additive partials, all_reduce of the row sums, per-rank finalize -- is product code and runs here
+# all_reduce of the row sums, the owner's fold of the target-row terms, ONE reduce_scatter of the additive partials,
+# per-rank finalize -- is product code and runs here
 # over gloo; the per-rank CUDA calls are replaced by a CPU emulation of the SAME sums (include/spn_b200.h:
 # spn_bank_ce_prep / spn_bank_ce_fused / spn_bank_ce_finalize) in fp64.
 class CpuShardCompute:
     def cast(self, q_local):
         return q_local.to(torch.bfloat16).double()  # the kernels score the bf16-rounded query
 
+    def check_tau(self, bank, inv_tau, group):
+        pass
+
     def maxnorm(self, bank, group):
         mx = bank.data.norm(dim=-1).max().reshape(1).clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
         return mx
+
+    def colsum(self, bank, group):
+        cs = bank.data.sum(0)
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM, group=group)
+        return cs
 
     def prep(self, q_all, lab_all, bank, inv_tau, maxnorm):
         # prep_query_kernel: Cauchy-Schwarz bound, clamped around the target logit by the rank that owns the label
@@ -112,17 +121,34 @@ class CpuShardCompute:
         es = (p * s).sum(-1)
         s_t = torch.full_like(l_acc, -float("inf"))
         s_t[own] = s[rows, g[own]]
-        bank_t = torch.zeros_like(o_acc)
-        bank_t[own] = bank.data[g[own]]
         lbl_row = torch.where(own, g, torch.full_like(g, -1))
-        return o_acc, bank_t, torch.stack([l_acc, s_t, es]), lbl_row
+        return o_acc, l_acc, s_t, (es if tau_grad else None), lbl_row
 
-    def finalize(self, sw, bank, inv_tau, B, eps):
-        L = sw["l_acc"] + torch.exp(sw["s_t"] - sw["ref"])
-        lse = sw["ref"] + torch.log(L)
-        loss = (lse - sw["s_t"]).mean()
-        dq = (inv_tau / B) * (sw["o_acc"] - sw["l_acc"][:, None] * sw["bank_t"]) / L[:, None]
-        return loss, dq, None
+    def pack(self, l_acc, s_t, es_acc, lbl_row):                            # shard_pack_kernel
+        own = lbl_row >= 0
+        z = torch.zeros_like(l_acc)
+        return torch.stack([l_acc, torch.where(own, s_t, z), es_acc if es_acc is not None else z, own.to(l_acc.dtype)])
+
+    def fold(self, o_acc, vec, ref, lbl_row, bank, eps):                    # shard_fold_kernel
+        own = lbl_row >= 0
+        L = vec[0] + torch.exp(vec[1] - ref)
+        coef = -vec[0] + eps * L
+        o_acc[own] += coef[own, None] * bank.data[lbl_row[own]]
+        return torch.where(vec[3] > 0.5, vec[1], torch.full_like(vec[1], -float("inf")))
+
+    def finalize(self, o_mine, l_mine, st_mine, ref_mine, es_mine, q16, colsum, bank, inv_tau, B, eps):
+        # fused_finalize_kernel with the target-row terms already folded into o (bank_t == NULL)
+        L = l_mine + torch.exp(st_mine - ref_mine)
+        lse = ref_mine + torch.log(L)
+        ssum_over_n = inv_tau * (q16 @ colsum) / bank.n_total if eps != 0.0 else 0.0
+        loss = (lse - (1.0 - eps) * st_mine - eps * ssum_over_n).mean()
+        dq = o_mine / L[:, None]
+        if eps != 0.0:
+            dq = dq - (eps / bank.n_total) * colsum[None, :]
+        ddot = None
+        if es_mine is not None:
+            ddot = (es_mine - l_mine * st_mine) / L + eps * st_mine - eps * ssum_over_n
+        return loss, (inv_tau / B) * dq, ddot
 
 
 class _Shard:  # the attributes of DeviceBank the exchange reads
@@ -143,16 +169,25 @@ def _worker_fused(rank, world, port, out):
         lo, hi = shard_bounds(N, rank, world)
         shard = _Shard(bank[lo:hi].contiguous(), lo, N)
         # dense fp64 oracle on this rank's queries (bf16-rounded, as the kernels see them)
-        qd = q.to(torch.bfloat16).double().requires_grad_(True)
-        dense = obank.infonce_loss(qd, bank, labels, tau)
-        dense.backward()
-        for fold in ("0", "1"):  # the shipped exchange and the experimental one-reduce_scatter variant
-            os.environ["SPN_SHARD_FOLD"] = fold
-            loss, dq, _ = _sharded_sweep(q, shard, labels, 1.0 / tau, 0.0, False, None, compute=CpuShardCompute())
-            assert abs(loss.item() - dense.item()) < 1e-9 * max(1.0, abs(dense.item())), (rank, fold, loss.item(), dense.item())
+        for eps in (0.0, 0.1):  # plain CE and the label-smoothing variant (zscir/models_bank.py:35)
+            qd = q.to(torch.bfloat16).double().requires_grad_(True)
+            logits = qd @ bank.T / tau
+            dense = torch.nn.functional.cross_entropy(logits, labels, label_smoothing=eps)
+            dense.backward()
+            loss, dq, ddot = _sharded_sweep(q, shard, labels, 1.0 / tau, eps, True, None, compute=CpuShardCompute())
+            assert abs(loss.item() - dense.item()) < 1e-9 * max(1.0, abs(dense.item())), (rank, eps, loss.item(), dense.item())
             err = (dq - qd.grad).abs().max().item() / qd.grad.abs().max().item()
-            assert err < 1e-9, (rank, fold, err)
-        os.environ.pop("SPN_SHARD_FOLD")
+            assert err < 1e-9, (rank, eps, err)
+            # d loss / d tau = -(inv_tau / B) sum_b dlogit_dot[b]
+            tt = torch.tensor(tau, dtype=torch.float64, requires_grad=True)
+            torch.nn.functional.cross_entropy(qd.detach() @ bank.T / tt, labels, label_smoothing=eps).backward()
+            dtau = -(1.0 / tau / B) * ddot.sum().item()
+            assert abs(dtau - tt.grad.item()) < 1e-8 * max(1.0, abs(tt.grad.item())), (rank, eps, dtau, tt.grad.item())
+        # a label that no rank owns: loss = +inf (what the single-GPU path returns), never a plausible finite value
+        bad = labels.clone()
+        bad[0] = N + 5
+        loss_bad, _, _ = _sharded_sweep(q, shard, bad, 1.0 / tau, 0.0, False, None, compute=CpuShardCompute())
+        assert torch.isinf(loss_bad) and loss_bad > 0, loss_bad
         labels_elsewhere = ((labels < lo) | (labels >= hi)).sum().item()
         out.put(("ok", rank, labels_elsewhere))
     finally:
