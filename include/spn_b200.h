@@ -68,9 +68,16 @@ int spn_cast_to_bf16(const void* src, int src_dtype, void* dst_bf16, int64_t n, 
 
 /* Prologue: q[b] = normalize(refer_bank[refer_idx[b]] + text[b]) -> bf16 (and fp32 copy
  * + inverse norm for the normalize-backward).  Replaces clip4cir/models_negplus.py:133-137.
- * refer_bank fp32 [R, D]; text fp32 [B, D]; q_f32 / inv_norm nullable. */
-int spn_query_assemble(const float* refer_bank, const int64_t* refer_idx, const float* text, int B, int D,
+ * refer_bank fp32 [R, D]; text fp32 [B, D]; q_f32 / inv_norm nullable.  An index outside [0, R) (an IndexError in the
+ * reference) yields a NaN row -- never an out-of-bounds read. */
+int spn_query_assemble(const float* refer_bank, const int64_t* refer_idx, const float* text, int B, int D, int64_t R,
                        void* q_bf16, float* q_f32, float* inv_norm, void* stream);
+
+/* Backward of that normalisation (autograd through F.normalize, clip4cir/models_negplus.py:137; the gathered reference
+ * rows are detached, :133-135, so only text receives a gradient):
+ *   dtext[b] = g * inv_norm[b] * (dq[b] - q[b] <q[b], dq[b]>),  g = *gscale_dev (device scalar, nullable -> 1). */
+int spn_query_assemble_bwd(const float* dq, const float* q_f32, const float* inv_norm, const float* gscale_dev, int B,
+                           int D, float* dtext, void* stream);
 
 /* Forward statistics of CrossEntropy((q @ bank^T) * inv_tau, labels) over one bank shard.
  * Replaces the logits + log-softmax of CIRPlus.infonce_loss (clip4cir/models_negplus.py:150-154,

@@ -105,7 +105,8 @@ _SIGNATURES = {
     "spn_device_supported": [c_int],
     "spn_workspace_bytes": [c_int, c_int, c_int64, c_int, c_int, c_int, POINTER(c_size_t)],
     "spn_cast_to_bf16": [c_void_p, c_int, c_void_p, c_int64, c_void_p],
-    "spn_query_assemble": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "spn_query_assemble": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
+    "spn_query_assemble_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p],
     "spn_bank_ce_fwd": [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int64, c_int, c_int, c_int64,
                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     "spn_merge_stats": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,

@@ -51,13 +51,22 @@ int spn_cast_to_bf16(const void* src, int src_dtype, void* dst_bf16, int64_t n, 
   return cast_to_bf16(src, src_dtype, dst_bf16, n, as_stream(stream));
 }
 
-int spn_query_assemble(const float* refer_bank, const int64_t* refer_idx, const float* text, int B, int D,
+int spn_query_assemble(const float* refer_bank, const int64_t* refer_idx, const float* text, int B, int D, int64_t R,
                        void* q_bf16, float* q_f32, float* inv_norm, void* stream) {
   SPN_REQUIRE(refer_bank && refer_idx && text && q_bf16, SPN_ERR_BAD_ARG, "spn_query_assemble: NULL pointer");
+  SPN_REQUIRE(R > 0, SPN_ERR_BAD_SHAPE, "spn_query_assemble: the refer bank has no rows");
   int rc = require_sm100();
   if (rc != SPN_OK) return rc;
-  return query_assemble(refer_bank, reinterpret_cast<const long long*>(refer_idx), text, B, D, q_bf16, q_f32, inv_norm,
+  return query_assemble(refer_bank, reinterpret_cast<const long long*>(refer_idx), text, B, D, R, q_bf16, q_f32, inv_norm,
                         as_stream(stream));
+}
+
+int spn_query_assemble_bwd(const float* dq, const float* q_f32, const float* inv_norm, const float* gscale_dev, int B,
+                           int D, float* dtext, void* stream) {
+  SPN_REQUIRE(dq && q_f32 && inv_norm && dtext, SPN_ERR_BAD_ARG, "spn_query_assemble_bwd: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return query_assemble_bwd(dq, q_f32, inv_norm, gscale_dev, B, D, dtext, as_stream(stream));
 }
 
 int spn_bank_ce_fwd(const void* q_bf16, const void* bank_bf16, const int64_t* labels, float inv_tau, int B,

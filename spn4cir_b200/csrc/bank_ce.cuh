@@ -116,7 +116,9 @@ int debug_dsmem_bench(int iters, int ndst, unsigned long long* out_cycles, int g
 
 // prologue kernels (prologue.cu)
 int cast_to_bf16(const void* src, int src_dtype, void* dst, long long n, cudaStream_t stream);
-int query_assemble(const float* refer_bank, const long long* refer_idx, const float* text, int B, int D, void* q_bf16,
-                   float* q_f32, float* inv_norm, cudaStream_t stream);
+int query_assemble(const float* refer_bank, const long long* refer_idx, const float* text, int B, int D, long long R,
+                   void* q_bf16, float* q_f32, float* inv_norm, cudaStream_t stream);
+int query_assemble_bwd(const float* dq, const float* q_f32, const float* inv_norm, const float* gscale_dev, int B, int D,
+                       float* dtext, cudaStream_t stream);
 
 }  // namespace spn

@@ -157,7 +157,7 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t
 
 extern "C" {
 
-int spn_version(void) { return 1; }
+int spn_version(void) { return 2; }
 
 const char* spn_last_error(void) { return spn::g_err; }
 

@@ -52,12 +52,23 @@ __global__ void cast_bf16_kernel(const SrcT* __restrict__ src, __nv_bfloat16* __
 
 // one warp per query row
 __global__ void query_assemble_kernel(const float* __restrict__ refer_bank, const long long* __restrict__ refer_idx,
-                                      const float* __restrict__ text, int B, int D, __nv_bfloat16* __restrict__ q_bf16,
-                                      float* __restrict__ q_f32, float* __restrict__ inv_norm) {
+                                      const float* __restrict__ text, int B, int D, long long R,
+                                      __nv_bfloat16* __restrict__ q_bf16, float* __restrict__ q_f32,
+                                      float* __restrict__ inv_norm) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
-  const float* r = refer_bank + size_t(refer_idx[b]) * D;
+  const long long ri = refer_idx[b];
+  if (ri < 0 || ri >= R) {  // the reference raises an IndexError here: make it loud (NaN rows), never read out of bounds
+    const float nan = __int_as_float(0x7fc00000);
+    for (int d = lane; d < D; d += 32) {
+      q_bf16[size_t(b) * D + d] = __float2bfloat16_rn(nan);
+      if (q_f32) q_f32[size_t(b) * D + d] = nan;
+    }
+    if (lane == 0 && inv_norm) inv_norm[b] = nan;
+    return;
+  }
+  const float* r = refer_bank + size_t(ri) * D;
   const float* t = text + size_t(b) * D;
   float ss = 0.f;
   for (int d = lane * 4; d < D; d += 128) {
@@ -78,6 +89,32 @@ __global__ void query_assemble_kernel(const float* __restrict__ refer_bank, cons
     o2.y = pack_bf16x2(x2, x3);
     *reinterpret_cast<uint2*>(q_bf16 + size_t(b) * D + d) = o2;
     if (q_f32) *reinterpret_cast<float4*>(q_f32 + size_t(b) * D + d) = make_float4(x0, x1, x2, x3);
+  }
+}
+
+// one warp per query row: backward of q = x / |x| (x = refer_bank[idx] + text), i.e. the gradient w.r.t. text:
+//   dtext = g * inv_norm * (dq - q <q, dq>)
+__global__ void query_assemble_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ q_f32,
+                                          const float* __restrict__ inv_norm, const float* __restrict__ gscale_dev, int B,
+                                          int D, float* __restrict__ dtext) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* g = dq + size_t(b) * D;
+  const float* q = q_f32 + size_t(b) * D;
+  float dot = 0.f;
+  for (int d = lane * 4; d < D; d += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(g + d);
+    const float4 c = *reinterpret_cast<const float4*>(q + d);
+    dot += a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w;
+  }
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  const float s = inv_norm[b] * (gscale_dev ? __ldg(gscale_dev) : 1.f);
+  for (int d = lane * 4; d < D; d += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(g + d);
+    const float4 c = *reinterpret_cast<const float4*>(q + d);
+    *reinterpret_cast<float4*>(dtext + size_t(b) * D + d) =
+        make_float4(s * (a.x - c.x * dot), s * (a.y - c.y * dot), s * (a.z - c.z * dot), s * (a.w - c.w * dot));
   }
 }
 
@@ -107,14 +144,24 @@ int cast_to_bf16(const void* src, int src_dtype, void* dst, long long n, cudaStr
   return SPN_OK;
 }
 
-int query_assemble(const float* refer_bank, const long long* refer_idx, const float* text, int B, int D, void* q_bf16,
-                   float* q_f32, float* inv_norm, cudaStream_t stream) {
+int query_assemble(const float* refer_bank, const long long* refer_idx, const float* text, int B, int D, long long R,
+                   void* q_bf16, float* q_f32, float* inv_norm, cudaStream_t stream) {
   SPN_REQUIRE(B > 0 && D > 0 && D % 4 == 0, SPN_ERR_BAD_SHAPE, "query_assemble: need B > 0 and D %% 4 == 0 (B=%d D=%d)", B, D);
   SPN_REQUIRE(aligned16(refer_bank) && aligned16(text) && aligned16(q_bf16), SPN_ERR_BAD_ALIGN,
               "query_assemble: pointers must be 16-byte aligned");
   const int warps_per_block = 8;
   query_assemble_kernel<<<(B + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
-      refer_bank, refer_idx, text, B, D, static_cast<__nv_bfloat16*>(q_bf16), q_f32, inv_norm);
+      refer_bank, refer_idx, text, B, D, R, static_cast<__nv_bfloat16*>(q_bf16), q_f32, inv_norm);
+  SPN_CUDA_CHECK(cudaGetLastError());
+  return SPN_OK;
+}
+
+int query_assemble_bwd(const float* dq, const float* q_f32, const float* inv_norm, const float* gscale_dev, int B, int D,
+                       float* dtext, cudaStream_t stream) {
+  SPN_REQUIRE(B > 0 && D > 0 && D % 4 == 0, SPN_ERR_BAD_SHAPE, "query_assemble_bwd: need B > 0 and D %% 4 == 0 (B=%d D=%d)", B, D);
+  SPN_REQUIRE(aligned16(dq) && aligned16(q_f32) && aligned16(dtext), SPN_ERR_BAD_ALIGN,
+              "query_assemble_bwd: pointers must be 16-byte aligned");
+  query_assemble_bwd_kernel<<<(B + 7) / 8, 256, 0, stream>>>(dq, q_f32, inv_norm, gscale_dev, B, D, dtext);
   SPN_CUDA_CHECK(cudaGetLastError());
   return SPN_OK;
 }

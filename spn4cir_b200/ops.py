@@ -500,5 +500,6 @@ def query_assemble(refer_bank: torch.Tensor, refer_idx: torch.Tensor, text_feats
     q32 = torch.empty((B, D), dtype=torch.float32, device=dev)
     inv = torch.empty(B, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        call("spn_query_assemble", _ptr(rb), _ptr(idx), _ptr(tx), B, D, _ptr(q16), _ptr(q32), _ptr(inv), _stream(dev))
+        call("spn_query_assemble", _ptr(rb), _ptr(idx), _ptr(tx), B, D, rb.shape[0], _ptr(q16), _ptr(q32), _ptr(inv),
+             _stream(dev))
     return q16, q32, inv

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     lib = spn.load_library()
-    assert lib.spn_version() == 1
+    assert lib.spn_version() == 2
     assert isinstance(lib.spn_last_error(), bytes)
 
 

@@ -1,5 +1,8 @@
 """Multi-GPU parity (needs >= 2 GPUs, NCCL): the row-sharded fused path must reproduce the single-GPU loss and
-gradient for every rank's queries.  Launched as a subprocess under torch.distributed.run."""
+gradient for every rank's queries.  Launched as a subprocess under torch.distributed.run.  The comparison is against this
+repo's own single-GPU path on the full bank, which tests/test_gpu_bank_ce.py pins to the oracle and the executed-reference
+fixtures -- so parity with the reference holds transitively; tests/test_gpu_shard.py checks the same per-rank kernels
+against the oracle directly (fake ranks on one GPU)."""
 import os
 import subprocess
 import sys
@@ -41,6 +44,25 @@ assert abs(loss.item() - ref.item()) <= 1e-5 * max(1.0, abs(ref.item())), (rank,
 rel = float((q.grad - q2.grad).norm() / q2.grad.norm())
 assert rel < 1e-4, (rank, rel)
 assert abs(tt.grad.item() - t2.grad.item()) <= 1e-3 * max(abs(t2.grad.item()), 1e-3), (tt.grad, t2.grad)
+# label smoothing over the sharded bank (zscir/models_bank.py:35): all-reduced column sums
+q3 = qs[rank].to(dev).requires_grad_(True)
+ls = bank_infonce_sharded(q3, shard, labs[rank].to(dev), tau, label_smoothing=0.1)
+ls.backward()
+q4 = qs[rank].to(dev).requires_grad_(True)
+lr = spn.bank_infonce(q4, full, labs[rank].to(dev), tau, label_smoothing=0.1, single_pass=True)
+lr.backward()
+assert abs(ls.item() - lr.item()) <= 1e-5 * max(1.0, abs(lr.item())), (rank, ls.item(), lr.item())
+assert float((q3.grad - q4.grad).norm() / q4.grad.norm()) < 1e-4
+# the step primitive (what bench.py times at N > 1) and a bigger two-pass shape with B a multiple of 128
+from spn4cir_b200.dist import bank_ce_step_sharded
+bank2 = synth.make_bank(6000, 640, 1, seed=78)
+lab2 = synth.make_labels(256, 6000, seed=300 + rank)
+qq2 = synth.make_queries(bank2, lab2, "S", seed=400 + rank).to(dev)
+sh2 = spn.DeviceBank.from_tensor(bank2, dev, shard_rank=rank, shard_world=world)
+l_s, dq_s = bank_ce_step_sharded(qq2, sh2, lab2.to(dev), tau)
+l_f, dq_f = spn.bank_ce_step(qq2, spn.DeviceBank.from_tensor(bank2, dev), lab2.to(dev), tau)
+assert abs(l_s.item() - l_f.item()) <= 1e-5 * max(1.0, abs(l_f.item())), (rank, l_s.item(), l_f.item())
+assert float((dq_s - dq_f).norm() / dq_f.norm()) < 1e-4
 # retrieval
 qq, gal, _, refi, tgt, grp = synth.make_retrieval_case(70, 1000, 128, 1, 10, noise=6.0)
 lo, hi = shard_bounds(1000, rank, world)
@@ -65,5 +87,5 @@ def test_sharded_matches_single_gpu(tmp_path):
     env = dict(os.environ, SPN_REPO=str(REPO))
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
                           "--master-addr", "127.0.0.1", "--master-port", "29511", str(script)],
-                         capture_output=True, text=True, env=env, timeout=600)
+                         capture_output=True, text=True, env=env, timeout=420)
     assert res.returncode == 0 and "DIST_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]

@@ -2,8 +2,12 @@
 import csv, json, subprocess, sys
 from pathlib import Path
 REPO = Path(__file__).resolve().parent.parent
+# usage: summarize_ncu.py <tag> [report.ncu-rep] [out name] [launches.csv] [description]
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-rep = REPO / "gpurun_out" / "prof_bank_ce.ncu-rep"
+rep = Path(sys.argv[2]) if len(sys.argv) > 2 else REPO / "gpurun_out" / "prof_bank_ce.ncu-rep"
+out_name = sys.argv[3] if len(sys.argv) > 3 else "ncu_bank_ce_fused"
+ll_path = Path(sys.argv[4]) if len(sys.argv) > 4 else REPO / "gpurun_out" / "launches.csv"
+desc = sys.argv[5] if len(sys.argv) > 5 else "C3: B=512, N=100000, D=640"
 raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
@@ -33,14 +37,14 @@ def to_bytes(d, k):
     u = d[k]["unit"].lower()
     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
 main = out[-1]
-summary = {"source": "ncu --set full --clock-control none --import-source on -k regex:bank_ce_kernel (python bench.py --profile --steps 1), C3: B=512, N=100000, D=640",
+summary = {"source": "ncu --set full --clock-control none --import-source on -k regex:bank_ce_kernel (python bench.py --profile --steps 1), " + desc,
            "kernels": out,
            "dram_bytes_per_launch": (to_bytes(main, "dram__bytes_read.sum") or 0) + (to_bytes(main, "dram__bytes_write.sum") or 0),
            "l2_to_sm_bytes_per_launch": to_bytes(main, "l1tex__m_xbar2l1tex_read_bytes.sum")}
 (REPO / "profiles").mkdir(exist_ok=True)
-(REPO / "profiles" / f"{tag}_ncu_bank_ce_fused.json").write_text(json.dumps(summary, indent=1))
+(REPO / "profiles" / f"{tag}_{out_name}.json").write_text(json.dumps(summary, indent=1))
 # launch list
-ll = REPO / "gpurun_out" / "launches.csv"
+ll = ll_path
 if ll.exists():
     lines = [l for l in ll.read_text().splitlines() if not l.startswith("==")]
     rr = list(csv.reader(lines))
@@ -57,7 +61,7 @@ if ll.exists():
     for n, v in sorted(tot.items(), key=lambda kv: -kv[1]):
         md.append(f"| `{n[:90]}` | {sum(1 for s in seq if s[0] == n)} | {v / 1e3:.1f} | {100 * v / total:.1f} % |")
     md += ["", "## in launch order (last step)", ""] + [f"- `{n[:90]}` {v / 1e3:.2f} us" for n, v in seq[-12:]]
-    (REPO / "profiles" / f"{tag}_ncu_launch_list.md").write_text("\n".join(md) + "\n")
+    (REPO / "profiles" / f"{tag}_{out_name}_launch_list.md").write_text("\n".join(md) + "\n")
 print(json.dumps({k: v for k, v in summary.items() if k != "kernels"}))
 for d in out:
     print(d["kernel"][:80], {k.split(".")[0]: v["value"] for k, v in d.items() if k != "kernel"})
