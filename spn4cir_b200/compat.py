@@ -30,7 +30,9 @@ import torch.nn.functional as F
 from ._lib import SpnError, call
 import random
 
-from .ops import DeviceBank, _ptr, _require_cuda, _stream, bank_infonce, cast_to_bf16, part_infonce
+from . import _torch_ext
+from .ops import (DeviceBank, _ptr, _require_cuda, _split_tau, _stream, _use_torch_ext, bank_infonce, cast_to_bf16,
+                  part_infonce)
 from .retrieval import _prep_gallery, names_to_ids, recall_at, sim_rank, sim_topk
 
 
@@ -91,6 +93,17 @@ class BankLossMixin:
         self.refer_bank = refer_bank.detach().to(self.device, torch.float32).contiguous()
         self.target_bank = DeviceBank.from_tensor(target_bank, self.device)
 
+    def load_banks(self, bank_path: str, unlabeled_path: Optional[str] = None) -> None:
+        """The load branches of ``extract_bank_features`` (/root/reference/clip4cir/models_negplus.py:79-80; BLIP-2's
+        2- or 3-element list, blip24cir/models.py:82-89) and ``extract_unlabeled_bank_features`` (:115-125): read the cached
+        ``torch.save([refer_bank, target_bank])`` file, append the unlabeled rows after the labeled ones (``self.M`` =
+        number of labeled rows) and make both banks resident -- once, instead of the per-step upload of :138."""
+        from .ops import load_bank_file
+        banks = load_bank_file(bank_path, unlabeled_path=unlabeled_path, neg_num=getattr(self, "neg_num", 0))
+        self.M = banks["M"]
+        self.query_bank = banks["query_bank"]
+        self.set_banks(banks["refer_bank"], banks["target_bank"])
+
     def combining_function(self, image_features, text_features):  # models_negplus.py:48-49
         return image_features + text_features
 
@@ -98,7 +111,20 @@ class BankLossMixin:
         return infonce_loss(query_features, target_features, labels, tau, self.label_smoothing)
 
     def bank_large_step(self, loss: dict, text_feats, indexs, target_indexs, refer_indexs=None):
+        """``CIRPlus.bank_large_step`` (/root/reference/clip4cir/models_negplus.py:130-142).  With the reference's own
+        combiner (element-wise sum, :48-49) and the full-bank loss the whole method is ONE operator
+        (``torch.ops.spn4cir.bank_large_step_loss``): query assembly ``normalize(refer_bank[idx] + text)`` in a prologue
+        kernel, the fused sweep, and the backward through the normalisation in one kernel."""
         idx = refer_indexs if getattr(self, "plus", False) else indexs
+        if self._fused_large_step_ok():
+            tau_t, tau_v = _split_tau(self.tau)
+            bank = self.target_bank
+            eps = float(self.label_smoothing)
+            maxnorm, colsum = bank.stats(eps != 0.0)
+            loss["bank_loss"] = _torch_ext.ops().bank_large_step_loss(
+                self.refer_bank, idx, text_feats, tau_t, bank.data, target_indexs.to(self.device), maxnorm,
+                colsum if eps != 0.0 else None, 1.0 / tau_v, eps, bank.T)
+            return
         reference_image_feats = self.refer_bank[idx.to(self.refer_bank.device)].detach()
         query_feats = F.normalize(self.combining_function(reference_image_feats, text_feats))
         target_indexs = target_indexs.to(self.device)
@@ -109,6 +135,22 @@ class BankLossMixin:
 
     def part_infonce_loss(self, query_feats, target_feats_all, target_indexs):
         return part_infonce_loss(query_feats, target_feats_all, target_indexs, self.neg_num, self.tau)
+
+    def _fused_large_step_ok(self) -> bool:
+        """One-operator bank_large_step applies when nothing of the method was customised: the class's own sum combiner,
+        the full-bank loss (no sampled negatives), an un-sharded resident bank and a temperature the fused sweep's static
+        soft-max reference covers (same rule as ops.bank_infonce)."""
+        bank = getattr(self, "target_bank", None)
+        if not (_use_torch_ext() and isinstance(bank, DeviceBank) and bank.row_base == 0 and bank.n_total == bank.N):
+            return False
+        if getattr(self, "neg_num", 0) > 0 or type(self).combining_function is not BankLossMixin.combining_function:
+            return False
+        if type(self).infonce_loss is not BankLossMixin.infonce_loss:
+            return False
+        _, tau_v = _split_tau(self.tau)
+        if not tau_v > 0.0:
+            return False
+        return (1.0 / tau_v) * bank.maxnorm_host() * 1.03 <= 109.0 and not (self.label_smoothing != 0.0 and bank.T > 1)
 
 
 def forward_stage2_loss(fusion_feats: torch.Tensor, target_feats: Union[DeviceBank, torch.Tensor],

@@ -9,14 +9,21 @@ tail (/root/reference/blip24cir/lavis/models/blip2_models/blip2_qformer_cir_alig
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Union
 
 import torch
 
-from . import _lib
+from . import _lib, _torch_ext
 from ._lib import DT_BF16, DT_F16, DT_F32, OP_BANK_CE_FWD, SpnError, call
 
 _TORCH2SPN = {torch.float32: DT_F32, torch.float16: DT_F16, torch.bfloat16: DT_BF16}
+
+
+def _use_torch_ext() -> bool:
+    """The torch.library operators (C++ autograd node, ~4x less host time per step) are the default entry into the fused
+    step; SPN_TORCH_EXT=0 selects the ctypes + Python autograd.Function route (same kernels) for A/B tests."""
+    return os.environ.get("SPN_TORCH_EXT", "1") != "0"
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -118,12 +125,45 @@ class DeviceBank:
         return cls(cast_to_bf16(part), t, row_base=lo, n_total=n)
 
     @classmethod
-    def from_file(cls, path: str, device: Union[str, torch.device] = "cuda", index: int = 1, **kw) -> "DeviceBank":
-        """Load the reference's cached bank file: ``torch.save([refer_bank, target_bank])``
-        (/root/reference/clip4cir/models_negplus.py:78) -> element ``index`` (1 = target bank)."""
-        obj = torch.load(path, map_location="cpu")
-        bank = obj[index] if isinstance(obj, (list, tuple)) else obj
-        return cls.from_tensor(bank, device, **kw)
+    def from_file(cls, path: str, device: Union[str, torch.device] = "cuda", index: int = 1,
+                  unlabeled_path: Optional[str] = None, neg_num: int = 0, **kw) -> "DeviceBank":
+        """Load the reference's cached bank file(s) and make the target bank resident: see :func:`load_bank_file`.
+        ``index`` selects the list element (1 = target bank); ``unlabeled_path`` appends the unlabeled rows after the
+        labeled ones (labels keep pointing into the first ``bank.M`` rows)."""
+        banks = load_bank_file(path, unlabeled_path=unlabeled_path, neg_num=neg_num)
+        src = banks["target_bank"] if index == 1 else banks["items"][index]
+        bank = cls.from_tensor(src, device, **kw)
+        bank.M = banks["M"]
+        return bank
+
+
+def load_bank_file(path: str, unlabeled_path: Optional[str] = None, neg_num: int = 0) -> dict:
+    """The on-disk bank contract of the reference, read on the host:
+
+    * ``torch.save([refer_bank, target_bank], bank_path)`` (/root/reference/clip4cir/models_negplus.py:78, loaded :80) --
+      BLIP-2 stores three elements ``[refer_bank, target_bank, query_bank]`` (/root/reference/blip24cir/models.py:81,
+      loaded :83-89); a bare tensor is accepted as the target bank;
+    * ``torch.save([unlabeled_target_bank], path)`` (:114, loaded :116), optionally truncated to the first ``neg_num``
+      rows (:117-122), concatenated AFTER the labeled rows (:123-125): ``M`` = number of labeled rows, labels only
+      point into ``[0, M)``.
+
+    Returns ``{"refer_bank", "target_bank", "query_bank", "M", "items"}`` (CPU tensors, not cast)."""
+    obj = torch.load(path, map_location="cpu")
+    items = list(obj) if isinstance(obj, (list, tuple)) else [None, obj]
+    if len(items) not in (2, 3):
+        raise SpnError("load_bank_file", -1, f"{path}: expected [refer_bank, target_bank(, query_bank)], got {len(items)} items")
+    refer_bank, target_bank = items[0], items[1]
+    query_bank = items[2] if len(items) == 3 else None
+    M = int(target_bank.shape[0])
+    if unlabeled_path is not None:
+        un = torch.load(unlabeled_path, map_location="cpu")
+        un = un[0] if isinstance(un, (list, tuple)) else un
+        if neg_num > 0:
+            un = un[:neg_num]
+        if un.shape[1:] != target_bank.shape[1:]:
+            raise SpnError("load_bank_file", -1, f"unlabeled rows {tuple(un.shape)} do not match the bank {tuple(target_bank.shape)}")
+        target_bank = torch.cat([target_bank, un.to(target_bank.dtype)])
+    return {"refer_bank": refer_bank, "target_bank": target_bank, "query_bank": query_bank, "M": M, "items": items}
 
 
 def _fwd_stats(q_bf16: torch.Tensor, bank: DeviceBank, labels: torch.Tensor, inv_tau: float, want_ssum: bool):
@@ -381,6 +421,12 @@ def bank_infonce(query_features: torch.Tensor, bank: Union[DeviceBank, torch.Ten
         # the fused finalize forms sum_n s_n from the bank's column sums, which for a multi-token bank would sum every
         # token row instead of the per-entry max: the two-pass path accumulates it on the entry max
         single_pass = False
+    if single_pass and _use_torch_ext() and bank.row_base == 0 and bank.n_total == bank.N:
+        # the training hot path: one torch.library operator with a C++ autograd node (csrc_torch/spn_torch.cpp)
+        eps = float(label_smoothing)
+        maxnorm, colsum = bank.stats(eps != 0.0)
+        return _torch_ext.ops().bank_infonce(query_features, tau_t, bank.data, lab, maxnorm, colsum if eps != 0.0 else None,
+                                             1.0 / tau_v, eps, bank.T)
     fn = _BankCEFused if single_pass else _BankCE
     return fn.apply(query_features, tau_t, bank, lab, 1.0 / tau_v, float(label_smoothing))
 
@@ -411,7 +457,12 @@ def bank_ce_step(query_features: torch.Tensor, bank: DeviceBank, labels: Optiona
     # the fused sweep's static soft-max reference is provably safe; multi-token banks with label smoothing take the
     # two-pass path (see bank_infonce)
     if inv_tau * bank.maxnorm_host() * 1.03 <= 109.0 and not (eps != 0.0 and bank.T > 1):
-        _, _, loss, dq, ddot = _fused_step(query_features, bank, lab, inv_tau, eps, want_dtau)
+        if _use_torch_ext():
+            maxnorm, colsum = bank.stats(eps != 0.0)
+            loss, dq, ddot = _torch_ext.ops().bank_ce_step(query_features, bank.data, lab, maxnorm,
+                                                           colsum if eps != 0.0 else None, inv_tau, eps, bank.T, want_dtau)
+        else:
+            _, _, loss, dq, ddot = _fused_step(query_features, bank, lab, inv_tau, eps, want_dtau)
     else:  # colder temperatures: forward statistics (exact running maximum) + recompute backward
         q16 = cast_to_bf16(query_features)
         stats = _fwd_stats(q16, bank, lab, inv_tau, eps != 0.0)

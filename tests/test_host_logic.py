@@ -71,3 +71,43 @@ def test_rank_window_draw_matches_restated_reference():
     a = compat.get_diff_id(4, 50, 3)
     random.seed(2)
     assert a == oretr.get_diff_id(4, 50, 3) and 4 not in a
+
+
+def test_load_bank_file_contract(tmp_path):
+    """the reference's cached bank files (clip4cir/models_negplus.py:78-80,114-125; BLIP-2's three-element
+    list blip24cir/models.py:81-89): labeled rows first, unlabeled rows appended, labels point into [0, M)."""
+    g = torch.Generator().manual_seed(3)
+    refer, target = torch.randn(7, 16, generator=g), torch.nn.functional.normalize(torch.randn(9, 16, generator=g))
+    unl = torch.nn.functional.normalize(torch.randn(5, 16, generator=g))
+    p2, p3, pu, pb = tmp_path / "b2.pth", tmp_path / "b3.pth", tmp_path / "u.pth", tmp_path / "bare.pth"
+    torch.save([refer, target], p2)                                   # models_negplus.py:78
+    torch.save([refer, target, torch.zeros(7, 4)], p3)                # blip24cir/models.py:81
+    torch.save([unl], pu)                                             # models_negplus.py:114
+    torch.save(target, pb)
+    b = spn.load_bank_file(str(p2))
+    assert torch.equal(b["refer_bank"], refer) and torch.equal(b["target_bank"], target) and b["M"] == 9 and b["query_bank"] is None
+    assert spn.load_bank_file(str(p3))["query_bank"].shape == (7, 4)
+    assert torch.equal(spn.load_bank_file(str(pb))["target_bank"], target)
+    c = spn.load_bank_file(str(p2), unlabeled_path=str(pu))
+    assert c["M"] == 9 and torch.equal(c["target_bank"], torch.cat([target, unl]))      # :123-125
+    d = spn.load_bank_file(str(p2), unlabeled_path=str(pu), neg_num=2)                  # :117-122
+    assert d["target_bank"].shape[0] == 11 and torch.equal(d["target_bank"][9:], unl[:2])
+    torch.save([torch.zeros(3, 8)], pu)
+    with pytest.raises(spn.SpnError):
+        spn.load_bank_file(str(p2), unlabeled_path=str(pu))
+    torch.save([refer], p2)
+    with pytest.raises(spn.SpnError):
+        spn.load_bank_file(str(p2))
+
+
+def test_device_generators_shard_consistently():
+    """bench.py / the full-size tests build the bank chunk by chunk on the device: every world size sees the same rows."""
+    cpu = torch.device("cpu")
+    full, rb, q, lab = synth.make_device_case(6, 1000, 64, 1, cpu)
+    assert rb == 0 and full.shape == (1000, 64) and full.dtype == torch.bfloat16
+    parts = [synth.make_device_case(6, 1000, 64, 1, cpu, rank=r, world=4, sharded=True) for r in range(4)]
+    assert [p[1] for p in parts] == [0, 250, 500, 750]
+    assert torch.equal(torch.cat([p[0] for p in parts]), full)
+    assert not torch.equal(parts[0][3], parts[1][3])  # every rank brings its own queries / labels
+    with pytest.raises(ValueError):
+        synth.make_device_case(6, 1000, 64, 1, cpu, rank=0, world=3, sharded=True)
