@@ -175,6 +175,37 @@ int spn_shard_pack(const float* l_acc, const float* s_t, const float* es_acc, co
 int spn_shard_fold(float* o_acc, const float* vec, const float* ref, const int64_t* lbl_row, const void* bank_bf16, int Bt,
                    int D, float label_smoothing, float* s_t_out, void* stream);
 
+/* ---- the same exchange WITHOUT NCCL: kernels that read and write the other ranks' memory over NVLink / NVSwitch ----
+ * All windows live in peer-mapped symmetric memory (allocated and exchanged by the host side, spn4cir_b200/dist.py:
+ * SymmExchange over torch.distributed._symmetric_memory); every `void* const*` / `float* const*` argument is a HOST array of
+ * `world` DEVICE pointers (entry r = rank r's buffer as mapped into THIS process, own rank included).  One step is
+ *   spn_shard_home_prologue -> spn_peer_barrier -> spn_bank_ce_fused_peers -> spn_peer_barrier -> spn_bank_ce_finalize.
+ *
+ * spn_shard_home_prologue: for each of this rank's B queries -- cast to bf16 and STORE the row into every rank's query window
+ * qall [world * B, D] at row rank * B + b (the all-gather); LOAD the target entry's T rows from the bank shard of the rank
+ * that owns the label (owner = label / rows_per_rank) and form s_t (exact fp32 chain, max over tokens) and the final static
+ * soft-max reference ref = min(bound, max(s_t + 30, bound - 64)) -- identical on every rank by construction, so no MIN
+ * all-reduce; store ref / label into every rank's metadata windows; keep s_t, ref and the fp32 target row (arg-max token)
+ * locally for the finalize step; zero this rank's accumulation windows o_window [B, D], l_window [B], es_window [B]
+ * (nullable).  A label outside [0, N_total) gives s_t = -inf (loss +inf, as on one GPU). */
+int spn_shard_home_prologue(const void* q_src, int src_dtype, const int64_t* labels, void* const* bank_peers,
+                            int64_t rows_per_rank, int64_t N_total, int T, float inv_tau, const float* bank_maxnorm, int B, int D,
+                            int rank, int world, void* const* qall_peers, void* const* ref_peers, void* const* label_peers,
+                            float* s_t, float* ref, float* target_rows, float* o_window, float* l_window, float* es_window,
+                            void* stream);
+/* Barrier across the ranks on `stream`: flag_peers[r] = rank r's uint32 [world] flag array; rank i stores `epoch` into
+ * slot i of every peer (release, system scope) and waits until its own slots all reached `epoch` (acquire).  `epoch` must
+ * grow by one per call on every rank.  A peer that never arrives fails the launch after ~10 s instead of hanging the GPU. */
+int spn_peer_barrier(void* const* flag_peers, int rank, int world, uint32_t epoch, void* stream);
+/* spn_bank_ce_fused with the reduce-scatter folded into the kernel: queries [h * home_rows, (h + 1) * home_rows) of q_bf16
+ * (= the query window) belong to rank h, and their partial sums are reduce-added into o_windows[h] [home_rows, D] (TMA
+ * reduce-add over NVLink from the sweep's epilogue), l_windows[h] and es_windows[h] (nullable) [home_rows].  home_rows must
+ * be a multiple of 128 and B = world * home_rows an even number of 128-query tiles.  s_t / lbl_row [B] are scratch. */
+int spn_bank_ce_fused_peers(const void* q_bf16, const void* bank_bf16, const int64_t* labels, const float* ref, float inv_tau,
+                            int B, int64_t N, int D, int T, int64_t row_base, int home_rows, int world,
+                            float* const* o_windows, float* const* l_windows, float* const* es_windows, float* s_t,
+                            int64_t* lbl_row, void* ws, size_t ws_bytes, void* stream);
+
 /* One whole training step on one GPU (un-sharded bank, row_base = 0) in a single call:
  * spn_bank_ce_prep (+ zeroing of the accumulators) -> spn_bank_ce_fused -> spn_bank_ce_finalize (the target row is read
  * from the resident bank).  Three kernel launches; every intermediate lives in `ws`

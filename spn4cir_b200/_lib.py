@@ -11,7 +11,7 @@ import os
 import shutil
 import subprocess
 import threading
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
@@ -125,6 +125,12 @@ _SIGNATURES = {
                              c_void_p],
     "spn_shard_pack": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     "spn_shard_fold": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p],
+    "spn_shard_home_prologue": [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p, c_int, c_int,
+                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p],
+    "spn_peer_barrier": [c_void_p, c_int, c_int, c_uint32, c_void_p],
+    "spn_bank_ce_fused_peers": [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int64, c_int, c_int, c_int64, c_int,
+                                c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     "spn_bank_ce_step": [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float, c_int, c_int64, c_int,
                          c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     "spn_part_ce": [c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,

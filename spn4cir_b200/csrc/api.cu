@@ -172,6 +172,41 @@ int spn_shard_fold(float* o_acc, const float* vec, const float* ref, const int64
                     s_t_out, as_stream(stream));
 }
 
+int spn_shard_home_prologue(const void* q_src, int src_dtype, const int64_t* labels, void* const* bank_peers,
+                            int64_t rows_per_rank, int64_t N_total, int T, float inv_tau, const float* bank_maxnorm, int B, int D,
+                            int rank, int world, void* const* qall_peers, void* const* ref_peers, void* const* label_peers,
+                            float* s_t, float* ref, float* target_rows, float* o_window, float* l_window, float* es_window,
+                            void* stream) {
+  SPN_REQUIRE(q_src && labels && bank_peers && bank_maxnorm && qall_peers && ref_peers && label_peers && s_t && ref &&
+                  target_rows && o_window && l_window, SPN_ERR_BAD_ARG, "spn_shard_home_prologue: NULL pointer");
+  SPN_REQUIRE(aligned16(o_window) && aligned16(target_rows), SPN_ERR_BAD_ALIGN, "spn_shard_home_prologue: 16-byte alignment");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return shard_home_prologue(q_src, src_dtype, reinterpret_cast<const long long*>(labels), bank_peers, rows_per_rank, N_total,
+                             T, inv_tau, bank_maxnorm, B, D, rank, world, qall_peers, ref_peers, label_peers, s_t, ref,
+                             target_rows, o_window, l_window, es_window, as_stream(stream));
+}
+
+int spn_peer_barrier(void* const* flag_peers, int rank, int world, uint32_t epoch, void* stream) {
+  SPN_REQUIRE(flag_peers, SPN_ERR_BAD_ARG, "spn_peer_barrier: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return peer_barrier(flag_peers, rank, world, epoch, as_stream(stream));
+}
+
+int spn_bank_ce_fused_peers(const void* q_bf16, const void* bank_bf16, const int64_t* labels, const float* ref, float inv_tau,
+                            int B, int64_t N, int D, int T, int64_t row_base, int home_rows, int world,
+                            float* const* o_windows, float* const* l_windows, float* const* es_windows, float* s_t,
+                            int64_t* lbl_row, void* ws, size_t ws_bytes, void* stream) {
+  SPN_REQUIRE(q_bf16 && bank_bf16 && labels && ref && o_windows && l_windows && s_t && lbl_row, SPN_ERR_BAD_ARG,
+              "spn_bank_ce_fused_peers: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return bank_ce_fused_peers(q_bf16, bank_bf16, reinterpret_cast<const long long*>(labels), ref, inv_tau, B, N, D, T, row_base,
+                             home_rows, world, o_windows, l_windows, es_windows, s_t, reinterpret_cast<long long*>(lbl_row),
+                             ws, ws_bytes, as_stream(stream));
+}
+
 int spn_bank_ce_step(const void* q_src, int src_dtype, const void* bank_bf16, const int64_t* labels, float inv_tau,
                      const float* bank_maxnorm, const float* colsum, float label_smoothing, int B, int64_t N, int D, int T,
                      float* lse, float* loss_per_query, float* loss_mean, float* dq, float* dlogit_dot, void* ws,

@@ -10,6 +10,7 @@ constexpr int kBN = 128;      // bank rows per S tile (UMMA N of GEMM1, K extent
 constexpr int kBK = 64;       // bf16 elements per 128-byte swizzle row
 constexpr int kUmmaK = 16;    // K per tcgen05.mma for 16-bit inputs
 constexpr uint32_t kBlockBytes = kBM * kBK * 2;  // one [128 x 64] bf16 block = 16 KiB
+constexpr int kMaxPeers = 8;   // ranks of one NVSwitch box
 constexpr int kBankCEThreads = 320;  // TMA producer warp + MMA warp + 8 soft-max / epilogue warps
 
 struct BankCEParams {
@@ -50,6 +51,18 @@ struct BankCEParams {
   long long* lbl_row_out;  // fused: [B] LOCAL token row of the target (arg-max token for T = 32)
   float* dq;          // [B, D] fp32, +=  (fused: unnormalised O, label column excluded)
   float* dlogit_dot;  // [B] fp32, += (nullable)
+  // fused sweep over a ROW-SHARDED bank with the reduce-scatter folded into the epilogue (shard.cu): query tile t belongs
+  // to home rank t * 128 / home_rows, and its partial sums are reduce-added straight into THAT rank's window over NVLink
+  // (peer-mapped symmetric memory).  home_rows == 0: single destination (dq / l_acc / dlogit_dot above).
+  int home_rows;                 // queries per home rank (multiple of 128)
+  float* dq_peers[kMaxPeers];    // [home_rows, D] fp32 window of every rank (own window included)
+  float* l_peers[kMaxPeers];     // [home_rows] fp32
+  float* es_peers[kMaxPeers];    // [home_rows] fp32 (nullable as a group)
+};
+
+// TMA reduce-add destinations of the peer windows (two-pass kernel), passed by value as a kernel parameter
+struct PeerMaps {
+  CUtensorMap m[kMaxPeers];
 };
 
 struct BankCEPlan {
@@ -79,6 +92,12 @@ int bank_ce_fused(const void* q, const void* bank, const long long* labels, cons
                   long long N, int D, int T, long long row_base, int init, float* o_acc, float* l_acc, float* s_t,
                   long long* lbl_row, float* es_acc, float* bank_t, void* ws, size_t ws_bytes, cudaStream_t stream,
                   int pdl = 0);
+// the same sweep with per-home-rank destinations (peer windows); l_peers / es_peers / o_peers are HOST arrays of `world`
+// device pointers
+int bank_ce_fused_peers(const void* q, const void* bank, const long long* labels, const float* ref, float inv_tau, int B,
+                        long long N, int D, int T, long long row_base, int home_rows, int world, float* const* o_peers,
+                        float* const* l_peers, float* const* es_peers, float* s_t, long long* lbl_row, void* ws,
+                        size_t ws_bytes, cudaStream_t stream);
 size_t bank_ce_fused_ws_bytes(int B, long long N, int D, int T);
 int bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, const float* bank_t, const void* bank,
                      const long long* lbl_row, int zero_loss, const float* ref, const float* es_acc, const void* q16, const float* colsum, float inv_tau, float gscale, float eps,
@@ -99,6 +118,15 @@ int shard_pack(const float* l_acc, const float* s_t, const float* es_acc, const 
                cudaStream_t stream);
 int shard_fold(float* o_acc, const float* vec, const float* ref, const long long* lbl_row, const void* bank, int Bt,
                int D, float eps, float* s_t_out, cudaStream_t stream);
+
+// NVLink exchange kernels over peer-mapped symmetric memory (shard.cu); the pointer arguments `void* const*` are HOST
+// arrays of `world` device pointers (one per rank, own rank included)
+int shard_home_prologue(const void* q_src, int dtype, const long long* labels, void* const* bank_peers,
+                        long long rows_per_rank, long long n_total, int T, float inv_tau, const float* maxnorm, int B, int D,
+                        int rank, int world, void* const* qall_peers, void* const* ref_peers, void* const* lab_peers,
+                        float* s_t, float* ref_out, float* tgt_rows, float* o_win, float* l_win, float* es_win,
+                        cudaStream_t stream);
+int peer_barrier(void* const* flag_peers, int rank, int world, unsigned int epoch, cudaStream_t stream);
 
 // sampled-negatives loss (part_ce.cu)
 int part_ce(const void* q_src, int dtype, const void* bank, const long long* cand, float inv_tau, int B, int K1, int D,

@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(kBankCEThreads, 1)
 bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_bank,
                const __grid_constant__ CUtensorMap tmap_bank_half, const __grid_constant__ CUtensorMap tmap_p,
                const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tmap_bank3,
-               const BankCEParams p) {
+               const __grid_constant__ PeerMaps peer_maps, const BankCEParams p) {
   constexpr bool kTP = (MODE == 2 && CG == 2);  // the only variant that carries the second pass
   const bool do_pass2 = kTP && p.two_pass && !(p.hg & 2);   // bring-up knobs (SPN_DEBUG_HG): 2 = no second pass,
   const bool do_pstore = kTP && p.two_pass && !(p.hg & 4);  // 4 = no P~ stores (timing experiments only)
@@ -372,6 +372,12 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   int chunk = bid / p.num_dsplit;
   if (p.hg & 128) chunk = (chunk + (qt & 1) * (p.num_chunks / 2)) % p.num_chunks;  // experiment: no two pairs share a tile
   const int q0 = (qt * CG + int(crank)) * kBM;
+  // row-sharded bank with peer windows: this query tile's sums go to its home rank's window (home_rows % 128 == 0, so a
+  // tile never straddles two homes); q_dst0 = the tile's first row inside that window
+  const int home = p.home_rows ? q0 / p.home_rows : 0;
+  const int q_dst0 = p.home_rows ? q0 - home * p.home_rows : q0;
+  const CUtensorMap* dq_map = p.home_rows ? &peer_maps.m[home] : &tmap_dq;
+  float* const dq_base = p.home_rows ? p.dq_peers[home] : p.dq;
   const int t_begin = int((long long)chunk * p.n_tiles / p.num_chunks);
   const int t_end = int((long long)(chunk + 1) * p.n_tiles / p.num_chunks);
   const int ntl = t_end - t_begin;
@@ -408,7 +414,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     if (CG == 2) tma_prefetch_desc(&tmap_bank_half);
     if (kTP && p.two_pass) {
       tma_prefetch_desc(&tmap_p);
-      tma_prefetch_desc(&tmap_dq);
+      tma_prefetch_desc(dq_map);
       tma_prefetch_desc(&tmap_bank3);
     }
   }
@@ -1044,7 +1050,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && rows_ok && do_red) {
-            tma_reduce_add_2d(slot, &tmap_dq, d_col0 + c * 32, q0 + int(quarter) * 32);
+            tma_reduce_add_2d(slot, dq_map, d_col0 + c * 32, q_dst0 + int(quarter) * 32);
             bulk_commit_group();
           }
         }
@@ -1069,7 +1075,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           tmem_ld_32x32b_x32(t_row + uint32_t(c) * 32u, x0);
           tmem_ld_wait();
           if (q_ok && do_red) {
-            float* dst = p.dq + size_t(q) * p.D + size_t(ds) * p.ow_blocks * 64 + size_t(c) * 32;
+            float* dst = dq_base + size_t(q_dst0 + row) * p.D + size_t(ds) * p.ow_blocks * 64 + size_t(c) * 32;
             if (p.hg & 16) {
 #pragma unroll
               for (int v = 0; v < 8; ++v)
@@ -1102,7 +1108,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             tmem_ld_32x32b_x32(t_row + uint32_t(c) * 32u, x0);
             tmem_ld_wait();
             if (q_ok && do_red) {
-              float* dst = p.dq + size_t(q) * p.D + size_t(my_blocks) * 64 + size_t(c) * 32;
+              float* dst = dq_base + size_t(q_dst0 + row) * p.D + size_t(my_blocks) * 64 + size_t(c) * 32;
               if (p.hg & 16) {
 #pragma unroll
                 for (int v = 0; v < 8; ++v)
@@ -1116,9 +1122,9 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
           }
         }
-        if (EXTRA && q_ok && ds == 0) atomicAdd(&p.dlogit_dot[q], es * kLn2);
+        if (EXTRA && q_ok && ds == 0) atomicAdd(p.home_rows ? p.es_peers[home] + q_dst0 + row : &p.dlogit_dot[q], es * kLn2);
         if (MODE == 2 && q_ok && ds == 0) {
-          atomicAdd(&p.l_acc[q], l_run);
+          atomicAdd(p.home_rows ? p.l_peers[home] + q_dst0 + row : &p.l_acc[q], l_run);
           if (st > -INFINITY) {  // this thread owned the label column
             p.st_out[q] = st * kLn2;
             p.lbl_row_out[q] = (T == 1) ? lbl : lbl * 32 + st_tok;  // LOCAL token row whose gradient is -(1 - p_t)
@@ -1150,11 +1156,11 @@ __global__ void fused_init_kernel(float* o_acc, long long n_o, float* l_acc, flo
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long k = i; k < n_o / 4; k += stride) reinterpret_cast<float4*>(o_acc)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (i < B) {
-    l_acc[i] = 0.f;
-    st[i] = -INFINITY;
-    lbl_row[i] = -1;
-    if (es) es[i] = 0.f;
+  for (long long b = i; b < B; b += stride) {
+    if (l_acc) l_acc[b] = 0.f;
+    st[b] = -INFINITY;
+    lbl_row[b] = -1;
+    if (es) es[b] = 0.f;
   }
   if (i == 0 && loss_mean) *loss_mean = 0.f;
 }
@@ -1420,7 +1426,8 @@ int launch_one(const CUtensorMap& tq, const CUtensorMap& tb, const BankCEParams&
                cudaStream_t stream) {
   auto kfn = bank_ce_kernel<MODE, T, EXTRA, 1>;
   SPN_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kfn<<<grid, kBankCEThreads, smem, stream>>>(tq, tb, tb, tb, tb, tb, p);
+  static const PeerMaps no_peers{};
+  kfn<<<grid, kBankCEThreads, smem, stream>>>(tq, tb, tb, tb, tb, tb, no_peers, p);
   SPN_CUDA_CHECK(cudaGetLastError());
   return SPN_OK;
 }
@@ -1429,7 +1436,9 @@ int launch_one(const CUtensorMap& tq, const CUtensorMap& tb, const BankCEParams&
 template <int MODE, int T, bool EXTRA>
 int launch_pair(const CUtensorMap& tq, const CUtensorMap& tb, const CUtensorMap& tbh, const CUtensorMap& tp,
                 const CUtensorMap& tdq, const CUtensorMap& tpf, const BankCEParams& p, int grid, size_t smem,
-                cudaStream_t stream) {
+                cudaStream_t stream, const PeerMaps* pm = nullptr) {
+  static const PeerMaps no_peers{};
+  const PeerMaps& peers = pm ? *pm : no_peers;
   auto kfn = bank_ce_kernel<MODE, T, EXTRA, 2>;
   SPN_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   cudaLaunchConfig_t cfg = {};
@@ -1446,20 +1455,21 @@ int launch_pair(const CUtensorMap& tq, const CUtensorMap& tb, const CUtensorMap&
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = p.pdl ? 2 : 1;
-  SPN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kfn, tq, tb, tbh, tp, tdq, tpf, p));
+  SPN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kfn, tq, tb, tbh, tp, tdq, tpf, peers, p));
   return SPN_OK;
 }
 
 template <int MODE>
 int launch_mode(bool pair, int T, bool extra, const CUtensorMap& tq, const CUtensorMap& tb, const CUtensorMap& tbh,
                 const CUtensorMap& tp, const CUtensorMap& tdq, const CUtensorMap& tpf, const BankCEParams& p, int grid,
-                size_t smem, cudaStream_t stream) {
+                size_t smem, cudaStream_t stream, const PeerMaps* pm = nullptr) {
   if (pair) {
-    if (T == 1) return extra ? launch_pair<MODE, 1, true>(tq, tb, tbh, tp, tdq, tpf, p, grid, smem, stream)
-                             : launch_pair<MODE, 1, false>(tq, tb, tbh, tp, tdq, tpf, p, grid, smem, stream);
-    return extra ? launch_pair<MODE, 32, true>(tq, tb, tbh, tp, tdq, tpf, p, grid, smem, stream)
-                 : launch_pair<MODE, 32, false>(tq, tb, tbh, tp, tdq, tpf, p, grid, smem, stream);
+    if (T == 1) return extra ? launch_pair<MODE, 1, true>(tq, tb, tbh, tp, tdq, tpf, p, grid, smem, stream, pm)
+                             : launch_pair<MODE, 1, false>(tq, tb, tbh, tp, tdq, tpf, p, grid, smem, stream, pm);
+    return extra ? launch_pair<MODE, 32, true>(tq, tb, tbh, tp, tdq, tpf, p, grid, smem, stream, pm)
+                 : launch_pair<MODE, 32, false>(tq, tb, tbh, tp, tdq, tpf, p, grid, smem, stream, pm);
   }
+  if (pm) return fail(SPN_ERR_BAD_SHAPE, "peer windows need the CTA-pair kernels (an even number of 128-query tiles)");
   if (T == 1) return extra ? launch_one<MODE, 1, true>(tq, tb, p, grid, smem, stream)
                            : launch_one<MODE, 1, false>(tq, tb, p, grid, smem, stream);
   return extra ? launch_one<MODE, 32, true>(tq, tb, p, grid, smem, stream)
@@ -1665,10 +1675,13 @@ size_t bank_ce_fused_ws_bytes(int B, long long N, int D, int T) {
   return plan.two_pass ? plan.ws_bytes : 0;
 }
 
-int bank_ce_fused(const void* q, const void* bank, const long long* labels, const float* ref, float inv_tau, int B,
-                  long long N, int D, int T, long long row_base, int init, float* o_acc, float* l_acc, float* s_t,
-                  long long* lbl_row, float* es_acc, float* bank_t, void* ws, size_t ws_bytes, cudaStream_t stream,
-                  int pdl) {
+// shared body of spn_bank_ce_fused / spn_bank_ce_fused_peers.  home_rows == 0: every query tile accumulates into o_acc /
+// l_acc / es_acc; else into the window of its home rank (o_peers / l_peers / es_peers: `world` device pointers each).
+static int fused_launch(const void* q, const void* bank, const long long* labels, const float* ref, float inv_tau, int B,
+                        long long N, int D, int T, long long row_base, int init, float* o_acc, float* l_acc, float* s_t,
+                        long long* lbl_row, float* es_acc, float* bank_t, void* ws, size_t ws_bytes, cudaStream_t stream,
+                        int pdl, int home_rows, int world, float* const* o_peers, float* const* l_peers,
+                        float* const* es_peers) {
   BankCEPlan plan;
   int rc = bank_ce_plan(2, B, N, D, T, &plan);
   if (rc != SPN_OK) return rc;
@@ -1677,7 +1690,7 @@ int bank_ce_fused(const void* q, const void* bank, const long long* labels, cons
     if ((rc = bank_ce_plan(1, B, N, D, T, &plan)) != SPN_OK) return rc;
   }
   SPN_REQUIRE(inv_tau > 0.f && isfinite(inv_tau), SPN_ERR_BAD_ARG, "inv_tau must be positive and finite (got %g)", inv_tau);
-  SPN_REQUIRE(aligned16(o_acc), SPN_ERR_BAD_ALIGN, "bank_ce_fused: o_acc must be 16-byte aligned");
+  SPN_REQUIRE(home_rows || aligned16(o_acc), SPN_ERR_BAD_ALIGN, "bank_ce_fused: o_acc must be 16-byte aligned");
   SPN_REQUIRE(!plan.two_pass || aligned16(ws), SPN_ERR_BAD_ALIGN, "bank_ce_fused: workspace must be 16-byte aligned");
   CUtensorMap tq, tb, tbh, tp, tdq, tpf;
   if ((rc = make_tmap_bf16_2d(&tq, q, uint64_t(B), uint64_t(D), kBM)) != SPN_OK) return rc;
@@ -1686,16 +1699,32 @@ int bank_ce_fused(const void* q, const void* bank, const long long* labels, cons
   tp = tb;
   tdq = tb;
   tpf = tb;
+  PeerMaps pm{};
   if (plan.two_pass && (rc = make_tmap_bf16_3d(&tpf, bank, uint64_t(N) * T, uint64_t(D), kBN)) != SPN_OK) return rc;
-  if (plan.two_pass && (rc = make_tmap_f32_2d(&tdq, o_acc, uint64_t(B), uint64_t(D), 32)) != SPN_OK) return rc;
+  if (plan.two_pass && !home_rows && (rc = make_tmap_f32_2d(&tdq, o_acc, uint64_t(B), uint64_t(D), 32)) != SPN_OK) return rc;
   if (plan.two_pass &&
       (rc = make_tmap_bf16_3d(&tp, ws, uint64_t(plan.q_tiles) * plan.n_tiles * kBM, uint64_t(kBN), kBM)) != SPN_OK)
     return rc;
+  BankCEParams p{};
+  if (home_rows) {
+    SPN_REQUIRE(world >= 1 && world <= kMaxPeers && home_rows % kBM == 0 && B <= home_rows * world, SPN_ERR_BAD_SHAPE,
+                "bank_ce_fused_peers: need 1 <= world <= %d, home_rows %% 128 == 0 and B <= home_rows * world (home_rows=%d world=%d B=%d)",
+                kMaxPeers, home_rows, world, B);
+    SPN_REQUIRE(plan.cg == 2, SPN_ERR_BAD_SHAPE, "bank_ce_fused_peers: needs an even number of 128-query tiles (B=%d)", B);
+    for (int h = 0; h < world; ++h) {
+      SPN_REQUIRE(o_peers[h] && l_peers[h] && aligned16(o_peers[h]), SPN_ERR_BAD_ARG, "bank_ce_fused_peers: bad window of rank %d", h);
+      p.dq_peers[h] = o_peers[h];
+      p.l_peers[h] = l_peers[h];
+      p.es_peers[h] = es_peers ? es_peers[h] : nullptr;
+      if (plan.two_pass && (rc = make_tmap_f32_2d(&pm.m[h], o_peers[h], uint64_t(home_rows), uint64_t(D), 32)) != SPN_OK) return rc;
+    }
+    p.home_rows = home_rows;
+  }
   if (init) {
-    fused_init_kernel<<<148, 256, 0, stream>>>(o_acc, (long long)B * D, l_acc, s_t, lbl_row, es_acc, nullptr, B);
+    fused_init_kernel<<<148, 256, 0, stream>>>(home_rows ? nullptr : o_acc, home_rows ? 0 : (long long)B * D,
+                                               home_rows ? nullptr : l_acc, s_t, lbl_row, home_rows ? nullptr : es_acc, nullptr, B);
     SPN_CUDA_CHECK(cudaGetLastError());
   }
-  BankCEParams p{};
   p.B = B; p.D = D; p.N = N; p.n_rows = N * T; p.kblocks = plan.kblocks; p.stages = plan.stages; p.bps = plan.bps;
   p.n_tiles = plan.n_tiles; p.q_tiles = plan.q_tiles / plan.cg; p.num_chunks = plan.num_chunks;
   p.num_dsplit = plan.num_dsplit; p.ow_blocks = plan.ow_blocks; p.hg = plan.hg; p.scale_log2 = inv_tau * kLog2e;
@@ -1703,13 +1732,32 @@ int bank_ce_fused(const void* q, const void* bank, const long long* labels, cons
   p.l_acc = l_acc; p.st_out = s_t; p.lbl_row_out = lbl_row;
   p.two_pass = plan.two_pass; p.stages2 = plan.stages2; p.qt_blocks = plan.qt_blocks; p.pdl = pdl; p.p_scratch = static_cast<unsigned short*>(ws);
   p.p_ld = (long long)plan.n_tiles * kBN;
-  rc = launch_mode<2>(plan.cg == 2, T, es_acc != nullptr, tq, tb, tbh, tp, tdq, tpf, p, plan.grid, plan.smem_bytes, stream);
+  const bool extra = home_rows ? (es_peers != nullptr) : (es_acc != nullptr);
+  rc = launch_mode<2>(plan.cg == 2, T, extra, tq, tb, tbh, tp, tdq, tpf, p, plan.grid, plan.smem_bytes, stream,
+                      home_rows ? &pm : nullptr);
   if (rc != SPN_OK) return rc;
   if (bank_t) {
     gather_label_rows_kernel<<<(B + 7) / 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(bank), lbl_row, B, D, bank_t);
     SPN_CUDA_CHECK(cudaGetLastError());
   }
   return SPN_OK;
+}
+
+int bank_ce_fused(const void* q, const void* bank, const long long* labels, const float* ref, float inv_tau, int B,
+                  long long N, int D, int T, long long row_base, int init, float* o_acc, float* l_acc, float* s_t,
+                  long long* lbl_row, float* es_acc, float* bank_t, void* ws, size_t ws_bytes, cudaStream_t stream,
+                  int pdl) {
+  return fused_launch(q, bank, labels, ref, inv_tau, B, N, D, T, row_base, init, o_acc, l_acc, s_t, lbl_row, es_acc, bank_t,
+                      ws, ws_bytes, stream, pdl, 0, 0, nullptr, nullptr, nullptr);
+}
+
+int bank_ce_fused_peers(const void* q, const void* bank, const long long* labels, const float* ref, float inv_tau, int B,
+                        long long N, int D, int T, long long row_base, int home_rows, int world, float* const* o_peers,
+                        float* const* l_peers, float* const* es_peers, float* s_t, long long* lbl_row, void* ws,
+                        size_t ws_bytes, cudaStream_t stream) {
+  SPN_REQUIRE(home_rows > 0, SPN_ERR_BAD_ARG, "bank_ce_fused_peers: home_rows must be positive");
+  return fused_launch(q, bank, labels, ref, inv_tau, B, N, D, T, row_base, /*init=*/1, nullptr, nullptr, s_t, lbl_row, nullptr,
+                      nullptr, ws, ws_bytes, stream, 0, home_rows, world, o_peers, l_peers, es_peers);
 }
 
 int bank_ce_finalize(const float* o_acc, const float* l_acc, const float* s_t, const float* bank_t, const void* bank,

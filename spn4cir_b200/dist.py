@@ -202,6 +202,11 @@ def _sharded_sweep(q_local, bank, labels_local, inv_tau, eps, tau_grad, group, c
     is  all_gather(q bf16), all_gather(labels)  ->  MIN all_reduce(ref [Bt])  ->  [sweep]  ->  SUM all_reduce(vec [4, Bt])
     ->  [fold target rows]  ->  reduce_scatter(o_acc [Bt, D] fp32);  each rank finalises its own rows.
     Returns (loss_mean_of_local_queries, dq_unit [B, D] fp32, dlogit_dot | None)."""
+    if compute is None and symm_path_ok(bank, q_local.shape[0], group):
+        if eps != 0.0 and bank.T > 1:
+            from ._lib import SpnError
+            raise SpnError("bank_infonce_sharded", -7, "label smoothing over a multi-token (T > 1) sharded bank is not implemented")
+        return _sharded_sweep_symm(q_local, bank, labels_local, inv_tau, eps, tau_grad, group)
     compute = compute or _CudaShardCompute()
     rank, world = _world(group)
     B, D = q_local.shape
@@ -237,6 +242,173 @@ def _sharded_sweep(q_local, bank, labels_local, inv_tau, eps, tau_grad, group, c
     sl = slice(rank * B, (rank + 1) * B)
     return compute.finalize(o_mine, vec[0, sl], st_all[sl], ref[sl], vec[2, sl] if tau_grad else None, q16, colsum, bank,
                             inv_tau, B, eps)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The exchange WITHOUT NCCL: peer-mapped symmetric memory + kernels that read / write the other ranks' HBM over NVLink.
+#   home prologue (peer STORES of the bf16 query rows = the all-gather; peer LOADS of the target rows from the owner's
+#   shard = no MIN all-reduce, no second reduce-scatter)  ->  barrier  ->  fused sweep whose TMA reduce-add epilogue
+#   targets the home rank's window (= the reduce-scatter, inside the kernel)  ->  barrier  ->  finalize.
+# torch.distributed._symmetric_memory only allocates the buffers and exchanges their handles (plumbing).
+def _align(x: int, a: int = 256) -> int:
+    return (x + a - 1) // a * a
+
+
+def _ptr_array(ptrs):
+    import ctypes
+    return (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def symmetric_memory_available(dev: torch.device) -> bool:
+    """True when torch's symmetric-memory allocator can serve this process (CUDA device, process group up)."""
+    if not (dist.is_available() and dist.is_initialized()) or dev.type != "cuda":
+        return False
+    try:
+        import torch.distributed._symmetric_memory  # noqa: F401
+        return dist.get_backend() == "nccl"
+    except Exception:
+        return False
+
+
+def make_bank_symmetric(bank, group=None) -> None:
+    """Move this rank's bank shard into peer-mapped symmetric memory (one collective rendezvous, once per bank): every
+    rank can then LOAD target rows straight from the owner's shard.  All shards get the same capacity
+    (ceil(n_total / world) entries); ``bank.data`` becomes a view of the symmetric buffer."""
+    if getattr(bank, "peer_ptrs", None) is not None:
+        return
+    import torch.distributed._symmetric_memory as symm_mem
+    rank, world = _world(group)
+    per = (bank.n_total + world - 1) // world
+    if bank.row_base != rank * per or bank.N > per:
+        from ._lib import SpnError
+        raise SpnError("make_bank_symmetric", -1, f"rank {rank}: shard [{bank.row_base}, +{bank.N}) is not the uniform "
+                       f"ceil(n_total / world) = {per} split DeviceBank.from_tensor(shard_rank, shard_world) produces")
+    dev = bank.data.device
+    buf = symm_mem.empty(per * bank.T * bank.D, dtype=torch.bfloat16, device=dev)
+    hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+    view = buf[: bank.N * bank.T * bank.D].view(bank.N * bank.T, bank.D)
+    view.copy_(bank.data)
+    if bank.N < per:
+        buf[bank.N * bank.T * bank.D:].zero_()
+    bank.data = view
+    bank._symm = (buf, hdl)
+    bank.peer_ptrs = [int(p) for p in hdl.buffer_ptrs]
+    bank.rows_per_rank = per
+    torch.cuda.synchronize(dev)
+    dist.barrier(group)
+
+
+class SymmExchange:
+    """Windows of one (bank shard, B) pair in symmetric memory: the query window qall [world * B, D] bf16 with its ref /
+    label metadata, this rank's accumulation windows o [B, D], l [B], es [B] fp32, and the barrier flags."""
+
+    def __init__(self, bank, B: int, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.rank, self.world = _world(group)
+        self.group = group
+        self.B, self.D, self.Bt = B, bank.D, self.world * B
+        dev = bank.data.device
+        Bt, D = self.Bt, self.D
+        off, total = {}, 0
+        for name, nbytes in (("qall", Bt * D * 2), ("ref", Bt * 4), ("lab", Bt * 8), ("o", B * D * 4), ("l", B * 4),
+                             ("es", B * 4), ("flags", 256)):
+            off[name] = total
+            total += _align(nbytes)
+        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=dev)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        base = [int(p) for p in self.hdl.buffer_ptrs]
+        self.ptrs = {name: _ptr_array([b + o for b in base]) for name, o in off.items()}
+
+        def view(name, nbytes, dtype, shape):
+            return self.buf[off[name]: off[name] + nbytes].view(dtype).view(shape)
+
+        self.qall = view("qall", Bt * D * 2, torch.bfloat16, (Bt, D))
+        self.ref_all = view("ref", Bt * 4, torch.float32, (Bt,))
+        self.lab_all = view("lab", Bt * 8, torch.int64, (Bt,))
+        self.o_win = view("o", B * D * 4, torch.float32, (B, D))
+        self.l_win = view("l", B * 4, torch.float32, (B,))
+        self.es_win = view("es", B * 4, torch.float32, (B,))
+        self.bank_ptrs = _ptr_array(bank.peer_ptrs)
+        self.epoch = 0
+        # local scratch of the step (not shared): target rows, s_t, ref of the local queries; s_t / lbl_row of the sweep
+        self.tgt = torch.empty((B, D), dtype=torch.float32, device=dev)
+        self.s_t = torch.empty(B, dtype=torch.float32, device=dev)
+        self.ref = torch.empty(B, dtype=torch.float32, device=dev)
+        self.sw_st = torch.empty(Bt, dtype=torch.float32, device=dev)
+        self.sw_lbl = torch.empty(Bt, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)  # every rank's flags are zero before the first device-side barrier
+
+    def barrier(self, stream) -> None:
+        from ._lib import call
+        self.epoch += 1
+        call("spn_peer_barrier", self.ptrs["flags"], self.rank, self.world, self.epoch & 0xFFFFFFFF, stream)
+
+
+_exchanges = {}
+
+
+def _symm_exchange(bank, B: int, group) -> "SymmExchange":
+    key = (id(bank), B, id(group))
+    x = _exchanges.get(key)
+    if x is None:
+        make_bank_symmetric(bank, group)
+        x = _exchanges[key] = SymmExchange(bank, B, group)
+    return x
+
+
+def release_exchanges() -> None:
+    """Drop the cached symmetric-memory windows (collective: call on every rank)."""
+    _exchanges.clear()
+
+
+def symm_path_ok(bank, B: int, group=None) -> bool:
+    """The NCCL-free exchange needs symmetric memory, B % 128 == 0 (a query tile has ONE home rank), world <= 8 and the
+    uniform ceil(n_total / world) sharding."""
+    import os
+    rank, world = _world(group)
+    if os.environ.get("SPN_EXCHANGE", "symm") == "nccl" or world < 2 or world > 8 or B % 128 != 0 or (world * B // 128) % 2 != 0:
+        return False
+    per = (bank.n_total + world - 1) // world
+    return symmetric_memory_available(bank.data.device) and bank.row_base == rank * per and bank.N <= per
+
+
+def _sharded_sweep_symm(q_local, bank, labels_local, inv_tau, eps, tau_grad, group):
+    """One sharded step over NVLink-mapped windows: 3 kernels + 2 device-side barriers, no NCCL call.
+    Returns (loss_mean_of_local_queries, dq_unit [B, D] fp32, dlogit_dot | None)."""
+    from ._lib import call
+    from .ops import _TORCH2SPN, _ptr, _stream, fused_scratch
+    compute = _CudaShardCompute()
+    compute.check_tau(bank, inv_tau, group)
+    B, D = q_local.shape
+    dev = q_local.device
+    x = _symm_exchange(bank, B, group)
+    qc = q_local.detach()
+    if qc.dtype not in _TORCH2SPN:
+        qc = qc.float()
+    qc = qc.contiguous()
+    maxnorm = global_maxnorm(bank, group)
+    colsum = global_colsum(bank, group) if eps != 0.0 else None
+    out = torch.empty((2, B), dtype=torch.float32, device=dev)  # lse, loss_per_query
+    mean = torch.empty((), dtype=torch.float32, device=dev)
+    dq = torch.empty((B, D), dtype=torch.float32, device=dev)
+    ddot = torch.empty(B, dtype=torch.float32, device=dev) if tau_grad else None
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        call("spn_shard_home_prologue", _ptr(qc), _TORCH2SPN[qc.dtype], _ptr(labels_local), x.bank_ptrs, bank.rows_per_rank,
+             bank.n_total, bank.T, inv_tau, _ptr(maxnorm), B, D, x.rank, x.world, x.ptrs["qall"], x.ptrs["ref"], x.ptrs["lab"],
+             _ptr(x.s_t), _ptr(x.ref), _ptr(x.tgt), _ptr(x.o_win), _ptr(x.l_win), _ptr(x.es_win) if tau_grad else None, st)
+        x.barrier(st)  # every rank's queries / refs / labels have landed, every window is zeroed
+        ws, ws_bytes = fused_scratch(x.Bt, bank, dev)
+        call("spn_bank_ce_fused_peers", _ptr(x.qall), _ptr(bank.data), _ptr(x.lab_all), _ptr(x.ref_all), inv_tau, x.Bt, bank.N,
+             D, bank.T, bank.row_base, B, x.world, x.ptrs["o"], x.ptrs["l"], x.ptrs["es"] if tau_grad else None,
+             _ptr(x.sw_st), _ptr(x.sw_lbl), _ptr(ws), ws_bytes, st)
+        x.barrier(st)  # every rank's partial sums have been reduce-added into the home windows
+        call("spn_bank_ce_finalize", _ptr(x.o_win), _ptr(x.l_win), _ptr(x.s_t), _ptr(x.tgt), _ptr(x.ref),
+             _ptr(x.es_win) if tau_grad else None, _ptr(x.qall[x.rank * B:(x.rank + 1) * B]), _ptr(colsum), inv_tau,
+             inv_tau / B, eps, bank.n_total, B, D, _ptr(out[0]), _ptr(out[1]), _ptr(mean), _ptr(dq), _ptr(ddot), st)
+    return mean, dq, ddot
 
 
 class _ShardedBankCE(torch.autograd.Function):

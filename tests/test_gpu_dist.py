@@ -72,6 +72,41 @@ assert torch.equal(i, i1) and torch.equal(v, v1)
 r, g = sim_rank_sharded(qq.to(dev), gal[lo:hi].to(dev), tgt, lo, exclude=refi, group_members=grp)
 r1, g1 = spn.sim_rank(qq.to(dev), gal.to(dev), tgt, exclude=refi, group=grp)
 assert torch.equal(r, r1) and torch.equal(g, g1)
+# the NCCL-free exchange (peer-mapped symmetric memory, reduce-scatter inside the sweep's epilogue) against the NCCL exchange
+# and the single-GPU step: B % 128 == 0 selects it automatically; two-pass (D = 640) and single-pass (T = 32, D = 256) kernels
+from spn4cir_b200 import dist as sdist
+assert sdist.symm_path_ok(sh2, 256), "symmetric-memory path unavailable on this box"
+assert len(sdist._exchanges) >= 1, "bank_ce_step_sharded did not take the symmetric-memory path"
+os.environ["SPN_EXCHANGE"] = "nccl"
+l_n, dq_n = bank_ce_step_sharded(qq2, sh2, lab2.to(dev), tau)
+os.environ.pop("SPN_EXCHANGE")
+assert abs(l_s.item() - l_n.item()) <= 1e-5 * max(1.0, abs(l_n.item())), (rank, l_s.item(), l_n.item())
+assert float((dq_s - dq_n).norm() / dq_n.norm()) < 1e-4
+for it in range(3):  # repeated steps reuse the windows (zeroing + barriers between steps)
+    l_r, dq_r = bank_ce_step_sharded(qq2, sh2, lab2.to(dev), tau)
+    assert abs(l_r.item() - l_s.item()) <= 1e-6 * max(1.0, abs(l_s.item())) and float((dq_r - dq_s).norm() / dq_s.norm()) < 1e-5
+tq = torch.tensor(tau, device=dev, requires_grad=True)
+q5 = qq2.clone().requires_grad_(True)
+l5 = bank_infonce_sharded(q5, sh2, lab2.to(dev), tq, label_smoothing=0.1)
+l5.backward()
+tf = torch.tensor(tau, device=dev, requires_grad=True)
+q6 = qq2.clone().requires_grad_(True)
+l6 = spn.bank_infonce(q6, spn.DeviceBank.from_tensor(bank2, dev), lab2.to(dev), tf, label_smoothing=0.1, single_pass=True)
+l6.backward()
+assert abs(l5.item() - l6.item()) <= 1e-5 * max(1.0, abs(l6.item())), (rank, l5.item(), l6.item())
+assert float((q5.grad - q6.grad).norm() / q6.grad.norm()) < 1e-4
+assert abs(tq.grad.item() - tf.grad.item()) <= 1e-3 * max(abs(tf.grad.item()), 1e-3), (tq.grad, tf.grad)
+bank3 = synth.make_bank(1600, 256, 32, seed=79)                      # BLIP-2 shaped: whole entries per rank
+lab3 = synth.make_labels(128, 1600, seed=500 + rank)
+qq3 = synth.make_queries(bank3, lab3, "S", seed=600 + rank).to(dev)
+sh3 = spn.DeviceBank.from_tensor(bank3, dev, shard_rank=rank, shard_world=world)
+l_s3, dq_s3 = bank_ce_step_sharded(qq3, sh3, lab3.to(dev), 0.05)
+l_f3, dq_f3 = spn.bank_ce_step(qq3, spn.DeviceBank.from_tensor(bank3, dev), lab3.to(dev), 0.05)
+assert abs(l_s3.item() - l_f3.item()) <= 1e-5 * max(1.0, abs(l_f3.item())), (rank, l_s3.item(), l_f3.item())
+assert float((dq_s3 - dq_f3).norm() / dq_f3.norm()) < 1e-4
+bad = lab2.clone(); bad[0] = 10 ** 7                                  # a label nobody owns: +inf, as on one GPU
+l_bad, _ = bank_ce_step_sharded(qq2, sh2, bad.to(dev), tau)
+assert torch.isinf(l_bad).item() and l_bad.item() > 0
 dist.barrier()
 if rank == 0:
     print("DIST_OK world=%d" % world)
