@@ -265,22 +265,23 @@ def run_ours(args, cfg):
     lab_pin = labels_dev.cpu().pin_memory()
     timer = Timer(dev)
 
-    def step(qin, lab):
-        """one pass of the hot path: loss + dL/dq.  N = 1: the step primitive (one spn_bank_ce_step C-ABI call);
-        N > 1: the same sweep over this rank's bank rows for all ranks' queries + the NCCL exchange."""
+    def step_primitive(qin, lab):
+        """loss + dL/dq without the autograd engine.  N = 1: torch.ops.spn4cir.bank_ce_step (one spn_bank_ce_step C-ABI call);
+        N > 1: the same sweep over this rank's bank rows for all ranks' queries + the exchange."""
         if sharded:
             return bank_ce_step_sharded(qin, bank, lab, tau)
         return spn.bank_ce_step(qin, bank, lab, tau)
 
-    def step_autograd(qin, lab):
-        """the reference call shape: loss = infonce_loss(q, bank, labels, tau); loss.backward()"""
+    def step(qin, lab):
+        """one pass of the hot path in the REFERENCE CALL SHAPE (clip4cir/train_negplus.py:110-121 around
+        models_negplus.py:150-154): loss = infonce_loss(q, bank, labels, tau); loss.backward() -> (loss, dL/dq)."""
         qx = qin.detach().requires_grad_(True)
         if sharded:
             loss = spn.dist.bank_infonce_sharded(qx, bank, lab, tau)
         else:
             loss = spn.bank_infonce(qx, bank, lab, tau)
         loss.backward()
-        return loss, qx.grad
+        return loss.detach(), qx.grad
 
     dq_pin = torch.empty((B, D), dtype=torch.float32).pin_memory()
     loss_pin = torch.empty((), dtype=torch.float32).pin_memory()
@@ -376,9 +377,9 @@ def run_ours(args, cfg):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(3):
-        step_autograd(q_dev, labels_dev)
+        step_primitive(q_dev, labels_dev)
     barrier()
-    t_auto = timer.run(lambda: step_autograd(q_dev, labels_dev), steps)
+    t_auto = timer.run(lambda: step_primitive(q_dev, labels_dev), steps)
     auto_issue_ms = timer.cpu_issue_ms
     barrier()
     for _ in range(2):
@@ -432,9 +433,33 @@ def run_ours(args, cfg):
     del dq2, stats, q16
     barrier()
 
-    # ---- exchange breakdown (N > 1): every collective of the step alone, same buffers' shapes, CUDA events, max over ranks
+    # ---- exchange breakdown (N > 1): (a) the stages of the NCCL-free step (CUDA events inside the step, max over ranks),
+    # (b) the SAME step through the NCCL exchange (SPN_EXCHANGE=nccl) and every collective of it alone
     exchange = None
     if sharded:
+        from spn4cir_b200 import dist as sdist
+        from spn4cir_b200.ops import _prep_labels
+        exchange = {"path": "symmetric-memory (NVLink peer stores / loads / TMA reduce-add, no NCCL)" if sdist.symm_path_ok(bank, B) else "NCCL"}
+        if sdist.symm_path_ok(bank, B):
+            acc = [0.0] * 5
+            for _ in range(steps):
+                timer.flush.zero_()
+                evs = []
+                sdist._sharded_sweep_symm(q_dev, bank, _prep_labels(labels_dev, B, dev), 1.0 / tau, 0.0, False, None, stage_events=evs)
+                torch.cuda.synchronize(dev)
+                for i in range(5):
+                    acc[i] += evs[i].elapsed_time(evs[i + 1])
+            names = ["home_prologue_ms (cast + peer stores of q/ref/labels + peer loads of the target rows)", "barrier_1_ms",
+                     "sweep_with_remote_reduce_epilogue_ms", "barrier_2_ms", "finalize_ms"]
+            exchange["stages"] = {n: agree_max(a / steps) for n, a in zip(names, acc)}
+            exchange["stages"]["sweep_local_accumulation_ms"] = None  # filled below from the kernel timed alone
+            os.environ["SPN_EXCHANGE"] = "nccl"
+            for _ in range(3):
+                step_primitive(q_dev, labels_dev)
+            barrier()
+            exchange["nccl_step_ms"] = agree_max(timer.run(lambda: step_primitive(q_dev, labels_dev), steps)) * 1e3
+            os.environ.pop("SPN_EXCHANGE")
+            barrier()
         o_full = torch.zeros((Bt, D), dtype=torch.float32, device=dev)
         o_mine = torch.empty((B, D), dtype=torch.float32, device=dev)
         q16l = cast_to_bf16(q_dev)
@@ -448,14 +473,15 @@ def run_ours(args, cfg):
             "all_reduce_sum_vec": (lambda: dist.all_reduce(vec), 4 * Bt * 4),
             "reduce_scatter_o_fp32": (lambda: dist.reduce_scatter_tensor(o_mine, o_full), Bt * D * 4),
         }
-        exchange = {}
+        coll = {}
         for name, (fn, nbytes) in parts.items():
             for _ in range(3):
                 fn()
             barrier()
             ms = agree_max(timer.run(fn, steps, flush=False)) * 1e3
-            exchange[name] = {"ms": ms, "bytes": nbytes}
-        exchange["sum_ms"] = sum(v["ms"] for v in exchange.values())
+            coll[name] = {"ms": ms, "bytes": nbytes}
+        coll["sum_ms"] = sum(v["ms"] for v in coll.values())
+        exchange["nccl_collectives_alone"] = coll
         del o_full, o_mine, q16a
     barrier()
 
@@ -480,7 +506,12 @@ def run_ours(args, cfg):
                 roof["traffic"] = json.loads(prof.read_text()).get("dram_bytes_per_launch")
             except Exception:
                 pass
+        symm = sharded and exchange is not None and "stages" in exchange
         par = ("single GPU, whole bank resident" if world == 1 else
+               f"bank row-sharded x{world} ({bank.N} rows/rank), queries data-parallel, exchange over peer-mapped symmetric memory (no NCCL call): "
+               f"home prologue kernel stores the bf16 queries into every rank's window and loads the target rows from the owner's shard -> "
+               f"device barrier -> fused sweep whose TMA reduce-add epilogue targets the home rank's [{B}, {D}] fp32 window over NVLink -> "
+               f"device barrier -> finalize" if symm else
                f"bank row-sharded x{world} ({bank.N} rows/rank), queries data-parallel: all_gather(q bf16, labels) -> MIN all_reduce(ref) "
                f"-> fused sweep -> SUM all_reduce([4, {Bt}]) -> owner folds the target rows -> reduce_scatter(o fp32 [{Bt}, {D}]) over NCCL"
                if sharded else
@@ -493,11 +524,15 @@ def run_ours(args, cfg):
                            "global_batch": B * world, "per_rank_flops_per_step": fl},
                 "clocks": clocks, "roofline": roof, "self_check": self_check,
                 "host_issue_ms_per_step": host_issue_ms,
-                "api": ("spn4cir_b200.dist.bank_ce_step_sharded (step primitive over the row-sharded bank, NCCL exchange)" if sharded else
-                        "spn4cir_b200.bank_ce_step -> spn_bank_ce_step (C ABI step primitive: loss + dL/dq)"),
-                "autograd_api": {"call": "loss = bank_infonce(q, bank, labels, tau); loss.backward()",
-                                 "value": (B * world) / t_auto, "unit": "queries/s",
-                                 "ms_per_step": t_auto * 1e3, "host_issue_ms_per_step": auto_issue_ms},
+                "api": ("loss = spn4cir_b200.dist.bank_infonce_sharded(q, bank_shard, labels, tau); loss.backward()  (reference call shape over the row-sharded bank)"
+                        if sharded else
+                        "loss = spn4cir_b200.bank_infonce(q, bank, labels, tau); loss.backward()  (reference call shape; torch.ops.spn4cir.bank_infonce: "
+                        "torch.library operator + C++ autograd node over the C ABI -> spn_bank_ce_step)"),
+                "step_primitive_api": {"call": ("spn4cir_b200.dist.bank_ce_step_sharded(q, bank_shard, labels, tau)" if sharded else
+                                                "spn4cir_b200.bank_ce_step(q, bank, labels, tau) -> torch.ops.spn4cir.bank_ce_step -> spn_bank_ce_step"),
+                                       "value": (B * world) / t_auto, "unit": "queries/s",
+                                       "ms_per_step": t_auto * 1e3, "host_issue_ms_per_step": auto_issue_ms,
+                                       "note": "loss + dL/dq without the autograd engine, same kernels"},
                 "step_ms_min_median_max": [min(per_iter), statistics.median(per_iter), max(per_iter)],
                 "e2e": {"value": (B * world) / t_e2e, "unit": "queries/s",
                         "h2d_bytes_per_step": q_pin.numel() * 4 + lab_pin.numel() * 8,
@@ -508,13 +543,19 @@ def run_ours(args, cfg):
                                 "around the K steps; the bank stays resident in HBM",
                         "serial": {"value": (B * world) / t_e2e_serial, "ms_per_step": t_e2e_serial * 1e3,
                                    "note": "the same step with its copies serialised on one stream, L2 flushed before each (latency of one isolated step)"}},
-                "gpu_launches": (7 if sharded else 3) * steps,
-                "gpu_launches_detail": ("per step: cast_bf16_kernel, prep_query_kernel, fused_init_kernel, bank_ce_kernel<2>, shard_pack_kernel, "
+                "gpu_launches": ((6 if symm else 7) if sharded else 3) * steps,  # + 1 torch elementwise kernel (dq_unit * upstream grad) in backward
+                "gpu_launches_detail": ("per step: shard_home_prologue_kernel, peer_barrier_kernel, fused_init_kernel, bank_ce_kernel<2> (peer windows), "
+                                        "peer_barrier_kernel, fused_finalize_kernel (no NCCL call)" if symm else
+                                        "per step: cast_bf16_kernel, prep_query_kernel, fused_init_kernel, bank_ce_kernel<2>, shard_pack_kernel, "
                                         "shard_fold_kernel, fused_finalize_kernel (+ 5 NCCL collectives)"
                                         if sharded else
-                                        "per step (one spn_bank_ce_step call): prep_query_kernel, bank_ce_kernel<2>, fused_finalize_kernel")}
+                                        "per step (one spn_bank_ce_step call): prep_query_kernel, bank_ce_kernel<2>, fused_finalize_kernel; "
+                                        "backward = one torch elementwise kernel (dq_unit * upstream grad)")}
         if exchange is not None:
-            exchange["step_minus_sweep_ms"] = (t_dev - t_fused) * 1e3
+            exchange["step_minus_local_sweep_ms"] = (t_dev - t_fused) * 1e3
+            if "stages" in exchange:
+                exchange["stages"]["sweep_local_accumulation_ms"] = t_fused * 1e3
+                exchange["symm_step_ms"] = t_auto * 1e3  # the step primitive through the NCCL-free exchange (vs nccl_step_ms)
             line["exchange"] = exchange
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = time_cpu_reference(cfg, budget_s=20.0, steps=3, warmup=1)

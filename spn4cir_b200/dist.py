@@ -374,9 +374,11 @@ def symm_path_ok(bank, B: int, group=None) -> bool:
     return symmetric_memory_available(bank.data.device) and bank.row_base == rank * per and bank.N <= per
 
 
-def _sharded_sweep_symm(q_local, bank, labels_local, inv_tau, eps, tau_grad, group):
+def _sharded_sweep_symm(q_local, bank, labels_local, inv_tau, eps, tau_grad, group, stage_events=None):
     """One sharded step over NVLink-mapped windows: 3 kernels + 2 device-side barriers, no NCCL call.
-    Returns (loss_mean_of_local_queries, dq_unit [B, D] fp32, dlogit_dot | None)."""
+    Returns (loss_mean_of_local_queries, dq_unit [B, D] fp32, dlogit_dot | None).
+    ``stage_events``: optional list that receives 6 timing events (start, after the home prologue, barrier 1, the sweep,
+    barrier 2, finalize) -- bench.py's exchange breakdown."""
     from ._lib import call
     from .ops import _TORCH2SPN, _ptr, _stream, fused_scratch
     compute = _CudaShardCompute()
@@ -394,20 +396,32 @@ def _sharded_sweep_symm(q_local, bank, labels_local, inv_tau, eps, tau_grad, gro
     mean = torch.empty((), dtype=torch.float32, device=dev)
     dq = torch.empty((B, D), dtype=torch.float32, device=dev)
     ddot = torch.empty(B, dtype=torch.float32, device=dev) if tau_grad else None
+    def mark():
+        if stage_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            stage_events.append(ev)
+
     with torch.cuda.device(dev):
         st = _stream(dev)
+        mark()
         call("spn_shard_home_prologue", _ptr(qc), _TORCH2SPN[qc.dtype], _ptr(labels_local), x.bank_ptrs, bank.rows_per_rank,
              bank.n_total, bank.T, inv_tau, _ptr(maxnorm), B, D, x.rank, x.world, x.ptrs["qall"], x.ptrs["ref"], x.ptrs["lab"],
              _ptr(x.s_t), _ptr(x.ref), _ptr(x.tgt), _ptr(x.o_win), _ptr(x.l_win), _ptr(x.es_win) if tau_grad else None, st)
+        mark()
         x.barrier(st)  # every rank's queries / refs / labels have landed, every window is zeroed
+        mark()
         ws, ws_bytes = fused_scratch(x.Bt, bank, dev)
         call("spn_bank_ce_fused_peers", _ptr(x.qall), _ptr(bank.data), _ptr(x.lab_all), _ptr(x.ref_all), inv_tau, x.Bt, bank.N,
              D, bank.T, bank.row_base, B, x.world, x.ptrs["o"], x.ptrs["l"], x.ptrs["es"] if tau_grad else None,
              _ptr(x.sw_st), _ptr(x.sw_lbl), _ptr(ws), ws_bytes, st)
+        mark()
         x.barrier(st)  # every rank's partial sums have been reduce-added into the home windows
+        mark()
         call("spn_bank_ce_finalize", _ptr(x.o_win), _ptr(x.l_win), _ptr(x.s_t), _ptr(x.tgt), _ptr(x.ref),
              _ptr(x.es_win) if tau_grad else None, _ptr(x.qall[x.rank * B:(x.rank + 1) * B]), _ptr(colsum), inv_tau,
              inv_tau / B, eps, bank.n_total, B, D, _ptr(out[0]), _ptr(out[1]), _ptr(mean), _ptr(dq), _ptr(ddot), st)
+        mark()
     return mean, dq, ddot
 
 
