@@ -144,42 +144,49 @@ __global__ void shard_home_prologue_kernel(const SrcT* __restrict__ q_src, const
       if (d < D) dst[d >> 1] = qbits[k];
     }
   }
-  // target logit from the owner's shard (peer loads), exact fp32 chain over the bf16 values; T > 1: first arg-max token
+  // target logit from the owner's shard (peer loads over NVLink: one round trip per token row, the values stay in
+  // registers for the fp32 target row), exact fp32 chain over the bf16 values; T > 1: first arg-max token
   float r = inv_tau * sqrtf(ss) * (*maxnorm) * 1.01f + 1e-3f;
   const long long lab = labels[b];
   float best = -INFINITY;
-  const __nv_bfloat16* best_row = nullptr;
+  bool have = false;
+  float2 bestv[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) bestv[k] = make_float2(0.f, 0.f);
   if (lab >= 0 && lab < n_total) {
     const int owner = int(lab / rows_per_rank);
     const long long local = lab - (long long)owner * rows_per_rank;
     const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(bank_peers.p[owner]) + size_t(local) * T * D;
     for (int tok = 0; tok < T; ++tok) {
       const __nv_bfloat16* row = base + size_t(tok) * D;
+      float2 v[12];
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < 12; ++k) {
         const int d = k * 64 + lane * 2;
-        if (d < D) {
-          const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + d));
-          acc = fmaf(qv[k].x, v.x, fmaf(qv[k].y, v.y, acc));
-        }
+        v[k] = make_float2(0.f, 0.f);
+        if (d < D) v[k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + d));
       }
+#pragma unroll
+      for (int k = 0; k < 12; ++k) acc = fmaf(qv[k].x, v[k].x, fmaf(qv[k].y, v[k].y, acc));
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (acc > best) {
+      if (acc > best || !have) {
         best = acc;
-        best_row = row;
+        have = true;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) bestv[k] = v[k];
       }
     }
     r = fminf(r, fmaxf(best * inv_tau + 30.f, r - 64.f));
   }
   // target row (fp32) for the finalize step; zeros when the label is out of range (loss = +inf, as on one GPU)
-  for (int d = lane * 2; d < D; d += 64) {
-    float2 v = make_float2(0.f, 0.f);
-    if (best_row) v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(best_row + d));
-    *reinterpret_cast<float2*>(tgt_rows + size_t(b) * D + d) = v;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    const int d = k * 64 + lane * 2;
+    if (d < D) *reinterpret_cast<float2*>(tgt_rows + size_t(b) * D + d) = bestv[k];
   }
   if (lane == 0) {
-    s_t[b] = best_row ? best * inv_tau : -INFINITY;
+    s_t[b] = have ? best * inv_tau : -INFINITY;
     ref_out[b] = r;
     for (int rr = 0; rr < world; ++rr) {
       static_cast<float*>(ref_peers.p[rr])[grow] = r;
