@@ -133,8 +133,14 @@ def retrieval_cases(validate):
                             input_digest=digest(q, gallery, reference, target, groups))
         print(name, [round(x, 3) for x in ref])
 
-    for name, (Q, G, D, seed, noise) in {"fiq_small": (150, 400, 64, 7, 3.0), "fiq_dress": (2017, 3817, 640, 8, 8.5)}.items():
-        q, gallery, names, reference, target, _ = synth.make_retrieval_case(Q, G, D, 1, seed, noise=noise)
+    # FashionIQ-shaped sets: dress / shirt / toptee (public dataset statistics) + a set whose queries sit close
+    # to their REFERENCE image (ref_pull), so that the clip4cir flavour (reference removed, validate.py:38-45) and the
+    # blip4cir / tgcir / blip2 flavour (no removal, blip4cir/validate.py:45-56) give different recalls
+    fiq = {"fiq_small": (150, 400, 64, 7, 3.0, 0.0), "fiq_dress": (2017, 3817, 640, 8, 8.5, 0.0),
+           "fiq_shirt": (2038, 6346, 640, 9, 8.5, 0.0), "fiq_toptee": (1961, 5373, 640, 10, 8.5, 0.0),
+           "fiq_refnear": (600, 900, 128, 11, 5.0, 1.2)}
+    for name, (Q, G, D, seed, noise, pull) in fiq.items():
+        q, gallery, names, reference, target, _ = synth.make_retrieval_case(Q, G, D, 1, seed, noise=noise, ref_pull=pull)
         ds = synth.FakeFIQDataset(names, reference, target)
         caps = [f"is q{i} and and more {i}" for i in range(Q)]
         text = {c: q[i] * 2.0 - gallery[reference[i]] for i, c in enumerate(caps)}
@@ -144,10 +150,21 @@ def retrieval_cases(validate):
         orc = oretr.fiq_metrics(pred, gallery, names, [names[int(i)] for i in target], [names[int(i)] for i in reference])
         assert np.allclose(orc, ref), (orc, ref)
         orc_noremove = oretr.fiq_metrics(pred, gallery, names, [names[int(i)] for i in target], None)
-        np.savez_compressed(OUT / f"{name}.npz", Q=Q, G=G, D=D, seed=seed, noise=noise, metrics=np.array(ref, dtype=np.float64),
-                            metrics_noremove=np.array(orc_noremove, dtype=np.float64),
+        # the no-removal flavour EXECUTED from the reference: blip4cir/validate.py:42-56 verbatim on prepared locals
+        # (blip4cir cannot be imported offline: med.py needs a transformers API that no longer exists)
+        env = exec_reference_lines(Path("/root/reference/blip4cir/validate.py"), 42, 56,
+                                   dict(torch=torch, np=np, predicted_features=pred, index_names=names,
+                                        index_features_normed_pooled=torch.nn.functional.normalize(gallery, dim=-1),
+                                        target_names=[names[int(i)] for i in target]))
+        ref_noremove = (env["recall_at10"], env["recall_at50"])
+        assert np.allclose(orc_noremove, ref_noremove), (orc_noremove, ref_noremove)
+        if pull:
+            assert abs(ref[0] - ref_noremove[0]) > 0.3 and abs(ref[1] - ref_noremove[1]) > 0.3, "the two flavours must differ on this set"
+        np.savez_compressed(OUT / f"{name}.npz", Q=Q, G=G, D=D, seed=seed, noise=noise, ref_pull=pull,
+                            metrics=np.array(ref, dtype=np.float64),
+                            metrics_noremove=np.array(ref_noremove, dtype=np.float64),
                             input_digest=digest(q, gallery, reference, target))
-        print(name, ref, orc_noremove)
+        print(name, ref, ref_noremove)
 
 
 def blip2_cases():

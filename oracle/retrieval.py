@@ -108,6 +108,10 @@ def fiq_metrics(q: torch.Tensor, index_features: torch.Tensor, index_names: List
             r50 += 1
         elif target_names[i] in row[:50]:
             r50 += 1
+    if refer_names is None:
+        # blip4cir/validate.py:55-56: `(torch.sum(labels[:, :k]) / len(labels)).item() * 100` -- an int64 tensor divided by
+        # an int gives a float32 tensor, so this flavour's recalls carry float32 rounding
+        return ((torch.tensor(r10) / N).item() * 100, (torch.tensor(r50) / N).item() * 100)
     return (r10 / N) * 100, (r50 / N) * 100                                          # :48-49
 
 

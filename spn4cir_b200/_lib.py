@@ -19,6 +19,7 @@ CSRC_DIR = PKG_DIR / "csrc"
 REPO_ROOT = PKG_DIR.parent
 LIB_PATH = PKG_DIR / "libspn_b200.so"
 HEADER_PATH = REPO_ROOT / "include" / "spn_b200.h"
+DEBUG_HEADER_PATH = REPO_ROOT / "include" / "spn_b200_debug.h"  # bring-up / test-only entry points
 
 SOURCES = ["common.cu", "bank_ce_tc.cu", "shard.cu", "part_ce.cu", "umma_selftest.cu", "prologue.cu", "sim_rank.cu", "sim_tc.cu", "api.cu"]
 NVCC_FLAGS = [
@@ -54,7 +55,7 @@ def _stale() -> bool:
     if not LIB_PATH.exists():
         return True
     t = LIB_PATH.stat().st_mtime
-    deps = list(CSRC_DIR.glob("*.cu")) + list(CSRC_DIR.glob("*.cuh")) + [HEADER_PATH]
+    deps = list(CSRC_DIR.glob("*.cu")) + list(CSRC_DIR.glob("*.cuh")) + [HEADER_PATH, DEBUG_HEADER_PATH]
     return any(p.stat().st_mtime > t for p in deps)
 
 
@@ -70,7 +71,7 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=(), ou
     tag = "obj" if not extra_flags else "obj_" + "".join(c if c.isalnum() else "_" for c in "".join(extra_flags))
     objdir = REPO_ROOT / "build" / tag
     objdir.mkdir(parents=True, exist_ok=True)
-    hdr_t = max(p.stat().st_mtime for p in list(CSRC_DIR.glob("*.cuh")) + [HEADER_PATH])
+    hdr_t = max(p.stat().st_mtime for p in list(CSRC_DIR.glob("*.cuh")) + [HEADER_PATH, DEBUG_HEADER_PATH])
 
     def compile_one(src: str):
         s, o = CSRC_DIR / src, objdir / (Path(src).stem + ".o")

@@ -9,6 +9,7 @@
 #include <stdio.h>
 
 #include "../../include/spn_b200.h"
+#include "../../include/spn_b200_debug.h"
 
 namespace spn {
 

@@ -58,17 +58,22 @@ def make_bank_case(B: int, N: int, D: int, T: int = 1, mode: str = "S", seed: in
 
 
 def make_retrieval_case(Q: int, G: int, D: int, T: int = 1, seed: int = 0, group_size: int = 6,
-                        noise: float = 3.0):
+                        noise: float = 3.0, ref_pull: float = 0.0):
     """CIRR-shaped set: gallery [G, D] (or [G, T, D]); per query a group of `group_size` distinct gallery
     members (reference = member 0, target = member 1); q = normalize(gallery[target] + noise * randn / sqrt(D))
-    (noise 3 -> easy, ~8 at D=640 -> target rank spread over the top few dozen)."""
+    (noise 3 -> easy, ~8 at D=640 -> target rank spread over the top few dozen).  ``ref_pull`` > 0 adds
+    ref_pull * gallery[reference] to the query direction: the reference image then ranks near the top, so metrics that
+    remove it (clip4cir/validate.py:38-45) differ from those that do not (blip4cir/validate.py:45-56)."""
     g = _gen(4321 + seed)
     shape = (G, D) if T == 1 else (G, T, D)
     gallery = F.normalize(torch.randn(shape, generator=g), dim=-1)
     groups = torch.stack([torch.randperm(G, generator=g)[:group_size] for _ in range(Q)])  # [Q, group_size]
     reference, target = groups[:, 0].clone(), groups[:, 1].clone()
     base = gallery[target] if T == 1 else gallery[target].mean(dim=1)
-    q = F.normalize(base + noise * torch.randn((Q, D), generator=g) / D ** 0.5, dim=-1)
+    noise_t = noise * torch.randn((Q, D), generator=g) / D ** 0.5
+    if ref_pull:
+        base = base + ref_pull * (gallery[reference] if T == 1 else gallery[reference].mean(dim=1))
+    q = F.normalize(base + noise_t, dim=-1)
     names = [f"img{i:07d}" for i in range(G)]
     return q, gallery, names, reference, target, groups
 

@@ -11,7 +11,7 @@ from spn4cir_b200 import _lib
 
 
 def declared_symbols():
-    text = _lib.HEADER_PATH.read_text()
+    text = _lib.HEADER_PATH.read_text() + _lib.DEBUG_HEADER_PATH.read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(spn_[a-z0-9_]+)\s*\(", text)))
 
@@ -22,7 +22,9 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 15
     for n in names:
         assert hasattr(lib, n), f"{n} declared in spn_b200.h but not exported"
-    assert set(names) == set(_lib.EXPORTED_SYMBOLS), "ctypes signature table out of sync with the header"
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS), "ctypes signature table out of sync with the headers"
+    product = re.sub(r"/\*.*?\*/", "", _lib.HEADER_PATH.read_text(), flags=re.S)
+    assert "spn_debug_" not in product, "bring-up entry points belong in spn_b200_debug.h"
 
 
 def test_version_and_error_string():

@@ -77,11 +77,12 @@ def test_cirr_recall_identical_to_reference(golden, name):
     assert (gr.cpu().numpy() != g["group_rank"]).mean() < 0.005
 
 
-@pytest.mark.parametrize("name", ["fiq_small", "fiq_dress"])
+@pytest.mark.parametrize("name", ["fiq_small", "fiq_dress", "fiq_shirt", "fiq_toptee", "fiq_refnear"])
 def test_fiq_recall_identical_to_reference(golden, name):
     g = golden(name)
     Q, G, D = int(g["Q"]), int(g["G"]), int(g["D"])
-    q, gallery, names, reference, target, _ = synth.make_retrieval_case(Q, G, D, 1, int(g["seed"]), noise=float(g["noise"]))
+    q, gallery, names, reference, target, _ = synth.make_retrieval_case(Q, G, D, 1, int(g["seed"]), noise=float(g["noise"]),
+                                                                        ref_pull=float(g["ref_pull"]))
     ds = synth.FakeFIQDataset(names, reference, target)
     caps = [f"is q{i} and and more {i}" for i in range(Q)]
     text = {c: (q[i] * 2.0 - gallery[reference[i]]).to(DEV) for i, c in enumerate(caps)}
@@ -90,6 +91,8 @@ def test_fiq_recall_identical_to_reference(golden, name):
     np.testing.assert_allclose(got, g["metrics"], rtol=0, atol=1e-9)
     got2 = compat.compute_fiq_val_metrics(ds, model, gallery.to(DEV), names, device=torch.device(DEV), remove_reference=False)
     np.testing.assert_allclose(got2, g["metrics_noremove"], rtol=0, atol=1e-9)
+    if float(g["ref_pull"]) > 0:  # the reference image ranks near the top here: removal must change the answer
+        assert abs(got[0] - got2[0]) > 0.3
 
 
 @pytest.mark.parametrize("Q,G,seed", [(5, 20, 4), (33, 150, 5), (1, 40, 6)])

@@ -130,16 +130,22 @@ def test_cirr_metrics_match_reference_outputs(golden, name):
         np.testing.assert_allclose(full, g["metrics"], atol=1e-5)
 
 
-@pytest.mark.parametrize("name", ["fiq_small", "fiq_dress"])
+@pytest.mark.parametrize("name", ["fiq_small", "fiq_dress", "fiq_shirt", "fiq_toptee", "fiq_refnear"])
 def test_fiq_metrics_match_reference_outputs(golden, name):
     g = golden(name)
     Q, G, D = int(g["Q"]), int(g["G"]), int(g["D"])
-    q, gallery, names, reference, target, _ = synth.make_retrieval_case(Q, G, D, 1, int(g["seed"]), noise=float(g["noise"]))
+    q, gallery, names, reference, target, _ = synth.make_retrieval_case(Q, G, D, 1, int(g["seed"]), noise=float(g["noise"]),
+                                                                        ref_pull=float(g["ref_pull"]))
     assert digest(q, gallery, reference, target) == str(g["input_digest"])
     text = torch.stack([q[i] * 2.0 - gallery[reference[i]] for i in range(Q)])
     pred = F.normalize(gallery[reference] + text, dim=-1)
     got = oretr.fiq_metrics(pred, gallery, names, [names[int(i)] for i in target], [names[int(i)] for i in reference])
     np.testing.assert_allclose(got, g["metrics"], atol=1e-9)
+    # the no-removal flavour: fixture = blip4cir/validate.py:42-56 executed verbatim
+    got2 = oretr.fiq_metrics(pred, gallery, names, [names[int(i)] for i in target], None)
+    np.testing.assert_allclose(got2, g["metrics_noremove"], rtol=0, atol=1e-9)
+    if float(g["ref_pull"]) > 0:
+        assert abs(got[0] - got2[0]) > 0.3, "this set must tell the two flavours apart"
 
 
 def test_topk_and_rank_consistency():
