@@ -1507,7 +1507,13 @@ int bank_ce_plan(int mode, int B, long long N, int D, int T, BankCEPlan* plan) {
   // backward / fused: an odd number (>= 3) of query tiles is padded with one empty tile so that the CTA-pair kernels
   // apply (TMA zero-fills the missing queries, nothing of them is written back): a pair with one idle half still beats
   // two single-CTA kernels on the shared-memory port
-  if (mode >= 1 && plan->q_tiles >= 3 && plan->q_tiles % 2 == 1 && !(getenv("SPN_DEBUG_CG") && atoi(getenv("SPN_DEBUG_CG")) == 1))
+  // A single query tile (B <= 128, the reference's batch 128 setting) is padded too when D > 320: the two-pass pair kernel
+  // with one empty half beats the single-CTA D-split kernel, which recomputes S per split (measured, 128 x 100k: D = 768
+  // 93 vs 160 us, D = 640 75 vs 77 us).  For D <= 320 (single pass, no recompute; BLIP-2's 32 x 256 shapes) the single-CTA
+  // kernel is the faster one (0.80 vs 1.20 ms at 128 x 200k x 32 x 256) and stays.  SPN_DEBUG_PAD1=0 restores the old plan.
+  const bool pad1 = D > 320 && !(getenv("SPN_DEBUG_PAD1") && atoi(getenv("SPN_DEBUG_PAD1")) == 0);
+  if (mode >= 1 && (plan->q_tiles >= 3 || (pad1 && plan->q_tiles == 1)) && plan->q_tiles % 2 == 1 &&
+      !(getenv("SPN_DEBUG_CG") && atoi(getenv("SPN_DEBUG_CG")) == 1))
     plan->q_tiles += 1;
   const long long n_rows = N * T;
   plan->n_tiles = int((n_rows + kBN - 1) / kBN);
