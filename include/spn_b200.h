@@ -295,6 +295,17 @@ int spn_sim_rank_tc(const float* q, const float* gallery, int Q, int G, int D, i
  * above never materialise it. */
 int spn_sim_matrix(const float* q, const float* gallery, int Q, int G, int D, int T, float* out, void* stream);
 
+
+/* Rank-window selection: for every row r of a score block scores[R, pitch] (G valid columns), the columns
+ * whose rank in the descending order (ties -> lower column) falls in [lo, hi), written in rank order to
+ * out_idx[R, hi - lo].  Replaces `i2i_ranks = torch.argsort(sims_intra_i2i, descending=True)` + the slices
+ * `i2i_ranks[i][rank:rank_max]` (zscir/get_cir_data.py:33-34,58-64; CIRR twin :106-109,131-137): two radix selects find the
+ * two boundary scores, the band between them is compacted into shared memory and sorted there -- the row itself is never
+ * sorted.  hi - lo <= 12288 per call (split wider windows); *overflow (device int32) is set to 1 when the ties of the
+ * boundary values do not fit the band (the caller then sorts that block). */
+int spn_rank_window(const float* scores, int R, int G, int64_t pitch, int lo, int hi, int32_t* out_idx, int32_t* overflow,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ LIB_PATH = PKG_DIR / "libspn_b200.so"
 HEADER_PATH = REPO_ROOT / "include" / "spn_b200.h"
 DEBUG_HEADER_PATH = REPO_ROOT / "include" / "spn_b200_debug.h"  # bring-up / test-only entry points
 
-SOURCES = ["common.cu", "bank_ce_tc.cu", "shard.cu", "part_ce.cu", "umma_selftest.cu", "prologue.cu", "sim_rank.cu", "sim_tc.cu", "api.cu"]
+SOURCES = ["common.cu", "bank_ce_tc.cu", "shard.cu", "rank_window.cu", "part_ce.cu", "umma_selftest.cu", "prologue.cu", "sim_rank.cu", "sim_tc.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177",
@@ -149,6 +149,7 @@ _SIGNATURES = {
     "spn_sim_rank_tc": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                         c_int, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     "spn_debug_sim_tc_layout": [c_int, c_int, c_int, c_int, POINTER(c_size_t), POINTER(c_int), POINTER(c_int)],
+    "spn_rank_window": [c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "spn_sim_matrix": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "spn_debug_read_timeline": [c_void_p, c_int],
     "spn_debug_umma_bench": [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],

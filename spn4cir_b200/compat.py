@@ -337,25 +337,41 @@ def srm_out(clip_image_feats: torch.Tensor, clip_text_feats: torch.Tensor, srm_i
     return r_fn, m_fn, t_fn, rt, rm, mt
 
 
+RANK_WINDOW_MAX = 12288  # ranks per spn_rank_window call (the band + boundary ties are sorted in 128 KiB of shared memory)
+
+
 def i2i_rank_window(image_feats: torch.Tensor, rank_lo: int, rank_hi: Optional[int] = None, *, block_rows: int = 2048):
     """Rows ``[rank_lo:rank_hi]`` of ``i2i_ranks = torch.argsort(sims_intra_i2i, descending=True)``
     (/root/reference/zscir/get_cir_data.py:33-34 and the slices of ``get_diff_id`` :60-64; the CIRR twin :106-109,131-141):
     for every image the gallery indices whose similarity rank falls in the window (``rank_hi=None`` or
-    ``rank_hi <= rank_lo``: to the end, as :61-64 do).  The N x N matrix never exists: blocks of ``block_rows`` rows of
-    exact fp32 scores (``spn_sim_matrix``) are ordered on the device (descending, ties -> lower index) and only the
-    window is kept.  One-off preprocessing; the ordering itself is torch's stable sort.  Returns int64 ``[N, width]``."""
+    ``rank_hi <= rank_lo``: to the end, as :61-64 do).  Neither the N x N matrix nor any full sort exists: blocks of
+    ``block_rows`` rows of exact fp32 scores (``spn_sim_matrix``) go through ``spn_rank_window`` (two radix selects for the
+    boundary scores, the band in between compacted and sorted in shared memory; descending score, ties -> lower index).
+    Windows wider than RANK_WINDOW_MAX are cut into consecutive sub-windows.  Returns int64 ``[N, width]``."""
     _require_cuda(image_feats, "image_feats")
     f = image_feats.detach().float().contiguous()
     n = f.shape[0]
     hi = n if (rank_hi is None or rank_hi <= rank_lo) else min(int(rank_hi), n)
     lo = min(max(int(rank_lo), 0), hi)
     out = torch.empty((n, hi - lo), dtype=torch.int64, device=f.device)
+    if hi == lo:
+        return out
+    overflow = torch.zeros(1, dtype=torch.int32, device=f.device)
     for r0 in range(0, n, block_rows):
         blk = f[r0:r0 + block_rows]
         sim = inference_sim(blk, f)
         if sim.dim() == 1:
             sim = sim[None, :]
-        out[r0:r0 + blk.shape[0]] = torch.sort(sim, dim=1, descending=True, stable=True).indices[:, lo:hi]
+        sim = sim.contiguous()
+        rows = blk.shape[0]
+        for w0 in range(lo, hi, RANK_WINDOW_MAX):
+            w1 = min(hi, w0 + RANK_WINDOW_MAX)
+            idx = torch.empty((rows, w1 - w0), dtype=torch.int32, device=f.device)
+            with torch.cuda.device(f.device):
+                call("spn_rank_window", _ptr(sim), rows, n, n, w0, w1, _ptr(idx), _ptr(overflow), _stream(f.device))
+            if int(overflow.item()):  # a boundary score shared by thousands of columns (degenerate galleries): sort this block
+                idx = torch.sort(sim, dim=1, descending=True, stable=True).indices[:, w0:w1]
+            out[r0:r0 + rows, w0 - lo:w1 - lo] = idx
     return out
 
 

@@ -304,6 +304,14 @@ int spn_debug_sim_tc_layout(int Q, int G, int D, int T, size_t* scores_offset, i
   return sim_tc_debug_layout(Q, G, D, T, scores_offset, pitch, block_rows);
 }
 
+int spn_rank_window(const float* scores, int R, int G, int64_t pitch, int lo, int hi, int32_t* out_idx, int32_t* overflow,
+                    void* stream) {
+  SPN_REQUIRE(scores && out_idx && overflow, SPN_ERR_BAD_ARG, "spn_rank_window: NULL pointer");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return rank_window(scores, R, G, pitch, lo, hi, out_idx, overflow, as_stream(stream));
+}
+
 int spn_sim_matrix(const float* q, const float* gallery, int Q, int G, int D, int T, float* out, void* stream) {
   SPN_REQUIRE(q && gallery && out, SPN_ERR_BAD_ARG, "spn_sim_matrix: NULL pointer");
   int rc = require_sm100();

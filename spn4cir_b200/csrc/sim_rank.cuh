@@ -17,6 +17,10 @@ int sim_rank(const float* q, const float* g, int Q, int G, int D, int T, const i
              const int* exclude, const int* group, int M, int col_base, int* rank, int* group_rank,
              cudaStream_t stream);
 
+// rank-window selection (rank_window.cu): columns with rank in [lo, hi) of every row of a score block, in rank order
+int rank_window(const float* scores, int R, int G, long long pitch, int lo, int hi, int32_t* out, int* overflow,
+                cudaStream_t stream);
+
 // tensor-core pruned variants (sim_tc.cu): same results as sim_topk / sim_rank
 size_t sim_tc_ws_bytes(int Q, int G, int D, int T);
 int sim_topk_tc(const float* q, const float* g, int Q, int G, int D, int T, int K, const int* exclude, int col_base,

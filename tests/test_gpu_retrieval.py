@@ -246,3 +246,47 @@ def test_cirr_submission_against_executed_reference_lines(golden):
     sim = (q @ F.normalize(gallery * float(g["scale"]), dim=-1).T).numpy()
     assert_same_up_to_ties(got50, g["top50"].astype(np.int64), sim)
     assert_same_up_to_ties(got3, g["top3"].astype(np.int64), sim)
+
+
+def test_rank_window_kernel_sizes_ties_and_overflow():
+    """spn_rank_window at the README's window sizes (zscir: --i2i_rank 10000 --i2i_rank_max 20000 / 15000), a window wider
+    than one call (cut into sub-windows), rows full of exact ties (quantised scores: ties -> lower index, like a stable
+    sort), +0.0 / -0.0, and the degenerate all-equal row whose band overflows (the caller sorts that block)."""
+    from spn4cir_b200._lib import call
+    g = torch.Generator().manual_seed(11)
+    n, D = 21000, 64
+    f = torch.nn.functional.normalize(torch.randn(n, D, generator=g), dim=-1).to(DEV)
+    rows = f[:96]
+    sim = compat.inference_sim(rows, f)
+    ranks = torch.argsort(sim, dim=1, descending=True, stable=True)
+
+    def window(scores, lo, hi):
+        R, G = scores.shape
+        out = torch.empty((R, hi - lo), dtype=torch.int32, device=DEV)
+        ovf = torch.zeros(1, dtype=torch.int32, device=DEV)
+        call("spn_rank_window", scores.data_ptr(), R, G, G, lo, hi, out.data_ptr(), ovf.data_ptr(),
+             torch.cuda.current_stream().cuda_stream)
+        return out.long(), int(ovf.item())
+
+    for lo, hi in ((10000, 20000), (10000, 15000), (0, 50), (20990, 21000), (0, 12288)):
+        got, ovf = window(sim, lo, hi)
+        assert ovf == 0 and torch.equal(got, ranks[:, lo:hi]), (lo, hi)
+    # quantised scores: thousands of exact ties per value, window boundaries inside runs of equal scores
+    q = torch.round(sim * 64) / 64
+    q[:, 5] = 0.0
+    q[:, 6] = -0.0
+    rq = torch.argsort(q, dim=1, descending=True, stable=True)
+    got, ovf = window(q, 9000, 14000)
+    assert ovf == 0 and torch.equal(got, rq[:, 9000:14000])
+    # all-equal row: every column ties with both boundaries -> overflow is reported, never a wrong answer
+    flat = torch.zeros((2, n), device=DEV)
+    _, ovf = window(flat, 100, 200)
+    assert ovf == 1
+    # the compat call cuts a 16 000-wide window into two kernel calls and falls back to a sort on overflow
+    sub = f[:3000]
+    wide = compat.i2i_rank_window(sub, 500, 0, block_rows=1024)
+    simsub = compat.inference_sim(sub, sub)
+    assert torch.equal(wide, torch.argsort(simsub, dim=1, descending=True, stable=True)[:, 500:])
+    allsame = torch.ones((300, 64), device=DEV)
+    w = compat.i2i_rank_window(allsame, 10, 40)
+    assert torch.equal(w, torch.arange(10, 40, device=DEV).expand(300, 30))
