@@ -210,8 +210,9 @@ def fiq_metrics_from_features(predicted_features: torch.Tensor, index_features: 
     rank, _ = sim_rank(predicted_features, gallery, tgt_ids, exclude=ref_ids)
     n = rank.numel()
     if ref_ids is None:
-        # blip4cir/validate.py:55-56: (torch.sum(labels[:, :k]) / len(labels)).item() * 100 -- float32 tensor arithmetic
-        return ((torch.sum(rank < 10) / n).item() * 100, (torch.sum(rank < 50) / n).item() * 100)
+        # blip4cir/validate.py:55-56: (torch.sum(labels[:, :k]) / len(labels)).item() * 100 -- float32 tensor arithmetic, on
+        # the host like the reference (its labels tensor lives on the CPU; CUDA's int / int division rounds differently)
+        return ((torch.sum(rank < 10).cpu() / n).item() * 100, (torch.sum(rank < 50).cpu() / n).item() * 100)
     # clip4cir/validate.py:38-49: python-int arithmetic, (count / N) * 100
     r10 = (int(torch.sum(rank < 10).item()) / n) * 100
     r50 = (int(torch.sum(rank < 50).item()) / n) * 100
