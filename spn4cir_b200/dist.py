@@ -77,16 +77,13 @@ class _CudaShardCompute:
     def colsum(self, bank, group):
         return global_colsum(bank, group)
 
-    def check_tau(self, bank, inv_tau, group):
+    def fused_ok(self, bank, inv_tau, group) -> bool:
         """The fused sweep's static soft-max reference is provably safe while inv_tau |q| max|bank| <= 109 nats (same
-        guard as ops.bank_infonce; one cached host read of the GLOBAL max row norm)."""
-        from ._lib import SpnError
+        guard as ops.bank_infonce; one cached host read of the GLOBAL max row norm).  Colder temperatures (a learnable
+        temp drifting below ~0.0092) take the two-pass sharded path (exact running maximum)."""
         if getattr(bank, "_maxnorm_global_host", None) is None:
             bank._maxnorm_global_host = float(global_maxnorm(bank, group).item())
-        if inv_tau * bank._maxnorm_global_host * 1.03 > 109.0:
-            raise SpnError("bank_infonce_sharded", -7,
-                           f"tau = {1.0 / inv_tau:.5g} is too cold for the single-sweep sharded path (needs inv_tau * max|bank| "
-                           f"<= 105; got {inv_tau * bank._maxnorm_global_host:.1f}): use tau >= 0.0095 for unit-norm features")
+        return inv_tau * bank._maxnorm_global_host * 1.03 <= 109.0
 
     def prep(self, q_all, lab_all, bank, inv_tau, maxnorm):
         """-> ref [Bt]: this shard's static soft-max reference (owner rows clamped around the target logit)."""
@@ -202,19 +199,16 @@ def _sharded_sweep(q_local, bank, labels_local, inv_tau, eps, tau_grad, group, c
     is  all_gather(q bf16), all_gather(labels)  ->  MIN all_reduce(ref [Bt])  ->  [sweep]  ->  SUM all_reduce(vec [4, Bt])
     ->  [fold target rows]  ->  reduce_scatter(o_acc [Bt, D] fp32);  each rank finalises its own rows.
     Returns (loss_mean_of_local_queries, dq_unit [B, D] fp32, dlogit_dot | None)."""
+    if compute is None and (not _CudaShardCompute().fused_ok(bank, inv_tau, group) or (eps != 0.0 and bank.T > 1)):
+        # cold temperature, or label smoothing over a multi-token bank (the fused finalize cannot form sum_n s_n from column
+        # sums there): forward statistics with an exact running maximum + recompute backward, merged across the ranks
+        return _sharded_two_pass(q_local, bank, labels_local, inv_tau, eps, tau_grad, group)
     if compute is None and symm_path_ok(bank, q_local.shape[0], group):
-        if eps != 0.0 and bank.T > 1:
-            from ._lib import SpnError
-            raise SpnError("bank_infonce_sharded", -7, "label smoothing over a multi-token (T > 1) sharded bank is not implemented")
         return _sharded_sweep_symm(q_local, bank, labels_local, inv_tau, eps, tau_grad, group)
     compute = compute or _CudaShardCompute()
     rank, world = _world(group)
     B, D = q_local.shape
     dev = q_local.device
-    if eps != 0.0 and bank.T > 1:
-        from ._lib import SpnError
-        raise SpnError("bank_infonce_sharded", -7, "label smoothing over a multi-token (T > 1) sharded bank is not implemented")
-    compute.check_tau(bank, inv_tau, group)
     q16 = compute.cast(q_local)
     if world > 1:
         _check_uniform_batch(B, dev, group)
@@ -381,8 +375,6 @@ def _sharded_sweep_symm(q_local, bank, labels_local, inv_tau, eps, tau_grad, gro
     barrier 2, finalize) -- bench.py's exchange breakdown."""
     from ._lib import call
     from .ops import _TORCH2SPN, _ptr, _stream, fused_scratch
-    compute = _CudaShardCompute()
-    compute.check_tau(bank, inv_tau, group)
     B, D = q_local.shape
     dev = q_local.device
     x = _symm_exchange(bank, B, group)
@@ -423,6 +415,39 @@ def _sharded_sweep_symm(q_local, bank, labels_local, inv_tau, eps, tau_grad, gro
              inv_tau / B, eps, bank.n_total, B, D, _ptr(out[0]), _ptr(out[1]), _ptr(mean), _ptr(dq), _ptr(ddot), st)
         mark()
     return mean, dq, ddot
+
+
+def _sharded_two_pass(q_local, bank, labels_local, inv_tau, eps, tau_grad, group):
+    """The sharded step through the two-pass kernels (any temperature, any T / label-smoothing combination): forward
+    statistics (m, l, s_t, s_sum) of ALL queries on this shard -> all_gather + spn_merge_stats -> global lse -> recompute
+    backward on this shard -> reduce_scatter of dq.  Slower than the fused sweep (S is computed twice); the fallback."""
+    from .ops import _bwd, _fwd_stats, _loss_from_stats, cast_to_bf16
+    rank, world = _world(group)
+    B, D = q_local.shape
+    dev = q_local.device
+    q16 = cast_to_bf16(q_local)
+    if world > 1:
+        _check_uniform_batch(B, dev, group)
+        q_all = torch.empty((world * B, D), dtype=q16.dtype, device=dev)
+        dist.all_gather_into_tensor(q_all, q16, group=group)
+        lab_all = torch.empty(world * B, dtype=labels_local.dtype, device=dev)
+        dist.all_gather_into_tensor(lab_all, labels_local, group=group)
+    else:
+        q_all, lab_all = q16, labels_local
+    stats = merge_stats_across_ranks(_fwd_stats(q_all, bank, lab_all, inv_tau, eps != 0.0), group)
+    lse, loss_q, _ = _loss_from_stats(stats, bank.n_total, eps)
+    dq_part = torch.zeros((world * B, D), dtype=torch.float32, device=dev)
+    ddot = torch.zeros(world * B, dtype=torch.float32, device=dev) if tau_grad else None
+    _bwd(q_all, bank, lab_all, inv_tau, lse, inv_tau / B, None, eps, dq_part, ddot)
+    sl = slice(rank * B, (rank + 1) * B)
+    if world > 1:
+        dq = torch.empty((B, D), dtype=torch.float32, device=dev)
+        _reduce_scatter_sum(dq, dq_part, rank, group)
+        if tau_grad:
+            dist.all_reduce(ddot, group=group)
+    else:
+        dq = dq_part
+    return loss_q[sl].mean(), dq, (ddot[sl].contiguous() if tau_grad else None)
 
 
 class _ShardedBankCE(torch.autograd.Function):

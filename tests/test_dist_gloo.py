@@ -87,8 +87,6 @@ class CpuShardCompute:
     def cast(self, q_local):
         return q_local.to(torch.bfloat16).double()  # the kernels score the bf16-rounded query
 
-    def check_tau(self, bank, inv_tau, group):
-        pass
 
     def maxnorm(self, bank, group):
         mx = bank.data.norm(dim=-1).max().reshape(1).clone()

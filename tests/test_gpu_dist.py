@@ -104,6 +104,18 @@ l_s3, dq_s3 = bank_ce_step_sharded(qq3, sh3, lab3.to(dev), 0.05)
 l_f3, dq_f3 = spn.bank_ce_step(qq3, spn.DeviceBank.from_tensor(bank3, dev), lab3.to(dev), 0.05)
 assert abs(l_s3.item() - l_f3.item()) <= 1e-5 * max(1.0, abs(l_f3.item())), (rank, l_s3.item(), l_f3.item())
 assert float((dq_s3 - dq_f3).norm() / dq_f3.norm()) < 1e-4
+# cold temperature (the fused sweep's static reference is not provably safe below tau ~ 0.0092) and label smoothing over a
+# multi-token bank: both are routed to the two-pass sharded path and still agree with the single-GPU result
+for (qq_, sh_, full_, lab_, tau_, eps_) in ((qq2, sh2, spn.DeviceBank.from_tensor(bank2, dev), lab2, 0.005, 0.0),
+                                            (qq3, sh3, spn.DeviceBank.from_tensor(bank3, dev), lab3, 0.05, 0.1)):
+    qa = qq_.clone().requires_grad_(True)
+    la = bank_infonce_sharded(qa, sh_, lab_.to(dev), tau_, label_smoothing=eps_)
+    la.backward()
+    qb = qq_.clone().requires_grad_(True)
+    lb = spn.bank_infonce(qb, full_, lab_.to(dev), tau_, label_smoothing=eps_)
+    lb.backward()
+    assert abs(la.item() - lb.item()) <= 1e-5 * max(1.0, abs(lb.item())), (rank, tau_, eps_, la.item(), lb.item())
+    assert float((qa.grad - qb.grad).norm() / qb.grad.norm()) < 1e-4, (rank, tau_, eps_)
 bad = lab2.clone(); bad[0] = 10 ** 7                                  # a label nobody owns: +inf, as on one GPU
 l_bad, _ = bank_ce_step_sharded(qq2, sh2, bad.to(dev), tau)
 assert torch.isinf(l_bad).item() and l_bad.item() > 0
