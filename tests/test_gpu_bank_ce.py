@@ -113,7 +113,7 @@ def test_fused_two_pass_matches_split_recompute(B, N, D, tau, seed, monkeypatch)
     monkeypatch.setenv("SPN_DEBUG_TWO_PASS", "0")
     loss1, dq1, dtau1 = run_ours(q, bank, labels, tau, tau_tensor=True, single_pass=True)
     monkeypatch.delenv("SPN_DEBUG_TWO_PASS")
-    assert abs(loss.item() - loss1.item()) <= 1e-6 * max(abs(loss1.item()), 1e-3), (loss, loss1)
+    assert abs(loss.item() - loss1.item()) <= 1e-5 * max(abs(loss1.item()), 1e-3), (loss, loss1)
     assert rel_l2(dq, dq1) < 1e-5, rel_l2(dq, dq1)
     assert abs(dtau.item() - dtau1.item()) <= 1e-4 * max(abs(dtau1.item()), 1e-2), (dtau, dtau1)
     r_loss, r_dq, _ = obank.infonce_loss_and_grads(bf16_round(q), bf16_round(bank), labels, tau, dtype=torch.float64)
@@ -389,7 +389,8 @@ def test_step_primitive_equals_autograd(B, N, D, tau):
     t = torch.tensor(tau, device=DEV, requires_grad=True)
     ref = spn.bank_infonce(qd, db, labels.to(DEV), t)
     (3.0 * ref).backward()
-    assert abs(loss.item() - ref.item()) <= 1e-6 * max(abs(ref.item()), 1e-3)
+    # (two launches of the same kernels: the fp32 sums are accumulated with atomics / TMA reduces in a run-dependent order)
+    assert abs(loss.item() - ref.item()) <= 1e-5 * max(abs(ref.item()), 1e-3)
     assert rel_l2(dq.cpu(), qd.grad.cpu()) < 1e-4
     assert abs(dtau.item() - t.grad.item()) <= 1e-3 * max(abs(t.grad.item()), 1e-2)
     o_loss, o_dq, _ = obank.infonce_loss_and_grads(q, bank, labels, tau, grad_out=3.0)
