@@ -253,15 +253,30 @@ def _ptr_array(ptrs):
     return (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
 
 
-def symmetric_memory_available(dev: torch.device) -> bool:
-    """True when torch's symmetric-memory allocator can serve this process (CUDA device, process group up)."""
+_symm_probe = {}
+
+
+def symmetric_memory_available(dev: torch.device, group=None) -> bool:
+    """True when torch's symmetric-memory allocator can serve EVERY rank of the group (CUDA device, NCCL group up, a probe
+    allocation succeeds everywhere).  Collective on first use per group (one tiny MIN all-reduce), cached afterwards: all
+    ranks take the same exchange path, or a one-sided failure would dead-lock the rendezvous."""
     if not (dist.is_available() and dist.is_initialized()) or dev.type != "cuda":
         return False
-    try:
-        import torch.distributed._symmetric_memory  # noqa: F401
-        return dist.get_backend() == "nccl"
-    except Exception:
-        return False
+    key = id(group)
+    if key not in _symm_probe:
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            if dist.get_backend(group) != "nccl":
+                ok = 0
+            else:
+                symm_mem.empty(256, dtype=torch.uint8, device=dev)
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        _symm_probe[key] = bool(flag.item())
+    return _symm_probe[key]
 
 
 def make_bank_symmetric(bank, group=None) -> None:
@@ -365,7 +380,7 @@ def symm_path_ok(bank, B: int, group=None) -> bool:
     if os.environ.get("SPN_EXCHANGE", "symm") == "nccl" or world < 2 or world > 8 or B % 128 != 0 or (world * B // 128) % 2 != 0:
         return False
     per = (bank.n_total + world - 1) // world
-    return symmetric_memory_available(bank.data.device) and bank.row_base == rank * per and bank.N <= per
+    return bank.row_base == rank * per and bank.N <= per and symmetric_memory_available(bank.data.device, group)
 
 
 def _sharded_sweep_symm(q_local, bank, labels_local, inv_tau, eps, tau_grad, group, stage_events=None):

@@ -38,7 +38,7 @@ def time_fused(B, N, D, T, tau, iters=10):
 
 cases = [("B384", 384, 100000, 640, 1, 0.02), ("B128", 128, 100000, 640, 1, 0.02), ("N25k", 512, 25000, 640, 1, 0.02), ("N50k", 512, 50000, 640, 1, 0.02), ("N200k", 512, 200000, 640, 1, 0.02),
          ("N400k", 512, 400000, 640, 1, 0.02), ("C3", 512, 100000, 640, 1, 0.02), ("C5/8", 1024, 125000, 768, 1, 0.02), ("D512", 512, 100000, 512, 1, 0.02),
-         ("D256", 512, 100000, 256, 1, 0.03), ("C4/8", 256, 25000, 256, 32, 0.05), ("1Mx640", 1024, 1000000, 640, 1, 0.02)]
+         ("D256", 512, 100000, 256, 1, 0.03), ("C4/8", 256, 25000, 256, 32, 0.05), ("1Mx640", 1024, 1000000, 640, 1, 0.02), ("C5", 1024, 1000000, 768, 1, 0.02)]
 which = sys.argv[1].split(",") if len(sys.argv) > 1 and sys.argv[1] != "all" else None
 for name, B, N, D, T, tau in cases:
     if which and name not in which:
