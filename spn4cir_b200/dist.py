@@ -522,6 +522,9 @@ def sim_topk_sharded(query: torch.Tensor, gallery_shard: torch.Tensor, k: int, c
                      group=None):
     """Top-k over a row-sharded gallery: local fused top-k, all_gather of the [Q, k] lists, device merge."""
     from .retrieval import merge_topk, sim_topk
+    if k > 64:
+        from ._lib import SpnError
+        raise SpnError("sim_topk_sharded", -1, f"k = {k}: the device merge of per-shard lists handles k <= 64 (page deeper lists per shard with sim_topk)")
     vals, idx = sim_topk(query, gallery_shard, k, exclude=exclude, col_base=col_base)
     rank, world = _world(group)
     if world == 1:
