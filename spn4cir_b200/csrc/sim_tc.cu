@@ -86,9 +86,19 @@ struct TcGemmParams {
   int q_tiles, g_tiles;
   int nterms;     // 3: hi*hi + hi*lo + lo*hi, 1: hi*hi only
   float* scores;  // [qn, Gp]
+  // fused rank epilogue (RANK = true, T = 1): no S~ matrix -- each epilogue thread counts its query's entries that
+  // certainly sort before the target (S~ > ts + eps), records the undecided ones (within eps) as a 128-bit mask per
+  // (query, gallery tile) and the S~ of the few columns that need individual treatment (the CIRR subset members)
+  const float* thr;      // [qn, 2]  (ts - eps, ts + eps)
+  const int* cols;       // [qn, M1] local columns to extract (members; -1 = none)
+  float* col_s;          // [qn, M1] their S~ (pre-set to -inf)
+  int M1;
+  const int* skip;       // [qn, 2]  local columns excluded from the count: the removed reference image, the target
+  uint4* umask;          // [qn, g_tiles]
+  int* rank;             // [qn] += certain count
 };
 
-template <bool T32>
+template <bool T32, bool RANK = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sim_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_qh, const __grid_constant__ CUtensorMap tmap_ql,
                    const __grid_constant__ CUtensorMap tmap_gh, const __grid_constant__ CUtensorMap tmap_gl,
@@ -197,6 +207,10 @@ sim_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_qh, const __grid_con
     uint8_t* my_slots = slots + size_t(warp - 2u) * 2 * kSlotBytes;
     uint32_t x[32];
     uint32_t j = 0, k = 0;
+    int rk_cnt = 0, rk_row = 0, rk_s0 = -1, rk_s1 = -1;
+    bool rk_ok = false;
+    float rk_lo = 0.f, rk_hi = 0.f;
+    uint32_t rk_mask[4] = {0u, 0u, 0u, 0u};
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
       const int qt = tile / p.g_tiles, gt = tile % p.g_tiles;
       const uint32_t b = j & 1u, aph = (j >> 1) & 1u;
@@ -213,6 +227,47 @@ sim_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_qh, const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[b]);
         }
+        if (RANK) {
+          // fused rank epilogue: thread == query row; count / mask this 32-column chunk against the row's two thresholds
+          if (c == 0) {
+            rk_cnt = 0;
+            rk_row = r0 + int(lane);
+            rk_ok = rk_row < p.qn;
+            rk_lo = rk_ok ? p.thr[2 * rk_row] : INFINITY;
+            rk_hi = rk_ok ? p.thr[2 * rk_row + 1] : INFINITY;
+            rk_s0 = rk_ok ? p.skip[2 * rk_row] : -1;
+            rk_s1 = rk_ok ? p.skip[2 * rk_row + 1] : -1;
+          }
+          const int col0 = gt * kBN + c * 32;
+          uint32_t m = 0u;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float a = __uint_as_float(x[i]);
+            const int col = col0 + i;
+            const bool ok = col < p.G && col != rk_s0 && col != rk_s1;
+            const bool before = ok && a > rk_hi;
+            const bool unsure = ok && !before && !(a < rk_lo);
+            rk_cnt += before ? 1 : 0;
+            m |= unsure ? (1u << i) : 0u;
+          }
+          rk_mask[c] = m;
+          if (rk_ok) {  // columns whose S~ the resolve kernel wants individually (rare: a handful per query over all tiles)
+            for (int mm = 0; mm < p.M1; ++mm) {
+              const unsigned d = unsigned(p.cols[size_t(rk_row) * p.M1 + mm] - col0);
+              if (d < 32u) {
+                float v = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (unsigned(i) == d) v = __uint_as_float(x[i]);
+                p.col_s[size_t(rk_row) * p.M1 + mm] = v;
+              }
+            }
+          }
+          if (c == 3 && rk_ok) {
+            if (rk_cnt) atomicAdd(&p.rank[rk_row], rk_cnt);
+            p.umask[size_t(rk_row) * p.g_tiles + gt] = make_uint4(rk_mask[0], rk_mask[1], rk_mask[2], rk_mask[3]);
+          }
+        } else
         if (T32) {
           float m = __uint_as_float(x[0]);
 #pragma unroll
@@ -251,7 +306,7 @@ sim_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_qh, const __grid_con
         }
       }
     }
-    if (!T32) {
+    if (!T32 && !RANK) {
       if (lane == 0) bulk_wait_group<0>();
       __syncwarp();
     }
@@ -865,6 +920,153 @@ row_rank_kernel(const RowParams p) {
   }
 }
 
+// ---- fused rank path (T = 1): rank_prep_kernel -> sim_tc_gemm_kernel<false, true> -> rank_resolve_kernel -------------
+struct RankFusedParams {
+  RowParams r;
+  float* thr;     // [qn, 2]
+  int* cols;      // [qn, M1]
+  float* col_s;   // [qn, M1]
+  int* skip;      // [qn, 2]
+  uint4* umask;   // [qn, g_tiles]
+  int M1, g_tiles;
+};
+
+// one warp per query: the target's exact score (unless the caller supplies it), the row's eps, the two thresholds, the
+// local columns of the subset members (validated exactly as row_rank_kernel does: in this shard, not the reference, not
+// the target, first occurrence only) and the two columns left out of the count
+__global__ void __launch_bounds__(kRowWarps * 32)
+rank_prep_kernel(const RankFusedParams f) {
+  __shared__ float chain_sm[kRowWarps][kChainFloats];
+  const RowParams& p = f.r;
+  const int wib = threadIdx.x >> 5;
+  const int row = blockIdx.x * kRowWarps + wib;
+  const int lane = threadIdx.x & 31;
+  if (row >= p.qn) return;
+  const float* qrow = p.q + size_t(row) * p.D;
+  const int ex = p.exclude ? p.exclude[row] : -1;
+  const int tg = p.target[row];
+  float ts;
+  if (p.tscore) {
+    ts = p.tscore[row];
+  } else {
+    const int t = tg - p.col_base;
+    ts = -INFINITY;
+    if (t >= 0 && t < p.G) {  // warp-uniform
+      const float v = warp_chains_few(qrow, p.g, p.D, lane == 0 ? t : -1, chain_sm[wib], lane);
+      ts = __shfl_sync(kFull, v, 0);
+    }
+  }
+  const float eps = row_eps(qrow, p.D, *p.gmax, lane);
+  if (lane == 0) {
+    f.thr[2 * row] = ts - eps;
+    f.thr[2 * row + 1] = ts + eps;
+    const int exl = ex - p.col_base, tgl = tg - p.col_base;
+    f.skip[2 * row] = (ex >= 0 && exl >= 0 && exl < p.G) ? exl : -1;
+    f.skip[2 * row + 1] = (tgl >= 0 && tgl < p.G) ? tgl : -1;
+  }
+  if (f.M1 > 0) {
+    const int greg = lane < p.M ? p.group[size_t(row) * p.M + lane] : -2;
+    const int ml = greg - p.col_base;
+    bool valid = lane < p.M && ml >= 0 && ml < p.G && greg != ex && greg != tg;
+    for (int mm = 0; mm < p.M; ++mm) {  // a member listed twice counts once
+      const int o = __shfl_sync(kFull, greg, mm);
+      if (mm < lane && o == greg) valid = false;
+    }
+    if (lane < f.M1) {
+      f.cols[size_t(row) * f.M1 + lane] = valid ? ml : -1;
+      f.col_s[size_t(row) * f.M1 + lane] = -INFINITY;
+    }
+  }
+}
+
+// one warp per query: rescore the undecided entries recorded by the sweep's epilogue (exact fp32 chains, up to 32 at a
+// time) and decide the subset members from their extracted S~ (exact chain only when within eps)
+__global__ void __launch_bounds__(kRowWarps * 32, 5)
+rank_resolve_kernel(const RankFusedParams f) {
+  __shared__ float chain_sm[kRowWarps][kChainFloats];
+  __shared__ int unsure_g[kRowWarps][352];
+  const RowParams& p = f.r;
+  const int wib = threadIdx.x >> 5;
+  const int row = blockIdx.x * kRowWarps + wib;
+  const int lane = threadIdx.x & 31;
+  if (row >= p.qn) return;
+  const float* qrow = p.q + size_t(row) * p.D;
+  const int tg = p.target[row];
+  const float lo = f.thr[2 * row], hi = f.thr[2 * row + 1];
+  const float ts = 0.5f * (lo + hi);  // only used for the -inf case below; exact comparisons use ts_exact
+  (void)ts;
+  // the exact target score again (bit-identical chain) for sorts_before
+  float ts_exact;
+  if (p.tscore) {
+    ts_exact = p.tscore[row];
+  } else {
+    const int t = tg - p.col_base;
+    ts_exact = -INFINITY;
+    if (t >= 0 && t < p.G) {
+      const float v = warp_chains_few(qrow, p.g, p.D, lane == 0 ? t : -1, chain_sm[wib], lane);
+      ts_exact = __shfl_sync(kFull, v, 0);
+    }
+  }
+  int cnt = 0, gcnt = 0;
+  unsigned n_unsure = 0;
+  if (f.M1 > 0) {
+    const int ml = lane < f.M1 ? f.cols[size_t(row) * f.M1 + lane] : -1;
+    const bool valid = ml >= 0;
+    const float a = valid ? f.col_s[size_t(row) * f.M1 + lane] : -INFINITY;
+    const bool before = valid && a > hi;
+    const bool unsure = valid && !before && !(a < lo);
+    gcnt = __popc(__ballot_sync(kFull, before));
+    const unsigned um = __ballot_sync(kFull, unsure);
+    if (unsure) unsure_g[wib][__popc(um & ((1u << lane) - 1u))] = ~ml;
+    n_unsure = __popc(um);
+  }
+  auto flush = [&](bool last) {
+    while (n_unsure >= 32u || (last && n_unsure > 0u)) {
+      const unsigned take = n_unsure < 32u ? n_unsure : 32u;
+      __syncwarp();
+      const bool have = unsigned(lane) < take;
+      const int raw = have ? unsure_g[wib][n_unsure - take + lane] : 0;
+      const bool member = raw < 0;
+      const int g = member ? ~raw : raw;
+      n_unsure -= take;
+      const float e = warp_exact(qrow, p.g, p.D, p.T, have, g, chain_sm[wib], lane);
+      const bool before = have && sorts_before(e, p.col_base + g, ts_exact, tg);
+      cnt += __popc(__ballot_sync(kFull, before && !member));
+      gcnt += __popc(__ballot_sync(kFull, before && member));
+    }
+  };
+  // each lane owns 4 of the 128 bits of a tile mask; tiles are visited one at a time only when their mask is non-zero
+  for (int t0 = 0; t0 < f.g_tiles; t0 += 32) {
+    const int t = t0 + lane;
+    uint4 m = make_uint4(0u, 0u, 0u, 0u);
+    if (t < f.g_tiles) m = f.umask[size_t(row) * f.g_tiles + t];
+    unsigned nz = __ballot_sync(kFull, (m.x | m.y | m.z | m.w) != 0u);
+    while (nz) {
+      const int src = __ffs(nz) - 1;
+      nz &= nz - 1;
+      const uint32_t w0 = __shfl_sync(kFull, m.x, src), w1 = __shfl_sync(kFull, m.y, src);
+      const uint32_t w2 = __shfl_sync(kFull, m.z, src), w3 = __shfl_sync(kFull, m.w, src);
+      const uint32_t word = (lane >> 3) == 0 ? w0 : (lane >> 3) == 1 ? w1 : (lane >> 3) == 2 ? w2 : w3;
+      const uint32_t nib = (word >> ((lane & 7) * 4)) & 0xFu;  // bits 4 lane .. 4 lane + 3 of the 128
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const bool unsure = (nib >> b) & 1u;
+        const unsigned um = __ballot_sync(kFull, unsure);
+        if (um) {
+          if (unsure) unsure_g[wib][n_unsure + __popc(um & ((1u << lane) - 1u))] = (t0 + src) * kBN + lane * 4 + b;
+          n_unsure += __popc(um);
+        }
+      }
+      flush(false);  // keeps the list below 32 + 128 entries (+ the members)
+    }
+  }
+  flush(true);
+  if (lane == 0) {
+    if (cnt) atomicAdd(&p.rank[row], cnt);
+    if (p.group_rank && gcnt) atomicAdd(&p.group_rank[row], gcnt);
+  }
+}
+
 // score[b] of the target entry with the exact chain (same bits as target_score_kernel of sim_rank.cu), one warp per query
 __global__ void __launch_bounds__(kRowWarps * 32)
 target_score_warp_kernel(const float* __restrict__ q, const float* __restrict__ g, int Q, int G, int D, int T,
@@ -969,6 +1171,21 @@ int tc_run(bool rank_mode, const float* q, const float* g, int Q, int G, int D, 
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
 
+  // rank, T = 1: the fused path -- no S~ matrix; the sweep's epilogue counts and the resolve kernel rescored the undecided
+  // entries (SPN_TC_RANK_FUSED=0 keeps the S~ + row_rank_kernel path, also taken when the workspace block is too small)
+  bool rank_fused = rank_mode && T == 1;
+  if (const char* e = getenv("SPN_TC_RANK_FUSED")) {
+    if (atoi(e) == 0) rank_fused = false;
+  }
+  const int M1 = rp.group ? rp.M : 0;
+  const int g_tiles_all = int((grows + kBN - 1) / kBN);
+  auto up256 = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t fused_need = up256(size_t(L.qb) * 8) + 2 * up256(size_t(L.qb) * (M1 > 0 ? M1 : 1) * 4) + up256(size_t(L.qb) * 8) +
+                            up256(size_t(L.qb) * g_tiles_all * 16);
+  if (fused_need > up256(size_t(L.qb) * L.Gp * 4)) rank_fused = false;
+  if (rank_fused)
+    SPN_CUDA_CHECK(cudaFuncSetAttribute(sim_tc_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+
   for (int qb0 = 0; qb0 < Q; qb0 += L.qb) {
     const int qn = (Q - qb0 < L.qb) ? Q - qb0 : L.qb;
     if ((rc = make_tmap_f32_2d(&ts, scores, uint64_t(qn), uint64_t(L.Gp), 32)) != SPN_OK) return rc;
@@ -980,10 +1197,6 @@ int tc_run(bool rank_mode, const float* q, const float* g, int Q, int G, int D, 
     gp.scores = scores;
     const long long n_tiles = (long long)gp.q_tiles * gp.g_tiles;
     const int grid = int(n_tiles < sms ? n_tiles : sms);
-    if (T == 1) sim_tc_gemm_kernel<false><<<grid, kTcThreads, smem, stream>>>(tqh, tql, tgh, tgl, ts, gp);
-    else        sim_tc_gemm_kernel<true><<<grid, kTcThreads, smem, stream>>>(tqh, tql, tgh, tgl, ts, gp);
-    SPN_CUDA_CHECK(cudaGetLastError());
-
     RowParams r = rp;
     r.q = q + size_t(qb0) * D; r.g = g; r.scores = scores; r.gmax = gmax; r.qn = qn; r.G = G; r.Gp = L.Gp; r.D = D; r.T = T;
     r.n_second = n_second;
@@ -994,6 +1207,29 @@ int tc_run(bool rank_mode, const float* q, const float* g, int Q, int G, int D, 
       if (r.group) r.group += size_t(qb0) * r.M;
       r.rank += qb0;
       if (r.group_rank) r.group_rank += qb0;
+    }
+    if (rank_fused) {
+      RankFusedParams f{};
+      uint8_t* o = reinterpret_cast<uint8_t*>(scores);
+      f.thr = reinterpret_cast<float*>(o); o += up256(size_t(L.qb) * 8);
+      f.cols = reinterpret_cast<int*>(o); o += up256(size_t(L.qb) * (M1 > 0 ? M1 : 1) * 4);
+      f.col_s = reinterpret_cast<float*>(o); o += up256(size_t(L.qb) * (M1 > 0 ? M1 : 1) * 4);
+      f.skip = reinterpret_cast<int*>(o); o += up256(size_t(L.qb) * 8);
+      f.umask = reinterpret_cast<uint4*>(o);
+      f.M1 = M1; f.g_tiles = gp.g_tiles; f.r = r;
+      const int rblocks = (qn + kRowWarps - 1) / kRowWarps;
+      rank_prep_kernel<<<rblocks, kRowWarps * 32, 0, stream>>>(f);
+      gp.thr = f.thr; gp.cols = f.cols; gp.col_s = f.col_s; gp.M1 = M1; gp.skip = f.skip; gp.umask = f.umask; gp.rank = r.rank;
+      sim_tc_gemm_kernel<false, true><<<grid, kTcThreads, smem, stream>>>(tqh, tql, tgh, tgl, ts, gp);
+      rank_resolve_kernel<<<rblocks, kRowWarps * 32, 0, stream>>>(f);
+      SPN_CUDA_CHECK(cudaGetLastError());
+      continue;
+    }
+    if (T == 1) sim_tc_gemm_kernel<false><<<grid, kTcThreads, smem, stream>>>(tqh, tql, tgh, tgl, ts, gp);
+    else        sim_tc_gemm_kernel<true><<<grid, kTcThreads, smem, stream>>>(tqh, tql, tgh, tgl, ts, gp);
+    SPN_CUDA_CHECK(cudaGetLastError());
+
+    if (rank_mode) {
       row_rank_kernel<<<(qn + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, stream>>>(r);
     } else {
       r.out_val += size_t(qb0) * r.K; r.out_idx += size_t(qb0) * r.K;

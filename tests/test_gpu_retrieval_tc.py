@@ -216,3 +216,21 @@ def test_pair_mining_shape():
     v0, i0 = spn.sim_topk(x, x, K, exclude=me, mode="fp32")
     v1, i1 = spn.sim_topk(x, x, K, exclude=me, mode="tc")
     assert torch.equal(i0, i1) and _same_bits(v0, v1)
+
+
+@pytest.mark.parametrize("Q,G,D,seed", [(300, 2297, 640, 71), (4181, 2297, 640, 72), (130, 129, 64, 73), (257, 5000, 128, 74)])
+def test_rank_fused_epilogue_equals_score_matrix_path(Q, G, D, seed, monkeypatch):
+    """spn_sim_rank_tc, T = 1: the fused path (the sweep's epilogue counts, no S~ matrix) against the S~ + row kernel
+    path (SPN_TC_RANK_FUSED=0) and the fp32 kernels -- incl. the CIRR shape, a ragged last tile, duplicates in the group."""
+    q, g, reference, target, groups = _case(Q, G, D, 1, seed, noise=7.0)
+    groups = groups.clone()
+    groups[::5, 3] = groups[::5, 2]  # a member listed twice counts once
+    r0, g0 = spn.sim_rank(q, g, target, exclude=reference, group=groups, mode="fp32")
+    r1, g1 = spn.sim_rank(q, g, target, exclude=reference, group=groups, mode="tc")
+    monkeypatch.setenv("SPN_TC_RANK_FUSED", "0")
+    r2, g2 = spn.sim_rank(q, g, target, exclude=reference, group=groups, mode="tc")
+    monkeypatch.delenv("SPN_TC_RANK_FUSED")
+    assert torch.equal(r0, r1) and torch.equal(g0, g1) and torch.equal(r0, r2) and torch.equal(g0, g2)
+    r3, _ = spn.sim_rank(q, g, target, mode="tc")  # no exclusion, no group
+    r4, _ = spn.sim_rank(q, g, target, mode="fp32")
+    assert torch.equal(r3, r4)
