@@ -89,7 +89,7 @@ struct TcGemmParams {
   // fused rank epilogue (RANK = true, T = 1): no S~ matrix -- each epilogue thread counts its query's entries that
   // certainly sort before the target (S~ > ts + eps), records the undecided ones (within eps) as a 128-bit mask per
   // (query, gallery tile) and the S~ of the few columns that need individual treatment (the CIRR subset members)
-  const float* thr;      // [qn, 2]  (ts - eps, ts + eps)
+  const float* thr;      // [qn, 3]  (ts - eps, ts + eps, ts)
   const int* cols;       // [qn, M1] local columns to extract (members; -1 = none)
   float* col_s;          // [qn, M1] their S~ (pre-set to -inf)
   int M1;
@@ -233,8 +233,8 @@ sim_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_qh, const __grid_con
             rk_cnt = 0;
             rk_row = r0 + int(lane);
             rk_ok = rk_row < p.qn;
-            rk_lo = rk_ok ? p.thr[2 * rk_row] : INFINITY;
-            rk_hi = rk_ok ? p.thr[2 * rk_row + 1] : INFINITY;
+            rk_lo = rk_ok ? p.thr[3 * rk_row] : INFINITY;
+            rk_hi = rk_ok ? p.thr[3 * rk_row + 1] : INFINITY;
             rk_s0 = rk_ok ? p.skip[2 * rk_row] : -1;
             rk_s1 = rk_ok ? p.skip[2 * rk_row + 1] : -1;
           }
@@ -923,7 +923,7 @@ row_rank_kernel(const RowParams p) {
 // ---- fused rank path (T = 1): rank_prep_kernel -> sim_tc_gemm_kernel<false, true> -> rank_resolve_kernel -------------
 struct RankFusedParams {
   RowParams r;
-  float* thr;     // [qn, 2]
+  float* thr;     // [qn, 3]  (ts - eps, ts + eps, ts)
   int* cols;      // [qn, M1]
   float* col_s;   // [qn, M1]
   int* skip;      // [qn, 2]
@@ -931,51 +931,52 @@ struct RankFusedParams {
   int M1, g_tiles;
 };
 
-// one warp per query: the target's exact score (unless the caller supplies it), the row's eps, the two thresholds, the
-// local columns of the subset members (validated exactly as row_rank_kernel does: in this shard, not the reference, not
-// the target, first occurrence only) and the two columns left out of the count
-__global__ void __launch_bounds__(kRowWarps * 32)
+// one THREAD per query: the target's exact score (unless the caller supplies it) -- the fp32 chain is sequential in k, so
+// a warp per query would leave 31 lanes idle; here 32 queries walk their own (q row, target row) pair side by side, the
+// float4 loads running ahead of the dependent fmaf chain -- the row's eps, the thresholds (ts - eps, ts + eps, ts), the
+// local columns of the subset members (validated exactly as row_rank_kernel does: in this shard, not the reference, not the
+// target, first occurrence only) and the two columns left out of the count
+__global__ void __launch_bounds__(128)
 rank_prep_kernel(const RankFusedParams f) {
-  __shared__ float chain_sm[kRowWarps][kChainFloats];
   const RowParams& p = f.r;
-  const int wib = threadIdx.x >> 5;
-  const int row = blockIdx.x * kRowWarps + wib;
-  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= p.qn) return;
-  const float* qrow = p.q + size_t(row) * p.D;
+  const float4* q4 = reinterpret_cast<const float4*>(p.q + size_t(row) * p.D);
   const int ex = p.exclude ? p.exclude[row] : -1;
   const int tg = p.target[row];
-  float ts;
-  if (p.tscore) {
-    ts = p.tscore[row];
-  } else {
-    const int t = tg - p.col_base;
-    ts = -INFINITY;
-    if (t >= 0 && t < p.G) {  // warp-uniform
-      const float v = warp_chains_few(qrow, p.g, p.D, lane == 0 ? t : -1, chain_sm[wib], lane);
-      ts = __shfl_sync(kFull, v, 0);
-    }
+  const int t = tg - p.col_base;
+  const bool here = t >= 0 && t < p.G;
+  const float4* g4 = reinterpret_cast<const float4*>(p.g + size_t(here ? t : 0) * p.D);
+  float acc = 0.f, ss = 0.f;
+#pragma unroll 4
+  for (int c = 0; c < p.D / 4; ++c) {
+    const float4 a = q4[c];
+    const float4 b = g4[c];
+    acc = fmaf(a.x, b.x, acc);
+    acc = fmaf(a.y, b.y, acc);
+    acc = fmaf(a.z, b.z, acc);
+    acc = fmaf(a.w, b.w, acc);
+    ss = fmaf(a.x, a.x, ss);
+    ss = fmaf(a.y, a.y, ss);
+    ss = fmaf(a.z, a.z, ss);
+    ss = fmaf(a.w, a.w, ss);
   }
-  const float eps = row_eps(qrow, p.D, *p.gmax, lane);
-  if (lane == 0) {
-    f.thr[2 * row] = ts - eps;
-    f.thr[2 * row + 1] = ts + eps;
-    const int exl = ex - p.col_base, tgl = tg - p.col_base;
-    f.skip[2 * row] = (ex >= 0 && exl >= 0 && exl < p.G) ? exl : -1;
-    f.skip[2 * row + 1] = (tgl >= 0 && tgl < p.G) ? tgl : -1;
-  }
-  if (f.M1 > 0) {
-    const int greg = lane < p.M ? p.group[size_t(row) * p.M + lane] : -2;
-    const int ml = greg - p.col_base;
-    bool valid = lane < p.M && ml >= 0 && ml < p.G && greg != ex && greg != tg;
-    for (int mm = 0; mm < p.M; ++mm) {  // a member listed twice counts once
-      const int o = __shfl_sync(kFull, greg, mm);
-      if (mm < lane && o == greg) valid = false;
-    }
-    if (lane < f.M1) {
-      f.cols[size_t(row) * f.M1 + lane] = valid ? ml : -1;
-      f.col_s[size_t(row) * f.M1 + lane] = -INFINITY;
-    }
+  const float ts = p.tscore ? p.tscore[row] : (here ? acc : -INFINITY);
+  const float eps = kEpsRel * sqrtf(ss) * (*p.gmax) * 1.0001f;  // (a different summation order than row_eps: keep a margin)
+  f.thr[3 * row] = ts - eps;
+  f.thr[3 * row + 1] = ts + eps;
+  f.thr[3 * row + 2] = ts;
+  const int exl = ex - p.col_base;
+  f.skip[2 * row] = (ex >= 0 && exl >= 0 && exl < p.G) ? exl : -1;
+  f.skip[2 * row + 1] = here ? t : -1;
+  for (int mm = 0; mm < f.M1; ++mm) {
+    const int gid = p.group[size_t(row) * p.M + mm];
+    const int ml = gid - p.col_base;
+    bool valid = ml >= 0 && ml < p.G && gid != ex && gid != tg;
+    for (int o = 0; o < mm; ++o)  // a member listed twice counts once
+      if (p.group[size_t(row) * p.M + o] == gid) valid = false;
+    f.cols[size_t(row) * f.M1 + mm] = valid ? ml : -1;
+    f.col_s[size_t(row) * f.M1 + mm] = -INFINITY;
   }
 }
 
@@ -992,21 +993,8 @@ rank_resolve_kernel(const RankFusedParams f) {
   if (row >= p.qn) return;
   const float* qrow = p.q + size_t(row) * p.D;
   const int tg = p.target[row];
-  const float lo = f.thr[2 * row], hi = f.thr[2 * row + 1];
-  const float ts = 0.5f * (lo + hi);  // only used for the -inf case below; exact comparisons use ts_exact
-  (void)ts;
-  // the exact target score again (bit-identical chain) for sorts_before
-  float ts_exact;
-  if (p.tscore) {
-    ts_exact = p.tscore[row];
-  } else {
-    const int t = tg - p.col_base;
-    ts_exact = -INFINITY;
-    if (t >= 0 && t < p.G) {
-      const float v = warp_chains_few(qrow, p.g, p.D, lane == 0 ? t : -1, chain_sm[wib], lane);
-      ts_exact = __shfl_sync(kFull, v, 0);
-    }
-  }
+  const float lo = f.thr[3 * row], hi = f.thr[3 * row + 1];
+  const float ts_exact = f.thr[3 * row + 2];  // the exact fp32 chain of the target (rank_prep_kernel) or the caller's value
   int cnt = 0, gcnt = 0;
   unsigned n_unsure = 0;
   if (f.M1 > 0) {
@@ -1180,7 +1168,7 @@ int tc_run(bool rank_mode, const float* q, const float* g, int Q, int G, int D, 
   const int M1 = rp.group ? rp.M : 0;
   const int g_tiles_all = int((grows + kBN - 1) / kBN);
   auto up256 = [](size_t x) { return (x + 255) / 256 * 256; };
-  const size_t fused_need = up256(size_t(L.qb) * 8) + 2 * up256(size_t(L.qb) * (M1 > 0 ? M1 : 1) * 4) + up256(size_t(L.qb) * 8) +
+  const size_t fused_need = up256(size_t(L.qb) * 12) + 2 * up256(size_t(L.qb) * (M1 > 0 ? M1 : 1) * 4) + up256(size_t(L.qb) * 8) +
                             up256(size_t(L.qb) * g_tiles_all * 16);
   if (fused_need > up256(size_t(L.qb) * L.Gp * 4)) rank_fused = false;
   if (rank_fused)
@@ -1211,14 +1199,14 @@ int tc_run(bool rank_mode, const float* q, const float* g, int Q, int G, int D, 
     if (rank_fused) {
       RankFusedParams f{};
       uint8_t* o = reinterpret_cast<uint8_t*>(scores);
-      f.thr = reinterpret_cast<float*>(o); o += up256(size_t(L.qb) * 8);
+      f.thr = reinterpret_cast<float*>(o); o += up256(size_t(L.qb) * 12);
       f.cols = reinterpret_cast<int*>(o); o += up256(size_t(L.qb) * (M1 > 0 ? M1 : 1) * 4);
       f.col_s = reinterpret_cast<float*>(o); o += up256(size_t(L.qb) * (M1 > 0 ? M1 : 1) * 4);
       f.skip = reinterpret_cast<int*>(o); o += up256(size_t(L.qb) * 8);
       f.umask = reinterpret_cast<uint4*>(o);
       f.M1 = M1; f.g_tiles = gp.g_tiles; f.r = r;
       const int rblocks = (qn + kRowWarps - 1) / kRowWarps;
-      rank_prep_kernel<<<rblocks, kRowWarps * 32, 0, stream>>>(f);
+      rank_prep_kernel<<<(qn + 127) / 128, 128, 0, stream>>>(f);
       gp.thr = f.thr; gp.cols = f.cols; gp.col_s = f.col_s; gp.M1 = M1; gp.skip = f.skip; gp.umask = f.umask; gp.rank = r.rank;
       sim_tc_gemm_kernel<false, true><<<grid, kTcThreads, smem, stream>>>(tqh, tql, tgh, tgl, ts, gp);
       rank_resolve_kernel<<<rblocks, kRowWarps * 32, 0, stream>>>(f);
