@@ -87,9 +87,9 @@ struct TcGemmParams {
   int nterms;     // 3: hi*hi + hi*lo + lo*hi, 1: hi*hi only
   float* scores;  // [qn, Gp]
   // fused rank epilogue (RANK = true, T = 1): no S~ matrix -- each epilogue thread counts its query's entries that
-  // certainly sort before the target (S~ > ts + eps), records the undecided ones (within eps) as a 128-bit mask per
+  // certainly sort before the target (S~ above the decision band), records the undecided ones (inside the band) as a 128-bit mask per
   // (query, gallery tile) and the S~ of the few columns that need individual treatment (the CIRR subset members)
-  const float* thr;      // [qn, 3]  (ts - eps, ts + eps, ts)
+  const float* thr;      // [qn, 3]  decision band (ts - eps, ts + eps) and ts
   const int* cols;       // [qn, M1] local columns to extract (members; -1 = none)
   float* col_s;          // [qn, M1] their S~ (pre-set to -inf)
   int M1;
@@ -923,7 +923,7 @@ row_rank_kernel(const RowParams p) {
 // ---- fused rank path (T = 1): rank_prep_kernel -> sim_tc_gemm_kernel<false, true> -> rank_resolve_kernel -------------
 struct RankFusedParams {
   RowParams r;
-  float* thr;     // [qn, 3]  (ts - eps, ts + eps, ts)
+  float* thr;     // [qn, 3]  decision band (ts - eps, ts + eps) and the exact target score ts
   int* cols;      // [qn, M1]
   float* col_s;   // [qn, M1]
   int* skip;      // [qn, 2]
@@ -931,38 +931,83 @@ struct RankFusedParams {
   int M1, g_tiles;
 };
 
-// one THREAD per query: the target's exact score (unless the caller supplies it) -- the fp32 chain is sequential in k, so
-// a warp per query would leave 31 lanes idle; here 32 queries walk their own (q row, target row) pair side by side, the
-// float4 loads running ahead of the dependent fmaf chain -- the row's eps, the thresholds (ts - eps, ts + eps, ts), the
-// local columns of the subset members (validated exactly as row_rank_kernel does: in this shard, not the reference, not the
-// target, first occurrence only) and the two columns left out of the count
-__global__ void __launch_bounds__(128)
+// one warp per 32 queries: every lane owns one query and walks the exact fp32 chain of (q row, target row) -- the chain
+// is sequential in k, so a warp per query would idle 31 lanes.  The warp loads 64-column chunks of its 32 + 32 rows with
+// coalesced 16-byte loads (the next chunk is in flight in registers while the current one is walked from shared memory).
+// Outputs per query: the decision band (ts - eps, ts + eps) and ts itself, the two columns left out of the count (the
+// removed reference image, the target), the local columns of the subset members (validated exactly as row_rank_kernel
+// does: in this shard, not the reference, not the target, first occurrence only).
+constexpr int kPrepCols = 64;
+constexpr int kPrepPitch = kPrepCols + 4;
+
+__global__ void __launch_bounds__(32)
 rank_prep_kernel(const RankFusedParams f) {
+  __shared__ __align__(16) float sq[32][kPrepPitch];
+  __shared__ __align__(16) float sg[32][kPrepPitch];
   const RowParams& p = f.r;
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= p.qn) return;
-  const float4* q4 = reinterpret_cast<const float4*>(p.q + size_t(row) * p.D);
-  const int ex = p.exclude ? p.exclude[row] : -1;
-  const int tg = p.target[row];
+  const int lane = threadIdx.x;
+  const int row0 = blockIdx.x * 32;
+  const int row = row0 + lane;
+  const bool live = row < p.qn;
+  const int ex = (live && p.exclude) ? p.exclude[row] : -1;
+  const int tg = live ? p.target[row] : -1;
   const int t = tg - p.col_base;
-  const bool here = t >= 0 && t < p.G;
-  const float4* g4 = reinterpret_cast<const float4*>(p.g + size_t(here ? t : 0) * p.D);
-  float acc = 0.f, ss = 0.f;
-#pragma unroll 4
-  for (int c = 0; c < p.D / 4; ++c) {
-    const float4 a = q4[c];
-    const float4 b = g4[c];
-    acc = fmaf(a.x, b.x, acc);
-    acc = fmaf(a.y, b.y, acc);
-    acc = fmaf(a.z, b.z, acc);
-    acc = fmaf(a.w, b.w, acc);
-    ss = fmaf(a.x, a.x, ss);
-    ss = fmaf(a.y, a.y, ss);
-    ss = fmaf(a.z, a.z, ss);
-    ss = fmaf(a.w, a.w, ss);
+  const bool here = live && t >= 0 && t < p.G;
+  // cooperative loads: step h covers rows 4 h + (lane >> 3), 16 floats (4 float4) per lane and row
+  const int sub = lane >> 3, c16 = (lane & 7) * 8;  // this lane's 8 floats = 2 float4 inside a 64-column chunk
+  int qrow_of[8], grow_of[8];
+#pragma unroll
+  for (int h = 0; h < 8; ++h) {
+    const int r = h * 4 + sub;
+    qrow_of[h] = (row0 + r < p.qn) ? row0 + r : -1;
+    const int tr = __shfl_sync(kFull, here ? t : -1, r);
+    grow_of[h] = tr;
   }
+  float4 qa[8][2], ga[8][2];
+  auto load_chunk = [&](int k0) {
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        qa[h][v] = qrow_of[h] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.q + size_t(qrow_of[h]) * p.D + k0 + c16) + v)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        ga[h][v] = grow_of[h] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.g + size_t(grow_of[h]) * p.D + k0 + c16) + v)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+  float acc = 0.f, ss = 0.f;
+  load_chunk(0);
+  for (int k0 = 0; k0 < p.D; k0 += kPrepCols) {
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const int r = h * 4 + sub;
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        *reinterpret_cast<float4*>(&sq[r][c16 + 4 * v]) = qa[h][v];
+        *reinterpret_cast<float4*>(&sg[r][c16 + 4 * v]) = ga[h][v];
+      }
+    }
+    __syncwarp();
+    if (k0 + kPrepCols < p.D) load_chunk(k0 + kPrepCols);  // in flight while this chunk is walked
+#pragma unroll 4
+    for (int j = 0; j < kPrepCols; j += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(&sq[lane][j]);
+      const float4 b = *reinterpret_cast<const float4*>(&sg[lane][j]);
+      acc = fmaf(a.x, b.x, acc);
+      acc = fmaf(a.y, b.y, acc);
+      acc = fmaf(a.z, b.z, acc);
+      acc = fmaf(a.w, b.w, acc);
+      ss = fmaf(a.x, a.x, ss);
+      ss = fmaf(a.y, a.y, ss);
+      ss = fmaf(a.z, a.z, ss);
+      ss = fmaf(a.w, a.w, ss);
+    }
+  }
+  if (!live) return;
   const float ts = p.tscore ? p.tscore[row] : (here ? acc : -INFINITY);
-  const float eps = kEpsRel * sqrtf(ss) * (*p.gmax) * 1.0001f;  // (a different summation order than row_eps: keep a margin)
+  const float eps = kEpsRel * sqrtf(ss) * (*p.gmax) * 1.0001f;  // (another summation order than row_eps: keep a margin)
   f.thr[3 * row] = ts - eps;
   f.thr[3 * row + 1] = ts + eps;
   f.thr[3 * row + 2] = ts;
@@ -977,6 +1022,24 @@ rank_prep_kernel(const RankFusedParams f) {
       if (p.group[size_t(row) * p.M + o] == gid) valid = false;
     f.cols[size_t(row) * f.M1 + mm] = valid ? ml : -1;
     f.col_s[size_t(row) * f.M1 + mm] = -INFINITY;
+  }
+}
+
+// the rare part of rank_resolve_kernel: rescore the listed undecided entries (up to 32 per round) with the exact chain
+__device__ __noinline__ void resolve_batches(const RowParams& p, const float* qrow, int tg, bool last, int* list,
+                                             float* chain, unsigned& n_unsure, float ts_exact, int& cnt, int& gcnt, int lane) {
+  while (n_unsure >= 32u || (last && n_unsure > 0u)) {
+    const unsigned take = n_unsure < 32u ? n_unsure : 32u;
+    __syncwarp();
+    const bool have = unsigned(lane) < take;
+    const int raw = have ? list[n_unsure - take + lane] : 0;
+    const bool member = raw < 0;
+    const int g = member ? ~raw : raw;
+    n_unsure -= take;
+    const float e = warp_exact(qrow, p.g, p.D, p.T, have, g, chain, lane);
+    const bool before = have && sorts_before(e, p.col_base + g, ts_exact, tg);
+    cnt += __popc(__ballot_sync(kFull, before && !member));
+    gcnt += __popc(__ballot_sync(kFull, before && member));
   }
 }
 
@@ -1009,19 +1072,8 @@ rank_resolve_kernel(const RankFusedParams f) {
     n_unsure = __popc(um);
   }
   auto flush = [&](bool last) {
-    while (n_unsure >= 32u || (last && n_unsure > 0u)) {
-      const unsigned take = n_unsure < 32u ? n_unsure : 32u;
-      __syncwarp();
-      const bool have = unsigned(lane) < take;
-      const int raw = have ? unsure_g[wib][n_unsure - take + lane] : 0;
-      const bool member = raw < 0;
-      const int g = member ? ~raw : raw;
-      n_unsure -= take;
-      const float e = warp_exact(qrow, p.g, p.D, p.T, have, g, chain_sm[wib], lane);
-      const bool before = have && sorts_before(e, p.col_base + g, ts_exact, tg);
-      cnt += __popc(__ballot_sync(kFull, before && !member));
-      gcnt += __popc(__ballot_sync(kFull, before && member));
-    }
+    if (n_unsure >= 32u || (last && n_unsure > 0u))  // rare: kept out of line so the common path stays in registers
+      resolve_batches(p, qrow, tg, last, unsure_g[wib], chain_sm[wib], n_unsure, ts_exact, cnt, gcnt, lane);
   };
   // each lane owns 4 of the 128 bits of a tile mask; tiles are visited one at a time only when their mask is non-zero
   for (int t0 = 0; t0 < f.g_tiles; t0 += 32) {
@@ -1206,7 +1258,7 @@ int tc_run(bool rank_mode, const float* q, const float* g, int Q, int G, int D, 
       f.umask = reinterpret_cast<uint4*>(o);
       f.M1 = M1; f.g_tiles = gp.g_tiles; f.r = r;
       const int rblocks = (qn + kRowWarps - 1) / kRowWarps;
-      rank_prep_kernel<<<(qn + 127) / 128, 128, 0, stream>>>(f);
+      rank_prep_kernel<<<(qn + 31) / 32, 32, 0, stream>>>(f);
       gp.thr = f.thr; gp.cols = f.cols; gp.col_s = f.col_s; gp.M1 = M1; gp.skip = f.skip; gp.umask = f.umask; gp.rank = r.rank;
       sim_tc_gemm_kernel<false, true><<<grid, kTcThreads, smem, stream>>>(tqh, tql, tgh, tgl, ts, gp);
       rank_resolve_kernel<<<rblocks, kRowWarps * 32, 0, stream>>>(f);
