@@ -355,21 +355,26 @@ class SymmExchange:
         call("spn_peer_barrier", self.ptrs["flags"], self.rank, self.world, self.epoch & 0xFFFFFFFF, stream)
 
 
-_exchanges = {}
+_exchanges = []  # one token per SymmExchange ever created (tests check that the path was taken); the objects hang off their bank
 
 
 def _symm_exchange(bank, B: int, group) -> "SymmExchange":
-    key = (id(bank), B, id(group))
-    x = _exchanges.get(key)
+    """The windows of (bank, B, group), created on first use (collective) and kept ON the bank object -- never keyed by
+    id(bank): a recycled id must not resurrect another bank's peer pointers."""
+    cache = bank.__dict__.setdefault("_symm_exchanges", {})
+    key = (B, None if group is None else id(group))
+    x = cache.get(key)
     if x is None:
         make_bank_symmetric(bank, group)
-        x = _exchanges[key] = SymmExchange(bank, B, group)
+        x = cache[key] = SymmExchange(bank, B, group)
+        _exchanges.append((B, bank.N, bank.D))
     return x
 
 
-def release_exchanges() -> None:
-    """Drop the cached symmetric-memory windows (collective: call on every rank)."""
-    _exchanges.clear()
+def release_exchanges(bank=None) -> None:
+    """Drop the symmetric-memory windows cached on `bank` (collective: call on every rank)."""
+    if bank is not None:
+        bank.__dict__.pop("_symm_exchanges", None)
 
 
 def symm_path_ok(bank, B: int, group=None) -> bool:
