@@ -579,8 +579,8 @@ def run_ours(args, cfg):
                                 "around the K steps; the bank stays resident in HBM",
                         "serial": {"value": (B * world) / t_e2e_serial, "ms_per_step": t_e2e_serial * 1e3,
                                    "note": "the same step with its copies serialised on one stream, L2 flushed before each (latency of one isolated step)"}},
-                "gpu_launches": ((6 if symm else 7) if sharded else 3) * steps,  # + 1 torch elementwise kernel (dq_unit * upstream grad) in backward
-                "gpu_launches_detail": ("per step: shard_home_prologue_kernel, peer_barrier_kernel, fused_init_kernel, bank_ce_kernel<2> (peer windows), "
+                "gpu_launches": ((5 if symm else 7) if sharded else 3) * steps,  # + 1 torch elementwise kernel (dq_unit * upstream grad) in backward
+                "gpu_launches_detail": ("per step: shard_home_prologue_kernel, peer_barrier_kernel, bank_ce_kernel<2> (peer windows), "
                                         "peer_barrier_kernel, fused_finalize_kernel (no NCCL call)" if symm else
                                         "per step: cast_bf16_kernel, prep_query_kernel, fused_init_kernel, bank_ce_kernel<2>, shard_pack_kernel, "
                                         "shard_fold_kernel, fused_finalize_kernel (+ 5 NCCL collectives)"

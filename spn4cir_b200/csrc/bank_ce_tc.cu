@@ -1762,7 +1762,9 @@ int bank_ce_fused_peers(const void* q, const void* bank, const long long* labels
                         float* const* l_peers, float* const* es_peers, float* s_t, long long* lbl_row, void* ws,
                         size_t ws_bytes, cudaStream_t stream) {
   SPN_REQUIRE(home_rows > 0, SPN_ERR_BAD_ARG, "bank_ce_fused_peers: home_rows must be positive");
-  return fused_launch(q, bank, labels, ref, inv_tau, B, N, D, T, row_base, /*init=*/1, nullptr, nullptr, s_t, lbl_row, nullptr,
+  // no init launch: the accumulation windows were zeroed by the home prologue of their owners; s_t / lbl_row are scratch here
+  // (the home rank computed the target logit itself)
+  return fused_launch(q, bank, labels, ref, inv_tau, B, N, D, T, row_base, /*init=*/0, nullptr, nullptr, s_t, lbl_row, nullptr,
                       nullptr, ws, ws_bytes, stream, 0, home_rows, world, o_peers, l_peers, es_peers);
 }
 
