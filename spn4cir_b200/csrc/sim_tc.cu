@@ -94,8 +94,13 @@ struct TcGemmParams {
   float* col_s;          // [qn, M1] their S~ (pre-set to -inf)
   int M1;
   const int* skip;       // [qn, 2]  local columns excluded from the count: the removed reference image, the target
-  uint4* umask;          // [qn, g_tiles]
+  uint4* umask;          // [qn, g_tiles]          (1-CTA sweep: one 128-bit mask per 128-column tile)
+  uint32_t* umask32;     // [qn, n_chunks]         (pair sweep: one 32-bit mask per 32-column chunk)
+  int n_chunks;
   int* rank;             // [qn] += certain count
+  // pair sweep (sim_tc_gemm2_kernel): 256 queries x tile_n gallery rows per cluster tile
+  int tile_n;            // multiple of 32, <= 256
+  int q_tiles2, g_tiles2;
 };
 
 template <bool T32, bool RANK = false>
@@ -314,6 +319,214 @@ sim_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_qh, const __grid_con
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------ pair sweep
+// The same sweep on CTA pairs (cta_group::2): one cluster tile = 256 queries x tile_n gallery rows.  Each CTA stages its own
+// 128 query rows (hi, lo) and HALF of the tile's gallery rows (hi, lo); rank 0 issues M256 x N(tile_n) x K16 MMAs for the
+// pair, so every operand byte fetched from L2 feeds twice the output of the 1-CTA tile (the 1-CTA sweep is L2 -> SM bound:
+// 389 MB of operand traffic at CIRR size) and the fixed cost of an SS instruction (the 4 KiB A fetch, ~43 cycles) is
+// amortised over up to 256 columns instead of 128.  tile_n is chosen per problem (multiple of 32, <= 256) to minimise
+// ceil(tiles / clusters) x instruction time -- at CIRR size 192 (204 tiles on 74 clusters: 2.76 -> 3 rounds).
+template <bool T32, bool RANK>
+__global__ void __launch_bounds__(kTcThreads, 1)
+sim_tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_qh, const __grid_constant__ CUtensorMap tmap_ql,
+                    const __grid_constant__ CUtensorMap tmap_gh, const __grid_constant__ CUtensorMap tmap_gl,
+                    const __grid_constant__ CUtensorMap tmap_s, const TcGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~uintptr_t(1023u));
+  uint8_t* ring = base;                                        // kTcStages x 64 KiB: Qh | Ql | Gh half | Gl half
+  uint8_t* slots = ring + size_t(kTcStages) * kStageBytes;     // 4 warps x 2 slots x 4 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slots + 8 * kSlotBytes);
+  uint64_t* full = bars;                    // [kTcStages] TMA (both CTAs) -> MMA, rank 0's are used
+  uint64_t* empty = bars + kTcStages;       // [kTcStages] MMA -> TMA, multicast to both CTAs
+  uint64_t* acc_full = bars + 2 * kTcStages;      // [2] MMA -> epilogue, multicast
+  uint64_t* acc_empty = bars + 2 * kTcStages + 2; // [2] epilogue (4 warps x 2 CTAs) -> MMA, rank 0's are used
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 4);
+  const uint32_t crank = cluster_ctarank();
+  const int cluster_id = int(blockIdx.x >> 1), n_clusters = int(gridDim.x >> 1);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 8);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_qh);
+    tma_prefetch_desc(&tmap_ql);
+    tma_prefetch_desc(&tmap_gh);
+    tma_prefetch_desc(&tmap_gl);
+    if (!T32 && !RANK) tma_prefetch_desc(&tmap_s);
+  }
+  if (warp == 1) {
+    tmem_alloc_cg2(tmem_slot, 512);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // the peer's barriers must be initialised before anything is signalled remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_tiles = p.q_tiles2 * p.g_tiles2;
+  const int half_n = p.tile_n >> 1;
+  const uint32_t g_bytes = uint32_t(half_n) * 128u;  // one k-block of this CTA's gallery half
+
+  if (warp == 0) {
+    // ---------------- TMA producer (both CTAs; completions are credited to rank 0's barrier)
+    uint32_t it = 0;
+    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+      const int qt = tile / p.g_tiles2, gt = tile % p.g_tiles2;
+      const int qrow = p.q_row0 + qt * 2 * kBM + int(crank) * kBM;
+      const int grow = gt * p.tile_n + int(crank) * half_n;
+      for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+        const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        const uint32_t fbar = mapa_shared(smem_u32(&full[s]), 0);
+        if (elect_one()) {
+          uint8_t* st = ring + size_t(s) * kStageBytes;
+          if (crank == 0) mbar_arrive_expect_tx(&full[s], 2u * (2u * kBlockBytes + 2u * g_bytes));
+          tma_load_2d_cg2(st, &tmap_qh, fbar, kb * kBK, qrow);
+          tma_load_2d_cg2(st + kBlockBytes, &tmap_ql, fbar, kb * kBK, qrow);
+          tma_load_2d_cg2(st + 2 * kBlockBytes, &tmap_gh, fbar, kb * kBK, grow);
+          tma_load_2d_cg2(st + 3 * kBlockBytes, &tmap_gl, fbar, kb * kBK, grow);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (rank 0 issues for the pair)
+    if (crank == 0) {
+      const uint32_t idesc = make_idesc_bf16_f32(2 * kBM, p.tile_n, 0, 0);
+      uint32_t it = 0, j = 0;
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++j) {
+        const uint32_t b = j & 1u, aph = (j >> 1) & 1u;
+        mbar_wait(&acc_empty[b], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + b * 256u;
+        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(ring + size_t(s) * kStageBytes);
+            const uint64_t qh = make_smem_desc_sw128(sa, 16, 1024);
+            const uint64_t ql = make_smem_desc_sw128(sa + kBlockBytes, 16, 1024);
+            const uint64_t gh = make_smem_desc_sw128(sa + 2 * kBlockBytes, 16, 1024);
+            const uint64_t gl = make_smem_desc_sw128(sa + 3 * kBlockBytes, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              const uint64_t o = uint64_t(k * 2);
+              umma_ss_f16_cg2(d, qh + o, gl + o, idesc, (kb | k) != 0);  // small terms first
+              umma_ss_f16_cg2(d, ql + o, gh + o, idesc, 1);
+              umma_ss_f16_cg2(d, qh + o, gh + o, idesc, 1);
+            }
+            umma_commit_cg2(&empty[s], 3);
+            if (kb == p.kblocks - 1) umma_commit_cg2(&acc_full[b], 3);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs): TMEM -> registers -> (staging slot -> TMA store | token max | rank count)
+    const uint32_t quarter = warp & 3u;
+    const uint32_t t_row = tmem_base + ((quarter * 32u) << 16);
+    uint8_t* my_slots = slots + size_t(warp - 2u) * 2 * kSlotBytes;
+    const int nchunk = p.tile_n >> 5;
+    uint32_t x[32];
+    uint32_t j = 0, k = 0;
+    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++j) {
+      const int qt = tile / p.g_tiles2, gt = tile % p.g_tiles2;
+      const uint32_t b = j & 1u, aph = (j >> 1) & 1u;
+      const int r0 = qt * 2 * kBM + int(crank) * kBM + int(quarter) * 32;  // first block-relative query row of this warp
+      const int row = r0 + int(lane);
+      const bool row_ok = row < p.qn;
+      float rk_lo = INFINITY, rk_hi = INFINITY;
+      int rk_s0 = -1, rk_s1 = -1, rk_cnt = 0;
+      if (RANK && row_ok) {
+        rk_lo = p.thr[3 * row];
+        rk_hi = p.thr[3 * row + 1];
+        rk_s0 = p.skip[2 * row];
+        rk_s1 = p.skip[2 * row + 1];
+      }
+      mbar_wait(&acc_full[b], aph);
+      tc_fence_after();
+      for (int c = 0; c < nchunk; ++c) {
+        tmem_ld_32x32b_x32(t_row + b * 256u + uint32_t(c) * 32u, x);
+        tmem_ld_wait();
+        if (c == nchunk - 1) {  // accumulator drained: the MMA warp may start the tile after next
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(&acc_empty[b]), 0));
+        }
+        const int col0 = gt * p.tile_n + c * 32;
+        if (RANK) {
+          uint32_t m = 0u;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float a = __uint_as_float(x[i]);
+            const int col = col0 + i;
+            const bool ok = col < p.G && col != rk_s0 && col != rk_s1;
+            const bool before = ok && a > rk_hi;
+            const bool unsure = ok && !before && !(a < rk_lo);
+            rk_cnt += before ? 1 : 0;
+            m |= unsure ? (1u << i) : 0u;
+          }
+          if (row_ok && col0 < p.G) {
+            p.umask32[size_t(row) * p.n_chunks + (col0 >> 5)] = m;
+            for (int mm = 0; mm < p.M1; ++mm) {  // columns whose S~ the resolve kernel wants individually (rare hits)
+              const unsigned dd = unsigned(p.cols[size_t(row) * p.M1 + mm] - col0);
+              if (dd < 32u) {
+                float v = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (unsigned(i) == dd) v = __uint_as_float(x[i]);
+                p.col_s[size_t(row) * p.M1 + mm] = v;
+              }
+            }
+          }
+        } else if (T32) {
+          float m = __uint_as_float(x[0]);
+#pragma unroll
+          for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(x[i]));
+          const int e = col0 >> 5;
+          if (row_ok && e < p.G) p.scores[size_t(row) * p.Gp + e] = m;
+        } else {
+          if (r0 < p.qn && col0 < p.Gp) {  // warp-uniform
+            uint8_t* slot = my_slots + size_t(k & 1u) * kSlotBytes;
+            if (k >= 2) {
+              if (lane == 0) bulk_wait_group_read<1>();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+              *reinterpret_cast<uint4*>(slot + lane * 128u + ((uint32_t(v) ^ (lane & 7u)) << 4)) =
+                  make_uint4(x[4 * v], x[4 * v + 1], x[4 * v + 2], x[4 * v + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(slot, &tmap_s, col0, r0);
+              bulk_commit_group();
+            }
+            ++k;
+          }
+        }
+      }
+      if (RANK && row_ok && rk_cnt) atomicAdd(&p.rank[row], rk_cnt);
+    }
+    if (!T32 && !RANK) {
+      if (lane == 0) bulk_wait_group<0>();
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();  // neither CTA may exit (or free TMEM) while the pair's MMAs / remote arrivals can still land
+  if (warp == 1) tmem_dealloc_cg2(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ exact rescoring
@@ -927,8 +1140,9 @@ struct RankFusedParams {
   int* cols;      // [qn, M1]
   float* col_s;   // [qn, M1]
   int* skip;      // [qn, 2]
-  uint4* umask;   // [qn, g_tiles]
-  int M1, g_tiles;
+  uint4* umask;   // [qn, g_tiles]   (1-CTA sweep)
+  uint32_t* umask32;  // [qn, n_chunks] (pair sweep; non-NULL selects it)
+  int M1, g_tiles, n_chunks;
 };
 
 // one warp per 32 queries: every lane owns one query and walks the exact fp32 chain of (q row, target row) -- the chain
@@ -1075,6 +1289,24 @@ rank_resolve_kernel(const RankFusedParams f) {
     if (n_unsure >= 32u || (last && n_unsure > 0u))  // rare: kept out of line so the common path stays in registers
       resolve_batches(p, qrow, tg, last, unsure_g[wib], chain_sm[wib], n_unsure, ts_exact, cnt, gcnt, lane);
   };
+  if (f.umask32) {
+    // pair sweep: one 32-bit mask per 32-column chunk; lane == chunk, chunks with a non-zero mask are visited one at a time
+    for (int c0 = 0; c0 < f.n_chunks; c0 += 32) {
+      const int c = c0 + lane;
+      const uint32_t w = c < f.n_chunks ? f.umask32[size_t(row) * f.n_chunks + c] : 0u;
+      unsigned nz = __ballot_sync(kFull, w != 0u);
+      while (nz) {
+        const int src = __ffs(nz) - 1;
+        nz &= nz - 1;
+        const uint32_t word = __shfl_sync(kFull, w, src);
+        const bool unsure = (word >> lane) & 1u;
+        const unsigned um = __ballot_sync(kFull, unsure);
+        if (unsure) unsure_g[wib][n_unsure + __popc(um & ((1u << lane) - 1u))] = (c0 + src) * 32 + lane;
+        n_unsure += __popc(um);
+        flush(false);  // keeps the list below 32 + 32 entries (+ the members)
+      }
+    }
+  } else {
   // each lane owns 4 of the 128 bits of a tile mask; tiles are visited one at a time only when their mask is non-zero
   for (int t0 = 0; t0 < f.g_tiles; t0 += 32) {
     const int t = t0 + lane;
@@ -1099,6 +1331,7 @@ rank_resolve_kernel(const RankFusedParams f) {
       }
       flush(false);  // keeps the list below 32 + 128 entries (+ the members)
     }
+  }
   }
   flush(true);
   if (lane == 0) {
@@ -1194,22 +1427,75 @@ int tc_run(bool rank_mode, const float* q, const float* g, int Q, int G, int D, 
   split_rows_kernel<<<unsigned((grows + 7) / 8), 256, 0, stream>>>(g, grows, D, gh, gl, gmax);
   SPN_CUDA_CHECK(cudaGetLastError());
 
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  // pair sweep (default): cluster tile = 256 queries x tile_n gallery rows; tile_n (multiple of 32, <= 256) minimises
+  // rounds x instruction time, an SS M256 x N x K16 instruction costing ~N / 2 + 43 cycles (profiles/r01_exp_mma_rate_ss_ts)
+  bool pair = true;
+  if (const char* e = getenv("SPN_TC_SWEEP_CG")) {
+    if (atoi(e) == 1) pair = false;
+  }
+  const int qb_for_plan = Q < L.qb ? Q : L.qb;
+  const int q_tiles2_plan = (qb_for_plan + 2 * kBM - 1) / (2 * kBM);
+  const int n_clusters = sms / 2;
+  int tile_n = 256;
+  {
+    double best = 1e30;
+    for (int n = 256; n >= 128; n -= 32) {
+      const long long tiles = (long long)q_tiles2_plan * ((grows + n - 1) / n);
+      const long long rounds = (tiles + n_clusters - 1) / n_clusters;
+      const double cost = double(rounds) * (n / 2 + 43);
+      if (cost < best - 1e-9) {
+        best = cost;
+        tile_n = n;
+      }
+    }
+  }
+  if (const char* e = getenv("SPN_TC_TILE_N")) {
+    const int v = atoi(e);
+    if (v >= 32 && v <= 256 && v % 32 == 0) tile_n = v;
+  }
+
   CUtensorMap tqh, tql, tgh, tgl, ts;
   if ((rc = make_tmap_bf16_2d(&tqh, qh, uint64_t(Q), uint64_t(D), kBM)) != SPN_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&tql, ql, uint64_t(Q), uint64_t(D), kBM)) != SPN_OK) return rc;
-  if ((rc = make_tmap_bf16_2d(&tgh, gh, uint64_t(grows), uint64_t(D), kBN)) != SPN_OK) return rc;
-  if ((rc = make_tmap_bf16_2d(&tgl, gl, uint64_t(grows), uint64_t(D), kBN)) != SPN_OK) return rc;
+  const uint32_t g_box = pair ? uint32_t(tile_n / 2) : uint32_t(kBN);  // pair sweep: each CTA stages half of the tile's rows
+  if ((rc = make_tmap_bf16_2d(&tgh, gh, uint64_t(grows), uint64_t(D), g_box)) != SPN_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tgl, gl, uint64_t(grows), uint64_t(D), g_box)) != SPN_OK) return rc;
 
   const size_t smem = tc_gemm_smem();
   // per launch, like the bank-CE kernels: the attribute is per device and the call costs a few microseconds of host time
   SPN_REQUIRE(size_t(device_max_smem_optin()) >= smem, SPN_ERR_CUDA, "device offers %d B of shared memory, %zu needed",
               device_max_smem_optin(), smem);
-  if (T == 1)
+  if (pair) {
+    SPN_CUDA_CHECK(cudaFuncSetAttribute(sim_tc_gemm2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    SPN_CUDA_CHECK(cudaFuncSetAttribute(sim_tc_gemm2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    SPN_CUDA_CHECK(cudaFuncSetAttribute(sim_tc_gemm2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  } else if (T == 1) {
     SPN_CUDA_CHECK(cudaFuncSetAttribute(sim_tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  else
+  } else {
     SPN_CUDA_CHECK(cudaFuncSetAttribute(sim_tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  int sms = device_sm_count();
-  if (sms <= 0) sms = 148;
+  }
+  auto launch_pair_sweep = [&](int variant, const TcGemmParams& gp2) -> int {  // 0: S~ store, 1: token max, 2: rank count
+    const long long tiles = (long long)gp2.q_tiles2 * gp2.g_tiles2;
+    const int clusters = int(tiles < n_clusters ? tiles : n_clusters);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(2 * clusters), 1, 1);
+    cfg.blockDim = dim3(kTcThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (variant == 0) SPN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sim_tc_gemm2_kernel<false, false>, tqh, tql, tgh, tgl, ts, gp2));
+    else if (variant == 1) SPN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sim_tc_gemm2_kernel<true, false>, tqh, tql, tgh, tgl, ts, gp2));
+    else SPN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sim_tc_gemm2_kernel<false, true>, tqh, tql, tgh, tgl, ts, gp2));
+    return SPN_OK;
+  };
 
   // rank, T = 1: the fused path -- no S~ matrix; the sweep's epilogue counts and the resolve kernel rescored the undecided
   // entries (SPN_TC_RANK_FUSED=0 keeps the S~ + row_rank_kernel path, also taken when the workspace block is too small)
@@ -1219,11 +1505,12 @@ int tc_run(bool rank_mode, const float* q, const float* g, int Q, int G, int D, 
   }
   const int M1 = rp.group ? rp.M : 0;
   const int g_tiles_all = int((grows + kBN - 1) / kBN);
+  const int n_chunks = int((grows + 31) / 32);
   auto up256 = [](size_t x) { return (x + 255) / 256 * 256; };
   const size_t fused_need = up256(size_t(L.qb) * 12) + 2 * up256(size_t(L.qb) * (M1 > 0 ? M1 : 1) * 4) + up256(size_t(L.qb) * 8) +
-                            up256(size_t(L.qb) * g_tiles_all * 16);
+                            up256(size_t(L.qb) * g_tiles_all * 16);  // (the chunk-mask layout of the pair sweep is no larger)
   if (fused_need > up256(size_t(L.qb) * L.Gp * 4)) rank_fused = false;
-  if (rank_fused)
+  if (rank_fused && !pair)
     SPN_CUDA_CHECK(cudaFuncSetAttribute(sim_tc_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 
   for (int qb0 = 0; qb0 < Q; qb0 += L.qb) {
@@ -1235,6 +1522,10 @@ int tc_run(bool rank_mode, const float* q, const float* g, int Q, int G, int D, 
     gp.g_tiles = int((grows + kBN - 1) / kBN);
     gp.nterms = 3;
     gp.scores = scores;
+    gp.tile_n = tile_n;
+    gp.q_tiles2 = (qn + 2 * kBM - 1) / (2 * kBM);
+    gp.g_tiles2 = int((grows + tile_n - 1) / tile_n);
+    gp.n_chunks = n_chunks;
     const long long n_tiles = (long long)gp.q_tiles * gp.g_tiles;
     const int grid = int(n_tiles < sms ? n_tiles : sms);
     RowParams r = rp;
@@ -1259,14 +1550,26 @@ int tc_run(bool rank_mode, const float* q, const float* g, int Q, int G, int D, 
       f.M1 = M1; f.g_tiles = gp.g_tiles; f.r = r;
       const int rblocks = (qn + kRowWarps - 1) / kRowWarps;
       rank_prep_kernel<<<(qn + 31) / 32, 32, 0, stream>>>(f);
+      f.umask32 = pair ? reinterpret_cast<uint32_t*>(f.umask) : nullptr;
+      f.n_chunks = n_chunks;
       gp.thr = f.thr; gp.cols = f.cols; gp.col_s = f.col_s; gp.M1 = M1; gp.skip = f.skip; gp.umask = f.umask; gp.rank = r.rank;
-      sim_tc_gemm_kernel<false, true><<<grid, kTcThreads, smem, stream>>>(tqh, tql, tgh, tgl, ts, gp);
+      gp.umask32 = f.umask32;
+      if (pair) {
+        if ((rc = launch_pair_sweep(2, gp)) != SPN_OK) return rc;
+      } else {
+        sim_tc_gemm_kernel<false, true><<<grid, kTcThreads, smem, stream>>>(tqh, tql, tgh, tgl, ts, gp);
+      }
       rank_resolve_kernel<<<rblocks, kRowWarps * 32, 0, stream>>>(f);
       SPN_CUDA_CHECK(cudaGetLastError());
       continue;
     }
-    if (T == 1) sim_tc_gemm_kernel<false><<<grid, kTcThreads, smem, stream>>>(tqh, tql, tgh, tgl, ts, gp);
-    else        sim_tc_gemm_kernel<true><<<grid, kTcThreads, smem, stream>>>(tqh, tql, tgh, tgl, ts, gp);
+    if (pair) {
+      if ((rc = launch_pair_sweep(T == 1 ? 0 : 1, gp)) != SPN_OK) return rc;
+    } else if (T == 1) {
+      sim_tc_gemm_kernel<false><<<grid, kTcThreads, smem, stream>>>(tqh, tql, tgh, tgl, ts, gp);
+    } else {
+      sim_tc_gemm_kernel<true><<<grid, kTcThreads, smem, stream>>>(tqh, tql, tgh, tgl, ts, gp);
+    }
     SPN_CUDA_CHECK(cudaGetLastError());
 
     if (rank_mode) {
