@@ -102,6 +102,32 @@ class DeviceBank:
     def device(self) -> torch.device:
         return self.data.device
 
+    # ---- tensor-like no-ops, so that reference code written for a CPU tensor bank keeps working unchanged when the
+    # attribute holds a resident bank: `self.target_bank.detach().to(self.device)` (clip4cir/models_negplus.py:138,
+    # blip4cir/models.py:102, tgcir/models.py:279, blip24cir/models.py:119) and the gather `target_feats_all[target_indexs]`
+    # (models_negplus.py:140; its result is unused there)
+    def detach(self) -> "DeviceBank":
+        return self
+
+    def to(self, device=None, *args, **kwargs) -> "DeviceBank":
+        if device is not None and not isinstance(device, torch.dtype) and torch.device(device).type == "cuda" and \
+                torch.device(device).index not in (None, self.data.device.index):
+            raise SpnError("DeviceBank", -7, f"the bank is resident on {self.data.device}; build another DeviceBank for {device}")
+        return self
+
+    @property
+    def shape(self):
+        return (self.N, self.D) if self.T == 1 else (self.N, self.T, self.D)
+
+    def __len__(self) -> int:
+        return self.N
+
+    def __getitem__(self, idx) -> torch.Tensor:
+        """rows of the resident bank as fp32 (``[len, D]``, or ``[len, T, D]`` for multi-token banks)"""
+        idx = torch.as_tensor(idx, device=self.data.device)
+        rows = self.data.view(self.N, self.T, self.D)[idx].float()
+        return rows.squeeze(-2) if self.T == 1 else rows
+
     @classmethod
     def from_tensor(cls, bank: torch.Tensor, device: Union[str, torch.device] = "cuda", *, shard_rank: int = 0,
                     shard_world: int = 1) -> "DeviceBank":

@@ -143,3 +143,31 @@ def test_query_assemble_rejects_bad_index_loudly():
     idx = torch.tensor([0, 3, 10, -1], device=DEV)
     q16, q32, inv = spn.query_assemble(refer, idx, text)
     assert torch.isfinite(q32[:2]).all() and torch.isnan(q32[2:]).all() and torch.isnan(inv[2:]).all()
+
+
+def test_device_bank_is_tensor_like_for_unchanged_reference_code():
+    """Reference methods kept verbatim around the swapped loss (blip4cir/models.py:95-105, tgcir/models.py:272-282: their own
+    fusion network, then `self.target_bank.detach().to(self.device)` and `infonce_loss`) must run with a resident bank."""
+    q, bank, labels = synth.make_bank_case(64, 900, 128, 1, "S", 54)
+
+    class Model(compat.BankLossMixin):
+        device, tau, plus = torch.device(DEV), 0.02, False
+
+        def bank_large_step(self, loss, query_feats, indexs, target_indexs, refer_indexs=None):  # tgcir-style body
+            target_feats_all = self.target_bank.detach().to(self.device)
+            target_indexs = target_indexs.to(self.device)
+            target_feats = target_feats_all[target_indexs]  # the reference's (unused) gather
+            assert target_feats.shape == (64, 128)
+            loss["bank_loss"] = self.infonce_loss(query_feats, target_feats_all, target_indexs, tau=self.tau)
+
+    m = Model()
+    m.set_banks(torch.zeros(4, 128), bank)
+    assert m.target_bank.shape == (900, 128) and len(m.target_bank) == 900
+    qd = q.to(DEV).requires_grad_(True)
+    loss = {}
+    m.bank_large_step(loss, qd, None, labels)
+    loss["bank_loss"].backward()
+    o_loss, o_dq, _ = obank.infonce_loss_and_grads(q, bank, labels, 0.02, dtype=torch.float64)
+    assert abs(loss["bank_loss"].item() - o_loss.item()) <= 1e-2 * max(abs(o_loss.item()), 1e-3)
+    assert rel_l2(qd.grad, o_dq) < 1e-2
+    np.testing.assert_allclose(m.target_bank[labels[:5]].cpu().numpy(), bank[labels[:5]].to(torch.bfloat16).float().numpy())
