@@ -400,6 +400,21 @@ class _BankCEFused(torch.autograd.Function):
         return dq, dtau, None, None, None, None
 
 
+_warned_raw_bank = False
+
+
+def _warn_raw_bank(bank: torch.Tensor) -> None:
+    """A raw tensor bank is uploaded, cast to bf16 and scanned for its max row norm on EVERY call (the reference's per-step
+    `.to(device)`, models_negplus.py:138, made worse): fine for tests, a bug in a training loop.  Said once."""
+    global _warned_raw_bank
+    if not _warned_raw_bank and bank.numel() >= (1 << 22):
+        import warnings
+        warnings.warn("spn4cir_b200: a raw tensor was passed as the memory bank; it is re-uploaded and re-cast on every call. "
+                      "Build a DeviceBank once (DeviceBank.from_tensor / from_file, BankLossMixin.set_banks / load_banks).",
+                      RuntimeWarning, stacklevel=3)
+        _warned_raw_bank = True
+
+
 def _prep_labels(labels: Optional[torch.Tensor], B: int, dev: torch.device) -> torch.Tensor:
     if labels is None:  # models_negplus.py:152-153
         return torch.arange(B, dtype=torch.int64, device=dev)
@@ -430,6 +445,7 @@ def bank_infonce(query_features: torch.Tensor, bank: Union[DeviceBank, torch.Ten
     if query_features.dim() != 2:
         raise SpnError("bank_infonce", -1, f"query_features must be [B, D], got {tuple(query_features.shape)}")
     if not isinstance(bank, DeviceBank):
+        _warn_raw_bank(bank)
         bank = DeviceBank.from_tensor(bank, query_features.device)
     if bank.D != query_features.shape[1]:
         raise SpnError("bank_infonce", -1, f"feature dims differ: q {query_features.shape[1]} vs bank {bank.D}")
