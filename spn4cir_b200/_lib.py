@@ -59,13 +59,38 @@ def _stale() -> bool:
     return any(p.stat().st_mtime > t for p in deps)
 
 
+class build_lock:
+    """Exclusive inter-process lock around a build (the ranks of a torchrun job may all find the library stale at once;
+    they must not write the same object files concurrently: the first one builds, the others wait and find it fresh)."""
+
+    def __enter__(self):
+        import fcntl
+        (REPO_ROOT / "build").mkdir(parents=True, exist_ok=True)
+        self.f = open(REPO_ROOT / "build" / ".lock", "w")
+        fcntl.flock(self.f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        fcntl.flock(self.f, fcntl.LOCK_UN)
+        self.f.close()
+        return False
+
+
 def build_library(force: bool = False, verbose: bool = False, extra_flags=(), out: Path = None) -> Path:
     """Compile csrc/*.cu into spn4cir_b200/libspn_b200.so (sm_100a). Cross-compiles without a GPU.
     One nvcc -c per source (in parallel, objects cached under build/ by mtime), then one link."""
-    from concurrent.futures import ThreadPoolExecutor
     out = Path(out) if out is not None else LIB_PATH
     if out == LIB_PATH and not force and not _stale():
         return LIB_PATH
+    with build_lock():
+        if out == LIB_PATH and not force and not _stale():  # another process built it while this one waited
+            return LIB_PATH
+        return _build_library_locked(force, verbose, extra_flags, out)
+
+
+def _build_library_locked(force: bool, verbose: bool, extra_flags, out: Path) -> Path:
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = _nvcc()
     flags = [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags)
     tag = "obj" if not extra_flags else "obj_" + "".join(c if c.isalnum() else "_" for c in "".join(extra_flags))

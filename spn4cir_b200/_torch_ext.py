@@ -13,7 +13,7 @@ import subprocess
 import threading
 from pathlib import Path
 
-from ._lib import CSRC_DIR, HEADER_PATH, LIB_PATH, PKG_DIR, REPO_ROOT, SpnError, build_library
+from ._lib import CSRC_DIR, HEADER_PATH, LIB_PATH, PKG_DIR, REPO_ROOT, SpnError, build_library, build_lock
 
 EXT_PATH = PKG_DIR / "_spn_torch.so"
 EXT_SRC = PKG_DIR / "csrc_torch" / "spn_torch.cpp"
@@ -33,9 +33,16 @@ def build_torch_extension(force: bool = False, verbose: bool = False) -> Path:
     """g++ -shared csrc_torch/spn_torch.cpp -> spn4cir_b200/_spn_torch.so (works without a GPU)."""
     if not force and not _stale():
         return EXT_PATH
+    build_library()  # the extension links against libspn_b200.so
+    with build_lock():
+        if not force and not _stale():  # another process built it while this one waited for the lock
+            return EXT_PATH
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose: bool) -> Path:
     import torch
     from torch.utils import cpp_extension as ce
-    build_library()  # the extension links against libspn_b200.so
     cxx = os.environ.get("CXX") or shutil.which("g++")
     if not cxx:
         raise SpnError("build", -5, "g++ not found: the torch extension cannot be built")
