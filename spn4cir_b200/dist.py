@@ -203,7 +203,7 @@ def _sharded_sweep(q_local, bank, labels_local, inv_tau, eps, tau_grad, group, c
         # cold temperature, or label smoothing over a multi-token bank (the fused finalize cannot form sum_n s_n from column
         # sums there): forward statistics with an exact running maximum + recompute backward, merged across the ranks
         return _sharded_two_pass(q_local, bank, labels_local, inv_tau, eps, tau_grad, group)
-    if compute is None and symm_path_ok(bank, q_local.shape[0], group):
+    if compute is None and symm_path_ok(bank, q_local.shape[0], group) and _symm_setup_ok(bank, q_local.shape[0], group):
         return _sharded_sweep_symm(q_local, bank, labels_local, inv_tau, eps, tau_grad, group)
     compute = compute or _CudaShardCompute()
     rank, world = _world(group)
@@ -369,6 +369,27 @@ def _symm_exchange(bank, B: int, group) -> "SymmExchange":
         x = cache[key] = SymmExchange(bank, B, group)
         _exchanges.append((B, bank.N, bank.D))
     return x
+
+
+def _symm_setup_ok(bank, B: int, group) -> bool:
+    """Create the windows of (bank, B) on first use and AGREE across the ranks that everybody succeeded (one MIN all-reduce,
+    once): if any rank could not map its peers (no P2P, allocation failure) every rank takes the NCCL exchange instead."""
+    cache = bank.__dict__.setdefault("_symm_setup", {})
+    key = (B, None if group is None else id(group))
+    if key not in cache:
+        ok = 1
+        try:
+            _symm_exchange(bank, B, group)
+        except Exception as exc:  # noqa: BLE001 -- any failure means "not available here"
+            import warnings
+            warnings.warn(f"spn4cir_b200: symmetric-memory exchange unavailable ({exc!r}); using the NCCL exchange", RuntimeWarning)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=bank.data.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        cache[key] = bool(flag.item())
+        if not cache[key]:
+            _symm_probe[id(group)] = False
+    return cache[key]
 
 
 def release_exchanges(bank=None) -> None:
