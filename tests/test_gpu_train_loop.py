@@ -28,7 +28,7 @@ class ToyReference(nn.Module):
         super().__init__()
         self.text_proj = nn.Linear(dim, dim)
         self.tau, self.plus = tau, plus
-        self.refer_bank, self.target_bank = refer_bank, target_bank
+        self.refer_bank, self.target_bank = refer_bank.to(DEV), target_bank.to(DEV)  # (the reference keeps them on the CPU)
         self.crossentropy_criterion = nn.CrossEntropyLoss()
         self.to(DEV)
 
