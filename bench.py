@@ -617,6 +617,30 @@ def run_ours(args, cfg):
                     sec[key] = bench_shape(spn, timer, dev, peaks, tag, b, n, d, t, ta, min(steps, 20), kernel_split=split)
                 except Exception as exc:  # the headline line must survive a failure of a secondary workload
                     sec[key] = {"workload": tag, "error": repr(exc)}
+            # CPU reference beside the secondary configs: C3 at full size, C4 through the reference's per-sample loop
+            # (blip2_qformer_cir_align_prompt.py:254-265, restated in oracle.bank_ce) at a reduced bank, scaled linearly
+            try:
+                c3 = synth.CONFIGS["C3"]
+                cb3, _ = time_cpu_reference(c3, budget_s=6.0, steps=2, warmup=1)
+                sec["c3"]["cpu_reference"] = cb3
+                from oracle import bank_ce as obank
+                c4 = synth.CONFIGS["C4"]
+                n_red = 2000
+                f4, bank4, lab4 = synth.make_bank_case(c4["B"], n_red, c4["D"], c4["T"], "S", 0)
+                torch.set_num_threads(os.cpu_count() or 1)
+                ff = f4.clone().requires_grad_(True)
+                obank.blip2_stage2_loss_loop(ff, bank4, lab4, torch.tensor(c4["tau"])).backward()
+                t0 = time.perf_counter()
+                ff = f4.clone().requires_grad_(True)
+                obank.blip2_stage2_loss_loop(ff, bank4, lab4, torch.tensor(c4["tau"])).backward()
+                t_red = time.perf_counter() - t0
+                t_full = t_red * c4["N"] / n_red
+                sec["c4_blip2"]["cpu_reference"] = {
+                    "value": c4["B"] / t_full, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+                    "sample": f"1 timed step (+1 warm-up) of the per-sample loop, B={c4['B']} x N'={n_red} of {c4['N']} entries x 32 x 256 "
+                              f"fp32 fwd+bwd, scaled linearly to N={c4['N']}"}
+            except Exception as exc:
+                sec["cpu_reference_error"] = repr(exc)
             line["secondary"] = sec
             try:
                 line["retrieval"] = bench_retrieval(dev, args, peaks, timer)
