@@ -29,6 +29,7 @@ struct BankCEParams {
   int qt_blocks;     // two-pass: leading k-blocks of the Q tile that live in TMEM (TS operand) instead of shared memory
   int pdl;           // launched with programmatic stream serialization (spn_bank_ce_step chains prep -> sweep -> finalize)
   int two_pass;      // fused CTA-pair kernel: second pass over the chunk for dq[:, X:D) (no S recompute)
+  int tma_single;    // fused CTA-pair kernel, single pass (D <= 320 or D-split): TMA reduce-add epilogue instead of per-thread reds
   int stages2;       // second-pass ring depth (stages of 2 blocks)
   unsigned short* p_scratch;  // two-pass: bf16 global scratch for P~, tile-major [q_tile][bank tile][128][128]
   long long p_ld;    // its row stride in elements (n_tiles * 128)

@@ -356,6 +356,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const bool do_pstore = kTP && p.two_pass && !(p.hg & 4);  // 4 = no P~ stores (timing experiments only)
   const bool do_red = !(p.hg & 8);                          // 8 = no dq reductions, 16 = plain stores instead
   const bool tma_epi = kTP && p.two_pass && !(p.hg & 32);   // 32 = per-thread red.global.add instead of TMA reduce
+  const bool tma_epi1 = kTP && !p.two_pass && p.tma_single && !(p.hg & 32);  // the same epilogue for the single-pass pair kernel
   static_assert(CG == 1 || (CG == 2 && MODE >= 1), "the CTA-pair variant exists for the backward / fused modes only");
   extern __shared__ uint8_t smem_raw[];
   EV_START
@@ -417,6 +418,7 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       tma_prefetch_desc(dq_map);
       tma_prefetch_desc(&tmap_bank3);
     }
+    if (kTP && !p.two_pass && p.tma_single) tma_prefetch_desc(dq_map);
   }
   if (warp == 1) {
     if (CG == 2) {
@@ -1070,6 +1072,10 @@ bank_ce_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         // (the reductions themselves drain while pass 2 runs; TMEM is released after the last read)
         tma_epilogue(0u, my_blocks * 2, 0, sm.q + size_t(region_blocks - 2) * kBlockBytes + (warp - 2u) * 4096u, 1, do_pass2,
                      !do_pass2);
+      } else if (ntl > 0 && tma_epi1) {
+        // single-pass pair kernel: every MMA has retired and every TMA load was consumed (o_full), so the whole Q / ring
+        // region is dead -- four 4 KiB slots per warp from its base, as in the final epilogue of the two-pass kernel
+        tma_epilogue(0u, my_blocks * 2, ds * p.ow_blocks * 64, sm.q + (warp - 2u) * 16384u, 4, false, true);
       } else if (ntl > 0) {
         for (int c = int(half); c < my_blocks * 2; c += 2) {
           tmem_ld_32x32b_x32(t_row + uint32_t(c) * 32u, x0);
@@ -1707,7 +1713,11 @@ static int fused_launch(const void* q, const void* bank, const long long* labels
   tpf = tb;
   PeerMaps pm{};
   if (plan.two_pass && (rc = make_tmap_bf16_3d(&tpf, bank, uint64_t(N) * T, uint64_t(D), kBN)) != SPN_OK) return rc;
-  if (plan.two_pass && !home_rows && (rc = make_tmap_f32_2d(&tdq, o_acc, uint64_t(B), uint64_t(D), 32)) != SPN_OK) return rc;
+  // TMA reduce-add epilogue: the two-pass kernel and the single-pass pair kernel (needs >= 8 x 16 KiB of dead ring: always
+  // true for the single-pass plans, whose ring has >= 8 stages)
+  const bool tma_single = !plan.two_pass && plan.cg == 2 && (plan.kblocks - plan.qt_blocks + plan.stages) >= 8 &&
+                          !(getenv("SPN_DEBUG_TMA_SINGLE") && atoi(getenv("SPN_DEBUG_TMA_SINGLE")) == 0);
+  if ((plan.two_pass || tma_single) && !home_rows && (rc = make_tmap_f32_2d(&tdq, o_acc, uint64_t(B), uint64_t(D), 32)) != SPN_OK) return rc;
   if (plan.two_pass &&
       (rc = make_tmap_bf16_3d(&tp, ws, uint64_t(plan.q_tiles) * plan.n_tiles * kBM, uint64_t(kBN), kBM)) != SPN_OK)
     return rc;
@@ -1722,7 +1732,7 @@ static int fused_launch(const void* q, const void* bank, const long long* labels
       p.dq_peers[h] = o_peers[h];
       p.l_peers[h] = l_peers[h];
       p.es_peers[h] = es_peers ? es_peers[h] : nullptr;
-      if (plan.two_pass && (rc = make_tmap_f32_2d(&pm.m[h], o_peers[h], uint64_t(home_rows), uint64_t(D), 32)) != SPN_OK) return rc;
+      if ((plan.two_pass || tma_single) && (rc = make_tmap_f32_2d(&pm.m[h], o_peers[h], uint64_t(home_rows), uint64_t(D), 32)) != SPN_OK) return rc;
     }
     p.home_rows = home_rows;
   }
@@ -1737,6 +1747,7 @@ static int fused_launch(const void* q, const void* bank, const long long* labels
   p.row_base = row_base; p.labels = labels; p.ref = ref; p.gscale = 1.f; p.dq = o_acc; p.dlogit_dot = es_acc;
   p.l_acc = l_acc; p.st_out = s_t; p.lbl_row_out = lbl_row;
   p.two_pass = plan.two_pass; p.stages2 = plan.stages2; p.qt_blocks = plan.qt_blocks; p.pdl = pdl; p.p_scratch = static_cast<unsigned short*>(ws);
+  p.tma_single = tma_single ? 1 : 0;
   p.p_ld = (long long)plan.n_tiles * kBN;
   const bool extra = home_rows ? (es_peers != nullptr) : (es_acc != nullptr);
   rc = launch_mode<2>(plan.cg == 2, T, extra, tq, tb, tbh, tp, tdq, tpf, p, plan.grid, plan.smem_bytes, stream,
