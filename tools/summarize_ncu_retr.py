@@ -24,7 +24,7 @@ for r in rows[2:]:
     st = sorted(((float(r[hdr.index(h)].replace(",", "")), h) for h in stall), reverse=True)[:4]
     d["top_stalls_per_issue"] = {h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""): v for v, h in st}
     out.append(d)
-summary = {"source": "ncu --set full --clock-control none --import-source on -k regex:'row_|sim_tc_gemm|target_score_warp' "
+summary = {"source": "ncu --set full --clock-control none --import-source on -k regex:'row_|sim_tc_gemm|target_score_warp|rank_prep|rank_resolve|split_rows' "
                      "(python tools/prof_retr.py), C2: 4181 queries x 2297 gallery x 640-d; launches in order: "
                      "top-50 exact values, top-50 index-exact, rank-of-target (+ their sweeps)",
            "kernels": out}
