@@ -446,17 +446,36 @@ def run_ours(args, cfg):
         from spn4cir_b200.ops import _prep_labels
         exchange = {"path": "symmetric-memory (NVLink peer stores / loads / TMA reduce-add, no NCCL)" if sdist.symm_path_ok(bank, B) else "NCCL"}
         if sdist.symm_path_ok(bank, B):
-            acc = [0.0] * 5
-            for _ in range(steps):
-                timer.flush.zero_()
-                evs = []
-                sdist._sharded_sweep_symm(q_dev, bank, _prep_labels(labels_dev, B, dev), 1.0 / tau, 0.0, False, None, stage_events=evs)
-                torch.cuda.synchronize(dev)
-                for i in range(5):
-                    acc[i] += evs[i].elapsed_time(evs[i + 1])
-            names = ["home_prologue_ms (cast + peer stores of q/ref/labels + peer loads of the target rows)", "barrier_1_ms",
-                     "sweep_with_remote_reduce_epilogue_ms", "barrier_2_ms", "finalize_ms"]
-            exchange["stages"] = {n: agree_max(a / steps) for n, a in zip(names, acc)}
+            default_mode = sdist.symm_exchange_mode(B, world, bank.N, D, bank.T)
+            exchange["mode"] = default_mode
+            stage_names = {
+                "push": ["home_prologue_ms (cast + peer stores of q/ref/labels + peer loads of the target rows)", "barrier_1_ms",
+                         "sweep_with_remote_reduce_epilogue_ms", "barrier_2_ms", "finalize_ms"],
+                "pull": ["home_prologue_ms (cast + peer stores of q/ref/labels + peer loads of the target rows)", "barrier_1_ms",
+                         "init_plus_sweep_local_accumulation_ms", "barrier_2_ms", "pull_reduce_ms (peer loads of this rank's rows)",
+                         "finalize_ms"]}
+            push_ok = sdist._push_shape_ok(B, world)
+            for mode in (("push", "pull") if push_ok else ("pull",)):
+                names = stage_names[mode]
+                acc = [0.0] * len(names)
+                for it in range(steps + 2):
+                    timer.flush.zero_()
+                    evs = []
+                    sdist._sharded_sweep_symm(q_dev, bank, _prep_labels(labels_dev, B, dev), 1.0 / tau, 0.0, False, None,
+                                              stage_events=evs, mode=mode)
+                    torch.cuda.synchronize(dev)
+                    if it >= 2:
+                        for i in range(len(names)):
+                            acc[i] += evs[i].elapsed_time(evs[i + 1])
+                exchange["stages_" + mode] = {n: agree_max(a / steps) for n, a in zip(names, acc)}
+                os.environ["SPN_EXCHANGE"] = mode
+                for _ in range(3):
+                    step_primitive(q_dev, labels_dev)
+                barrier()
+                exchange[mode + "_step_ms"] = agree_max(timer.run(lambda: step_primitive(q_dev, labels_dev), steps)) * 1e3
+                os.environ.pop("SPN_EXCHANGE")
+                barrier()
+            exchange["stages"] = dict(exchange["stages_" + default_mode])
             exchange["stages"]["sweep_local_accumulation_ms"] = None  # filled below from the kernel timed alone
             os.environ["SPN_EXCHANGE"] = "nccl"
             for _ in range(3):
@@ -544,6 +563,7 @@ def run_ours(args, cfg):
             except Exception:
                 pass
         symm = sharded and exchange is not None and "stages" in exchange
+        pull = symm and exchange.get("mode") == "pull"
         par = ("single GPU, whole bank resident" if world == 1 else
                f"bank row-sharded x{world} ({bank.N} rows/rank), queries data-parallel, exchange over peer-mapped symmetric memory (no NCCL call): "
                f"home prologue kernel stores the bf16 queries into every rank's window and loads the target rows from the owner's shard -> "
@@ -580,8 +600,10 @@ def run_ours(args, cfg):
                                 "around the K steps, taken after ~0.75 s of the same pipelined loop (sustained clocks, as `value`); the bank stays resident in HBM",
                         "serial": {"value": (B * world) / t_e2e_serial, "ms_per_step": t_e2e_serial * 1e3,
                                    "note": "the same step with its copies serialised on one stream, L2 flushed before each (latency of one isolated step)"}},
-                "gpu_launches": ((5 if symm else 7) if sharded else 3) * steps,  # + 1 torch elementwise kernel (dq_unit * upstream grad) in backward
-                "gpu_launches_detail": ("per step: shard_home_prologue_kernel, peer_barrier_kernel, bank_ce_kernel<2> (peer windows), "
+                "gpu_launches": (((7 if pull else 5) if symm else 7) if sharded else 3) * steps,  # + 1 torch elementwise kernel (dq_unit * upstream grad) in backward
+                "gpu_launches_detail": ("per step: shard_home_prologue_kernel, peer_barrier_kernel, fused_init_kernel, bank_ce_kernel<2>, "
+                                        "peer_barrier_kernel, shard_pull_kernel, fused_finalize_kernel (no NCCL call)" if symm and pull else
+                                        "per step: shard_home_prologue_kernel, peer_barrier_kernel, bank_ce_kernel<2> (peer windows), "
                                         "peer_barrier_kernel, fused_finalize_kernel (no NCCL call)" if symm else
                                         "per step: cast_bf16_kernel, prep_query_kernel, fused_init_kernel, bank_ce_kernel<2>, shard_pack_kernel, "
                                         "shard_fold_kernel, fused_finalize_kernel (+ 5 NCCL collectives)"
@@ -594,7 +616,7 @@ def run_ours(args, cfg):
             exchange["step_minus_local_sweep_ms"] = (t_dev - t_fused) * 1e3
             if "stages" in exchange:
                 exchange["stages"]["sweep_local_accumulation_ms"] = t_fused * 1e3
-                exchange["symm_step_ms"] = t_auto * 1e3  # the step primitive through the NCCL-free exchange (vs nccl_step_ms)
+                exchange["symm_step_ms"] = t_auto * 1e3  # the step primitive through the default NCCL-free exchange (vs nccl_step_ms)
             line["exchange"] = exchange
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = time_cpu_reference(cfg, budget_s=20.0, steps=3, warmup=1)

@@ -205,6 +205,14 @@ int spn_bank_ce_fused_peers(const void* q_bf16, const void* bank_bf16, const int
                             int B, int64_t N, int D, int T, int64_t row_base, int home_rows, int world,
                             float* const* o_windows, float* const* l_windows, float* const* es_windows, float* s_t,
                             int64_t* lbl_row, void* ws, size_t ws_bytes, void* stream);
+/* The "pull" form of the same reduce-scatter (fewer NVLink bytes when many CTA pairs share a query tile: small batches):
+ *   spn_shard_home_prologue -> spn_peer_barrier -> spn_bank_ce_fused(init = 1) into this rank's OWN peer-readable buffers
+ *   o_all [world * B, D], l_all, es_all [world * B] -> spn_peer_barrier -> spn_shard_pull -> spn_bank_ce_finalize.
+ * spn_shard_pull: o_out[b] = sum_r o_peers[r][rank * B + b] (r = 0 .. world - 1 in that order: loads over NVLink, no atomics,
+ * a deterministic cross-rank sum), likewise l_out and es_out (nullable, with es_peers).  Reference anchor as above
+ * (zscir/models_bank.py:90-101,130-134: one loss over ALL bank rows). */
+int spn_shard_pull(const float* const* o_peers, const float* const* l_peers, const float* const* es_peers, int rank, int world,
+                   int B, int D, float* o_out, float* l_out, float* es_out, void* stream);
 
 /* One whole training step on one GPU (un-sharded bank, row_base = 0) in a single call:
  * spn_bank_ce_prep (+ zeroing of the accumulators) -> spn_bank_ce_fused -> spn_bank_ce_finalize (the target row is read

@@ -155,6 +155,7 @@ _SIGNATURES = {
                                 c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p],
     "spn_peer_barrier": [c_void_p, c_int, c_int, c_uint32, c_void_p],
+    "spn_shard_pull": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "spn_bank_ce_fused_peers": [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int64, c_int, c_int, c_int64, c_int,
                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     "spn_bank_ce_step": [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float, c_int, c_int64, c_int,

@@ -194,6 +194,15 @@ int spn_peer_barrier(void* const* flag_peers, int rank, int world, uint32_t epoc
   return peer_barrier(flag_peers, rank, world, epoch, as_stream(stream));
 }
 
+int spn_shard_pull(const float* const* o_peers, const float* const* l_peers, const float* const* es_peers, int rank, int world,
+                   int B, int D, float* o_out, float* l_out, float* es_out, void* stream) {
+  SPN_REQUIRE(o_peers && l_peers && o_out && l_out && (!es_out || es_peers), SPN_ERR_BAD_ARG, "spn_shard_pull: NULL pointer");
+  SPN_REQUIRE(aligned16(o_out), SPN_ERR_BAD_ALIGN, "spn_shard_pull: o_out must be 16-byte aligned");
+  int rc = require_sm100();
+  if (rc != SPN_OK) return rc;
+  return shard_pull(o_peers, l_peers, es_peers, rank, world, B, D, o_out, l_out, es_out, as_stream(stream));
+}
+
 int spn_bank_ce_fused_peers(const void* q_bf16, const void* bank_bf16, const int64_t* labels, const float* ref, float inv_tau,
                             int B, int64_t N, int D, int T, int64_t row_base, int home_rows, int world,
                             float* const* o_windows, float* const* l_windows, float* const* es_windows, float* s_t,

@@ -128,6 +128,8 @@ int shard_home_prologue(const void* q_src, int dtype, const long long* labels, v
                         float* s_t, float* ref_out, float* tgt_rows, float* o_win, float* l_win, float* es_win,
                         cudaStream_t stream);
 int peer_barrier(void* const* flag_peers, int rank, int world, unsigned int epoch, cudaStream_t stream);
+int shard_pull(const float* const* o_peers, const float* const* l_peers, const float* const* es_peers, int rank, int world, int B,
+               int D, float* o_out, float* l_out, float* es_out, cudaStream_t stream);
 
 // sampled-negatives loss (part_ce.cu)
 int part_ce(const void* q_src, int dtype, const void* bank, const long long* cand, float inv_tau, int B, int K1, int D,

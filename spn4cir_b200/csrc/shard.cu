@@ -220,6 +220,44 @@ __global__ void peer_barrier_kernel(const PeerPtrs flag_peers, int rank, int wor
   __threadfence_system();
 }
 
+
+// The reduce-scatter of the "pull" exchange: every rank swept its shard for ALL world * B queries into its OWN (peer-readable)
+// buffers o_all [world * B, D], l_all, es_all; the home rank of rows [rank * B, rank * B + B) now LOADS those rows from every
+// rank over NVLink and sums them in the fixed order r = 0 .. world - 1 (no atomics: the cross-rank sum is deterministic).
+// All loads of one element are issued before the first add (<= 8 independent 16-byte loads in flight per thread).
+__global__ void __launch_bounds__(256)
+shard_pull_kernel(const PeerPtrs o_peers, const PeerPtrs l_peers, const PeerPtrs es_peers, int world, int rank, int B, int D,
+                  float* __restrict__ o_out, float* __restrict__ l_out, float* __restrict__ es_out) {
+  const size_t n4 = size_t(B) * D / 4, base4 = size_t(rank) * B * D / 4;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x) {
+    float4 v[kMaxPeers];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < world) v[r] = __ldcg(static_cast<const float4*>(o_peers.p[r]) + base4 + i);
+    float4 acc = v[0];
+#pragma unroll
+    for (int r = 1; r < kMaxPeers; ++r)
+      if (r < world) {
+        acc.x += v[r].x;
+        acc.y += v[r].y;
+        acc.z += v[r].z;
+        acc.w += v[r].w;
+      }
+    reinterpret_cast<float4*>(o_out)[i] = acc;
+  }
+  if (blockIdx.x == 0) {
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+      float l = 0.f, es = 0.f;
+      for (int r = 0; r < world; ++r) {
+        l += __ldcg(static_cast<const float*>(l_peers.p[r]) + size_t(rank) * B + b);
+        if (es_out) es += __ldcg(static_cast<const float*>(es_peers.p[r]) + size_t(rank) * B + b);
+      }
+      l_out[b] = l;
+      if (es_out) es_out[b] = es;
+    }
+  }
+}
+
 }  // namespace
 
 int shard_home_prologue(const void* q_src, int dtype, const long long* labels, void* const* bank_peers,
@@ -260,6 +298,25 @@ int peer_barrier(void* const* flag_peers, int rank, int world, unsigned int epoc
     fp.p[r] = flag_peers[r];
   }
   peer_barrier_kernel<<<1, 32, 0, stream>>>(fp, rank, world, epoch);
+  SPN_CUDA_CHECK(cudaGetLastError());
+  return SPN_OK;
+}
+
+int shard_pull(const float* const* o_peers, const float* const* l_peers, const float* const* es_peers, int rank, int world, int B,
+               int D, float* o_out, float* l_out, float* es_out, cudaStream_t stream) {
+  SPN_REQUIRE(B > 0 && D > 0 && D % 4 == 0, SPN_ERR_BAD_SHAPE, "shard_pull: bad shape B=%d D=%d", B, D);
+  SPN_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, SPN_ERR_BAD_ARG, "shard_pull: bad rank / world");
+  PeerPtrs op{}, lp{}, ep{};
+  for (int r = 0; r < world; ++r) {
+    SPN_REQUIRE(o_peers[r] && l_peers[r] && (!es_out || (es_peers && es_peers[r])), SPN_ERR_BAD_ARG, "shard_pull: NULL buffer of rank %d", r);
+    op.p[r] = const_cast<float*>(o_peers[r]);
+    lp.p[r] = const_cast<float*>(l_peers[r]);
+    ep.p[r] = es_out ? const_cast<float*>(es_peers[r]) : nullptr;
+  }
+  const long long n4 = (long long)B * D / 4;
+  const long long blocks = (n4 + 255) / 256;
+  const int grid = int(blocks < 148 * 8 ? blocks : 148 * 8);
+  shard_pull_kernel<<<grid, 256, 0, stream>>>(op, lp, ep, world, rank, B, D, o_out, l_out, es_out);
   SPN_CUDA_CHECK(cudaGetLastError());
   return SPN_OK;
 }

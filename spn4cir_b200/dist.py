@@ -243,6 +243,9 @@ def _sharded_sweep(q_local, bank, labels_local, inv_tau, eps, tau_grad, group, c
 #   home prologue (peer STORES of the bf16 query rows = the all-gather; peer LOADS of the target rows from the owner's
 #   shard = no MIN all-reduce, no second reduce-scatter)  ->  barrier  ->  fused sweep whose TMA reduce-add epilogue
 #   targets the home rank's window (= the reduce-scatter, inside the kernel)  ->  barrier  ->  finalize.
+# Short sweeps / batches that are not a multiple of 128 take the "pull" form instead (symm_exchange_mode): the sweep accumulates
+# into this rank's own peer-readable buffers, and after the barrier the home rank LOADS its rows from every rank and sums them
+# in rank order (shard_pull_kernel) -- fewer NVLink bytes when many CTA pairs share a query tile, no atomics across ranks.
 # torch.distributed._symmetric_memory only allocates the buffers and exchanges their handles (plumbing).
 def _align(x: int, a: int = 256) -> int:
     return (x + a - 1) // a * a
@@ -309,7 +312,8 @@ def make_bank_symmetric(bank, group=None) -> None:
 
 class SymmExchange:
     """Windows of one (bank shard, B) pair in symmetric memory: the query window qall [world * B, D] bf16 with its ref /
-    label metadata, this rank's accumulation windows o [B, D], l [B], es [B] fp32, and the barrier flags."""
+    label metadata, this rank's accumulation windows o [B, D], l [B], es [B] fp32, the barrier flags, and (pull exchange) this
+    rank's partial sums for all queries o_all [world * B, D], l_all, es_all."""
 
     def __init__(self, bank, B: int, group=None):
         import torch.distributed._symmetric_memory as symm_mem
@@ -320,7 +324,7 @@ class SymmExchange:
         Bt, D = self.Bt, self.D
         off, total = {}, 0
         for name, nbytes in (("qall", Bt * D * 2), ("ref", Bt * 4), ("lab", Bt * 8), ("o", B * D * 4), ("l", B * 4),
-                             ("es", B * 4), ("flags", 256)):
+                             ("es", B * 4), ("flags", 256), ("oall", Bt * D * 4), ("lall", Bt * 4), ("esall", Bt * 4)):
             off[name] = total
             total += _align(nbytes)
         self.buf = symm_mem.empty(total, dtype=torch.uint8, device=dev)
@@ -338,6 +342,10 @@ class SymmExchange:
         self.o_win = view("o", B * D * 4, torch.float32, (B, D))
         self.l_win = view("l", B * 4, torch.float32, (B,))
         self.es_win = view("es", B * 4, torch.float32, (B,))
+        # "pull" exchange: this rank's partial sums for ALL queries, read by the home ranks
+        self.o_all = view("oall", Bt * D * 4, torch.float32, (Bt, D))
+        self.l_all = view("lall", Bt * 4, torch.float32, (Bt,))
+        self.es_all = view("esall", Bt * 4, torch.float32, (Bt,))
         self.bank_ptrs = _ptr_array(bank.peer_ptrs)
         self.epoch = 0
         # local scratch of the step (not shared): target rows, s_t, ref of the local queries; s_t / lbl_row of the sweep
@@ -398,27 +406,59 @@ def release_exchanges(bank=None) -> None:
         bank.__dict__.pop("_symm_exchanges", None)
 
 
+def _push_shape_ok(B: int, world: int) -> bool:
+    """push: a 128-query tile must have ONE home rank and the sweep runs on CTA pairs (an even number of tiles)"""
+    return B % 128 == 0 and (world * B // 128) % 2 == 0
+
+
 def symm_path_ok(bank, B: int, group=None) -> bool:
-    """The NCCL-free exchange needs symmetric memory, B % 128 == 0 (a query tile has ONE home rank), world <= 8 and the
-    uniform ceil(n_total / world) sharding."""
+    """The NCCL-free exchange needs symmetric memory, world <= 8 and the uniform ceil(n_total / world) sharding (the push
+    form additionally B % 128 == 0 and an even number of query tiles; other batch sizes pull)."""
     import os
     rank, world = _world(group)
-    if os.environ.get("SPN_EXCHANGE", "symm") == "nccl" or world < 2 or world > 8 or B % 128 != 0 or (world * B // 128) % 2 != 0:
+    if os.environ.get("SPN_EXCHANGE", "symm") == "nccl" or world < 2 or world > 8:
         return False
     per = (bank.n_total + world - 1) // world
     return bank.row_base == rank * per and bank.N <= per and symmetric_memory_available(bank.data.device, group)
 
 
-def _sharded_sweep_symm(q_local, bank, labels_local, inv_tau, eps, tau_grad, group, stage_events=None):
-    """One sharded step over NVLink-mapped windows: 3 kernels + 2 device-side barriers, no NCCL call.
+PULL_BELOW_SWEEP_S = 0.7e-3  # sweeps estimated shorter than this pull (see symm_exchange_mode)
+
+
+def symm_exchange_mode(B: int, world: int, n_local: int = 0, D: int = 0, T: int = 1) -> str:
+    """"push" or "pull" -- how the partial sums reach the home rank (SPN_EXCHANGE=push / pull forces one).
+    push: every CTA pair's partial O block [256, D] is reduce-added into the home window by the sweep's TMA epilogue --
+          74 * 256 * D * 4 bytes per rank and step whatever the batch, all of it at the END of the sweep (every CTA pair
+          finishes at the same time): a ~50 us NVLink tail.
+    pull: the sweep accumulates locally, the home rank loads and sums its rows from every rank (B * D * 4 bytes per peer,
+          a deterministic cross-rank sum) -- two more launches, no batch-size constraint.
+    Measured on 8 GPUs (profiles/r02_notes_variance_and_exchange.md): equal at C5 (2.6 ms sweeps), pull 3.5 - 4 % faster at
+    C3 (0.12 ms sweeps).  Rule: short sweeps pull, long sweeps keep the reduce-scatter inside the sweep."""
+    import os
+    forced = os.environ.get("SPN_EXCHANGE", "symm")
+    if forced == "push" and not _push_shape_ok(B, world):
+        raise ValueError(f"SPN_EXCHANGE=push needs B % 128 == 0 and an even number of 128-query tiles (B={B}, world={world})")
+    if forced in ("push", "pull"):
+        return forced
+    if not _push_shape_ok(B, world):
+        return "pull"
+    per_pair = 4.0 if T == 1 else 2.0 * T + 2.0
+    sweep_s = per_pair * world * B * float(n_local) * D / 1.2e15  # ~ sustained tensor rate of the sweep
+    return "pull" if sweep_s < PULL_BELOW_SWEEP_S else "push"
+
+
+def _sharded_sweep_symm(q_local, bank, labels_local, inv_tau, eps, tau_grad, group, stage_events=None, mode=None):
+    """One sharded step over NVLink-mapped windows, no NCCL call.  push: 3 kernels + 2 device-side barriers; pull: 5 + 2.
     Returns (loss_mean_of_local_queries, dq_unit [B, D] fp32, dlogit_dot | None).
-    ``stage_events``: optional list that receives 6 timing events (start, after the home prologue, barrier 1, the sweep,
-    barrier 2, finalize) -- bench.py's exchange breakdown."""
+    ``stage_events``: optional list that receives the timing events (start, after the home prologue, barrier 1, the sweep,
+    barrier 2, [pull,] finalize) -- bench.py's exchange breakdown."""
     from ._lib import call
     from .ops import _TORCH2SPN, _ptr, _stream, fused_scratch
     B, D = q_local.shape
     dev = q_local.device
     x = _symm_exchange(bank, B, group)
+    if mode is None:
+        mode = symm_exchange_mode(B, x.world, bank.N, D, bank.T)
     qc = q_local.detach()
     if qc.dtype not in _TORCH2SPN:
         qc = qc.float()
@@ -445,11 +485,21 @@ def _sharded_sweep_symm(q_local, bank, labels_local, inv_tau, eps, tau_grad, gro
         x.barrier(st)  # every rank's queries / refs / labels have landed, every window is zeroed
         mark()
         ws, ws_bytes = fused_scratch(x.Bt, bank, dev)
-        call("spn_bank_ce_fused_peers", _ptr(x.qall), _ptr(bank.data), _ptr(x.lab_all), _ptr(x.ref_all), inv_tau, x.Bt, bank.N,
-             D, bank.T, bank.row_base, B, x.world, x.ptrs["o"], x.ptrs["l"], x.ptrs["es"] if tau_grad else None,
-             _ptr(x.sw_st), _ptr(x.sw_lbl), _ptr(ws), ws_bytes, st)
-        mark()
-        x.barrier(st)  # every rank's partial sums have been reduce-added into the home windows
+        if mode == "pull":
+            call("spn_bank_ce_fused", _ptr(x.qall), _ptr(bank.data), _ptr(x.lab_all), _ptr(x.ref_all), inv_tau, x.Bt, bank.N, D,
+                 bank.T, bank.row_base, 1, _ptr(x.o_all), _ptr(x.l_all), _ptr(x.sw_st), _ptr(x.sw_lbl),
+                 _ptr(x.es_all) if tau_grad else None, None, _ptr(ws), ws_bytes, st)
+            mark()
+            x.barrier(st)  # every rank's partial sums are complete in its own buffers
+            mark()
+            call("spn_shard_pull", x.ptrs["oall"], x.ptrs["lall"], x.ptrs["esall"] if tau_grad else None, x.rank, x.world, B, D,
+                 _ptr(x.o_win), _ptr(x.l_win), _ptr(x.es_win) if tau_grad else None, st)
+        else:
+            call("spn_bank_ce_fused_peers", _ptr(x.qall), _ptr(bank.data), _ptr(x.lab_all), _ptr(x.ref_all), inv_tau, x.Bt, bank.N,
+                 D, bank.T, bank.row_base, B, x.world, x.ptrs["o"], x.ptrs["l"], x.ptrs["es"] if tau_grad else None,
+                 _ptr(x.sw_st), _ptr(x.sw_lbl), _ptr(ws), ws_bytes, st)
+            mark()
+            x.barrier(st)  # every rank's partial sums have been reduce-added into the home windows
         mark()
         call("spn_bank_ce_finalize", _ptr(x.o_win), _ptr(x.l_win), _ptr(x.s_t), _ptr(x.tgt), _ptr(x.ref),
              _ptr(x.es_win) if tau_grad else None, _ptr(x.qall[x.rank * B:(x.rank + 1) * B]), _ptr(colsum), inv_tau,

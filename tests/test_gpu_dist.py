@@ -82,6 +82,19 @@ l_n, dq_n = bank_ce_step_sharded(qq2, sh2, lab2.to(dev), tau)
 os.environ.pop("SPN_EXCHANGE")
 assert abs(l_s.item() - l_n.item()) <= 1e-5 * max(1.0, abs(l_n.item())), (rank, l_s.item(), l_n.item())
 assert float((dq_s - dq_n).norm() / dq_n.norm()) < 1e-4
+# both forms of the NVLink exchange: push (TMA reduce-add from the sweep's epilogue into the home window) and pull (local
+# accumulation, the home rank loads and sums its rows from every rank: a deterministic cross-rank sum)
+assert sdist.symm_exchange_mode(256, world, sh2.N, 640) == "pull" and sdist.symm_exchange_mode(1024, 8, 125000, 768) == "push"
+assert sdist.symm_exchange_mode(96, world, 5000, 256) == "pull"          # B % 128 != 0: only the pull form applies
+for mode in ("push", "pull", "push", "pull"):  # alternating: the two forms share the windows and the barrier epoch
+    os.environ["SPN_EXCHANGE"] = mode
+    l_m, dq_m = bank_ce_step_sharded(qq2, sh2, lab2.to(dev), tau)
+    os.environ.pop("SPN_EXCHANGE")
+    assert abs(l_m.item() - l_n.item()) <= 1e-5 * max(1.0, abs(l_n.item())), (rank, mode, l_m.item(), l_n.item())
+    assert float((dq_m - dq_n).norm() / dq_n.norm()) < 1e-4, (rank, mode)
+    if mode == "pull":  # no atomics across ranks: bit-identical from step to step up to the local sweep's own atomics
+        l_m2, dq_m2 = bank_ce_step_sharded(qq2, sh2, lab2.to(dev), tau)
+        assert float((dq_m2 - dq_m).norm() / dq_m.norm()) < 1e-5
 for it in range(3):  # repeated steps reuse the windows (zeroing + barriers between steps)
     l_r, dq_r = bank_ce_step_sharded(qq2, sh2, lab2.to(dev), tau)
     assert abs(l_r.item() - l_s.item()) <= 1e-6 * max(1.0, abs(l_s.item())) and float((dq_r - dq_s).norm() / dq_s.norm()) < 1e-5
@@ -104,6 +117,12 @@ l_s3, dq_s3 = bank_ce_step_sharded(qq3, sh3, lab3.to(dev), 0.05)
 l_f3, dq_f3 = spn.bank_ce_step(qq3, spn.DeviceBank.from_tensor(bank3, dev), lab3.to(dev), 0.05)
 assert abs(l_s3.item() - l_f3.item()) <= 1e-5 * max(1.0, abs(l_f3.item())), (rank, l_s3.item(), l_f3.item())
 assert float((dq_s3 - dq_f3).norm() / dq_f3.norm()) < 1e-4
+for mode in ("push", "pull"):
+    os.environ["SPN_EXCHANGE"] = mode
+    l_m3, dq_m3 = bank_ce_step_sharded(qq3, sh3, lab3.to(dev), 0.05)
+    os.environ.pop("SPN_EXCHANGE")
+    assert abs(l_m3.item() - l_f3.item()) <= 1e-5 * max(1.0, abs(l_f3.item())), (rank, mode, l_m3.item(), l_f3.item())
+    assert float((dq_m3 - dq_f3).norm() / dq_f3.norm()) < 1e-4, (rank, mode)
 # cold temperature (the fused sweep's static reference is not provably safe below tau ~ 0.0092) and label smoothing over a
 # multi-token bank: both are routed to the two-pass sharded path and still agree with the single-GPU result
 for (qq_, sh_, full_, lab_, tau_, eps_) in ((qq2, sh2, spn.DeviceBank.from_tensor(bank2, dev), lab2, 0.008, 0.0),
