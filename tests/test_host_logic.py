@@ -111,3 +111,22 @@ def test_device_generators_shard_consistently():
     assert not torch.equal(parts[0][3], parts[1][3])  # every rank brings its own queries / labels
     with pytest.raises(ValueError):
         synth.make_device_case(6, 1000, 64, 1, cpu, rank=0, world=3, sharded=True)
+
+
+def test_symm_exchange_mode_rule(monkeypatch):
+    """dist.symm_exchange_mode: long sweeps keep the reduce-scatter inside the sweep (push), short sweeps and batches that are not
+    a multiple of 128 queries pull; SPN_EXCHANGE forces a form (push only where its tile-per-home-rank constraint holds)."""
+    from spn4cir_b200 import dist as sdist
+    monkeypatch.delenv("SPN_EXCHANGE", raising=False)
+    assert sdist.symm_exchange_mode(1024, 8, 125_000, 768) == "push"       # C5 x 8
+    assert sdist.symm_exchange_mode(1024, 2, 500_000, 768) == "push"       # C5 x 2
+    assert sdist.symm_exchange_mode(512, 8, 12_500, 640) == "pull"         # C3 x 8
+    assert sdist.symm_exchange_mode(256, 8, 12_500, 640) == "pull"         # the reference's batch size
+    assert sdist.symm_exchange_mode(96, 2, 500_000, 768) == "pull"         # B % 128 != 0
+    assert sdist.symm_exchange_mode(128, 3, 500_000, 768) == "pull"        # odd number of query tiles
+    monkeypatch.setenv("SPN_EXCHANGE", "pull")
+    assert sdist.symm_exchange_mode(1024, 8, 125_000, 768) == "pull"
+    monkeypatch.setenv("SPN_EXCHANGE", "push")
+    assert sdist.symm_exchange_mode(512, 8, 12_500, 640) == "push"
+    with pytest.raises(ValueError):
+        sdist.symm_exchange_mode(96, 2, 5000, 256)
