@@ -40,29 +40,59 @@ def build_torch_extension(force: bool = False, verbose: bool = False) -> Path:
         return _build_locked(verbose)
 
 
+def _compilers():
+    """g++ candidates, the system one first.  $CXX may point at a toolchain whose only libstdc++ is the static archive
+    (this image: /opt/gcc): an extension linked against it carries a second, never-initialised copy of the iostream
+    machinery next to the libstdc++.so torch uses -- formatting a number into an error message then crashes the process
+    instead of raising."""
+    seen, out = set(), []
+    for c in (shutil.which("g++"), "/usr/bin/g++", os.environ.get("CXX"), shutil.which("c++")):
+        if c and os.path.exists(c) and os.path.realpath(c) not in seen:
+            seen.add(os.path.realpath(c))
+            out.append(c)
+    return out
+
+
+def _embeds_libstdcxx(so: Path) -> bool:
+    """True when the shared object DEFINES ostream symbols itself (libstdc++ linked statically into it)."""
+    nm = shutil.which("nm")
+    if not nm:
+        return False
+    res = subprocess.run([nm, "-D", "--defined-only", str(so)], capture_output=True, text=True)
+    return res.returncode == 0 and "_ZNSo9_M_insertIlEERSoT_" in res.stdout
+
+
 def _build_locked(verbose: bool) -> Path:
     import torch
     from torch.utils import cpp_extension as ce
-    cxx = os.environ.get("CXX") or shutil.which("g++")
-    if not cxx:
+    compilers = _compilers()
+    if not compilers:
         raise SpnError("build", -5, "g++ not found: the torch extension cannot be built")
     cuda_home = os.environ.get("CUDA_HOME") or "/usr/local/cuda"
     incs = list(dict.fromkeys(ce.include_paths() + [str(Path(cuda_home) / "include")]))
     torch_lib = str(Path(torch.__file__).resolve().parent / "lib")
     tmp = EXT_PATH.with_suffix(".so.tmp%d" % os.getpid())
-    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-deprecated-declarations",
-           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}", "-DTORCH_EXTENSION_NAME=_spn_torch",
-           *[f"-I{i}" for i in incs], str(EXT_SRC), "-o", str(tmp),
-           f"-L{torch_lib}", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch",
-           f"-L{PKG_DIR}", f"-l:{LIB_PATH.name}", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{torch_lib}"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        tmp.unlink(missing_ok=True)
-        raise SpnError("build", -5, "g++ failed on spn_torch.cpp:\n" + (res.stdout + res.stderr)[-4000:])
-    os.replace(tmp, EXT_PATH)
-    if verbose:
-        print(res.stdout + res.stderr)
-    return EXT_PATH
+    errors = []
+    for cxx in compilers:
+        cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-deprecated-declarations",
+               f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}", "-DTORCH_EXTENSION_NAME=_spn_torch",
+               *[f"-I{i}" for i in incs], str(EXT_SRC), "-o", str(tmp),
+               f"-L{torch_lib}", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch",
+               f"-L{PKG_DIR}", f"-l:{LIB_PATH.name}", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{torch_lib}"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            tmp.unlink(missing_ok=True)
+            errors.append(f"{cxx} failed on spn_torch.cpp:\n" + (res.stdout + res.stderr)[-3000:])
+            continue
+        if _embeds_libstdcxx(tmp):
+            tmp.unlink(missing_ok=True)
+            errors.append(f"{cxx} links libstdc++ statically into the extension (a second copy next to torch's libstdc++.so)")
+            continue
+        os.replace(tmp, EXT_PATH)
+        if verbose:
+            print(f"[{cxx}]\n" + res.stdout + res.stderr)
+        return EXT_PATH
+    raise SpnError("build", -5, "no usable g++ for the torch extension:\n" + "\n".join(errors))
 
 
 def load_torch_extension() -> None:

@@ -48,8 +48,11 @@ struct StepOut {
 // bank: [N * T, D] bf16 resident rows, labels int64 [B], maxnorm fp32 [1], colsum fp32 [D] (label smoothing only).
 StepOut step_impl(const Tensor& q_in, const Tensor& bank, const Tensor& labels_in, const Tensor& maxnorm,
                   const c10::optional<Tensor>& colsum, double inv_tau, double eps, int64_t T, bool want_ddot) {
+  TORCH_CHECK(q_in.dim() == 2 && bank.dim() == 2 && q_in.size(1) == bank.size(1), "spn4cir: q [B, D] and bank [N*T, D] expected, got ",
+              q_in.dim(), "-d q and ", bank.dim(), "-d bank with last sizes ", q_in.dim() ? q_in.size(-1) : 0, " / ",
+              bank.dim() ? bank.size(-1) : 0);
   TORCH_CHECK(q_in.is_cuda() && bank.is_cuda() && labels_in.is_cuda(), "spn4cir: CUDA tensors required (no CPU fallback)");
-  TORCH_CHECK(q_in.dim() == 2 && bank.dim() == 2 && q_in.size(1) == bank.size(1), "spn4cir: q [B, D] and bank [N*T, D] expected");
+  TORCH_CHECK(q_in.size(0) > 0, "spn4cir: empty batch (B = 0)");
   TORCH_CHECK(bank.scalar_type() == at::kBFloat16 && bank.is_contiguous(), "spn4cir: bank must be contiguous bf16 rows");
   TORCH_CHECK(T >= 1 && bank.size(0) % T == 0, "spn4cir: bank rows not a multiple of T");
   TORCH_CHECK(eps == 0.0 || colsum.has_value(), "spn4cir: label smoothing needs the bank column sums");

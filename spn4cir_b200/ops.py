@@ -416,6 +416,11 @@ def _warn_raw_bank(bank: torch.Tensor) -> None:
 
 
 def _prep_labels(labels: Optional[torch.Tensor], B: int, dev: torch.device) -> torch.Tensor:
+    if B <= 0:
+        raise SpnError("bank_ce", -1, "empty batch (B = 0): the loss of zero queries is undefined (the reference's "
+                       "F.cross_entropy returns NaN); nothing was launched")
+    if labels is not None and labels.numel() != B:
+        raise SpnError("bank_ce", -1, f"{labels.numel()} labels for {B} queries")
     if labels is None:  # models_negplus.py:152-153
         return torch.arange(B, dtype=torch.int64, device=dev)
     return labels.to(device=dev, dtype=torch.int64).contiguous()

@@ -439,3 +439,39 @@ def test_part_infonce_edge_cases():
     assert abs(a.item() - b.item()) < 1e-6
     r_loss, _, _ = obank.part_loss_and_grads(bf16_round(q.half().float()), bf16_round(bank), cand, 0.05)
     assert abs(a.item() - r_loss.item()) <= 1e-4 * max(1.0, abs(r_loss.item()))
+
+
+def test_empty_and_malformed_inputs_fail_loudly():
+    """An empty batch / an empty query set / an unsupported feature width is rejected with an exception (the reference would
+    return NaN from an empty cross-entropy, clip4cir/models_negplus.py:150-154); nothing is silently skipped or computed on
+    the CPU, and an error raised by the C ABI below the PyTorch extension reaches Python as an exception (regression: a
+    statically linked libstdc++ in the extension crashed the process while formatting the status code)."""
+    from spn4cir_b200 import _torch_ext
+    from spn4cir_b200._lib import SpnError
+    bank = synth.make_bank(300, 64, 1, seed=5)
+    db = spn.DeviceBank.from_tensor(bank, DEV)
+    q0 = torch.zeros((0, 64), device=DEV)
+    lab0 = torch.zeros((0,), dtype=torch.int64, device=DEV)
+    with pytest.raises(SpnError, match="empty batch"):
+        spn.bank_infonce(q0, db, lab0, 0.02)
+    with pytest.raises(SpnError, match="empty batch"):
+        spn.bank_ce_step(q0, db, lab0, 0.02)
+    maxnorm, _ = db.stats(False)
+    with pytest.raises(RuntimeError, match="empty batch"):
+        _torch_ext.ops().bank_ce_step(q0, db.data, lab0, maxnorm, None, 50.0, 0.0, 1, False)
+    with pytest.raises(Exception):
+        spn.sim_topk(q0, bank.to(DEV).float(), 5)
+    # an error from the C ABI (D = 96 is not a multiple of 64) through the extension: status code + message, no crash
+    bank96 = torch.randn(200, 96, device=DEV).to(torch.bfloat16)
+    q96 = torch.randn(4, 96, device=DEV)
+    lab4 = torch.zeros(4, dtype=torch.int64, device=DEV)
+    with pytest.raises(RuntimeError, match=r"failed \(-1\).*bad shape"):
+        _torch_ext.ops().bank_ce_step(q96, bank96, lab4, maxnorm, None, 50.0, 0.0, 1, False)
+    with pytest.raises(SpnError, match="labels for"):
+        spn.bank_ce_step(torch.randn(4, 64, device=DEV), db, lab4[:3], 0.02)
+    torch.cuda.synchronize()
+    # and the device is still usable afterwards
+    lab = synth.make_labels(4, 300, seed=6)
+    q = synth.make_queries(bank, lab, "S", seed=7).to(DEV)
+    loss, dq = spn.bank_ce_step(q, db, lab.to(DEV), 0.02)
+    assert torch.isfinite(loss).item() and torch.isfinite(dq).all().item()

@@ -27,6 +27,20 @@ def test_extension_has_no_cpu_fallback():
         ops.bank_ce_step(q, bank, lab, mx, None, 50.0, 0.0, 1, False)
 
 
+def test_extension_errors_with_numbers_raise_instead_of_crashing():
+    """Regression: with $CXX pointing at a toolchain that only ships a static libstdc++ (this image's /opt/gcc) the extension
+    carried a second copy of the iostream machinery and formatting a NUMBER into an error message crashed the process.  The
+    build now prefers the system g++ and rejects such a link; a shape error (its message contains numbers) must raise."""
+    assert not _torch_ext._embeds_libstdcxx(_torch_ext.build_torch_extension())
+    ops = _torch_ext.ops()
+    q, bank = torch.randn(4, 64), torch.randn(10, 32).to(torch.bfloat16)
+    lab, mx = torch.zeros(4, dtype=torch.int64), torch.ones(1)
+    with pytest.raises(RuntimeError, match="last sizes 64 / 32"):
+        ops.bank_ce_step(q, bank, lab, mx, None, 50.0, 0.0, 1, False)
+    with pytest.raises(RuntimeError, match="last sizes 64 / 32"):
+        ops.bank_infonce(q, None, bank, lab, mx, None, 50.0, 0.0, 1)
+
+
 def test_compat_infonce_keeps_gradient_of_in_batch_targets():
     """`infonce_loss` is also called by the reference with in-batch targets that carry gradient
     (clip4cir/models.py:160, models_negtype.py:84-107): rebinding the method must not drop that gradient."""
