@@ -88,3 +88,31 @@ def test_tiny_galleries(Q, G, D, K):
     tgt = torch.randint(0, G, (Q,), generator=g, dtype=torch.int32)
     rank, _ = spn.sim_rank(qq.to(DEV), gg.to(DEV), tgt.to(DEV))
     assert torch.equal(rank.cpu().long(), (order == tgt.long()[:, None]).float().argmax(-1))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_non_current_device():
+    """Everything runs on the device of its inputs, not on the current device (one process driving two GPUs)."""
+    assert torch.cuda.current_device() == 0
+    bank = synth.make_bank(3000, 640, 1, seed=11)
+    lab = synth.make_labels(200, 3000, seed=12)
+    q = synth.make_queries(bank, lab, "S", seed=13)
+    out = {}
+    for d in ("cuda:0", "cuda:1"):
+        db = spn.DeviceBank.from_tensor(bank, d)
+        qd = q.to(d).requires_grad_(True)
+        loss = spn.bank_infonce(qd, db, lab.to(d), 0.02)
+        loss.backward()
+        l2, dq2 = spn.bank_ce_step(q.to(d), db, lab.to(d), 0.02)
+        gal = torch.nn.functional.normalize(bank[:500].float(), dim=-1).to(d)
+        qq = torch.nn.functional.normalize(q[:50], dim=-1).to(d)
+        _, idx = spn.sim_topk(qq, gal, 10)
+        _, idx_tc = spn.sim_topk(torch.nn.functional.normalize(q, dim=-1).to(d), gal, 10, mode="tc")
+        torch.cuda.synchronize(d)
+        assert qd.grad.device == torch.device(d) and dq2.device == torch.device(d) and idx.device == torch.device(d)
+        out[d] = (loss.item(), qd.grad.cpu(), l2.item(), idx.cpu(), idx_tc.cpu())
+    a, b = out["cuda:0"], out["cuda:1"]
+    assert abs(a[0] - b[0]) < 1e-6 and abs(a[2] - b[2]) < 1e-6
+    assert float((a[1] - b[1]).norm() / a[1].norm()) < 1e-5
+    assert torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
+    assert torch.cuda.current_device() == 0
